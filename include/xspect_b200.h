@@ -1,0 +1,165 @@
+/* xspect_b200.h — C ABI of libxspect_b200.so: the B200-native replacement for the k-mer
+ * scoring step behind XspecT's ProbabilisticFilterModel / ProbabilisticSingleFilterModel /
+ * ProbabilisticFilterSVMModel / ProbabilisticFilterMlstSchemeModel prediction.
+ *
+ * The reference reaches this path through two third-party Python extensions
+ * (cobs_index from cobs-reloaded, rbloom); every entry point below names the reference
+ * call site (file:line under /root/reference) it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no CUDA, torch or C++ types in any signature
+ *     (`void* stream` is a cudaStream_t passed as an opaque pointer; NULL = default stream)
+ *   - every function returns an int: XS_OK (0) or a negative xs_status; the message for the
+ *     calling thread is returned by xs_last_error()
+ *   - handles own their device (HBM) memory until xs_*_close; callers own all input and
+ *     output buffers; handles are immutable after open, so concurrent queries from several
+ *     host threads are allowed
+ *   - there is NO CPU fallback: every query needs a CUDA device and fails with XS_ERR_CUDA
+ *     otherwise
+ *   - sequences are described by two arrays seq_begin[i], seq_end[i] (byte offsets into
+ *     `bases`); a contiguous batch passes the same offsets array twice, shifted by one
+ *     (seq_end = seq_begin + 1); overlapping segments (MLST chunks) are allowed
+ */
+#ifndef XSPECT_B200_H
+#define XSPECT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xs_cobs xs_cobs;   /* a COBS classic/compact index resident in HBM */
+typedef struct xs_bloom xs_bloom; /* an rbloom bit array resident in HBM */
+
+enum xs_status {
+    XS_OK = 0,
+    XS_ERR_ARG = -1,         /* bad argument (NULL, k out of range, step == 0, ...) */
+    XS_ERR_IO = -2,          /* file missing / unreadable  -> FileNotFoundError / OSError */
+    XS_ERR_FORMAT = -3,      /* not a COBS / rbloom file, size identity violated */
+    XS_ERR_CUDA = -4,        /* CUDA runtime error, or no device */
+    XS_ERR_NOMEM = -5,       /* host or device allocation failed */
+    XS_ERR_UNSUPPORTED = -6  /* valid input this build does not handle (k > 32, ...) */
+};
+
+/* element type of the per-document count matrix written by xs_cobs_query* */
+enum xs_dtype { XS_U8 = 1, XS_U16 = 2, XS_U32 = 4 };
+
+/* what a COBS query does with a window that touches a byte outside upper-case ACGT
+ * (third-party behaviour, SURVEY.md A.2.5a — one switch): */
+enum xs_nonacgt_policy {
+    XS_NONACGT_SKIP = 0,   /* window contributes no hits (default) */
+    XS_NONACGT_LITERAL = 1 /* complement of such a byte is 0x00; hash min(literal, mapped revcomp) */
+};
+
+enum xs_cobs_kind { XS_COBS_CLASSIC = 1, XS_COBS_COMPACT = 2 };
+
+typedef struct {
+    uint32_t kind;          /* xs_cobs_kind */
+    uint32_t term_size;     /* k */
+    uint32_t canonicalize;  /* header flag */
+    uint32_t num_hashes;    /* h */
+    uint32_t n_docs_total;  /* documents in the file */
+    uint32_t doc_begin;     /* this handle's document-column shard [doc_begin, doc_end) */
+    uint32_t doc_end;
+    uint32_t n_pages;       /* 1 for classic */
+    uint64_t page_bytes;    /* bytes per row per page in the FILE */
+    uint64_t row_stride;    /* bytes per row per page in HBM (re-strided, power of two or x16) */
+    uint64_t sig_size_max;  /* largest signature_size over pages */
+    uint64_t hbm_bytes;     /* device bytes held */
+    int32_t device;
+    int32_t policy;         /* xs_nonacgt_policy */
+} xs_cobs_info_t;
+
+typedef struct {
+    uint64_t n_bits;
+    uint64_t k_hashes;   /* rbloom's k (number of LCG probes) */
+    uint32_t term_size;  /* k-mer length this handle hashes */
+    int32_t device;
+    uint64_t hbm_bytes;
+} xs_bloom_info_t;
+
+/* ---- library ------------------------------------------------------------------------ */
+int xs_version(void);
+const char* xs_last_error(void);           /* thread-local, never NULL */
+int xs_device_count(int* n);
+/* pinned host memory for the host-buffer query entry points (pageable memory also works,
+ * but is copied through the driver's bounce buffer) */
+int xs_host_alloc(uint64_t bytes, void** out);
+int xs_host_free(void* p);
+
+/* ---- COBS index ------------------------------------------------------------------------
+ * Replaces cobs_index.Search(path, load_complete)
+ *   probabilistic_filter_model.py:194,389; probabilistic_filter_svm_model.py:313;
+ *   probabilistic_filter_mlst_model.py:142,188
+ * Loads index.cobs_classic / <locus>.cobs_compact unchanged into HBM.  [doc_begin, doc_end)
+ * selects a document-column shard (multiples of 8; (0, 0) = all documents; classic only).
+ * Missing file -> XS_ERR_IO. */
+int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_end, xs_cobs** out);
+int xs_cobs_info(const xs_cobs* ix, xs_cobs_info_t* info);
+/* document names of the whole file, '\n'-separated, no trailing NUL counted in *needed */
+int xs_cobs_doc_names(const xs_cobs* ix, char* buf, uint64_t cap, uint64_t* needed);
+int xs_cobs_set_policy(xs_cobs* ix, int policy);
+int xs_cobs_close(xs_cobs* ix);
+
+/* Replaces the per-record loop around cobs Search.search(str(sequence), step=step)
+ *   probabilistic_filter_model.py:227 (called from :291-297);
+ *   probabilistic_filter_mlst_model.py:242,274
+ * For every sequence i and local document d:
+ *   out[i*n_local + d] = #{sampled windows p = 0, step, 2*step, ... <= len_i - k :
+ *                          AND_{j<h} bit_d(row[XXH64(term_p, k, seed=j) % signature_size])}
+ * Sequences shorter than k produce zeros (the len > k ValueError of
+ * probabilistic_filter_model.py:224-225 is raised by the Python layer before the call).
+ * XS_U8 / XS_U16 outputs saturate at 255 / 65535.
+ * Host variant: all pointers are host memory; copies are pipelined inside; returns when
+ * `out` is complete.  Device variant: all pointers are device memory on the handle's device;
+ * asynchronous on `stream`. */
+int xs_cobs_query(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const uint64_t* seq_begin,
+                  const uint64_t* seq_end, uint64_t n_seq, uint32_t step, int out_dtype, void* out);
+int xs_cobs_query_device(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
+                         const uint64_t* d_seq_begin, const uint64_t* d_seq_end, uint64_t n_seq,
+                         uint32_t step, int out_dtype, void* d_out, void* stream);
+
+/* Result order of cobs Search.search (what _convert_cobs_result_to_dict iterates,
+ * probabilistic_filter_model.py:393-409; MLST tie-breaks, probabilistic_filter_mlst_model.py:254-256,284):
+ * all documents, std::partial_sort by score descending.  Host-only helper. */
+int xs_cobs_result_order(const uint32_t* scores, uint32_t n_docs, uint32_t* order);
+
+/* ---- Bloom filter ------------------------------------------------------------------------
+ * Replaces rbloom.Bloom.load(path, hash_func=xxh3_64_intdigest)
+ *   probabilistic_single_filter_model.py:155-158
+ * term_size is the model's k (the .bloom file does not store it). */
+int xs_bloom_open(const char* path, uint32_t term_size, int device, xs_bloom** out);
+int xs_bloom_info(const xs_bloom* bf, xs_bloom_info_t* info);
+int xs_bloom_close(xs_bloom* bf);
+
+/* Replaces sum(1 for kmer in _generate_kmers(sequence, step) if kmer in self.bf)
+ *   probabilistic_single_filter_model.py:122-124 with :161-180
+ * out_hits[i] = #{sampled windows whose min(kmer, revcomp) (Biopython complement, literal
+ * bytes, no filtering) passes all k_hashes LCG probes seeded by XXH3-64}. */
+int xs_bloom_query(xs_bloom* bf, const uint8_t* bases, uint64_t n_bases, const uint64_t* seq_begin,
+                   const uint64_t* seq_end, uint64_t n_seq, uint32_t step, uint32_t* out_hits);
+int xs_bloom_query_device(xs_bloom* bf, const uint8_t* d_bases, uint64_t n_bases,
+                          const uint64_t* d_seq_begin, const uint64_t* d_seq_end, uint64_t n_seq,
+                          uint32_t step, uint32_t* d_out_hits, void* stream);
+
+/* ---- single stages (host buffers; used by the parity tests to pin each kernel alone) ----- */
+/* 2-bit packing: packed[w] holds bases [32w, 32w+32), base j in bits [2j, 2j+1], A=0 C=1 G=2 T=3;
+ * invalid[w] bit j = 1 when the byte is not one of upper-case ACGT.  n_words = n_bases/32 + 1. */
+int xs_pack_2bit(const uint8_t* bases, uint64_t n_bases, int device, uint64_t* packed, uint32_t* invalid);
+/* canonical k-mer of every window p = 0..n_bases-k of one sequence: codes[p] = 2-bit code of
+ * min(kmer, revcomp), first base in the most significant position; valid[p] = 0 when the
+ * window touches a non-ACGT byte. */
+int xs_canonical_kmers(const uint8_t* bases, uint64_t n_bases, uint32_t k, int device,
+                       uint64_t* codes, uint8_t* valid);
+/* row ids of one sequence's sampled windows: rows[(w*h + j)*n_pages + page], valid[w] */
+int xs_cobs_rows(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, uint32_t step,
+                 uint64_t* rows, uint8_t* valid);
+/* XXH3-64 of the Bloom term of every sampled window of one sequence */
+int xs_bloom_hashes(xs_bloom* bf, const uint8_t* bases, uint64_t n_bases, uint32_t step, uint64_t* hashes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XSPECT_B200_H */
