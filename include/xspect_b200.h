@@ -84,6 +84,8 @@ typedef struct {
 int xs_version(void);
 const char* xs_last_error(void);           /* thread-local, never NULL */
 int xs_device_count(int* n);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t xs_launch_count(void);
 /* pinned host memory for the host-buffer query entry points (pageable memory also works,
  * but is copied through the driver's bounce buffer) */
 int xs_host_alloc(uint64_t bytes, void** out);

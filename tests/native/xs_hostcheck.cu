@@ -47,13 +47,17 @@ uint64_t hc_canonical(const uint8_t* ascii, uint64_t n, uint64_t g, uint32_t k, 
     return msb;
 }
 void hc_literal(const uint8_t* bases, uint64_t g, uint32_t k, const uint8_t* comp, int canonicalize, uint8_t* out) {
-    Term t; literal_term(bases, g, k, comp, canonicalize != 0, t);
+    Term t;
+    if (comp) literal_term(bases, g, k, TableComp{comp}, canonicalize != 0, t);
+    else literal_term(bases, g, k, BioComp(), canonicalize != 0, t);
     for (uint32_t i = 0; i < k; ++i) out[i] = (uint8_t)(t.w[i >> 3] >> (8 * (i & 7)));
 }
 void hc_lcg(uint64_t h0, uint32_t n, uint64_t* out) {
     uint64_t hi = 0, lo = h0;
     for (uint32_t i = 0; i < n; ++i) out[i] = lcg_next(hi, lo);
 }
+uint8_t hc_biocomp(uint8_t c) { return BioComp()(c); }
+uint8_t hc_cobscomp(uint8_t c) { return CobsComp()(c); }
 uint64_t hc_mod(uint64_t x, uint64_t m) {
     uint64_t magic = m == 1 ? ~0ULL : (uint64_t)((((unsigned __int128)1) << 64) / m);
     return mod_barrett(x, m, magic);

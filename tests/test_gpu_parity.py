@@ -1,0 +1,286 @@
+"""GPU parity: every count the CUDA path produces equals the CPU oracle's on the same seeded inputs.
+All calls go through the C ABI (xspect2_b200.engine -> libxspect_b200.so).  Bit-exact (integer path)."""
+import numpy as np
+import pytest
+
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk_classic(oracle, tmp_path, rng, n_docs, k, h, length=3000, name="index.cobs_classic", fpr=0.01, **kw):
+    docs = synth.make_genomes(rng, n_docs, length)
+    p = tmp_path / name
+    oracle.write_classic(p, docs, k=k, num_hashes=h, fpr=fpr, **kw)
+    return p, docs
+
+
+def _check_cobs(gpu, oracle, path, bases, b, e, step=1, dtype=None, policy=0, **open_kw):
+    ix = gpu.CobsIndex(path, **open_kw)
+    ix.set_policy(policy)
+    orc = oracle.CobsOracle(path, policy=policy)
+    got = ix.query(bases, b, e, step=step, dtype=dtype)
+    exp = orc.counts_batch(bases, b, e, step=step, threads=4)
+    lo, hi = ix.info.doc_begin, ix.info.doc_end
+    exp = exp[:, lo:hi]
+    if dtype in (1, 2):
+        exp = np.minimum(exp, 255 if dtype == 1 else 65535)
+    assert got.shape == exp.shape
+    bad = np.argwhere(got.astype(np.uint32) != exp)
+    assert bad.size == 0, f"{bad.shape[0]} mismatches, first {bad[:5].tolist()}: got {got[tuple(bad[0])]} exp {exp[tuple(bad[0])]}"
+    ix.close()
+    return got
+
+
+# ------------------------------------------------------------------------------------------ stages
+def test_pack_2bit(gpu):
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 31, 32, 33, 1000, 4097):
+        a = synth.mutate(rng, synth.random_dna(rng, n), n_rate=0.05, lower=0.05, iupac=0.02)
+        packed, invalid = gpu.pack_2bit(a)
+        for i in range(n):
+            ok = a[i] in b"ACGT"
+            assert ((int(invalid[i // 32]) >> (i % 32)) & 1) == (0 if ok else 1)
+            if ok:
+                assert ((int(packed[i // 32]) >> (2 * (i % 32))) & 3) == b"ACGT".index(a[i])
+
+
+@pytest.mark.parametrize("k", [1, 8, 21, 31, 32])
+def test_canonical_kmers(gpu, oracle, k):
+    rng = np.random.default_rng(2)
+    a = synth.mutate(rng, synth.random_dna(rng, 700), n_rate=0.01)
+    codes, valid = gpu.canonical_kmers(a, k)
+    raw = a.tobytes()
+    for p in range(len(raw) - k + 1):
+        t = oracle.cobs_term(raw[p:p + k])
+        assert valid[p] == (0 if t is None else 1)
+        if t is not None:
+            c = 0
+            for ch in t:
+                c = (c << 2) | b"ACGT".index(ch)
+            assert int(codes[p]) == c
+
+
+@pytest.mark.parametrize("k,h,step", [(21, 7, 1), (31, 1, 1), (21, 7, 3), (17, 3, 2), (32, 2, 1)])
+def test_cobs_row_ids(gpu, oracle, tmp_path, k, h, step):
+    rng = np.random.default_rng(3)
+    p, _ = _mk_classic(oracle, tmp_path, rng, 9, k, h, length=500)
+    a = synth.mutate(rng, synth.random_dna(rng, 900), n_rate=0.01)
+    ix = gpu.CobsIndex(p)
+    rows, valid = ix.rows(a, step)
+    erows, evalid = oracle.CobsOracle(p).rows(a, step)
+    assert np.array_equal(valid, evalid)
+    assert np.array_equal(rows, erows)
+
+
+# ------------------------------------------------------------------------------------------ narrow rows
+@pytest.mark.parametrize("n_docs", [1, 7, 8, 9, 90, 128])
+@pytest.mark.parametrize("k,h", [(21, 7), (31, 1), (15, 3)])
+def test_cobs_narrow_reads(gpu, oracle, tmp_path, n_docs, k, h):
+    rng = np.random.default_rng(100 + n_docs)
+    p, docs = _mk_classic(oracle, tmp_path, rng, n_docs, k, h)
+    genomes = [s for v in docs.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes, 600, (k, 300), sub=0.01, n_rate=0.003)
+    got = _check_cobs(gpu, oracle, p, bases, b, e)
+    assert got.sum() > 0
+
+
+@pytest.mark.parametrize("step", [1, 2, 3, 4, 500])
+def test_cobs_steps_and_long_sequences(gpu, oracle, tmp_path, step):
+    rng = np.random.default_rng(7)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 12, 21, 7, length=20000)
+    g = docs["doc00003"][0]
+    # one long contig (many tiles), a medium one, reads, and an exact-k sequence
+    parts = [synth.mutate(rng, g, n_rate=0.0005), g[:5000], g[100:250], g[:21], synth.random_dna(rng, 2500)]
+    bases = np.concatenate(parts)
+    lens = np.array([x.size for x in parts], np.uint64)
+    e = np.cumsum(lens, dtype=np.uint64)
+    b = e - lens
+    got = _check_cobs(gpu, oracle, p, bases, b, e, step=step)
+    if step == 1:
+        assert got.dtype == np.uint16 and got[1, 3] == 5000 - 20  # true positives: every k-mer of doc 3
+
+
+def test_cobs_golden_g1_shape(gpu, oracle, tmp_path):
+    """Shape of the reference's G1/G2 known answers (tests/test_probabilistic_filter_model.py:73-93,149-161):
+    an 80-bp substring of one training genome scores 60/step on it."""
+    rng = np.random.default_rng(9)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 3, 21, 7, length=30000)
+    q = docs["doc00000"][0][1000:1080]
+    ix = gpu.CobsIndex(p)
+    for step in (1, 2, 3, 4):
+        c = ix.counts(q, step)
+        assert c[0] == -(-60 // step)
+        assert np.array_equal(c, oracle.CobsOracle(p).counts(q, step))
+
+
+def test_cobs_edge_sequences(gpu, oracle, tmp_path):
+    rng = np.random.default_rng(11)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 20, 21, 7)
+    g = docs["doc00001"][0]
+    # empty, shorter than k, exactly k, all-N, lower-case, overlapping segments, unordered offsets
+    parts = [g[:0], g[:20], g[:21], np.full(100, ord("N"), np.uint8), g[:200] | 0x20, g[:400]]
+    bases = np.concatenate(parts)
+    lens = np.array([x.size for x in parts], np.uint64)
+    e = np.cumsum(lens, dtype=np.uint64)
+    b = e - lens
+    b = np.concatenate([b, b[-1:] + 50, b[-1:] + 10, b[-1:]]).astype(np.uint64)
+    e = np.concatenate([e, e[-1:] - 50, e[-1:] - 300, e[-1:]]).astype(np.uint64)
+    _check_cobs(gpu, oracle, p, bases, b, e)
+    _check_cobs(gpu, oracle, p, bases, b, e, policy=1)   # LITERAL non-ACGT policy
+    # no sequences at all
+    ix = gpu.CobsIndex(p)
+    assert ix.query(bases, np.zeros(0, np.uint64), np.zeros(0, np.uint64)).shape == (0, 20)
+
+
+def test_cobs_many_empty_sequences_fallback_tile(gpu, oracle, tmp_path):
+    """More than a tile's worth of zero-window sequences between real ones (staging fallback path)."""
+    rng = np.random.default_rng(12)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 10, 21, 7)
+    g = docs["doc00002"][0]
+    parts = [g[:300]] + [g[:5]] * 3000 + [g[300:700]] + [g[:0]] * 2500 + [g[700:1000]]
+    bases = np.concatenate(parts)
+    lens = np.array([x.size for x in parts], np.uint64)
+    e = np.cumsum(lens, dtype=np.uint64)
+    _check_cobs(gpu, oracle, p, bases, e - lens, e)
+    _check_cobs(gpu, oracle, p, bases, e - lens, e, dtype=1)
+
+
+@pytest.mark.parametrize("dtype", [1, 2, 4])
+def test_cobs_output_dtypes_saturate(gpu, oracle, tmp_path, dtype):
+    rng = np.random.default_rng(13)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 5, 21, 7, length=4000)
+    g = docs["doc00004"][0]
+    parts = [g, g[:150], g[:1500], synth.random_dna(rng, 150)]   # 3980 windows saturate u8
+    bases = np.concatenate(parts)
+    lens = np.array([x.size for x in parts], np.uint64)
+    e = np.cumsum(lens, dtype=np.uint64)
+    _check_cobs(gpu, oracle, p, bases, e - lens, e, dtype=dtype)
+
+
+def test_cobs_not_canonical_index(gpu, oracle, tmp_path):
+    rng = np.random.default_rng(14)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 6, 21, 3, canonicalize=0)
+    genomes = [s for v in docs.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes, 200, 150, n_rate=0.01)
+    _check_cobs(gpu, oracle, p, bases, b, e)
+
+
+# ------------------------------------------------------------------------------------------ wide rows
+@pytest.mark.parametrize("n_docs,k,h", [(129, 21, 7), (300, 21, 7), (1000, 31, 1), (2100, 21, 3), (5000, 21, 7)])
+def test_cobs_wide_reads(gpu, oracle, tmp_path, n_docs, k, h):
+    rng = np.random.default_rng(200 + n_docs)
+    p, docs = _mk_classic(oracle, tmp_path, rng, n_docs, k, h, length=400 if n_docs > 1000 else 800)
+    genomes = [s for v in docs.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes, 120, (k, 260), sub=0.01, n_rate=0.003)
+    long_seq = np.concatenate([genomes[1], genomes[5], genomes[7]])
+    bases = np.concatenate([bases, long_seq])
+    b = np.concatenate([b, [e[-1]]]).astype(np.uint64)
+    e = np.concatenate([e, [e[-1] + long_seq.size]]).astype(np.uint64)
+    got = _check_cobs(gpu, oracle, p, bases, b, e)
+    assert got.sum() > 0
+    _check_cobs(gpu, oracle, p, bases, b, e, step=3, dtype=1)
+
+
+def test_cobs_wide_kernel_on_narrow_index(gpu, oracle, tmp_path, monkeypatch):
+    rng = np.random.default_rng(15)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 90, 21, 7)
+    genomes = [s for v in docs.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes, 300, (21, 400), n_rate=0.002)
+    monkeypatch.setenv("XS_FORCE_WIDE", "1")
+    _check_cobs(gpu, oracle, p, bases, b, e)
+
+
+@pytest.mark.parametrize("n_docs,lo,hi", [(90, 0, 48), (90, 48, 90), (1000, 256, 768), (1000, 768, 1000)])
+def test_cobs_document_column_shards(gpu, oracle, tmp_path, n_docs, lo, hi):
+    rng = np.random.default_rng(16)
+    p, docs = _mk_classic(oracle, tmp_path, rng, n_docs, 21, 7, length=600)
+    genomes = [s for v in docs.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes, 150, 150)
+    _check_cobs(gpu, oracle, p, bases, b, e, doc_begin=lo, doc_end=hi)
+
+
+# ------------------------------------------------------------------------------------------ compact (MLST)
+@pytest.mark.parametrize("n_alleles,k,page_size", [(40, 21, None), (600, 31, None), (600, 21, 4), (3000, 31, 32)])
+def test_cobs_compact(gpu, oracle, tmp_path, n_alleles, k, page_size):
+    rng = np.random.default_rng(300 + n_alleles)
+    cons = synth.random_dna(rng, 450)
+    docs = {}
+    for a in range(n_alleles):
+        s = cons.copy()
+        for pos in rng.integers(0, 450, size=int(rng.integers(1, 6))):
+            s[pos] = synth.ACGT[rng.integers(0, 4)]
+        L = int(rng.integers(400, 451))
+        docs[f"Allele_ID_{a + 1}"] = [s[:L]]
+    p = tmp_path / "locus.cobs_compact"
+    meta = oracle.write_compact(p, docs, k=k, num_hashes=1, fpr=0.001, page_size=page_size)
+    genome = np.concatenate([synth.random_dna(rng, 5000), docs["Allele_ID_4"][0], synth.random_dna(rng, 5000)])
+    chunks_b = np.arange(0, genome.size - 450, 450 - k + 1, dtype=np.uint64)
+    chunks_e = np.minimum(chunks_b + 450, genome.size).astype(np.uint64)
+    got = _check_cobs(gpu, oracle, p, genome, chunks_b, chunks_e)
+    ix = gpu.CobsIndex(p)
+    assert ix.names == meta["names"]
+    col = ix.names.index("Allele_ID_4")
+    assert got[:, col].max() >= 400 - k + 1 - 60
+
+
+# ------------------------------------------------------------------------------------------ Bloom
+def _mk_bloom(oracle, tmp_path, rng, k, length=20000, **kw):
+    g = synth.random_dna(rng, length)
+    p = tmp_path / "filter.bloom"
+    meta = oracle.write_bloom(p, [g], k=k, **kw)
+    return p, g, meta
+
+
+@pytest.mark.parametrize("k", [21, 31, 13])
+@pytest.mark.parametrize("step", [1, 3])
+def test_bloom_reads(gpu, oracle, tmp_path, k, step):
+    rng = np.random.default_rng(400 + k)
+    p, g, meta = _mk_bloom(oracle, tmp_path, rng, k)
+    assert meta["k_hashes"] == 6
+    bases, b, e = synth.sample_reads(rng, [g], 500, (k, 300), sub=0.01, n_rate=0.004, lower=0.002, iupac=0.002)
+    bf = gpu.BloomFilter(p, k)
+    got = bf.query(bases, b, e, step)
+    exp = oracle.BloomOracle(p, k).hits_batch(bases, b, e, step, threads=4)
+    assert np.array_equal(got, exp)
+    assert got.sum() > 0
+
+
+def test_bloom_hash_stage_and_long_sequence(gpu, oracle, tmp_path):
+    rng = np.random.default_rng(17)
+    p, g, _ = _mk_bloom(oracle, tmp_path, rng, 21)
+    bf = gpu.BloomFilter(p, 21)
+    a = synth.mutate(rng, g[:3000], n_rate=0.003, lower=0.01)
+    hs = bf.hashes(a)
+    raw = a.tobytes()
+    for i in range(0, len(raw) - 20, 7):
+        assert int(hs[i]) == oracle.xxh3_64(oracle.bloom_term(raw[i:i + 21]))
+    assert bf.hits(g) == g.size - 20          # every training k-mer is a member
+    orc = oracle.BloomOracle(p, 21)
+    long_seq = np.concatenate([g[5000:15000], synth.random_dna(rng, 30000)])
+    assert bf.hits(long_seq) == orc.hits(long_seq)
+    # golden G5 shape (tests/test_probabilistic_single_filter_model.py:42-56): a 22-mer of the training
+    # genome has 2 member k-mers
+    assert bf.hits(g[777:799]) == 2
+    # many tiny sequences incl. shorter than k
+    parts = [g[i:i + 21 + (i % 3) - 1] for i in range(0, 4000, 2)]
+    bases = np.concatenate(parts)
+    lens = np.array([x.size for x in parts], np.uint64)
+    e = np.cumsum(lens, dtype=np.uint64)
+    assert np.array_equal(bf.query(bases, e - lens, e), orc.hits_batch(bases, e - lens, e))
+
+
+def test_single_record_shims(gpu, oracle, tmp_path):
+    rng = np.random.default_rng(18)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 5, 21, 7)
+    s = gpu.Search(str(p), True)
+    q = docs["doc00002"][0][100:400].tobytes().decode()
+    res = s.search(q, step=2)
+    exp = oracle.CobsOracle(p).search(q, step=2)
+    assert [(r.doc_name, r.score) for r in res] == [(r.doc_name, r.score) for r in exp]
+    pb, g, _ = _mk_bloom(oracle, tmp_path, rng, 21)
+    bf = gpu.Bloom.load(str(pb), 21)
+    km = oracle.bloom_term(g[50:71].tobytes()).decode()
+    assert km in bf
+    assert (oracle.bloom_term(b"ACGTTGCATGCATGCATGCAA").decode() in bf) == (
+        oracle.bloom_term(b"ACGTTGCATGCATGCATGCAA").decode() in oracle.BloomOracle(pb, 21))

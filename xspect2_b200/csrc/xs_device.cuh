@@ -138,15 +138,42 @@ XS_HD void expand_ascii(uint64_t c, uint32_t k, Term& t) {
 }
 
 // ------------------------------------------------------------------ literal-byte path
-// comp: 256-byte complement table.  Builds min(window, revcomp(window)) over literal bytes;
-// prefer_fwd_on_tie is irrelevant for the bytes produced (equal strings).
-XS_HD void literal_term(const uint8_t* __restrict__ bases, uint64_t g, uint32_t k,
-                                             const uint8_t* __restrict__ comp, bool canonicalize, Term& t) {
+// complement rules for windows that touch a byte outside upper-case ACGT
+struct CobsComp {   // cobs: ACGT only, anything else maps to 0x00 (LITERAL policy)
+    XS_HD uint8_t operator()(uint8_t c) const {
+        switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return 0; }
+    }
+};
+struct BioComp {    // Biopython DNA complement: IUPAC-aware, case-preserving, U->A, others identity
+    XS_HD uint8_t operator()(uint8_t c) const {
+        uint8_t u = c & 0xDF;
+        if (u < 'A' || u > 'Z') return c;
+        uint8_t m;
+        switch (u) {
+            case 'A': m = 'T'; break; case 'C': m = 'G'; break; case 'G': m = 'C'; break; case 'T': m = 'A'; break;
+            case 'M': m = 'K'; break; case 'R': m = 'Y'; break; case 'Y': m = 'R'; break; case 'K': m = 'M'; break;
+            case 'V': m = 'B'; break; case 'H': m = 'D'; break; case 'D': m = 'H'; break; case 'B': m = 'V'; break;
+            case 'U': m = 'A'; break;
+            default: m = u; break;  // W S X N and every other letter map to themselves
+        }
+        return (uint8_t)(m | (c & 0x20));
+    }
+};
+struct TableComp {  // 256-byte table (host unit tests)
+    const uint8_t* t;
+    XS_HD uint8_t operator()(uint8_t c) const { return t[c]; }
+};
+
+// Builds min(window, revcomp(window)) over literal bytes (the forward k-mer wins ties, the bytes
+// are equal then anyway).
+template <class Comp>
+XS_HD void literal_term(const uint8_t* __restrict__ bases, uint64_t g, uint32_t k, Comp comp,
+                        bool canonicalize, Term& t) {
     uint64_t f[4] = {0, 0, 0, 0}, r[4] = {0, 0, 0, 0};
     int cmp = 0;  // sign of (fwd - rc) at the first differing byte
     for (uint32_t i = 0; i < k; ++i) {
         uint8_t a = bases[g + i];
-        uint8_t b = comp[bases[g + k - 1 - i]];
+        uint8_t b = comp(bases[g + k - 1 - i]);
         f[i >> 3] |= (uint64_t)a << (8 * (i & 7));
         r[i >> 3] |= (uint64_t)b << (8 * (i & 7));
         if (cmp == 0 && a != b) cmp = a < b ? -1 : 1;

@@ -1,0 +1,810 @@
+// xs_lib.cu — host side of libxspect_b200.so (C ABI declared in include/xspect_b200.h).
+//
+// Loads the reference's own model files (index.cobs_classic, <locus>.cobs_compact,
+// filter.bloom) unchanged into HBM and runs the k-mer scoring kernels of xs_kernels.cuh.
+// There is no CPU path in this file: every query launches CUDA kernels or fails.
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/xspect_b200.h"
+#include "xs_kernels.cuh"
+
+using namespace xs;
+
+// ----------------------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define XS_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(e__ == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA,             \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                      \
+    } while (0)
+#define XS_TRY(expr)                 \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != XS_OK) return rc__; \
+    } while (0)
+
+static int launch_ok(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(XS_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+    return XS_OK;
+}
+
+static uint64_t magic_of(uint64_t m) {
+    return m <= 1 ? ~0ULL : (uint64_t)((((unsigned __int128)1) << 64) / m);
+}
+
+// ----------------------------------------------------------------------------------------
+// handles
+// ----------------------------------------------------------------------------------------
+struct xs_cobs {
+    xs_cobs_info_t info{};
+    std::vector<PageDesc> pages;
+    std::vector<ColBlock> blocks;
+    std::string names;  // '\n' separated
+    uint8_t* d_data = nullptr;
+    PageDesc* d_pages = nullptr;
+    ColBlock* d_blocks = nullptr;
+    bool narrow = true;
+    int n_sm = 148;
+    int force_wide = 0;
+};
+
+struct xs_bloom {
+    xs_bloom_info_t info{};
+    uint8_t* d_bits = nullptr;
+    int n_sm = 148;
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int device_setup(int device, int* n_sm) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(XS_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") +
+                                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= n) return fail(XS_ERR_ARG, "device index out of range");
+    XS_CUDA(cudaSetDevice(device));
+    XS_CUDA(cudaDeviceGetAttribute(n_sm, cudaDevAttrMultiProcessorCount, device));
+    // keep stream-ordered workspace memory cached between queries
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = ~0ULL;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    return XS_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// file parsing
+// ----------------------------------------------------------------------------------------
+struct CobsFile {
+    int kind = 0;
+    uint32_t k = 0, canonicalize = 0, n_docs = 0, n_pages = 0;
+    uint64_t page_bytes = 0, num_hashes = 0;
+    std::vector<uint64_t> sig;
+    std::string names;
+    uint64_t data_off = 0, file_size = 0;
+};
+
+template <typename T>
+static bool rd(FILE* f, T* v) { return fread(v, sizeof(T), 1, f) == 1; }
+
+static int parse_cobs_header(FILE* f, const char* path, CobsFile& cf) {
+    char magic[18];
+    if (fread(magic, 1, 18, f) != 18 || memcmp(magic, "COBS:", 5) != 0)
+        return fail(XS_ERR_FORMAT, std::string(path) + ": not a COBS index (missing 'COBS:')");
+    bool classic = memcmp(magic + 5, "CLASSIC_INDEX", 13) == 0;
+    bool compact = memcmp(magic + 5, "COMPACT_INDEX", 13) == 0;
+    if (!classic && !compact) return fail(XS_ERR_FORMAT, std::string(path) + ": unknown COBS magic word");
+    uint32_t version = 0; uint8_t canon = 0;
+    if (!rd(f, &version) || !rd(f, &cf.k) || !rd(f, &canon)) return fail(XS_ERR_FORMAT, "truncated COBS header");
+    cf.canonicalize = canon;
+    if (version != 1) return fail(XS_ERR_FORMAT, "unsupported COBS index version " + std::to_string(version));
+    uint64_t nh = 0;
+    if (classic) {
+        uint64_t sig = 0;
+        if (!rd(f, &cf.n_docs) || !rd(f, &sig) || !rd(f, &nh)) return fail(XS_ERR_FORMAT, "truncated COBS header");
+        cf.kind = XS_COBS_CLASSIC; cf.n_pages = 1; cf.sig.push_back(sig);
+        cf.page_bytes = ((uint64_t)cf.n_docs + 7) / 8;
+    } else {
+        if (!rd(f, &cf.n_pages) || !rd(f, &cf.n_docs) || !rd(f, &cf.page_bytes))
+            return fail(XS_ERR_FORMAT, "truncated COBS header");
+        cf.kind = XS_COBS_COMPACT;
+        if (cf.n_pages == 0 || cf.n_pages > (1u << 24)) return fail(XS_ERR_FORMAT, "implausible compact page count");
+        for (uint32_t i = 0; i < cf.n_pages; ++i) {
+            uint64_t s = 0, h = 0;
+            if (!rd(f, &s) || !rd(f, &h)) return fail(XS_ERR_FORMAT, "truncated COBS header");
+            if (i == 0) nh = h;
+            else if (h != nh) return fail(XS_ERR_UNSUPPORTED, "compact pages with differing num_hashes");
+            cf.sig.push_back(s);
+        }
+    }
+    cf.num_hashes = nh;
+    for (uint32_t i = 0; i < cf.n_docs; ++i) {
+        int c;
+        while ((c = fgetc(f)) != EOF && c != '\n') cf.names.push_back((char)c);
+        if (c == EOF) return fail(XS_ERR_FORMAT, "truncated COBS document list");
+        cf.names.push_back('\n');
+    }
+    long pos = ftell(f);
+    if (compact && cf.page_bytes) {
+        uint64_t pad = (cf.page_bytes - (((uint64_t)pos + 13) % cf.page_bytes)) % cf.page_bytes;
+        if (fseek(f, (long)pad, SEEK_CUR) != 0) return fail(XS_ERR_FORMAT, "truncated COBS header");
+    }
+    char endm[13];
+    if (fread(endm, 1, 13, f) != 13 || memcmp(endm, classic ? "CLASSIC_INDEX" : "COMPACT_INDEX", 13) != 0)
+        return fail(XS_ERR_FORMAT, std::string(path) + ": header end magic missing");
+    cf.data_off = (uint64_t)ftell(f);
+    if (fseek(f, 0, SEEK_END) != 0) return fail(XS_ERR_IO, "seek failed");
+    cf.file_size = (uint64_t)ftell(f);
+    unsigned __int128 need = 0;
+    for (uint64_t s : cf.sig) need += (unsigned __int128)s * cf.page_bytes;
+    if (need != (unsigned __int128)(cf.file_size - cf.data_off))
+        return fail(XS_ERR_FORMAT, std::string(path) + ": size identity violated (data bytes != sum signature_size x row bytes)");
+    if (cf.k == 0) return fail(XS_ERR_FORMAT, "term_size 0");
+    if (cf.k > 32) return fail(XS_ERR_UNSUPPORTED, "term_size > 32 is not supported");
+    if (cf.num_hashes == 0 || cf.num_hashes > 64) return fail(XS_ERR_UNSUPPORTED, "num_hashes must be in 1..64");
+    for (uint64_t s : cf.sig)
+        if (s == 0 || s > (1ULL << 62)) return fail(XS_ERR_FORMAT, "implausible signature_size");
+    return XS_OK;
+}
+
+// stream rows [n_rows x src_row] of the file into dst rows [dst_stride], keeping bytes [col0, col0+n_col)
+static int upload_rows(FILE* f, uint64_t file_off, uint64_t n_rows, uint32_t src_row, uint32_t col0, uint32_t n_col,
+                       uint8_t* d_dst, uint32_t dst_stride, int n_sm) {
+    const uint64_t STAGE = 32ULL << 20;
+    uint64_t rows_per = std::max<uint64_t>(1, STAGE / src_row);
+    uint64_t stage_bytes = rows_per * src_row;
+    uint8_t* h_stage[2] = {nullptr, nullptr};
+    uint8_t* d_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    cudaStream_t st;
+    XS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int rc = XS_OK;
+    bool direct = (src_row == dst_stride && col0 == 0 && n_col == src_row);
+    for (int i = 0; i < 2 && rc == XS_OK; ++i) {
+        if (cudaMallocHost(&h_stage[i], stage_bytes) != cudaSuccess) rc = fail(XS_ERR_NOMEM, "pinned staging allocation failed");
+        if (rc == XS_OK && !direct && cudaMalloc(&d_stage[i], stage_bytes) != cudaSuccess) rc = fail(XS_ERR_NOMEM, "device staging allocation failed");
+        if (rc == XS_OK && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) rc = fail(XS_ERR_CUDA, "event creation failed");
+    }
+    if (rc == XS_OK && fseek(f, (long)file_off, SEEK_SET) != 0) rc = fail(XS_ERR_IO, "seek failed");
+    uint64_t done = 0; int b = 0;
+    while (rc == XS_OK && done < n_rows) {
+        uint64_t n = std::min(rows_per, n_rows - done);
+        cudaEventSynchronize(ev[b]);
+        if (fread(h_stage[b], 1, n * src_row, f) != n * src_row) { rc = fail(XS_ERR_IO, "short read of index data"); break; }
+        cudaError_t e;
+        if (direct) {
+            e = cudaMemcpyAsync(d_dst + done * dst_stride, h_stage[b], n * src_row, cudaMemcpyHostToDevice, st);
+        } else {
+            e = cudaMemcpyAsync(d_stage[b], h_stage[b], n * src_row, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) {
+                k_restride<<<n_sm * 8, 256, 0, st>>>(d_stage[b], n, src_row, col0, n_col, d_dst + done * dst_stride, dst_stride);
+                rc = launch_ok("k_restride");
+            }
+        }
+        if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, std::string("index upload: ") + cudaGetErrorString(e)); break; }
+        cudaEventRecord(ev[b], st);
+        done += n; b ^= 1;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == XS_OK && e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("index upload: ") + cudaGetErrorString(e));
+    for (int i = 0; i < 2; ++i) {
+        if (h_stage[i]) cudaFreeHost(h_stage[i]);
+        if (d_stage[i]) cudaFree(d_stage[i]);
+        if (h_stage[i]) cudaEventDestroy(ev[i]);
+    }
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+// ----------------------------------------------------------------------------------------
+// workspace of one device-side query: 2-bit stream, bitmap, window prefix, scan temp
+// ----------------------------------------------------------------------------------------
+struct Workspace {
+    uint8_t* base = nullptr;
+    uint64_t* packed = nullptr;
+    uint32_t* invalid = nullptr;
+    uint64_t* prefix = nullptr;
+    uint64_t* prefix2 = nullptr;
+    void* scan_tmp = nullptr;
+    size_t scan_bytes = 0;
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// windows (or work items) per sequence, then an in-place exclusive scan (CUB: plumbing only)
+static int scan_windows(const WindowCountOp& op, uint64_t* d_prefix, void* tmp, size_t tmp_bytes, int n_sm, cudaStream_t s) {
+    uint64_t n = op.n_seq + 1;
+    uint64_t grid = std::max<uint64_t>(1, std::min<uint64_t>((n + 255) / 256, (uint64_t)n_sm * 16));
+    k_count_windows<<<(unsigned)grid, 256, 0, s>>>(op, d_prefix);
+    XS_TRY(launch_ok("k_count_windows"));
+    XS_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_prefix, d_prefix, (int64_t)n, s));
+    g_launches.fetch_add(2, std::memory_order_relaxed);  // init + scan kernels
+    return XS_OK;
+}
+
+static int workspace_alloc(Workspace& ws, uint64_t n_bases, uint64_t n_seq, bool two_prefix, cudaStream_t s) {
+    uint64_t n_words = n_bases / 32 + 2;
+    size_t tb = 0;
+    XS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint64_t*)nullptr, (uint64_t*)nullptr, (int64_t)(n_seq + 1), s));
+    size_t o_packed = 0;
+    size_t o_inv = o_packed + align256(n_words * 8);
+    size_t o_pre = o_inv + align256(n_words * 4);
+    size_t o_pre2 = o_pre + align256((n_seq + 1) * 8);
+    size_t o_tmp = o_pre2 + (two_prefix ? align256((n_seq + 1) * 8) : 0);
+    size_t total = o_tmp + align256(tb ? tb : 1);
+    XS_CUDA(cudaMallocAsync((void**)&ws.base, total, s));
+    ws.packed = reinterpret_cast<uint64_t*>(ws.base + o_packed);
+    ws.invalid = reinterpret_cast<uint32_t*>(ws.base + o_inv);
+    ws.prefix = reinterpret_cast<uint64_t*>(ws.base + o_pre);
+    ws.prefix2 = two_prefix ? reinterpret_cast<uint64_t*>(ws.base + o_pre2) : nullptr;
+    ws.scan_tmp = ws.base + o_tmp;
+    ws.scan_bytes = tb;
+    return XS_OK;
+}
+
+static int prepare_batch(Workspace& ws, SeqBatch& sb, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_begin,
+                         const uint64_t* d_end, uint64_t n_seq, uint64_t base_shift, uint32_t k, uint32_t step,
+                         uint32_t chunk, int n_sm, cudaStream_t s) {
+    XS_TRY(workspace_alloc(ws, n_bases, n_seq, chunk != 0, s));
+    uint64_t n_words = n_bases / 32 + 2;
+    uint64_t grid = std::min<uint64_t>((n_words + 255) / 256, (uint64_t)n_sm * 16);
+    k_pack2bit<<<(unsigned)std::max<uint64_t>(grid, 1), 256, 0, s>>>(d_bases, n_bases, ws.packed, ws.invalid, n_words);
+    XS_TRY(launch_ok("k_pack2bit"));
+    WindowCountOp op{d_begin, d_end, n_seq, base_shift, n_bases, k, step, 0};
+    XS_TRY(scan_windows(op, ws.prefix, ws.scan_tmp, ws.scan_bytes, n_sm, s));
+    if (chunk) {
+        op.chunk = chunk;
+        XS_TRY(scan_windows(op, ws.prefix2, ws.scan_tmp, ws.scan_bytes, n_sm, s));
+    }
+    sb.packed = ws.packed; sb.invalid = ws.invalid; sb.bases = d_bases;
+    sb.seq_begin = d_begin; sb.seq_end = d_end; sb.win_prefix = ws.prefix;
+    sb.n_seq = n_seq; sb.n_bases = n_bases; sb.base_shift = base_shift; sb.step = step; sb.k = k;
+    return XS_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// kernel dispatch
+// ----------------------------------------------------------------------------------------
+template <int K, int H>
+static void launch_narrow_t(const CobsParams& p, dim3 grid, int dt, cudaStream_t s) {
+    if (dt == XS_U8) k_cobs_narrow<K, H, uint8_t><<<grid, NARROW_NT, 0, s>>>(p);
+    else if (dt == XS_U16) k_cobs_narrow<K, H, uint16_t><<<grid, NARROW_NT, 0, s>>>(p);
+    else k_cobs_narrow<K, H, uint32_t><<<grid, NARROW_NT, 0, s>>>(p);
+}
+static void launch_narrow(const CobsParams& p, dim3 grid, int dt, cudaStream_t s) {
+    if (p.sb.k == 21 && p.num_hashes == 7) launch_narrow_t<21, 7>(p, grid, dt, s);
+    else if (p.sb.k == 31 && p.num_hashes == 1) launch_narrow_t<31, 1>(p, grid, dt, s);
+    else launch_narrow_t<0, 0>(p, grid, dt, s);
+}
+
+template <int K, int H, typename T>
+static cudaError_t launch_wide_tt(const WideParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(k_cobs_wide<K, H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_cobs_wide<K, H, T><<<grid, WIDE_NT, smem, s>>>(p);
+    return cudaSuccess;
+}
+template <int K, int H>
+static cudaError_t launch_wide_t(const WideParams& p, dim3 grid, size_t smem, int dt, cudaStream_t s) {
+    if (dt == XS_U8) return launch_wide_tt<K, H, uint8_t>(p, grid, smem, s);
+    if (dt == XS_U16) return launch_wide_tt<K, H, uint16_t>(p, grid, smem, s);
+    return launch_wide_tt<K, H, uint32_t>(p, grid, smem, s);
+}
+static cudaError_t launch_wide(const WideParams& p, dim3 grid, size_t smem, int dt, cudaStream_t s) {
+    if (p.cp.sb.k == 21 && p.cp.num_hashes == 7) return launch_wide_t<21, 7>(p, grid, smem, dt, s);
+    if (p.cp.sb.k == 31 && p.cp.num_hashes == 1) return launch_wide_t<31, 1>(p, grid, smem, dt, s);
+    return launch_wide_t<0, 0>(p, grid, smem, dt, s);
+}
+
+static int dtype_size(int dt) { return (dt == XS_U8 || dt == XS_U16 || dt == XS_U32) ? dt : 0; }
+
+// all pointers device; asynchronous on s
+static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_begin,
+                          const uint64_t* d_end, uint64_t n_seq, uint64_t base_shift, uint32_t step, int dt,
+                          void* d_out, cudaStream_t s) {
+    const uint64_t ld = ix->info.doc_end - ix->info.doc_begin;
+    XS_CUDA(cudaMemsetAsync(d_out, 0, n_seq * ld * (uint64_t)dt, s));
+    if (n_seq == 0) return XS_OK;
+    Workspace ws;
+    SeqBatch sb{};
+    const bool wide = !ix->narrow || ix->force_wide;
+    XS_TRY(prepare_batch(ws, sb, d_bases, n_bases, d_begin, d_end, n_seq, base_shift, ix->info.term_size, step,
+                         wide ? WIDE_CHUNK : 0, ix->n_sm, s));
+    CobsParams p{};
+    p.sb = sb; p.pages = ix->d_pages; p.n_pages = (uint32_t)ix->pages.size();
+    p.num_hashes = ix->info.num_hashes; p.canonicalize = ix->info.canonicalize; p.policy = ix->info.policy;
+    p.out = d_out; p.ld = ld; p.seq0 = 0;
+    if (!wide) {
+        dim3 grid((unsigned)(ix->n_sm * 4), (unsigned)ix->pages.size());
+        launch_narrow(p, grid, dt, s);
+        XS_TRY(launch_ok("k_cobs_narrow"));
+    } else {
+        WideParams wp{};
+        wp.cp = p; wp.blocks = ix->d_blocks; wp.chunk_prefix = ws.prefix2;
+        uint32_t max_cols = 0;
+        for (const ColBlock& b : ix->blocks) max_cols = std::max(max_cols, b.n_cols);
+        size_t smem = (size_t)WIDE_CHUNK * ix->info.num_hashes * 8 + (size_t)max_cols * 128 * 4;
+        dim3 grid((unsigned)(ix->n_sm * 2), (unsigned)ix->blocks.size());
+        cudaError_t e = launch_wide(wp, grid, smem, dt, s);
+        if (e != cudaSuccess) return fail(XS_ERR_CUDA, std::string("k_cobs_wide: ") + cudaGetErrorString(e));
+        XS_TRY(launch_ok("k_cobs_wide"));
+    }
+    XS_CUDA(cudaFreeAsync(ws.base, s));
+    return XS_OK;
+}
+
+static int bloom_query_dev(xs_bloom* bf, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_begin,
+                           const uint64_t* d_end, uint64_t n_seq, uint64_t base_shift, uint32_t step,
+                           uint32_t* d_out, cudaStream_t s) {
+    XS_CUDA(cudaMemsetAsync(d_out, 0, n_seq * 4, s));
+    if (n_seq == 0) return XS_OK;
+    Workspace ws;
+    BloomParams p{};
+    XS_TRY(prepare_batch(ws, p.sb, d_bases, n_bases, d_begin, d_end, n_seq, base_shift, bf->info.term_size, step, 0,
+                         bf->n_sm, s));
+    p.bits = bf->d_bits; p.n_bits = bf->info.n_bits; p.magic = magic_of(bf->info.n_bits);
+    p.k_hashes = (uint32_t)bf->info.k_hashes; p.out = d_out; p.seq0 = 0;
+    dim3 grid((unsigned)(bf->n_sm * 4));
+    if (bf->info.term_size == 21) k_bloom<21><<<grid, BLOOM_NT, 0, s>>>(p);
+    else if (bf->info.term_size == 31) k_bloom<31><<<grid, BLOOM_NT, 0, s>>>(p);
+    else k_bloom<0><<<grid, BLOOM_NT, 0, s>>>(p);
+    XS_TRY(launch_ok("k_bloom"));
+    XS_CUDA(cudaFreeAsync(ws.base, s));
+    return XS_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// host-buffer pipeline: batches of sequences, three streams, copies overlapped with kernels
+// ----------------------------------------------------------------------------------------
+struct HostBatchPlan {
+    uint64_t i0, i1;   // sequences [i0, i1)
+    uint64_t lo, hi;   // byte span of `bases` they touch
+};
+
+// next batch starting at i0: stops at max_bases of span or max_seq sequences
+static HostBatchPlan plan_batch(const uint64_t* b, const uint64_t* e, uint64_t n_seq, uint64_t i0, uint64_t max_span,
+                                uint64_t max_seq) {
+    HostBatchPlan pl{i0, i0, ~0ULL, 0};
+    uint64_t i = i0;
+    for (; i < n_seq && i - i0 < max_seq; ++i) {
+        uint64_t lo = std::min(pl.lo, b[i]), hi = std::max(pl.hi, std::max(e[i], b[i]));
+        if (i > i0 && hi - lo > max_span) break;
+        pl.lo = lo; pl.hi = hi;
+    }
+    pl.i1 = i;
+    if (pl.lo == ~0ULL) { pl.lo = 0; pl.hi = 0; }
+    return pl;
+}
+
+template <typename QueryFn>
+static int host_pipeline(const uint8_t* bases, uint64_t n_bases, const uint64_t* seq_begin, const uint64_t* seq_end,
+                         uint64_t n_seq, uint64_t out_row_bytes, uint8_t* out, QueryFn query) {
+    const int NS = 3;
+    const uint64_t MAX_SPAN = 64ULL << 20;
+    const uint64_t MAX_OUT = 256ULL << 20;
+    const uint64_t max_seq = std::max<uint64_t>(1, std::min<uint64_t>(MAX_OUT / std::max<uint64_t>(out_row_bytes, 1), 1ULL << 22));
+    cudaStream_t st[NS];
+    for (int i = 0; i < NS; ++i) XS_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    int rc = XS_OK;
+    uint64_t i0 = 0; int bi = 0;
+    while (rc == XS_OK && i0 < n_seq) {
+        HostBatchPlan pl = plan_batch(seq_begin, seq_end, n_seq, i0, MAX_SPAN, max_seq);
+        if (pl.hi > n_bases) { rc = fail(XS_ERR_ARG, "sequence offsets exceed n_bases"); break; }
+        cudaStream_t s = st[bi % NS];
+        uint64_t ns = pl.i1 - pl.i0, span = pl.hi - pl.lo;
+        uint8_t* d = nullptr;
+        size_t o_b = 0, o_e = align256(span + 64), o_o = o_e + 2 * align256(ns * 8);
+        size_t total = o_o + align256(ns * out_row_bytes + 4);
+        cudaError_t e = cudaMallocAsync((void**)&d, total, s);
+        if (e != cudaSuccess) { rc = fail(XS_ERR_NOMEM, std::string("batch buffers: ") + cudaGetErrorString(e)); break; }
+        uint64_t* d_b = reinterpret_cast<uint64_t*>(d + o_e);
+        uint64_t* d_e = reinterpret_cast<uint64_t*>(d + o_e + align256(ns * 8));
+        if (span) e = cudaMemcpyAsync(d + o_b, bases + pl.lo, span, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, seq_begin + pl.i0, ns * 8, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_e, seq_end + pl.i0, ns * 8, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e)); break; }
+        rc = query(d + o_b, span, d_b, d_e, ns, pl.lo, d + o_o, s);
+        if (rc != XS_OK) break;
+        e = cudaMemcpyAsync(out + pl.i0 * out_row_bytes, d + o_o, ns * out_row_bytes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaFreeAsync(d, s);
+        if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e)); break; }
+        i0 = pl.i1; ++bi;
+    }
+    for (int i = 0; i < NS; ++i) {
+        cudaError_t e = cudaStreamSynchronize(st[i]);
+        if (rc == XS_OK && e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("query failed: ") + cudaGetErrorString(e));
+        cudaStreamDestroy(st[i]);
+    }
+    return rc;
+}
+
+// ----------------------------------------------------------------------------------------
+// C ABI
+// ----------------------------------------------------------------------------------------
+extern "C" {
+
+int xs_version(void) { return 100; }
+const char* xs_last_error(void) { return g_err.c_str(); }
+uint64_t xs_launch_count(void) { return g_launches.load(); }
+
+int xs_device_count(int* n) {
+    if (!n) return fail(XS_ERR_ARG, "n is NULL");
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) { *n = 0; return fail(XS_ERR_CUDA, cudaGetErrorString(e)); }
+    return XS_OK;
+}
+
+int xs_host_alloc(uint64_t bytes, void** out) {
+    if (!out) return fail(XS_ERR_ARG, "out is NULL");
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA, cudaGetErrorString(e));
+    return XS_OK;
+}
+int xs_host_free(void* p) {
+    if (p) XS_CUDA(cudaFreeHost(p));
+    return XS_OK;
+}
+
+int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_end, xs_cobs** out) {
+    if (!path || !out) return fail(XS_ERR_ARG, "path/out is NULL");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(XS_ERR_IO, std::string(path) + ": " + strerror(errno));
+    CobsFile cf;
+    int rc = parse_cobs_header(f, path, cf);
+    if (rc != XS_OK) { fclose(f); return rc; }
+    if (doc_begin == 0 && doc_end == 0) doc_end = cf.n_docs;
+    if (doc_end > cf.n_docs || doc_begin >= doc_end || (doc_begin % 8) != 0 || (doc_end % 8 != 0 && doc_end != cf.n_docs)) {
+        fclose(f);
+        return fail(XS_ERR_ARG, "document shard must be [multiple of 8, multiple of 8 or n_docs) within the index");
+    }
+    if (cf.kind == XS_COBS_COMPACT && !(doc_begin == 0 && doc_end == cf.n_docs)) {
+        fclose(f);
+        return fail(XS_ERR_UNSUPPORTED, "document-column shards are supported for classic indices only");
+    }
+    DeviceGuard guard(device);
+    int n_sm = 0;
+    rc = device_setup(device, &n_sm);
+    if (rc != XS_OK) { fclose(f); return rc; }
+
+    xs_cobs* ix = new xs_cobs();
+    ix->n_sm = n_sm;
+    ix->names = cf.names;
+    const char* fw = getenv("XS_FORCE_WIDE");
+    ix->force_wide = (fw && fw[0] == '1') ? 1 : 0;
+    uint32_t col0 = doc_begin / 8;
+    uint32_t n_col = cf.kind == XS_COBS_CLASSIC ? (doc_end - doc_begin + 7) / 8 : (uint32_t)cf.page_bytes;
+    uint32_t stride = (n_col + 15) & ~15u;
+    ix->narrow = stride == 16;
+    uint64_t total = 0;
+    std::vector<uint64_t> offs;
+    for (uint64_t s : cf.sig) { offs.push_back(total); total += s * stride; }
+    cudaError_t e = cudaMalloc((void**)&ix->d_data, total + 256);
+    if (e != cudaSuccess) {
+        fclose(f); delete ix;
+        return fail(XS_ERR_NOMEM, "index of " + std::to_string(total) + " bytes does not fit in HBM: " + cudaGetErrorString(e));
+    }
+    uint64_t file_off = cf.data_off;
+    for (uint32_t pg = 0; pg < cf.n_pages && rc == XS_OK; ++pg) {
+        rc = upload_rows(f, file_off, cf.sig[pg], (uint32_t)cf.page_bytes, col0, n_col, ix->d_data + offs[pg], stride, n_sm);
+        file_off += cf.sig[pg] * cf.page_bytes;
+        PageDesc pd{};
+        pd.data = ix->d_data + offs[pg];
+        pd.sig_size = cf.sig[pg];
+        pd.magic = magic_of(cf.sig[pg]);
+        pd.row_stride = stride;
+        if (cf.kind == XS_COBS_CLASSIC) { pd.n_docs = doc_end - doc_begin; pd.doc_off = 0; }
+        else {
+            uint64_t d0 = (uint64_t)pg * 8 * cf.page_bytes;
+            pd.n_docs = d0 >= cf.n_docs ? 0 : (uint32_t)std::min<uint64_t>(8 * cf.page_bytes, cf.n_docs - d0);
+            pd.doc_off = (uint32_t)d0;
+        }
+        ix->pages.push_back(pd);
+        uint32_t C = stride / 16;
+        uint32_t nb = (C + WIDE_MAX_COLS - 1) / WIDE_MAX_COLS;
+        uint32_t per = (C + nb - 1) / nb;
+        for (uint32_t c0 = 0; c0 < C; c0 += per) {
+            ColBlock cb{pg, c0, std::min(per, C - c0), 0};
+            uint64_t dlo = (uint64_t)c0 * 128, dhi = std::min<uint64_t>((uint64_t)(c0 + cb.n_cols) * 128, pd.n_docs);
+            cb.n_docs = dhi > dlo ? (uint32_t)(dhi - dlo) : 0;
+            if (cb.n_docs) ix->blocks.push_back(cb);
+        }
+    }
+    fclose(f);
+    if (rc == XS_OK) {
+        if (cudaMalloc((void**)&ix->d_pages, ix->pages.size() * sizeof(PageDesc)) != cudaSuccess ||
+            cudaMalloc((void**)&ix->d_blocks, std::max<size_t>(1, ix->blocks.size()) * sizeof(ColBlock)) != cudaSuccess)
+            rc = fail(XS_ERR_NOMEM, "descriptor allocation failed");
+    }
+    if (rc == XS_OK) {
+        cudaMemcpy(ix->d_pages, ix->pages.data(), ix->pages.size() * sizeof(PageDesc), cudaMemcpyHostToDevice);
+        if (!ix->blocks.empty())
+            cudaMemcpy(ix->d_blocks, ix->blocks.data(), ix->blocks.size() * sizeof(ColBlock), cudaMemcpyHostToDevice);
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("index upload: ") + cudaGetErrorString(e));
+    }
+    if (rc != XS_OK) {
+        std::string keep = g_err;
+        xs_cobs_close(ix);
+        g_err = keep;
+        return rc;
+    }
+    xs_cobs_info_t& in = ix->info;
+    in.kind = (uint32_t)cf.kind; in.term_size = cf.k; in.canonicalize = cf.canonicalize;
+    in.num_hashes = (uint32_t)cf.num_hashes; in.n_docs_total = cf.n_docs;
+    in.doc_begin = doc_begin; in.doc_end = doc_end; in.n_pages = cf.n_pages;
+    in.page_bytes = cf.page_bytes; in.row_stride = stride;
+    in.sig_size_max = *std::max_element(cf.sig.begin(), cf.sig.end());
+    in.hbm_bytes = total; in.device = device; in.policy = XS_NONACGT_SKIP;
+    *out = ix;
+    return XS_OK;
+}
+
+int xs_cobs_info(const xs_cobs* ix, xs_cobs_info_t* info) {
+    if (!ix || !info) return fail(XS_ERR_ARG, "NULL argument");
+    *info = ix->info;
+    return XS_OK;
+}
+
+int xs_cobs_doc_names(const xs_cobs* ix, char* buf, uint64_t cap, uint64_t* needed) {
+    if (!ix) return fail(XS_ERR_ARG, "NULL index");
+    if (needed) *needed = ix->names.size();
+    if (buf && cap) memcpy(buf, ix->names.data(), std::min<uint64_t>(cap, ix->names.size()));
+    return XS_OK;
+}
+
+int xs_cobs_set_policy(xs_cobs* ix, int policy) {
+    if (!ix) return fail(XS_ERR_ARG, "NULL index");
+    if (policy != XS_NONACGT_SKIP && policy != XS_NONACGT_LITERAL) return fail(XS_ERR_ARG, "unknown policy");
+    ix->info.policy = policy;
+    return XS_OK;
+}
+
+int xs_cobs_close(xs_cobs* ix) {
+    if (!ix) return XS_OK;
+    DeviceGuard guard(ix->info.device);
+    if (ix->d_data) cudaFree(ix->d_data);
+    if (ix->d_pages) cudaFree(ix->d_pages);
+    if (ix->d_blocks) cudaFree(ix->d_blocks);
+    delete ix;
+    return XS_OK;
+}
+
+int xs_cobs_query_device(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_seq_begin,
+                         const uint64_t* d_seq_end, uint64_t n_seq, uint32_t step, int out_dtype, void* d_out,
+                         void* stream) {
+    if (!ix || (!d_out && n_seq) || (n_seq && (!d_seq_begin || !d_seq_end))) return fail(XS_ERR_ARG, "NULL argument");
+    if (step == 0) return fail(XS_ERR_ARG, "step must be >= 1");
+    if (!dtype_size(out_dtype)) return fail(XS_ERR_ARG, "out_dtype must be XS_U8, XS_U16 or XS_U32");
+    DeviceGuard guard(ix->info.device);
+    if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the index's device");
+    return cobs_query_dev(ix, d_bases, n_bases, d_seq_begin, d_seq_end, n_seq, 0, step, out_dtype, d_out,
+                          (cudaStream_t)stream);
+}
+
+int xs_cobs_query(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const uint64_t* seq_begin,
+                  const uint64_t* seq_end, uint64_t n_seq, uint32_t step, int out_dtype, void* out) {
+    if (!ix || (!out && n_seq) || (n_seq && (!seq_begin || !seq_end)) || (n_bases && !bases))
+        return fail(XS_ERR_ARG, "NULL argument");
+    if (step == 0) return fail(XS_ERR_ARG, "step must be >= 1");
+    if (!dtype_size(out_dtype)) return fail(XS_ERR_ARG, "out_dtype must be XS_U8, XS_U16 or XS_U32");
+    DeviceGuard guard(ix->info.device);
+    if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the index's device");
+    const uint64_t ld = ix->info.doc_end - ix->info.doc_begin;
+    return host_pipeline(bases, n_bases, seq_begin, seq_end, n_seq, ld * (uint64_t)out_dtype, (uint8_t*)out,
+                         [&](const uint8_t* db, uint64_t span, const uint64_t* d_b, const uint64_t* d_e, uint64_t ns,
+                             uint64_t shift, uint8_t* d_o, cudaStream_t s) {
+                             return cobs_query_dev(ix, db, span, d_b, d_e, ns, shift, step, out_dtype, d_o, s);
+                         });
+}
+
+int xs_cobs_result_order(const uint32_t* scores, uint32_t n_docs, uint32_t* order) {
+    if ((!scores || !order) && n_docs) return fail(XS_ERR_ARG, "NULL argument");
+    std::vector<uint32_t> idx(n_docs);
+    std::iota(idx.begin(), idx.end(), 0u);
+    std::partial_sort(idx.begin(), idx.end(), idx.end(), [&](uint32_t a, uint32_t b) { return scores[a] > scores[b]; });
+    std::copy(idx.begin(), idx.end(), order);
+    return XS_OK;
+}
+
+int xs_bloom_open(const char* path, uint32_t term_size, int device, xs_bloom** out) {
+    if (!path || !out) return fail(XS_ERR_ARG, "path/out is NULL");
+    *out = nullptr;
+    if (term_size == 0) return fail(XS_ERR_ARG, "term_size 0");
+    if (term_size > 32) return fail(XS_ERR_UNSUPPORTED, "term_size > 32 is not supported");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(XS_ERR_IO, std::string(path) + ": " + strerror(errno));
+    uint64_t kh = 0;
+    if (!rd(f, &kh)) { fclose(f); return fail(XS_ERR_FORMAT, std::string(path) + ": not an rbloom file (too small)"); }
+    fseek(f, 0, SEEK_END);
+    uint64_t size = (uint64_t)ftell(f);
+    if (size <= 8) { fclose(f); return fail(XS_ERR_FORMAT, std::string(path) + ": rbloom file has no bit array"); }
+    if (kh > 4096) { fclose(f); return fail(XS_ERR_FORMAT, std::string(path) + ": implausible number of hash functions"); }
+    uint64_t nbytes = size - 8;
+    DeviceGuard guard(device);
+    int n_sm = 0;
+    int rc = device_setup(device, &n_sm);
+    if (rc != XS_OK) { fclose(f); return rc; }
+    xs_bloom* bf = new xs_bloom();
+    bf->n_sm = n_sm;
+    cudaError_t e = cudaMalloc((void**)&bf->d_bits, nbytes + 256);
+    if (e != cudaSuccess) { fclose(f); delete bf; return fail(XS_ERR_NOMEM, std::string("bloom bit array: ") + cudaGetErrorString(e)); }
+    // upload in slices through the row uploader (1 "row" = 1 MiB, remainder separately)
+    const uint32_t ROW = 1u << 20;
+    uint64_t rows = nbytes / ROW, rem = nbytes % ROW;
+    if (rows) rc = upload_rows(f, 8, rows, ROW, 0, ROW, bf->d_bits, ROW, n_sm);
+    if (rc == XS_OK && rem) rc = upload_rows(f, 8 + rows * ROW, 1, (uint32_t)rem, 0, (uint32_t)rem, bf->d_bits + rows * ROW, (uint32_t)rem, n_sm);
+    fclose(f);
+    if (rc != XS_OK) { cudaFree(bf->d_bits); delete bf; return rc; }
+    bf->info.n_bits = nbytes * 8; bf->info.k_hashes = kh; bf->info.term_size = term_size;
+    bf->info.device = device; bf->info.hbm_bytes = nbytes;
+    *out = bf;
+    return XS_OK;
+}
+
+int xs_bloom_info(const xs_bloom* bf, xs_bloom_info_t* info) {
+    if (!bf || !info) return fail(XS_ERR_ARG, "NULL argument");
+    *info = bf->info;
+    return XS_OK;
+}
+
+int xs_bloom_close(xs_bloom* bf) {
+    if (!bf) return XS_OK;
+    DeviceGuard guard(bf->info.device);
+    if (bf->d_bits) cudaFree(bf->d_bits);
+    delete bf;
+    return XS_OK;
+}
+
+int xs_bloom_query_device(xs_bloom* bf, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_seq_begin,
+                          const uint64_t* d_seq_end, uint64_t n_seq, uint32_t step, uint32_t* d_out_hits, void* stream) {
+    if (!bf || (!d_out_hits && n_seq) || (n_seq && (!d_seq_begin || !d_seq_end))) return fail(XS_ERR_ARG, "NULL argument");
+    if (step == 0) return fail(XS_ERR_ARG, "step must be >= 1");
+    DeviceGuard guard(bf->info.device);
+    if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the filter's device");
+    return bloom_query_dev(bf, d_bases, n_bases, d_seq_begin, d_seq_end, n_seq, 0, step, d_out_hits, (cudaStream_t)stream);
+}
+
+int xs_bloom_query(xs_bloom* bf, const uint8_t* bases, uint64_t n_bases, const uint64_t* seq_begin,
+                   const uint64_t* seq_end, uint64_t n_seq, uint32_t step, uint32_t* out_hits) {
+    if (!bf || (!out_hits && n_seq) || (n_seq && (!seq_begin || !seq_end)) || (n_bases && !bases))
+        return fail(XS_ERR_ARG, "NULL argument");
+    if (step == 0) return fail(XS_ERR_ARG, "step must be >= 1");
+    DeviceGuard guard(bf->info.device);
+    if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the filter's device");
+    return host_pipeline(bases, n_bases, seq_begin, seq_end, n_seq, 4, (uint8_t*)out_hits,
+                         [&](const uint8_t* db, uint64_t span, const uint64_t* d_b, const uint64_t* d_e, uint64_t ns,
+                             uint64_t shift, uint8_t* d_o, cudaStream_t s) {
+                             return bloom_query_dev(bf, db, span, d_b, d_e, ns, shift, step, (uint32_t*)d_o, s);
+                         });
+}
+
+// ---- single stages -----------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) {
+        cudaError_t e = cudaMalloc(&p, n ? n : 1);
+        return e == cudaSuccess ? XS_OK : fail(XS_ERR_NOMEM, cudaGetErrorString(e));
+    }
+};
+
+static int stage_pack(const uint8_t* bases, uint64_t n_bases, int n_sm, DevBuf& d_bases, DevBuf& d_packed, DevBuf& d_inv) {
+    uint64_t n_words = n_bases / 32 + 2;
+    XS_TRY(d_bases.alloc(n_bases + 64));
+    XS_TRY(d_packed.alloc(n_words * 8));
+    XS_TRY(d_inv.alloc(n_words * 4));
+    if (n_bases) XS_CUDA(cudaMemcpy(d_bases.p, bases, n_bases, cudaMemcpyHostToDevice));
+    uint64_t grid = std::max<uint64_t>(1, std::min<uint64_t>((n_words + 255) / 256, (uint64_t)n_sm * 16));
+    k_pack2bit<<<(unsigned)grid, 256>>>((const uint8_t*)d_bases.p, n_bases, (uint64_t*)d_packed.p, (uint32_t*)d_inv.p, n_words);
+    return launch_ok("k_pack2bit");
+}
+
+int xs_pack_2bit(const uint8_t* bases, uint64_t n_bases, int device, uint64_t* packed, uint32_t* invalid) {
+    if ((n_bases && !bases) || !packed || !invalid) return fail(XS_ERR_ARG, "NULL argument");
+    DeviceGuard guard(device);
+    int n_sm = 0;
+    XS_TRY(device_setup(device, &n_sm));
+    DevBuf db, dp, di;
+    XS_TRY(stage_pack(bases, n_bases, n_sm, db, dp, di));
+    uint64_t n_words = n_bases / 32 + 1;
+    XS_CUDA(cudaMemcpy(packed, dp.p, n_words * 8, cudaMemcpyDeviceToHost));
+    XS_CUDA(cudaMemcpy(invalid, di.p, n_words * 4, cudaMemcpyDeviceToHost));
+    return XS_OK;
+}
+
+int xs_canonical_kmers(const uint8_t* bases, uint64_t n_bases, uint32_t k, int device, uint64_t* codes, uint8_t* valid) {
+    if (k == 0 || k > 32) return fail(XS_ERR_ARG, "k must be in 1..32");
+    if (n_bases < k) return XS_OK;
+    if (!bases || !codes || !valid) return fail(XS_ERR_ARG, "NULL argument");
+    DeviceGuard guard(device);
+    int n_sm = 0;
+    XS_TRY(device_setup(device, &n_sm));
+    DevBuf db, dp, di, dc, dv;
+    XS_TRY(stage_pack(bases, n_bases, n_sm, db, dp, di));
+    uint64_t n_win = n_bases - k + 1;
+    XS_TRY(dc.alloc(n_win * 8));
+    XS_TRY(dv.alloc(n_win));
+    k_stage_canonical<<<n_sm * 8, 256>>>((const uint64_t*)dp.p, (const uint32_t*)di.p, n_win, k, (uint64_t*)dc.p, (uint8_t*)dv.p);
+    XS_TRY(launch_ok("k_stage_canonical"));
+    XS_CUDA(cudaMemcpy(codes, dc.p, n_win * 8, cudaMemcpyDeviceToHost));
+    XS_CUDA(cudaMemcpy(valid, dv.p, n_win, cudaMemcpyDeviceToHost));
+    return XS_OK;
+}
+
+int xs_cobs_rows(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, uint32_t step, uint64_t* rows, uint8_t* valid) {
+    if (!ix) return fail(XS_ERR_ARG, "NULL index");
+    if (step == 0) return fail(XS_ERR_ARG, "step must be >= 1");
+    uint32_t k = ix->info.term_size;
+    if (n_bases < k) return XS_OK;
+    if (!bases || !rows || !valid) return fail(XS_ERR_ARG, "NULL argument");
+    DeviceGuard guard(ix->info.device);
+    DevBuf db, dp, di, dr, dv;
+    XS_TRY(stage_pack(bases, n_bases, ix->n_sm, db, dp, di));
+    uint64_t n_win = (n_bases - k) / step + 1;
+    uint32_t h = ix->info.num_hashes, np = (uint32_t)ix->pages.size();
+    XS_TRY(dr.alloc(n_win * h * np * 8));
+    XS_TRY(dv.alloc(n_win));
+    SeqBatch sb{};
+    sb.packed = (const uint64_t*)dp.p; sb.invalid = (const uint32_t*)di.p; sb.bases = (const uint8_t*)db.p;
+    sb.n_seq = 1; sb.n_bases = n_bases; sb.step = step; sb.k = k;
+    k_stage_cobs_rows<<<ix->n_sm * 8, 256>>>(sb, ix->d_pages, np, h, ix->info.canonicalize, ix->info.policy, n_win,
+                                             (uint64_t*)dr.p, (uint8_t*)dv.p);
+    XS_TRY(launch_ok("k_stage_cobs_rows"));
+    XS_CUDA(cudaMemcpy(rows, dr.p, n_win * h * np * 8, cudaMemcpyDeviceToHost));
+    XS_CUDA(cudaMemcpy(valid, dv.p, n_win, cudaMemcpyDeviceToHost));
+    return XS_OK;
+}
+
+int xs_bloom_hashes(xs_bloom* bf, const uint8_t* bases, uint64_t n_bases, uint32_t step, uint64_t* hashes) {
+    if (!bf) return fail(XS_ERR_ARG, "NULL filter");
+    if (step == 0) return fail(XS_ERR_ARG, "step must be >= 1");
+    uint32_t k = bf->info.term_size;
+    if (n_bases < k) return XS_OK;
+    if (!bases || !hashes) return fail(XS_ERR_ARG, "NULL argument");
+    DeviceGuard guard(bf->info.device);
+    DevBuf db, dp, di, dh;
+    XS_TRY(stage_pack(bases, n_bases, bf->n_sm, db, dp, di));
+    uint64_t n_win = (n_bases - k) / step + 1;
+    XS_TRY(dh.alloc(n_win * 8));
+    SeqBatch sb{};
+    sb.packed = (const uint64_t*)dp.p; sb.invalid = (const uint32_t*)di.p; sb.bases = (const uint8_t*)db.p;
+    sb.n_seq = 1; sb.n_bases = n_bases; sb.step = step; sb.k = k;
+    k_stage_bloom_hashes<<<bf->n_sm * 8, 256>>>(sb, n_win, (uint64_t*)dh.p);
+    XS_TRY(launch_ok("k_stage_bloom_hashes"));
+    XS_CUDA(cudaMemcpy(hashes, dh.p, n_win * 8, cudaMemcpyDeviceToHost));
+    return XS_OK;
+}
+
+}  // extern "C"

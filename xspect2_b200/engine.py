@@ -1,0 +1,300 @@
+"""Batched GPU engine behind the model classes: HBM-resident COBS indices and Bloom filters.
+
+``CobsIndex`` / ``BloomFilter`` wrap the C-ABI handles; ``Search`` and ``Bloom`` present the
+single-record shapes of the third-party objects the reference calls
+(``cobs_index.Search.search`` at probabilistic_filter_model.py:227, ``kmer in rbloom.Bloom`` at
+probabilistic_single_filter_model.py:122-124) on top of the same kernels.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+from . import _abi
+from ._abi import XS_U8, XS_U16, XS_U32, check, lib
+
+_DT = {XS_U8: np.uint8, XS_U16: np.uint16, XS_U32: np.uint32}
+
+
+# --------------------------------------------------------------------------------------
+# pinned host memory
+# --------------------------------------------------------------------------------------
+class _PinnedBlock:
+    """Page-locked host allocation (xs_host_alloc) exposed through the array interface."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        check(lib().xs_host_alloc(max(int(nbytes), 1), C.byref(p)))
+        self.ptr = p.value
+        self.nbytes = int(nbytes)
+        self.__array_interface__ = {"shape": (max(self.nbytes, 1),), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr:
+            try:
+                lib().xs_host_free(ptr)
+            except Exception:  # interpreter shutdown
+                pass
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """An uninitialised page-locked numpy array (fast, asynchronous host<->device copies)."""
+    dtype = np.dtype(dtype)
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    n = int(np.prod(shape, dtype=np.int64)) if shape else 1
+    block = _PinnedBlock(n * dtype.itemsize)
+    flat = np.asarray(block)[: n * dtype.itemsize]
+    return flat.view(dtype).reshape(shape)
+
+
+def _ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+def _as_bases(bases) -> np.ndarray:
+    if isinstance(bases, str):
+        bases = bases.encode("utf-8")
+    if isinstance(bases, (bytes, bytearray, memoryview)):
+        return np.frombuffer(bases, dtype=np.uint8)
+    a = np.asarray(bases)
+    if a.dtype != np.uint8 or not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
+def _as_u64(a) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype != np.uint64 or not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a
+
+
+def pick_dtype(max_windows: int) -> int:
+    """Smallest count type that cannot saturate for sequences of at most ``max_windows`` windows."""
+    return XS_U8 if max_windows <= 255 else XS_U16 if max_windows <= 65535 else XS_U32
+
+
+# --------------------------------------------------------------------------------------
+# COBS
+# --------------------------------------------------------------------------------------
+class CobsIndex:
+    """A COBS classic / compact index file resident in one GPU's HBM (optionally a column shard)."""
+
+    def __init__(self, path, device: int = 0, doc_begin: int = 0, doc_end: int = 0):
+        self._h = C.c_void_p()
+        self.path = str(path)
+        if not os.path.isfile(self.path):
+            raise FileNotFoundError(f"Index file not found at {self.path}")
+        check(lib().xs_cobs_open(self.path.encode(), int(device), int(doc_begin), int(doc_end), C.byref(self._h)))
+        info = _abi.CobsInfo()
+        check(lib().xs_cobs_info(self._h, C.byref(info)))
+        self.info = info
+        need = C.c_uint64()
+        check(lib().xs_cobs_doc_names(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value + 1)
+        check(lib().xs_cobs_doc_names(self._h, buf, need.value, C.byref(need)))
+        names = buf.raw[: need.value].decode("utf-8").split("\n")
+        self.all_names = names[:-1] if names and names[-1] == "" else names
+        self.names = self.all_names[info.doc_begin : info.doc_end]
+
+    # geometry
+    k = property(lambda self: self.info.term_size)
+    num_hashes = property(lambda self: self.info.num_hashes)
+    n_docs = property(lambda self: self.info.doc_end - self.info.doc_begin)
+    device = property(lambda self: self.info.device)
+
+    def set_policy(self, policy: int) -> None:
+        check(lib().xs_cobs_set_policy(self._h, int(policy)))
+        self.info.policy = int(policy)
+
+    def close(self) -> None:
+        h, self._h = self._h, C.c_void_p()
+        if h:
+            lib().xs_cobs_close(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def query(self, bases, seq_begin, seq_end, step: int = 1, dtype: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        """Per-sequence, per-document hit counts ``[n_seq, n_docs]`` (host buffers in, host array out)."""
+        bases = _as_bases(bases)
+        b, e = _as_u64(seq_begin), _as_u64(seq_end)
+        n = b.size
+        if e.size != n:
+            raise ValueError("seq_begin and seq_end differ in length")
+        if dtype is None:
+            mx = int((e - b).max()) if n else 0
+            dtype = pick_dtype(max(0, (mx - self.k) // step + 1))
+        if out is None:
+            out = pinned_empty((n, self.n_docs), _DT[dtype])
+        elif out.dtype != _DT[dtype] or out.shape != (n, self.n_docs) or not out.flags.c_contiguous:
+            raise ValueError("out has the wrong dtype/shape")
+        check(lib().xs_cobs_query(self._h, _ptr(bases), bases.size, _ptr(b), _ptr(e), n, int(step), int(dtype), _ptr(out)))
+        return out
+
+    def query_device(self, d_bases: int, n_bases: int, d_begin: int, d_end: int, n_seq: int, step: int, dtype: int,
+                     d_out: int, stream: int = 0) -> None:
+        """Same with raw device pointers on this index's GPU; asynchronous on ``stream``."""
+        check(lib().xs_cobs_query_device(self._h, d_bases, n_bases, d_begin, d_end, n_seq, int(step), int(dtype), d_out, stream))
+
+    def counts(self, sequence, step: int = 1) -> np.ndarray:
+        """uint32 hit counts of one sequence."""
+        a = _as_bases(sequence)
+        return self.query(a, np.array([0], np.uint64), np.array([a.size], np.uint64), step, XS_U32)[0]
+
+    def rows(self, sequence, step: int = 1):
+        """Row ids ``[n_windows, num_hashes, n_pages]`` and the per-window valid flags (parity tests)."""
+        a = _as_bases(sequence)
+        n_w = (a.size - self.k) // step + 1 if a.size >= self.k else 0
+        rows = np.zeros((n_w, self.num_hashes, self.info.n_pages), np.uint64)
+        valid = np.zeros(n_w, np.uint8)
+        if n_w:
+            check(lib().xs_cobs_rows(self._h, _ptr(a), a.size, int(step), _ptr(rows), _ptr(valid)))
+        return rows, valid
+
+    @staticmethod
+    def result_order(scores) -> np.ndarray:
+        s = np.ascontiguousarray(scores, dtype=np.uint32)
+        order = np.zeros(s.size, np.uint32)
+        check(lib().xs_cobs_result_order(_ptr(s), s.size, _ptr(order)))
+        return order
+
+
+class SearchResult:
+    """``doc_name`` / ``score`` pair, the shape probabilistic_filter_model.py:406-409 reads."""
+
+    __slots__ = ("doc_name", "score")
+
+    def __init__(self, doc_name: str, score: int):
+        self.doc_name = doc_name
+        self.score = score
+
+    def __repr__(self):
+        return f"SearchResult(doc_name={self.doc_name!r}, score={self.score})"
+
+
+class Search:
+    """Drop-in for ``cobs_index.Search(path, load_complete)``: the index lives in HBM either way."""
+
+    def __init__(self, path, load_complete: bool = True, device: int = 0):
+        self.index = CobsIndex(path, device=device)
+
+    def search(self, query: str, step: int = 1):
+        if len(query) < self.index.k:
+            raise RuntimeError("query too short for the index term size")
+        c = self.index.counts(query, step)
+        return [SearchResult(self.index.names[i], int(c[i])) for i in CobsIndex.result_order(c)]
+
+
+# --------------------------------------------------------------------------------------
+# Bloom
+# --------------------------------------------------------------------------------------
+class BloomFilter:
+    """An rbloom ``.bloom`` file resident in one GPU's HBM."""
+
+    def __init__(self, path, k: int, device: int = 0):
+        self._h = C.c_void_p()
+        self.path = str(path)
+        if not os.path.isfile(self.path):
+            raise FileNotFoundError(f"Bloom filter file not found at {self.path}")
+        check(lib().xs_bloom_open(self.path.encode(), int(k), int(device), C.byref(self._h)))
+        info = _abi.BloomInfo()
+        check(lib().xs_bloom_info(self._h, C.byref(info)))
+        self.info = info
+
+    k = property(lambda self: self.info.term_size)
+    device = property(lambda self: self.info.device)
+
+    def close(self) -> None:
+        h, self._h = self._h, C.c_void_p()
+        if h:
+            lib().xs_bloom_close(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def query(self, bases, seq_begin, seq_end, step: int = 1, out: np.ndarray | None = None) -> np.ndarray:
+        """Hits per sequence ``[n_seq]`` uint32."""
+        bases = _as_bases(bases)
+        b, e = _as_u64(seq_begin), _as_u64(seq_end)
+        if out is None:
+            out = pinned_empty((b.size,), np.uint32)
+        check(lib().xs_bloom_query(self._h, _ptr(bases), bases.size, _ptr(b), _ptr(e), b.size, int(step), _ptr(out)))
+        return out
+
+    def query_device(self, d_bases: int, n_bases: int, d_begin: int, d_end: int, n_seq: int, step: int, d_out: int,
+                     stream: int = 0) -> None:
+        check(lib().xs_bloom_query_device(self._h, d_bases, n_bases, d_begin, d_end, n_seq, int(step), d_out, stream))
+
+    def hits(self, sequence, step: int = 1) -> int:
+        a = _as_bases(sequence)
+        return int(self.query(a, np.array([0], np.uint64), np.array([a.size], np.uint64), step)[0])
+
+    def hashes(self, sequence, step: int = 1) -> np.ndarray:
+        a = _as_bases(sequence)
+        n_w = (a.size - self.k) // step + 1 if a.size >= self.k else 0
+        out = np.zeros(n_w, np.uint64)
+        if n_w:
+            check(lib().xs_bloom_hashes(self._h, _ptr(a), a.size, int(step), _ptr(out)))
+        return out
+
+
+class Bloom:
+    """Drop-in for the loaded ``rbloom.Bloom``: ``kmer in bf`` for a k-mer string of the model's k.
+    The k-mer is taken as given (the caller has already canonicalised it, like _generate_kmers does),
+    so membership is evaluated on ``min(kmer, revcomp(kmer))`` == kmer for canonical input."""
+
+    def __init__(self, path, k: int, device: int = 0):
+        self.filter = BloomFilter(path, k, device)
+
+    @classmethod
+    def load(cls, path, k: int, device: int = 0):
+        return cls(path, k, device)
+
+    def __contains__(self, kmer) -> bool:
+        s = str(kmer)
+        if len(s) != self.filter.k:
+            raise ValueError("k-mer length differs from the model's k")
+        return self.filter.hits(s, 1) == 1
+
+
+# --------------------------------------------------------------------------------------
+# stage helpers (parity tests)
+# --------------------------------------------------------------------------------------
+def pack_2bit(bases, device: int = 0):
+    a = _as_bases(bases)
+    n_words = a.size // 32 + 1
+    packed = np.zeros(n_words, np.uint64)
+    invalid = np.zeros(n_words, np.uint32)
+    check(lib().xs_pack_2bit(_ptr(a), a.size, device, _ptr(packed), _ptr(invalid)))
+    return packed, invalid
+
+
+def canonical_kmers(bases, k: int, device: int = 0):
+    a = _as_bases(bases)
+    n_w = max(0, a.size - k + 1)
+    codes = np.zeros(n_w, np.uint64)
+    valid = np.zeros(n_w, np.uint8)
+    check(lib().xs_canonical_kmers(_ptr(a), a.size, k, device, _ptr(codes), _ptr(valid)))
+    return codes, valid
+
+
+def device_count() -> int:
+    n = C.c_int()
+    rc = lib().xs_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def launch_count() -> int:
+    return int(lib().xs_launch_count())
