@@ -86,6 +86,12 @@ const char* xs_last_error(void);           /* thread-local, never NULL */
 int xs_device_count(int* n);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t xs_launch_count(void);
+/* measurement support (bench.py's roofline): when enabled, every query brackets its dominant kernel
+ * (k_cobs_narrow / k_cobs_wide / k_bloom) with CUDA events on the stream it is launched on;
+ * xs_profile_read synchronises those events, returns the summed kernel time and launch count since
+ * the last read, and clears them. */
+int xs_profile_enable(int on);
+int xs_profile_read(double* kernel_ms, uint64_t* launches);
 /* pinned host memory for the host-buffer query entry points (pageable memory also works,
  * but is copied through the driver's bounce buffer) */
 int xs_host_alloc(uint64_t bytes, void** out);
@@ -158,6 +164,10 @@ int xs_canonical_kmers(const uint8_t* bases, uint64_t n_bases, uint32_t k, int d
 /* row ids of one sequence's sampled windows: rows[(w*h + j)*n_pages + page], valid[w] */
 int xs_cobs_rows(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, uint32_t step,
                  uint64_t* rows, uint8_t* valid);
+/* the same without an index handle (classic geometry given explicitly): rows[w*h + j].  Used by the
+ * synthetic-workload generator to plant k-mers into an index before it is written to disk. */
+int xs_kmer_rows(const uint8_t* bases, uint64_t n_bases, uint32_t k, uint32_t canonicalize, uint32_t num_hashes,
+                 uint64_t sig_size, uint32_t step, int device, uint64_t* rows, uint8_t* valid);
 /* XXH3-64 of the Bloom term of every sampled window of one sequence */
 int xs_bloom_hashes(xs_bloom* bf, const uint8_t* bases, uint64_t n_bases, uint32_t step, uint64_t* hashes);
 

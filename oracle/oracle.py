@@ -439,6 +439,21 @@ class BloomOracle:
         return out
 
 
+def kmer_rows(seq, k: int, num_hashes: int, sig_size: int, canonicalize: int = 1, step: int = 1,
+              policy: int = POLICY_SKIP) -> tuple[np.ndarray, np.ndarray]:
+    """Row ids [n_windows, num_hashes] for an explicit classic geometry (no file needed)."""
+    a = _as_u8(seq)
+    n_w = (a.size - k) // step + 1 if a.size >= k else 0
+    rows = np.zeros((n_w, num_hashes, 1), dtype=np.uint64)
+    valid = np.zeros(n_w, dtype=np.uint8)
+    sig = np.array([sig_size], dtype=np.uint64)
+    off = np.array([0], dtype=np.uint64)
+    ct = _CobsT(None, 1, 1, sig.ctypes.data, off.ctypes.data, 1, num_hashes, k, canonicalize, policy)
+    if n_w:
+        lib().xso_cobs_rows(C.byref(ct), a.ctypes.data, a.size, step, rows.ctypes.data, valid.ctypes.data)
+    return rows[:, :, 0], valid
+
+
 def max_threads() -> int:
     return lib().xso_max_threads()
 

@@ -221,7 +221,7 @@ def test_cobs_compact(gpu, oracle, tmp_path, n_alleles, k, page_size):
     ix = gpu.CobsIndex(p)
     assert ix.names == meta["names"]
     col = ix.names.index("Allele_ID_4")
-    assert got[:, col].max() >= 400 - k + 1 - 60
+    assert got[:, col].sum() >= 400 - k + 1   # the planted allele, possibly split over two chunks
 
 
 # ------------------------------------------------------------------------------------------ Bloom

@@ -43,6 +43,8 @@ SYMBOLS = {
     "xs_last_error": (C.c_char_p, []),
     "xs_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "xs_launch_count": (C.c_uint64, []),
+    "xs_profile_enable": (C.c_int, [C.c_int]),
+    "xs_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "xs_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P)]),
     "xs_host_free": (C.c_int, [_P]),
     "xs_cobs_open": (C.c_int, [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
@@ -61,6 +63,7 @@ SYMBOLS = {
     "xs_pack_2bit": (C.c_int, [_P, C.c_uint64, C.c_int, _P, _P]),
     "xs_canonical_kmers": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_int, _P, _P]),
     "xs_cobs_rows": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, _P]),
+    "xs_kmer_rows": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_int, _P, _P]),
     "xs_bloom_hashes": (C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P]),
 }
 

@@ -49,6 +49,27 @@ static int launch_ok(const char* what) {
     return XS_OK;
 }
 
+// optional CUDA-event bracketing of the dominant kernel (xs_profile_enable / xs_profile_read)
+#include <mutex>
+static std::atomic<int> g_profile{0};
+static std::mutex g_prof_mu;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+struct KernelTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t s;
+    explicit KernelTimer(cudaStream_t st) : s(st) {
+        if (!g_profile.load(std::memory_order_relaxed)) return;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
+        cudaEventRecord(a, s);
+    }
+    ~KernelTimer() {
+        if (!a) return;
+        cudaEventRecord(b, s);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof_events.emplace_back(a, b);
+    }
+};
+
 static uint64_t magic_of(uint64_t m) {
     return m <= 1 ? ~0ULL : (uint64_t)((((unsigned __int128)1) << 64) / m);
 }
@@ -347,6 +368,7 @@ static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
     p.out = d_out; p.ld = ld; p.seq0 = 0;
     if (!wide) {
         dim3 grid((unsigned)(ix->n_sm * 4), (unsigned)ix->pages.size());
+        KernelTimer kt(s);
         launch_narrow(p, grid, dt, s);
         XS_TRY(launch_ok("k_cobs_narrow"));
     } else {
@@ -356,6 +378,7 @@ static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
         for (const ColBlock& b : ix->blocks) max_cols = std::max(max_cols, b.n_cols);
         size_t smem = (size_t)WIDE_CHUNK * ix->info.num_hashes * 8 + (size_t)max_cols * 128 * 4;
         dim3 grid((unsigned)(ix->n_sm * 2), (unsigned)ix->blocks.size());
+        KernelTimer kt(s);
         cudaError_t e = launch_wide(wp, grid, smem, dt, s);
         if (e != cudaSuccess) return fail(XS_ERR_CUDA, std::string("k_cobs_wide: ") + cudaGetErrorString(e));
         XS_TRY(launch_ok("k_cobs_wide"));
@@ -376,6 +399,7 @@ static int bloom_query_dev(xs_bloom* bf, const uint8_t* d_bases, uint64_t n_base
     p.bits = bf->d_bits; p.n_bits = bf->info.n_bits; p.magic = magic_of(bf->info.n_bits);
     p.k_hashes = (uint32_t)bf->info.k_hashes; p.out = d_out; p.seq0 = 0;
     dim3 grid((unsigned)(bf->n_sm * 4));
+    KernelTimer kt(s);
     if (bf->info.term_size == 21) k_bloom<21><<<grid, BLOOM_NT, 0, s>>>(p);
     else if (bf->info.term_size == 31) k_bloom<31><<<grid, BLOOM_NT, 0, s>>>(p);
     else k_bloom<0><<<grid, BLOOM_NT, 0, s>>>(p);
@@ -457,6 +481,31 @@ extern "C" {
 int xs_version(void) { return 100; }
 const char* xs_last_error(void) { return g_err.c_str(); }
 uint64_t xs_launch_count(void) { return g_launches.load(); }
+
+int xs_profile_enable(int on) {
+    g_profile.store(on ? 1 : 0);
+    return XS_OK;
+}
+int xs_profile_read(double* kernel_ms, uint64_t* launches) {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        ev.swap(g_prof_events);
+    }
+    double sum = 0;
+    int rc = XS_OK;
+    for (auto& pr : ev) {
+        float ms = 0;
+        cudaError_t e = cudaEventSynchronize(pr.second);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, pr.first, pr.second);
+        if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("profile events: ") + cudaGetErrorString(e));
+        sum += ms;
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    if (kernel_ms) *kernel_ms = sum;
+    if (launches) *launches = ev.size();
+    return rc;
+}
 
 int xs_device_count(int* n) {
     if (!n) return fail(XS_ERR_ARG, "n is NULL");
@@ -783,6 +832,34 @@ int xs_cobs_rows(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, uint32_t s
                                              (uint64_t*)dr.p, (uint8_t*)dv.p);
     XS_TRY(launch_ok("k_stage_cobs_rows"));
     XS_CUDA(cudaMemcpy(rows, dr.p, n_win * h * np * 8, cudaMemcpyDeviceToHost));
+    XS_CUDA(cudaMemcpy(valid, dv.p, n_win, cudaMemcpyDeviceToHost));
+    return XS_OK;
+}
+
+int xs_kmer_rows(const uint8_t* bases, uint64_t n_bases, uint32_t k, uint32_t canonicalize, uint32_t num_hashes,
+                 uint64_t sig_size, uint32_t step, int device, uint64_t* rows, uint8_t* valid) {
+    if (k == 0 || k > 32 || num_hashes == 0 || num_hashes > 64 || sig_size == 0 || step == 0) return fail(XS_ERR_ARG, "bad geometry");
+    if (n_bases < k) return XS_OK;
+    if (!bases || !rows || !valid) return fail(XS_ERR_ARG, "NULL argument");
+    DeviceGuard guard(device);
+    int n_sm = 0;
+    XS_TRY(device_setup(device, &n_sm));
+    DevBuf db, dp, di, dr, dv, dpg;
+    XS_TRY(stage_pack(bases, n_bases, n_sm, db, dp, di));
+    uint64_t n_win = (n_bases - k) / step + 1;
+    XS_TRY(dr.alloc(n_win * num_hashes * 8));
+    XS_TRY(dv.alloc(n_win));
+    XS_TRY(dpg.alloc(sizeof(PageDesc)));
+    PageDesc pd{};
+    pd.sig_size = sig_size; pd.magic = magic_of(sig_size); pd.row_stride = 16;
+    XS_CUDA(cudaMemcpy(dpg.p, &pd, sizeof(pd), cudaMemcpyHostToDevice));
+    SeqBatch sb{};
+    sb.packed = (const uint64_t*)dp.p; sb.invalid = (const uint32_t*)di.p; sb.bases = (const uint8_t*)db.p;
+    sb.n_seq = 1; sb.n_bases = n_bases; sb.step = step; sb.k = k;
+    k_stage_cobs_rows<<<n_sm * 8, 256>>>(sb, (const PageDesc*)dpg.p, 1, num_hashes, canonicalize, POLICY_SKIP, n_win,
+                                         (uint64_t*)dr.p, (uint8_t*)dv.p);
+    XS_TRY(launch_ok("k_stage_cobs_rows"));
+    XS_CUDA(cudaMemcpy(rows, dr.p, n_win * num_hashes * 8, cudaMemcpyDeviceToHost));
     XS_CUDA(cudaMemcpy(valid, dv.p, n_win, cudaMemcpyDeviceToHost));
     return XS_OK;
 }

@@ -290,6 +290,17 @@ def canonical_kmers(bases, k: int, device: int = 0):
     return codes, valid
 
 
+def kmer_rows(bases, k: int, num_hashes: int, sig_size: int, canonicalize: int = 1, step: int = 1, device: int = 0):
+    """Row ids ``[n_windows, num_hashes]`` of a sequence for an explicit classic geometry (no index handle)."""
+    a = _as_bases(bases)
+    n_w = (a.size - k) // step + 1 if a.size >= k else 0
+    rows = np.zeros((n_w, num_hashes), np.uint64)
+    valid = np.zeros(n_w, np.uint8)
+    if n_w:
+        check(lib().xs_kmer_rows(_ptr(a), a.size, k, canonicalize, num_hashes, sig_size, step, device, _ptr(rows), _ptr(valid)))
+    return rows, valid
+
+
 def device_count() -> int:
     n = C.c_int()
     rc = lib().xs_device_count(C.byref(n))
@@ -298,3 +309,14 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return int(lib().xs_launch_count())
+
+
+def profile_enable(on: bool = True) -> None:
+    check(lib().xs_profile_enable(1 if on else 0))
+
+
+def profile_read() -> tuple[float, int]:
+    """(summed dominant-kernel milliseconds, launches) since the last read; synchronises the events."""
+    ms, n = C.c_double(), C.c_uint64()
+    check(lib().xs_profile_read(C.byref(ms), C.byref(n)))
+    return ms.value, n.value
