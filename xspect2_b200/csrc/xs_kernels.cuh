@@ -12,9 +12,9 @@
 //   stage kernels     canonical codes / row ids / bloom hashes alone, for the parity tests
 //
 // Work decomposition.  The sampled windows of all sequences of a batch form one flat index
-// space (win_prefix = exclusive scan of windows per sequence).  Persistent CTAs walk tiles of
-// that space, so lanes stay dense whatever the read lengths are; the sequences a tile touches
-// are resolved once per tile into shared memory.
+// space (win_prefix = exclusive scan of windows per sequence).  Persistent warps walk tiles of
+// that space (warp_walk), so lanes stay dense whatever the read lengths are; all bookkeeping
+// is warp-uniform (no shared memory, no CTA barrier on the narrow and Bloom paths).
 #pragma once
 #include "xs_device.cuh"
 
@@ -198,69 +198,80 @@ __device__ __forceinline__ void bloom_term(const SeqBatch& sb, uint64_t pos, Ter
 }
 
 // ----------------------------------------------------------------------------------------
-// tile map: which sequences a tile of the flat window space touches
+// warp walk: one warp owns a tile [t0, t1) of the flat window space and walks the sequences it
+// touches.  Each round packs the next 32 windows into the lanes (a round may span several
+// sequences); `compute(has, pos)` is called once per lane with the base position of its window,
+// `accum(segmask)` once per (round, sequence) with the lanes of that sequence, `flush(seq, complete)`
+// when a sequence (or the tile) ends.  All bookkeeping is warp-uniform: no shared memory, no CTA
+// barrier, lanes stay dense whatever the read lengths are.
 // ----------------------------------------------------------------------------------------
-template <int TILE_W>
-struct TileMap {
-    int32_t rel[TILE_W + 2];     // window offset of local sequence i relative to the tile start, clamped to [0, tile_n]
-    uint64_t begin[TILE_W + 1];  // seq_begin - base_shift of local sequence i
-    uint64_t first_off;          // tile_start - prefix[seq_lo]
-    uint64_t seq_lo;
-    uint64_t seq_hi;
-    uint32_t ns;                 // sequences in [seq_lo, seq_hi]
-    uint32_t tile_n;             // windows in this tile
-    int32_t fallback;            // ns > TILE_W: too many (empty) sequences to stage
-    int32_t last_complete;       // last local sequence ends inside the tile
+struct WalkBatch {           // 32 consecutive sequences, one per lane
+    uint64_t pre, pre_next;  // win_prefix[s], win_prefix[s + 1]
+    uint64_t beg;            // seq_begin[s] - base_shift
 };
 
-template <int TILE_W, int NT>
-__device__ __forceinline__ void tile_setup(TileMap<TILE_W>& tm, const SeqBatch& sb, uint64_t tile_start, uint64_t total) {
-    const int tid = threadIdx.x;
-    uint32_t tile_n = (uint32_t)(total - tile_start < (uint64_t)TILE_W ? total - tile_start : (uint64_t)TILE_W);
-    if (tid == 0) {
-        uint64_t s = seq_of_window(sb.win_prefix, sb.n_seq, tile_start);
-        tm.seq_lo = s;
-        tm.first_off = tile_start - __ldg(sb.win_prefix + s);
-        tm.tile_n = tile_n;
-    }
-    if (tid == 32) tm.seq_hi = seq_of_window(sb.win_prefix, sb.n_seq, tile_start + tile_n - 1);
-    __syncthreads();
-    uint64_t ns64 = tm.seq_hi - tm.seq_lo + 1;
-    bool fb = ns64 > (uint64_t)TILE_W;
-    if (tid == 0) { tm.ns = fb ? 0u : (uint32_t)ns64; tm.fallback = fb ? 1 : 0; }
-    if (!fb) {
-        uint32_t ns = (uint32_t)ns64;
-        for (uint32_t i = tid; i <= ns; i += NT) {
-            uint64_t pv = __ldg(sb.win_prefix + tm.seq_lo + i);
-            int64_t r = (int64_t)(pv - tile_start);
-            if (i == ns) tm.last_complete = (r <= (int64_t)tile_n) ? 1 : 0;
-            r = r < 0 ? 0 : (r > (int64_t)tile_n ? (int64_t)tile_n : r);
-            tm.rel[i] = (int32_t)r;
-            if (i < ns) tm.begin[i] = __ldg(sb.seq_begin + tm.seq_lo + i) - sb.base_shift;
-        }
-    }
-    __syncthreads();
+__device__ __forceinline__ void walk_load(const SeqBatch& sb, uint64_t base, uint32_t lane, WalkBatch& wb) {
+    uint64_t s = base + lane;
+    uint64_t a = s < sb.n_seq ? s : sb.n_seq, b = s + 1 < sb.n_seq ? s + 1 : sb.n_seq;
+    wb.pre = __ldg(sb.win_prefix + a);
+    wb.pre_next = __ldg(sb.win_prefix + b);
+    wb.beg = s < sb.n_seq ? __ldg(sb.seq_begin + s) - sb.base_shift : 0;
 }
 
-// base position of local window lw; *seq_local receives the local sequence index (staged tiles)
-template <int TILE_W>
-__device__ __forceinline__ uint64_t tile_locate(const TileMap<TILE_W>& tm, const SeqBatch& sb, uint64_t tile_start,
-                                                uint32_t lw, uint64_t* seq_global) {
-    if (tm.fallback) {
-        uint64_t g = tile_start + lw;
-        uint64_t s = seq_of_window(sb.win_prefix, sb.n_seq, g);
-        *seq_global = s;
-        uint64_t wi = g - __ldg(sb.win_prefix + s);
-        return __ldg(sb.seq_begin + s) - sb.base_shift + wi * sb.step;
+template <class Compute, class Accum, class Flush>
+__device__ __forceinline__ void warp_walk(const SeqBatch& sb, uint64_t t0, uint64_t t1, uint32_t lane,
+                                          Compute compute, Accum accum, Flush flush) {
+    const uint32_t FULL = 0xFFFFFFFFu;
+    uint64_t base = seq_of_window(sb.win_prefix, sb.n_seq, t0);
+    WalkBatch wb;
+    walk_load(sb, base, lane, wb);
+    uint32_t cur = 0;
+    uint64_t f = t0;
+    while (f < t1) {
+        if (cur == 32) { base += 32; walk_load(sb, base, lane, wb); cur = 0; }
+        const uint32_t cur0 = cur;
+        const uint64_t f0 = f;
+        // ---- pack up to 32 windows into the lanes
+        uint32_t fill = 0;
+        bool has = false;
+        uint64_t pos = 0;
+        while (fill < 32 && f < t1 && cur < 32) {
+            uint64_t s_start = __shfl_sync(FULL, wb.pre, cur), s_end = __shfl_sync(FULL, wb.pre_next, cur);
+            uint64_t lim = s_end < t1 ? s_end : t1;
+            uint32_t avail = lim > f ? (uint32_t)(lim - f > 32 ? 32 : lim - f) : 0;
+            if (avail == 0) { ++cur; continue; }
+            uint32_t take = avail < 32 - fill ? avail : 32 - fill;
+            uint64_t b = __shfl_sync(FULL, wb.beg, cur);
+            if (lane >= fill && lane < fill + take) {
+                pos = b + (f - s_start + (lane - fill)) * sb.step;
+                has = true;
+            }
+            fill += take; f += take;
+            if (f == s_end) ++cur;
+        }
+        compute(has, pos);
+        // ---- replay the packing to attribute lanes to sequences
+        cur = cur0; f = f0; fill = 0;
+        while (fill < 32 && f < t1 && cur < 32) {
+            uint64_t s_start = __shfl_sync(FULL, wb.pre, cur), s_end = __shfl_sync(FULL, wb.pre_next, cur);
+            uint64_t lim = s_end < t1 ? s_end : t1;
+            uint32_t avail = lim > f ? (uint32_t)(lim - f > 32 ? 32 : lim - f) : 0;
+            if (avail == 0) { ++cur; continue; }
+            uint32_t take = avail < 32 - fill ? avail : 32 - fill;
+            uint32_t segmask = (take == 32 ? FULL : ((1u << take) - 1u)) << fill;
+            accum(segmask);
+            fill += take; f += take;
+            if (f == s_end || f == t1) flush(base + cur, s_start >= t0 && s_end <= t1);
+            if (f == s_end) ++cur;
+        }
     }
-    uint32_t lo = 0, hi = tm.ns;
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if ((uint32_t)tm.rel[mid] <= lw) lo = mid; else hi = mid;
-    }
-    *seq_global = tm.seq_lo + lo;
-    uint64_t wi = lo == 0 ? (uint64_t)lw + tm.first_off : (uint64_t)(lw - (uint32_t)tm.rel[lo]);
-    return tm.begin[lo] + wi * sb.step;
+}
+
+// rounds per warp tile: large enough that few sequences straddle tiles, small enough to fill the machine
+__device__ __forceinline__ uint64_t walk_tile_windows(uint64_t total, uint64_t n_warps) {
+    uint64_t r = (total + n_warps * 128 - 1) / (n_warps * 128);   // ~4 tiles per warp
+    r = r < 8 ? 8 : (r > 128 ? 128 : r);
+    return r * 32;
 }
 
 // ----------------------------------------------------------------------------------------
@@ -279,142 +290,84 @@ struct CobsParams {
 };
 
 constexpr int NARROW_NT = 256;
-constexpr int NARROW_R = 4;
-constexpr int NARROW_TILE = NARROW_NT * NARROW_R;
 
-// count the documents of masks[lo..hi) into per-lane counters: lane l holds documents l, l+32, l+64, l+96
-__device__ __forceinline__ void count_masks(const uint4* __restrict__ masks, uint32_t lo, uint32_t hi, uint32_t lane,
-                                            uint32_t cnt[4]) {
-    for (uint32_t base = lo; base < hi; base += 32) {
-        uint32_t i = base + lane;
-        uint4 m = i < hi ? masks[i] : make_uint4(0, 0, 0, 0);
-        uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+// 128-bit document mask of one window: h row gathers ANDed
+template <int K, int H>
+__device__ __forceinline__ uint4 cobs_mask16(const CobsParams& p, const PageDesc& pg, uint64_t pos) {
+    const SeqBatch& sb = p.sb;
+    const uint32_t k = K ? K : sb.k;
+    Term t;
+    if (!cobs_term<K>(sb, pos, p.canonicalize != 0, p.policy, t)) return make_uint4(0, 0, 0, 0);
+    Xxh64Pre pre;
+    xxh64_prepare(t, k, pre);
+    uint4 m = make_uint4(~0u, ~0u, ~0u, ~0u);
+    if (H) {
+        const uint8_t* addr[H ? H : 1];
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            uint32_t u = __reduce_or_sync(0xFFFFFFFFu, mw[w]);
-            while (u) {
-                uint32_t b = __ffs(u) - 1;
-                u &= u - 1;
-                uint32_t v = __popc(__ballot_sync(0xFFFFFFFFu, (mw[w] >> b) & 1u));
-                if (lane == b) cnt[w] += v;
-            }
+        for (int j = 0; j < (H ? H : 1); ++j) {
+            uint64_t hv = xxh64_finish(pre, k, (uint64_t)j);
+            addr[j] = pg.data + mod_barrett(hv, pg.sig_size, pg.magic) * 16;
+        }
+#pragma unroll
+        for (int j = 0; j < (H ? H : 1); ++j) {
+            uint4 v = ldg128(addr[j]);
+            m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
+        }
+    } else {
+        for (uint32_t j = 0; j < p.num_hashes; ++j) {
+            uint64_t hv = xxh64_finish(pre, k, (uint64_t)j);
+            uint4 v = ldg128(pg.data + mod_barrett(hv, pg.sig_size, pg.magic) * 16);
+            m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
         }
     }
+    return m;
 }
 
 template <int K, int H, typename OutT>
-__global__ void __launch_bounds__(NARROW_NT) k_cobs_narrow(const CobsParams p) {
-    __shared__ TileMap<NARROW_TILE> tm;
-    __shared__ uint4 s_mask[NARROW_TILE];
-
+__global__ void __launch_bounds__(NARROW_NT, 4) k_cobs_narrow(const CobsParams p) {
     const SeqBatch& sb = p.sb;
-    const uint32_t k = K ? K : sb.k;
-    const uint32_t h = H ? H : p.num_hashes;
     const PageDesc pg = p.pages[blockIdx.y];
-    const int tid = threadIdx.x;
-    const uint32_t lane = tid & 31, warp = tid >> 5;
-    constexpr int NWARP = NARROW_NT / 32;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp_g = ((uint64_t)blockIdx.x * NARROW_NT + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * NARROW_NT) >> 5;
     OutT* out = reinterpret_cast<OutT*>(p.out);
 
     const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
-    const uint64_t n_tiles = (total + NARROW_TILE - 1) / NARROW_TILE;
+    const uint64_t W = walk_tile_windows(total, n_warps);
+    const uint64_t n_tiles = (total + W - 1) / W;
 
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t tile_start = tile * NARROW_TILE;
-        tile_setup<NARROW_TILE, NARROW_NT>(tm, sb, tile_start, total);
-        const uint32_t tile_n = tm.tile_n;
-
-        // ---- phase A: one window per thread per round -> 128-bit document mask
-#pragma unroll 1
-        for (int r = 0; r < NARROW_R; ++r) {
-            uint32_t lw = r * NARROW_NT + tid;
-            uint4 m = make_uint4(0, 0, 0, 0);
-            uint64_t seq_g = 0;
-            if (lw < tile_n) {
-                uint64_t pos = tile_locate(tm, sb, tile_start, lw, &seq_g);
-                Term t;
-                if (cobs_term<K>(sb, pos, p.canonicalize != 0, p.policy, t)) {
-                    Xxh64Pre pre;
-                    xxh64_prepare(t, k, pre);
-                    m = make_uint4(~0u, ~0u, ~0u, ~0u);
-                    if (H) {
-                        const uint8_t* addr[H ? H : 1];
+    for (uint64_t tile = warp_g; tile < n_tiles; tile += n_warps) {
+        const uint64_t t0 = tile * W, t1 = t0 + W < total ? t0 + W : total;
+        uint4 m = make_uint4(0, 0, 0, 0);
+        uint32_t cnt[4] = {0, 0, 0, 0};   // lane l: documents l, l+32, l+64, l+96 of the current sequence
+        warp_walk(
+            sb, t0, t1, lane,
+            [&](bool has, uint64_t pos) { m = has ? cobs_mask16<K, H>(p, pg, pos) : make_uint4(0, 0, 0, 0); },
+            [&](uint32_t segmask) {
+                const bool mine = (segmask >> lane) & 1u;
+                uint32_t mw[4] = {mine ? m.x : 0u, mine ? m.y : 0u, mine ? m.z : 0u, mine ? m.w : 0u};
 #pragma unroll
-                        for (int j = 0; j < (H ? H : 1); ++j) {
-                            uint64_t hv = xxh64_finish(pre, k, (uint64_t)j);
-                            addr[j] = pg.data + mod_barrett(hv, pg.sig_size, pg.magic) * 16;
-                        }
-#pragma unroll
-                        for (int j = 0; j < (H ? H : 1); ++j) {
-                            uint4 v = ldg128(addr[j]);
-                            m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
-                        }
-                    } else {
-                        for (uint32_t j = 0; j < h; ++j) {
-                            uint64_t hv = xxh64_finish(pre, k, (uint64_t)j);
-                            uint4 v = ldg128(pg.data + mod_barrett(hv, pg.sig_size, pg.magic) * 16);
-                            m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
-                        }
+                for (int w = 0; w < 4; ++w) {
+                    uint32_t u = __reduce_or_sync(0xFFFFFFFFu, mw[w]);
+                    while (u) {
+                        uint32_t b = __ffs(u) - 1;
+                        u &= u - 1;
+                        uint32_t v = __popc(__ballot_sync(0xFFFFFFFFu, (mw[w] >> b) & 1u));
+                        if (lane == b) cnt[w] += v;
                     }
                 }
-                if (tm.fallback) {
-                    // too many (empty) sequences in this tile to stage: add set bits directly
-                    uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-                    for (int w = 0; w < 4; ++w) {
-                        uint32_t u = mw[w];
-                        while (u) {
-                            uint32_t b = __ffs(u) - 1; u &= u - 1;
-                            uint32_t d = w * 32 + b;
-                            if (d < pg.n_docs) out_add<OutT>(out + (p.seq0 + seq_g) * p.ld + pg.doc_off + d, 1u);
-                        }
-                    }
-                }
-            }
-            s_mask[lw] = m;
-        }
-        __syncthreads();
-
-        // ---- phase B: per-sequence document counts
-        if (!tm.fallback) {
-            const uint32_t ns = tm.ns;
-            if (ns >= 4) {
-                for (uint32_t i = warp; i < ns; i += NWARP) {
-                    uint32_t lo = (uint32_t)tm.rel[i], hi = (uint32_t)tm.rel[i + 1];
-                    if (i == 0) lo = 0;
-                    if (hi <= lo) continue;
-                    uint32_t cnt[4] = {0, 0, 0, 0};
-                    count_masks(s_mask, lo, hi, lane, cnt);
-                    bool complete = (i > 0 || tm.first_off == 0) && (i + 1 < ns || tm.last_complete);
-                    OutT* row = out + (p.seq0 + tm.seq_lo + i) * p.ld + pg.doc_off;
+            },
+            [&](uint64_t seq, bool complete) {
+                OutT* row = out + (p.seq0 + seq) * p.ld + pg.doc_off;
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        uint32_t d = w * 32 + lane;
-                        if (d < pg.n_docs) {
-                            if (complete) out_store<OutT>(row + d, cnt[w]); else out_add<OutT>(row + d, cnt[w]);
-                        }
+                for (int w = 0; w < 4; ++w) {
+                    uint32_t d = w * 32 + lane;
+                    if (d < pg.n_docs) {
+                        if (complete) out_store<OutT>(row + d, cnt[w]); else out_add<OutT>(row + d, cnt[w]);
                     }
+                    cnt[w] = 0;
                 }
-            } else {
-                // few long sequences: every warp takes a slice of each
-                for (uint32_t i = 0; i < ns; ++i) {
-                    uint32_t lo = (uint32_t)tm.rel[i], hi = (uint32_t)tm.rel[i + 1];
-                    if (i == 0) lo = 0;
-                    if (hi <= lo) continue;
-                    uint32_t span = (((hi - lo) + NWARP - 1) / NWARP + 31) & ~31u;
-                    uint32_t a = lo + warp * span, b = a + span < hi ? a + span : hi;
-                    if (a >= hi) continue;
-                    uint32_t cnt[4] = {0, 0, 0, 0};
-                    count_masks(s_mask, a, b, lane, cnt);
-                    OutT* row = out + (p.seq0 + tm.seq_lo + i) * p.ld + pg.doc_off;
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        uint32_t d = w * 32 + lane;
-                        if (d < pg.n_docs) out_add<OutT>(row + d, cnt[w]);
-                    }
-                }
-            }
-        }
-        __syncthreads();
+            });
     }
 }
 
@@ -579,8 +532,6 @@ struct BloomParams {
 };
 
 constexpr int BLOOM_NT = 256;
-constexpr int BLOOM_R = 4;
-constexpr int BLOOM_TILE = BLOOM_NT * BLOOM_R;
 
 __device__ __forceinline__ uint32_t ldg_byte(const uint8_t* p) {
     uint32_t v;
@@ -606,61 +557,39 @@ __device__ __forceinline__ bool bloom_member(const BloomParams& p, uint64_t h0) 
 }
 
 template <int K>
-__global__ void __launch_bounds__(BLOOM_NT) k_bloom(const BloomParams p) {
-    __shared__ TileMap<BLOOM_TILE> tm;
-    __shared__ uint32_t s_hit[BLOOM_TILE / 32];   // one bit per window
-
+__global__ void __launch_bounds__(BLOOM_NT, 4) k_bloom(const BloomParams p) {
     const SeqBatch& sb = p.sb;
     const uint32_t k = K ? K : sb.k;
-    const int tid = threadIdx.x;
-    const uint32_t lane = tid & 31, warp = tid >> 5;
-    constexpr int NWARP = BLOOM_NT / 32;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp_g = ((uint64_t)blockIdx.x * BLOOM_NT + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * BLOOM_NT) >> 5;
 
     const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
-    const uint64_t n_tiles = (total + BLOOM_TILE - 1) / BLOOM_TILE;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t tile_start = tile * BLOOM_TILE;
-        tile_setup<BLOOM_TILE, BLOOM_NT>(tm, sb, tile_start, total);
-        const uint32_t tile_n = tm.tile_n;
-#pragma unroll 1
-        for (int r = 0; r < BLOOM_R; ++r) {
-            uint32_t lw = r * BLOOM_NT + tid;
-            bool hit = false;
-            uint64_t seq_g = 0;
-            if (lw < tile_n) {
-                uint64_t pos = tile_locate(tm, sb, tile_start, lw, &seq_g);
-                Term t;
-                bloom_term<K>(sb, pos, t);
-                hit = bloom_member(p, xxh3_64(t, k));
-                if (tm.fallback && hit) atomicAdd(p.out + p.seq0 + seq_g, 1u);
-            }
-            uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
-            if (lane == 0) s_hit[lw >> 5] = bal;
-        }
-        __syncthreads();
-        if (!tm.fallback) {
-            const uint32_t ns = tm.ns;
-            for (uint32_t i = warp; i < ns; i += NWARP) {
-                uint32_t lo = (uint32_t)tm.rel[i], hi = (uint32_t)tm.rel[i + 1];
-                if (i == 0) lo = 0;
-                if (hi <= lo) continue;
-                uint32_t c = 0;
-                for (uint32_t wd = (lo >> 5) + lane; wd <= ((hi - 1) >> 5); wd += 32) {
-                    uint32_t v = s_hit[wd];
-                    uint32_t b0 = wd << 5;
-                    if (b0 < lo) v &= ~0u << (lo - b0);
-                    if (b0 + 32 > hi) v &= ~0u >> (b0 + 32 - hi);
-                    c += __popc(v);
+    const uint64_t W = walk_tile_windows(total, n_warps);
+    const uint64_t n_tiles = (total + W - 1) / W;
+    for (uint64_t tile = warp_g; tile < n_tiles; tile += n_warps) {
+        const uint64_t t0 = tile * W, t1 = t0 + W < total ? t0 + W : total;
+        uint32_t hits = 0;    // warp-uniform: hits of the current sequence inside this tile
+        uint32_t bal = 0;
+        warp_walk(
+            sb, t0, t1, lane,
+            [&](bool has, uint64_t pos) {
+                bool hit = false;
+                if (has) {
+                    Term t;
+                    bloom_term<K>(sb, pos, t);
+                    hit = bloom_member(p, xxh3_64(t, k));
                 }
-                c = __reduce_add_sync(0xFFFFFFFFu, c);
-                if (lane == 0 && c) {
-                    bool complete = (i > 0 || tm.first_off == 0) && (i + 1 < ns || tm.last_complete);
-                    uint32_t* o = p.out + p.seq0 + tm.seq_lo + i;
-                    if (complete) *o = c; else atomicAdd(o, c);
+                bal = __ballot_sync(0xFFFFFFFFu, hit);
+            },
+            [&](uint32_t segmask) { hits += __popc(bal & segmask); },
+            [&](uint64_t seq, bool complete) {
+                if (lane == 0 && hits) {
+                    uint32_t* o = p.out + p.seq0 + seq;
+                    if (complete) *o = hits; else atomicAdd(o, hits);
                 }
-            }
-        }
-        __syncthreads();
+                hits = 0;
+            });
     }
 }
 

@@ -115,6 +115,8 @@ static int device_setup(int device, int* n_sm) {
     if (device < 0 || device >= n) return fail(XS_ERR_ARG, "device index out of range");
     XS_CUDA(cudaSetDevice(device));
     XS_CUDA(cudaDeviceGetAttribute(n_sm, cudaDevAttrMultiProcessorCount, device));
+    // random 16-byte row gathers: fetch single 32-byte sectors from HBM, not 64/128-byte groups
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     // keep stream-ordered workspace memory cached between queries
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
