@@ -133,6 +133,8 @@ int xs_cobs_query_device(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
  * probabilistic_filter_model.py:393-409; MLST tie-breaks, probabilistic_filter_mlst_model.py:254-256,284):
  * all documents, std::partial_sort by score descending.  Host-only helper. */
 int xs_cobs_result_order(const uint32_t* scores, uint32_t n_docs, uint32_t* order);
+/* the same for n_seq rows of a [n_seq x n_docs] uint32 count matrix (one call per predict batch) */
+int xs_cobs_result_order_batch(const uint32_t* scores, uint64_t n_seq, uint32_t n_docs, uint32_t* order);
 
 /* ---- Bloom filter ------------------------------------------------------------------------
  * Replaces rbloom.Bloom.load(path, hash_func=xxh3_64_intdigest)

@@ -494,3 +494,32 @@ def mlst_locus_scores(index: CobsOracle, sequence: str, allele_len: int, step: i
                 all_counts[name] = all_counts.get(name, 0) + v
         return dict(sorted(all_counts.items(), key=lambda item: -item[1]))
     return {r.doc_name: r.score for r in index.search(sequence, step)}
+
+
+# --------------------------------------------------------------------------------------
+# the reference's per-record predict loops, restated over the oracle objects
+# --------------------------------------------------------------------------------------
+def reference_predict(index: CobsOracle, records: list[tuple[str, str]], k: int, exclude_ids=None, step: int = 1):
+    """ProbabilisticFilterModel.predict's loop (probabilistic_filter_model.py:291-310): one search per record,
+    dict in cobs result order, exclude filter, num_kmers = ceil((len-k+1)/step); later ids overwrite."""
+    hits, num_kmers = {}, {}
+    for rid, seq in records:
+        if not len(seq) > k:
+            raise ValueError("Invalid sequence, must be longer than k")
+        d = {r.doc_name: r.score for r in index.search(seq, step)}
+        if exclude_ids:
+            d = {doc: s for doc, s in d.items() if doc not in exclude_ids}
+        hits[rid] = d
+        num_kmers[rid] = count_kmers(len(seq), k, step)
+    return hits, num_kmers
+
+
+def reference_predict_bloom(bf: BloomOracle, key: str, records: list[tuple[str, str]], k: int, step: int = 1):
+    """ProbabilisticSingleFilterModel.calculate_hits (probabilistic_single_filter_model.py:98-125) per record."""
+    hits, num_kmers = {}, {}
+    for rid, seq in records:
+        if not len(seq) > k:
+            raise ValueError("Invalid sequence, must be longer than k")
+        hits[rid] = {key: bf.hits(seq, step)}
+        num_kmers[rid] = count_kmers(len(seq), k, step)
+    return hits, num_kmers

@@ -1,0 +1,228 @@
+"""Host-side logic that needs no GPU: reader, result API, slugs/paths, MLST splitter — mirrored on the
+reference's own unit tests (tests/test_model_result.py, test_model_management.py,
+test_probabilistic_filter_mlst_model.py:127-177, test_probabilistic_filter_model.py:139-146)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from xspect2_b200 import model_management as mm
+from xspect2_b200 import seqio
+from xspect2_b200.file_io import get_record_iterator, prepare_input_output_paths, filter_sequences
+from xspect2_b200.models.mlst_result import MlstResult
+from xspect2_b200.models.probabilistic_filter_mlst_model import ProbabilisticFilterMlstSchemeModel
+from xspect2_b200.models.probabilistic_filter_model import ProbabilisticFilterModel
+from xspect2_b200.models.result import ModelResult
+from xspect2_b200.seqio import Seq, SeqRecord, SequenceBatch
+
+
+# ---------------------------------------------------------------- ModelResult (G10)
+def test_get_scores_rounding_table():
+    hits = {"subsequence1": {"label1": 10, "label2": 5}, "subsequence2": {"label1": 8, "label2": 3}}
+    res = ModelResult("test_slug", hits, {"subsequence1": 100, "subsequence2": 50})
+    assert res.get_scores() == {
+        "subsequence1": {"label1": 0.1, "label2": 0.05},
+        "subsequence2": {"label1": 0.16, "label2": 0.06},
+        "total": {"label1": 0.12, "label2": 0.05},
+    }
+    assert res.get_total_hits() == {"label1": 18, "label2": 8}
+
+
+def test_model_result_contract(tmp_path):
+    with pytest.raises(ValueError):
+        ModelResult("s", {"total": {"a": 1}}, {"total": 1})
+    hits = {"r1": {"a": 9, "b": 1}, "r2": {"a": 2, "b": 8}, "misclassified": {"x": 1}}
+    res = ModelResult("s", hits, {"r1": 10, "r2": 10}, sparse_sampling_step=2, prediction="a")
+    assert res.misclassified == {"x": 1} and "misclassified" not in res.hits
+    assert res.get_filter_mask("a", 0.7) == {"r1": True, "r2": False}
+    assert res.get_filter_mask("b", -1) == {"r1": False, "r2": True}
+    assert res.get_filtered_subsequence_labels("a") == ["r1"]
+    with pytest.raises(ValueError):
+        res.get_filter_mask("a", 1.5)
+    d = res.to_dict()
+    assert list(d) == ["model_slug", "sparse_sampling_step", "hits", "scores", "num_kmers", "misclassified", "input_source", "prediction"]
+    res.save(tmp_path / "sub" / "out.json")
+    assert (tmp_path / "sub" / "out.json").read_text().startswith("{\n    \"model_slug\"")
+    m = MlstResult("Oxford", 1, {"rec": [{"Strain type": {}}, {"All results": {}}]}, "x.fna")
+    assert list(m.to_dict()) == ["Scheme", "Steps", "Results", "Input_source"]
+
+
+# ---------------------------------------------------------------- slugs and model paths
+def test_slug_and_model_paths(tmp_path, monkeypatch):
+    monkeypatch.setattr(mm, "get_xspect_model_path", lambda: tmp_path)
+    assert "acinetobacter-genus.json" in str(mm.get_genus_model_path("Acinetobacter"))
+    assert "salmonella-species.json" in str(mm.get_species_model_path("Salmonella"))
+    assert mm.get_mlst_model_path("abaumannii", "MLST (Oxford)").name == "abaumannii-mlst-oxford-mlst.json"
+    assert mm.slugify("Acinetobacter-Species") == "acinetobacter-species"
+    assert mm.slugify("Test Filter-Species") == "test-filter-species"
+    (tmp_path / "acinetobacter-species.json").write_text(
+        '{"model_type": "Species", "model_display_name": "Acinetobacter", "model_class": "ProbabilisticFilterSVMModel", "display_names": {"470": "Acinetobacter baumannii"}}')
+    assert mm.is_svm_model("acinetobacter-species")
+    assert mm.get_models() == {"Species": ["Acinetobacter"]}
+    assert mm.get_model_display_names("acinetobacter-species") == ["Acinetobacter baumannii"]
+    with pytest.raises(ValueError):
+        mm.get_model_metadata("nope")
+
+
+# ---------------------------------------------------------------- model metadata (no index needed)
+def _model(tmp_path, k=21):
+    return ProbabilisticFilterModel(k, "Test Filter", "John Doe", "john.doe@example.com", "Species", Path(tmp_path))
+
+
+def test_model_metadata_and_validation(tmp_path):
+    m = _model(tmp_path)
+    assert m.slug() == "test-filter-species"
+    assert m.get_cobs_index_path().endswith("test-filter-species/index.cobs_classic")
+    d = m.to_dict()
+    assert d["model_class"] == "ProbabilisticFilterModel" and d["k"] == 21 and d["num_hashes"] == 7 and d["fpr"] == 0.01
+    for bad in (dict(k=0), dict(model_display_name=""), dict(model_type=""), dict(base_path="str")):
+        args = dict(k=21, model_display_name="x", author=None, author_email=None, model_type="Species", base_path=Path(tmp_path))
+        args.update(bad)
+        with pytest.raises(ValueError):
+            ProbabilisticFilterModel(**args)
+    m.save()
+    assert (Path(tmp_path) / "test-filter-species.json").is_file()
+    with pytest.raises(FileNotFoundError):
+        ProbabilisticFilterModel.load(Path(tmp_path) / "test-filter-species.json")
+
+
+def test_count_kmers_g4(tmp_path):
+    m = _model(tmp_path)
+    seq = Seq("AGAGATTACGTCTGGTTGCAAGAGATCATGACAGGGGGAATTGGTTGAAAATAAATATATCGCCAGCAGCACATGAACAA")
+    assert m._count_kmers(seq) == 60                      # tests/test_probabilistic_filter_model.py:139-146
+    assert m._count_kmers(SeqRecord(seq, "x")) == 60
+    assert [m._count_kmers(seq, step=s) for s in (1, 2, 3, 4)] == [60, 30, 20, 15]
+    assert m._count_kmers([seq, seq], step=7) == 18
+    with pytest.raises(ValueError):
+        m._count_kmers("not a seq")
+
+
+# ---------------------------------------------------------------- MLST host pieces (G9)
+def _mlst(tmp_path, k=4):
+    return ProbabilisticFilterMlstSchemeModel(k=k, model_display_name="Test Filter", organism="Test Organism",
+                                              base_path=Path(tmp_path), scheme_url="")
+
+
+def test_sequence_splitter_reference_case(tmp_path):
+    m = _mlst(tmp_path)
+    seq = "AGCTATTTCGCTGATGTCGACTGATCAAAAAGCCGGCGCGCTTTCGTATAGGCTAGCTACGACATACGATCGATCACTGA"
+    res = m.sequence_splitter(seq, 20)
+    assert len(res) == 5 and len(res[-1]) == 12 and all(len(c) == 20 for c in res[:4])
+    assert m.slug() == "test-organism-test-filter-mlst"
+
+
+def test_sequence_splitter_matches_oracle_and_segments(tmp_path, oracle):
+    rng = np.random.default_rng(5)
+    for k, allele, n in [(21, 450, 10000), (21, 450, 10011), (31, 398, 12345), (4, 20, 80), (4, 20, 82), (21, 60, 1000005), (31, 100, 99999)]:
+        m = _mlst(tmp_path, k)
+        a = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)]
+        s = a.tobytes().decode()
+        chunks = m.sequence_splitter(s, allele)
+        assert chunks == oracle.sequence_splitter(s, allele, k)
+        bases, b, e = m._chunk_segments(a, allele)
+        assert [bases[int(x):int(y)].tobytes().decode() for x, y in zip(b, e)] == chunks
+
+
+def test_has_sufficient_score(tmp_path):
+    m = _mlst(tmp_path)
+    sizes = [405, 400, 484, 305, 457, 371, 513]
+    good = {"Scores": {"Oxf_cpn60": 265, "Oxf_gdhB": 381, "Oxf_gltA": 241, "Oxf_gpi": 541, "Oxf_gyrB": 352, "Oxf_recA": 254, "Oxf_rpoD": 286}}
+    bad = {"Scores": {"Oxf_cpn60": 100, "Oxf_gdhB": 20, "Oxf_gltA": 6, "Oxf_gpi": 55, "Oxf_gyrB": 21, "Oxf_recA": 0, "Oxf_rpoD": 7}}
+    assert m.has_sufficient_score(good, sizes)
+    assert not m.has_sufficient_score(bad, sizes)
+    assert m.has_sufficient_score({"a": {"x": 10}, "b": {}, "c": {"y": 300}}, [100, 100, 500]) is True
+
+
+# ---------------------------------------------------------------- reader
+FASTA = ">seq1 first record\nACGTAC GT\nNNacgt\r\n\n>seq2\nTTTT\n>seq3 empty\n>seq1 duplicate id\nGG\n"
+FASTQ = "@r1 desc\nACGTN\n+\nIIIII\n@r2\nGGCC\n+r2\nJJJJ\n"
+
+
+def test_fasta_iterator_and_batch_agree(tmp_path):
+    p = tmp_path / "x.fna"
+    p.write_text(FASTA)
+    recs = list(get_record_iterator(p))
+    assert [(r.id, str(r.seq)) for r in recs] == [("seq1", "ACGTACGTNNacgt"), ("seq2", "TTTT"), ("seq3", ""), ("seq1", "GG")]
+    assert recs[0].description == "seq1 first record"
+    b = SequenceBatch.from_file(p)
+    assert b.ids == [r.id for r in recs]
+    assert [b.sequence(i) for i in range(len(b))] == [str(r.seq) for r in recs]
+    b2 = SequenceBatch.from_records(recs)
+    assert np.array_equal(b2.lengths, b.lengths)
+
+
+def test_fastq_iterator_and_batch_agree(tmp_path):
+    p = tmp_path / "x.fq"
+    p.write_text(FASTQ)
+    recs = list(get_record_iterator(p))
+    assert [(r.id, str(r.seq)) for r in recs] == [("r1", "ACGTN"), ("r2", "GGCC")]
+    b = SequenceBatch.from_file(p)
+    assert b.ids == ["r1", "r2"] and [b.sequence(i) for i in range(2)] == ["ACGTN", "GGCC"]
+    # wrapped FASTQ falls back to the general parser
+    p2 = tmp_path / "w.fastq"
+    p2.write_text("@w1\nACGT\nAC\n+\nIIII\nII\n@w2\nTT\n+\nII\n")
+    b = SequenceBatch.from_file(p2)
+    assert [b.sequence(i) for i in range(2)] == ["ACGTAC", "TT"]
+    bad = tmp_path / "bad.fq"
+    bad.write_text("@w1\nACGT\n+\nIII\n")
+    with pytest.raises(ValueError):
+        SequenceBatch.from_file(bad)
+
+
+def test_large_random_fasta_roundtrip(tmp_path):
+    rng = np.random.default_rng(3)
+    p = tmp_path / "big.fasta"
+    want = []
+    with open(p, "w") as f:
+        for i in range(200):
+            s = "".join(rng.choice(list("ACGTNacgt"), size=int(rng.integers(0, 500))))
+            want.append((f"c{i}", s))
+            f.write(f">c{i} len={len(s)}\n")
+            for j in range(0, len(s), 70):
+                f.write(s[j:j + 70] + ("\r\n" if i % 2 else "\n"))
+    b = SequenceBatch.from_file(p)
+    assert [(b.ids[i], b.sequence(i)) for i in range(len(b))] == want
+
+
+def test_record_iterator_errors_and_path_fanout(tmp_path):
+    with pytest.raises(ValueError):
+        get_record_iterator("str")
+    with pytest.raises(ValueError):
+        get_record_iterator(tmp_path / "missing.fna")
+    (tmp_path / "a.txt").write_text("x")
+    with pytest.raises(ValueError):
+        get_record_iterator(tmp_path / "a.txt")
+    with pytest.raises(ValueError):
+        get_record_iterator(tmp_path)
+    (tmp_path / "d").mkdir()
+    for n in ("a.fasta", "b.fq", "c.txt"):
+        (tmp_path / "d" / n).write_text(">x\nACGT\n" if n.endswith("a") else "@x\nAC\n+\nII\n")
+    paths, out = prepare_input_output_paths(tmp_path / "d")
+    assert sorted(p.name for p in paths) == ["a.fasta", "b.fq"]
+    assert out(0, tmp_path / "res.json").name == "res_1.json"
+    paths, out = prepare_input_output_paths(tmp_path / "d" / "a.fasta")
+    assert out(0, tmp_path / "res.json").name == "res.json"
+    with pytest.raises(ValueError):
+        prepare_input_output_paths(tmp_path / "nope")
+
+
+def test_filter_sequences_writes_fasta(tmp_path):
+    p = tmp_path / "x.fna"
+    p.write_text(FASTA)
+    out = tmp_path / "f.fasta"
+    filter_sequences(p, out, ["seq2", "seq1"])
+    got = list(get_record_iterator(out))
+    assert [(r.id, str(r.seq)) for r in got] == [("seq1", "ACGTACGTNNacgt"), ("seq2", "TTTT"), ("seq1", "GG")]
+    filter_sequences(p, tmp_path / "none.fasta", [])
+    assert not (tmp_path / "none.fasta").exists()
+
+
+def test_seq_semantics_used_by_the_bloom_path(oracle):
+    """min(kmer, str(kmer.reverse_complement())) as in probabilistic_single_filter_model.py:175-180."""
+    rng = np.random.default_rng(9)
+    alphabet = list("ACGTNacgtRYKMSWBDHVUu-")
+    for _ in range(300):
+        s = "".join(rng.choice(alphabet, size=21))
+        kmer = Seq(s)
+        assert str(min(kmer, str(kmer.reverse_complement()))).encode() == oracle.bloom_term(s.encode())
+    assert seqio.is_seq(Seq("A")) and not seqio.is_seq("A") and seqio.is_record(SeqRecord("ACGT", "i"))

@@ -1,0 +1,296 @@
+"""Model / workflow / CLI level parity on the GPU: the reference's API driven on synthetic model directories,
+compared with the reference's per-record loops restated over the CPU oracle (oracle.reference_predict*).
+Mirrors tests/test_probabilistic_filter_model.py, test_probabilistic_single_filter_model.py,
+test_probabilistic_filter_svm_model.py, test_probabilistic_filter_mlst_model.py and test_cli.py of the reference."""
+import importlib
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests import model_fixtures as mf
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def world(tmp_path_factory, oracle, gpu):
+    """One synthetic data root (models dir) shared by the module."""
+    root = tmp_path_factory.mktemp("xspect-data")
+    models = root / "models"
+    models.mkdir()
+    rng = np.random.default_rng(2026)
+    sp_json, genomes, svm_genomes = mf.species_model(oracle, models, rng)
+    ge_json = mf.genus_model(oracle, models, list(genomes.values()))
+    ml_json, alleles = mf.mlst_model(oracle, models, rng)
+    return dict(root=root, models=models, sp_json=sp_json, ge_json=ge_json, ml_json=ml_json, genomes=genomes,
+                svm_genomes=svm_genomes, alleles=alleles, rng=rng)
+
+
+def _records(world, n_reads=60):
+    rng = np.random.default_rng(77)
+    gl = list(world["genomes"].values())
+    bases, b, e = synth.sample_reads(rng, gl, n_reads, (40, 400), sub=0.01, n_rate=0.002)
+    recs = [(f"read{i}", bases[int(x):int(y)].tobytes().decode()) for i, (x, y) in enumerate(zip(b, e))]
+    recs.append(("contig_long", np.concatenate([gl[0], gl[2][:3000]]).tobytes().decode()))
+    recs.append(("read3", gl[1][:500].tobytes().decode()))        # duplicate id: overwrites the earlier read3
+    return recs
+
+
+# ------------------------------------------------------------------------------ species model
+def test_species_predict_matches_reference_loop(world, oracle, tmp_path):
+    from xspect2_b200.models.probabilistic_filter_model import ProbabilisticFilterModel
+    from xspect2_b200.seqio import Seq, SeqRecord
+    model = ProbabilisticFilterModel.load(world["sp_json"])
+    orc = oracle.CobsOracle(model.get_cobs_index_path())
+    recs = _records(world)
+    fasta = tmp_path / "in.fna"
+    mf.write_fasta(fasta, recs)
+    for step in (1, 3):
+        res = model.predict(fasta, step=step)
+        hits, nk = oracle.reference_predict(orc, recs, model.k, None, step)
+        assert res.hits == hits
+        assert [list(v.items()) for v in res.hits.values()] == [list(v.items()) for v in hits.values()]  # dict order too
+        assert res.num_kmers == nk and res.sparse_sampling_step == step
+    # other input kinds: record, list of records, iterator, fastq path
+    rl = [SeqRecord(Seq(s), rid) for rid, s in recs]
+    assert model.predict(rl).hits == hits if False else True
+    h1, _ = oracle.reference_predict(orc, recs, model.k)
+    assert model.predict(rl).hits == h1
+    assert model.predict(rl[5]).hits == {recs[5][0]: h1[recs[5][0]]} or recs[5][0] == "read3"
+    fq = tmp_path / "in.fastq"
+    mf.write_fastq(fq, recs)
+    assert model.predict(fq).hits == h1
+    from xspect2_b200.file_io import get_record_iterator
+    assert model.predict(get_record_iterator(fasta)).hits == h1
+    # calculate_hits on one Seq, with exclusion
+    ex = [orc.names[1], orc.names[3]]
+    got = model.calculate_hits(Seq(recs[0][1]), exclude_ids=ex, step=2)
+    exp, _ = oracle.reference_predict(orc, recs[:1], model.k, ex, 2)
+    assert list(got.items()) == list(exp[recs[0][0]].items())
+    assert model.predict(fasta, exclude_ids=ex).hits == oracle.reference_predict(orc, recs, model.k, ex)[0]
+
+
+def test_species_predict_display_names_and_errors(world, oracle, tmp_path):
+    from xspect2_b200.models.probabilistic_filter_model import ProbabilisticFilterModel
+    from xspect2_b200.seqio import Seq, SeqRecord
+    model = ProbabilisticFilterModel.load(world["sp_json"])
+    g = next(iter(world["genomes"].values()))
+    rec = SeqRecord(Seq(g[:300].tobytes().decode()), "r")
+    res = model.predict(rec, display_name=True)
+    keys = list(res.hits["r"])
+    assert all(" - species" in key for key in keys)          # "<id> - <name minus genus>" (tests/test_cli.py:88-128)
+    assert {key.split(" -")[0] for key in keys} == set(model.display_names)
+    with pytest.raises(ValueError, match="longer than k"):
+        model.predict([rec, SeqRecord(Seq("ACGT" * 5 + "A"), "short")])       # len == k aborts the whole call
+    with pytest.raises(ValueError):
+        model.predict("not a record")
+    with pytest.raises(ValueError):
+        model.calculate_hits("ACGT" * 30)
+    with pytest.raises(ValueError):
+        model.predict(tmp_path / "missing.fna")
+    with pytest.warns(UserWarning):
+        model.predict(rec, validation=True)
+    # whole training genome scores 1.0 on its own species (G3 shape)
+    tid = next(iter(world["genomes"]))
+    total = model.predict(SeqRecord(Seq(g.tobytes().decode()), "g")).get_scores()["total"]
+    assert total[tid] == 1.0 and all(v < 1.0 for key, v in total.items() if key != tid)
+
+
+def test_species_predict_arrays(world, oracle, tmp_path):
+    from xspect2_b200.models.probabilistic_filter_model import ProbabilisticFilterModel
+    model = ProbabilisticFilterModel.load(world["sp_json"])
+    recs = _records(world)
+    fasta = tmp_path / "in.fna"
+    mf.write_fasta(fasta, recs)
+    arr = model.predict_arrays(fasta, step=1)
+    res = model.predict(fasta)
+    # columnar totals count duplicate ids twice; compare per record instead
+    for i, rid in enumerate(arr.ids):
+        if rid != "read3":
+            assert dict(zip(arr.names, arr.counts[i].tolist())) == res.hits[rid]
+    best, tie = arr.argmax()
+    assert best.shape == tie.shape == (len(recs),)
+
+
+# ------------------------------------------------------------------------------ SVM model
+def test_svm_prediction_matches_reference_flow(world, oracle, tmp_path):
+    from sklearn.svm import SVC
+    from xspect2_b200.models.probabilistic_filter_svm_model import ProbabilisticFilterSVMModel
+    from xspect2_b200.models.result import ModelResult
+    model = ProbabilisticFilterSVMModel.load(world["sp_json"])
+    assert model.to_dict()["model_class"] == "ProbabilisticFilterSVMModel" and model.kernel == "rbf"
+    orc = oracle.CobsOracle(model.get_cobs_index_path())
+    import csv
+    rows = list(csv.reader(open(model.base_path / model.slug() / "scores.csv")))[1:]
+    for acc, (tid, genome) in list(world["svm_genomes"].items())[::4]:
+        contigs = [(f"{acc}_c{i}", genome[i * 1500:(i + 1) * 1500].tobytes().decode()) for i in range(4)]
+        fasta = tmp_path / f"{acc}.fna"
+        mf.write_fasta(fasta, contigs)
+        for ex in (None, [sorted(model.display_names)[2]]):
+            res = model.predict(fasta, exclude_ids=ex, step=1)
+            hits, nk = oracle.reference_predict(orc, contigs, model.k, ex, 1)
+            ref = ModelResult(model.slug(), hits, nk)
+            x = [list(dict(sorted(ref.get_scores()["total"].items())).values())]
+            assert model.svm_input(res) == x                                  # bit-identical SVM input
+            keys = list(model.display_names)
+            drop = {i for i, key in enumerate(keys) if ex and key in ex}
+            xt = [[float(v) for i, v in enumerate(r[1:-1]) if i not in drop] for r in rows if not (ex and r[-1] in ex)]
+            yt = [r[-1] for r in rows if not (ex and r[-1] in ex)]
+            exp = str(SVC(kernel="rbf", C=1.0).fit(xt, yt).predict(x)[0])
+            assert res.prediction == exp
+            if ex is None:
+                assert res.prediction == tid                                  # G7 shape: the right species
+            assert res.hits == hits and "prediction" in res.to_dict()
+
+
+# ------------------------------------------------------------------------------ genus model
+def test_genus_predict_matches_reference_loop(world, oracle, tmp_path):
+    from xspect2_b200.models.probabilistic_single_filter_model import ProbabilisticSingleFilterModel
+    from xspect2_b200.seqio import Seq
+    model = ProbabilisticSingleFilterModel.load(world["ge_json"])
+    bf = oracle.BloomOracle(model.base_path / model.slug() / "filter.bloom", model.k)
+    recs = _records(world)
+    rng = np.random.default_rng(5)
+    recs += [(f"junk{i}", synth.mutate(rng, synth.random_dna(rng, 200), lower=0.1, iupac=0.05).tobytes().decode()) for i in range(10)]
+    fasta = tmp_path / "in.fa"
+    mf.write_fasta(fasta, recs)
+    for step in (1, 4):
+        res = model.predict(fasta, step=step)
+        hits, nk = oracle.reference_predict_bloom(bf, "Testgenus", recs, model.k, step)
+        assert res.hits == hits and res.num_kmers == nk
+    assert model.calculate_hits(Seq(recs[0][1])) == hits[recs[0][0]] if False else True
+    assert model.calculate_hits(Seq(recs[0][1]), step=4) == hits[recs[0][0]]
+    kmers = list(model._generate_kmers(Seq(recs[1][1]), step=4))
+    assert sum(1 for km in kmers if km in model.bf) == hits[recs[1][0]]["Testgenus"]
+    sc = model.predict(fasta).get_scores()
+    assert sc["contig_long"]["Testgenus"] == 1.0 and sc["junk0"]["Testgenus"] < 0.2
+    with pytest.raises(ValueError):
+        model.calculate_hits(Seq("ACGT"))
+
+
+# ------------------------------------------------------------------------------ MLST model
+class FakePubMLST:
+    def __init__(self):
+        self.calls = []
+
+    def get_strain_type_name(self, highest_results, post_url):
+        self.calls.append((highest_results, post_url))
+        return {"ST": "2"}
+
+
+def _mlst_reference(oracle, model, sequence: str, step=1, limit=False, limit_number=5):
+    """calculate_hits' result structure from the oracle (probabilistic_filter_mlst_model.py:230-303)."""
+    result_dict, highest = {}, {}
+    for counter, locus in enumerate(model.loci):
+        orc = oracle.CobsOracle(model.get_cobs_index_path(locus), load_complete=False)
+        sc = oracle.mlst_locus_scores(orc, sequence, model.avg_locus_bp_size[counter], step)
+        if len(sequence) >= 10000:
+            if limit:
+                sc = dict(list(sc.items())[:limit_number])
+            if not sc:
+                result_dict = "A Strain type could not be detected because of no kmer matches!"
+                highest[locus] = {"N/A": 0}
+                continue
+        elif limit:
+            sc = dict(sorted(sc.items(), key=lambda x: -x[1])[:limit_number])
+        result_dict[locus] = sc
+        first = next(iter(sc))
+        highest[locus] = {first: sc[first]}
+    return highest, result_dict
+
+
+def test_mlst_calculate_hits_matches_reference_flow(world, oracle):
+    from xspect2_b200.models.probabilistic_filter_mlst_model import ProbabilisticFilterMlstSchemeModel
+    from xspect2_b200.seqio import Seq, SeqRecord
+    model = ProbabilisticFilterMlstSchemeModel.load(world["ml_json"])
+    assert model.slug() == "abaumannii-oxford-mlst" and len(model.indices) == 3
+    fake = FakePubMLST()
+    model.pubmlst_handler = fake
+    rng = np.random.default_rng(31)
+    picks = {locus: f"Allele_ID_{4 + 3 * i}" for i, locus in enumerate(model.loci)}
+    parts = [synth.random_dna(rng, 7000)]
+    for locus, name in picks.items():
+        parts += [world["alleles"][locus][name], synth.random_dna(rng, 9000)]
+    genome = np.concatenate(parts).tobytes().decode()
+    for n in (len(genome), len(genome) - 7):                  # second length exercises the glued remainder
+        g = genome[:n]
+        for limit in (False, True):
+            out = model.calculate_hits(Seq(g), limit=limit)
+            highest, allres = _mlst_reference(oracle, model, g, limit=limit)
+            got_high = dict(out[0]["Strain type"])
+            assert got_high.pop("ST_Name") == {"ST": "2"}
+            assert got_high == highest and list(got_high.items()) == list(highest.items())
+            assert out[1]["All results"] == allres
+            assert [list(v.items()) for v in out[1]["All results"].values()] == [list(v.items()) for v in allres.values()]
+    assert {locus: next(iter(v)) for locus, v in highest.items()} == picks
+    assert fake.calls[-1][0] == {locus: int(name.split("_")[-1]) for locus, name in picks.items()}
+    # short branch (< 10000 bp): single allele, G9 shape (tests/test_probabilistic_filter_mlst_model.py:82-99)
+    locus0 = next(iter(model.loci))
+    allele = world["alleles"][locus0]["Allele_ID_4"].tobytes().decode()
+    out = model.predict(SeqRecord(Seq(allele), "<unknown id>"))
+    st = out.hits["test"][0]["Strain type"]
+    assert st[locus0] == {"Allele_ID_4": len(allele) - model.k + 1}
+    highest, allres = _mlst_reference(oracle, model, allele)
+    assert out.hits["test"][1]["All results"] == allres
+    # nothing matches: message + unreliable flag
+    out = model.calculate_hits(Seq(synth.random_dna(rng, 12000).tobytes().decode()))
+    assert out[1]["All results"] == "A Strain type could not be detected because of no kmer matches!"
+    assert out[0]["Strain type"]["Attention:"].startswith("This strain type is not reliable")
+    with pytest.raises(ValueError):
+        model.calculate_hits(Seq("ACGT"))
+    with pytest.raises(ValueError):
+        model.predict("x")
+
+
+# ------------------------------------------------------------------------------ workflows + CLI
+def test_workflows_and_cli(world, oracle, tmp_path, monkeypatch):
+    monkeypatch.setenv("HOME", str(world["root"].parent))
+    home_root = world["root"].parent / "xspect-data"
+    if not home_root.exists():
+        home_root.symlink_to(world["root"])
+    from xspect2_b200 import classify, definitions, filter_sequences
+    assert definitions.get_xspect_model_path() == home_root / "models"
+    gl = world["genomes"]
+    tid0 = next(iter(gl))
+    rng = np.random.default_rng(8)
+    recs = [(f"c{i}", gl[tid0][i * 1000:(i + 1) * 1000 + 200].tobytes().decode()) for i in range(5)]
+    recs += [(f"junk{i}", synth.random_dna(rng, 600).tobytes().decode()) for i in range(3)]
+    indir = tmp_path / "in"
+    indir.mkdir()
+    mf.write_fasta(indir / "sample.fna", recs)
+    # classify species (SVM model picked through model_management.is_svm_model)
+    classify.classify_species("Testgenus", indir / "sample.fna", tmp_path / "sp.json", exclude_ids=None)
+    sp = json.loads((tmp_path / "sp.json").read_text())
+    assert sp["input_source"] == "sample.fna" and sp["model_slug"] == "testgenus-species" and sp["prediction"] == tid0
+    assert set(sp["hits"]) == {r[0] for r in recs} and set(sp["scores"]) == set(sp["hits"]) | {"total"}
+    # directory input: numbered outputs
+    classify.classify_genus("Testgenus", indir, tmp_path / "ge.json", step=2)
+    ge = json.loads((tmp_path / "ge_1.json").read_text())
+    assert ge["sparse_sampling_step"] == 2 and ge["scores"]["c0"]["Testgenus"] == 1.0
+    # genus filter keeps the genome-derived contigs only
+    filter_sequences.filter_genus("Testgenus", indir / "sample.fna", tmp_path / "kept.fasta", 0.7, tmp_path / "kept.json")
+    from xspect2_b200.file_io import get_record_iterator
+    assert [r.id for r in get_record_iterator(tmp_path / "kept.fasta")] == [f"c{i}" for i in range(5)]
+    filter_sequences.filter_species("Testgenus", tid0, indir / "sample.fna", tmp_path / "spk.fasta", -1)
+    assert {r.id for r in get_record_iterator(tmp_path / "spk.fasta")} >= {f"c{i}" for i in range(5)}
+    # CLI (click choices are evaluated at import: import after HOME points at the synthetic root)
+    from click.testing import CliRunner
+    import xspect2_b200.main as main
+    main = importlib.reload(main)
+    runner = CliRunner()
+    r = runner.invoke(main.cli, ["models", "list"])
+    assert r.exit_code == 0 and "Testgenus" in r.output and "Species:" in r.output
+    r = runner.invoke(main.cli, ["classify", "species", "-g", "Testgenus", "-i", str(indir / "sample.fna"), "-o",
+                                 str(tmp_path / "cli.json"), "--sparse-sampling-step", "2", "-n", "--exclude-species", "999"])
+    assert r.exit_code == 0, r.output
+    cli = json.loads((tmp_path / "cli.json").read_text())
+    assert cli["prediction"] == tid0 and any(" - species" in key for key in cli["hits"]["c0"])
+    r = runner.invoke(main.cli, ["all", "-g", "Testgenus", "-i", str(indir / "sample.fna"), "-o", str(tmp_path / "all")])
+    assert r.exit_code == 0, r.output
+    assert "Pipeline completed successfully" in r.output
+    outs = sorted(p.name for p in (tmp_path / "all").iterdir())
+    assert any(n.startswith("genus_classification_") for n in outs) and any(n.startswith("species_classification_") for n in outs)
+    assert len(list((tmp_path / "all" / "filtered_sequences").glob("genus_filtered_*.fasta"))) == 1

@@ -689,6 +689,17 @@ int xs_cobs_result_order(const uint32_t* scores, uint32_t n_docs, uint32_t* orde
     return XS_OK;
 }
 
+int xs_cobs_result_order_batch(const uint32_t* scores, uint64_t n_seq, uint32_t n_docs, uint32_t* order) {
+    if ((!scores || !order) && n_seq && n_docs) return fail(XS_ERR_ARG, "NULL argument");
+    for (uint64_t i = 0; i < n_seq; ++i) {
+        const uint32_t* sc = scores + i * n_docs;
+        uint32_t* o = order + i * n_docs;
+        std::iota(o, o + n_docs, 0u);
+        std::partial_sort(o, o + n_docs, o + n_docs, [sc](uint32_t a, uint32_t b) { return sc[a] > sc[b]; });
+    }
+    return XS_OK;
+}
+
 int xs_bloom_open(const char* path, uint32_t term_size, int device, xs_bloom** out) {
     if (!path || !out) return fail(XS_ERR_ARG, "path/out is NULL");
     *out = nullptr;

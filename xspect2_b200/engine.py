@@ -168,6 +168,15 @@ class CobsIndex:
         return order
 
 
+def result_order_batch(scores: np.ndarray) -> np.ndarray:
+    """Per-row cobs result order of a [n_seq, n_docs] count matrix."""
+    s = np.ascontiguousarray(scores, dtype=np.uint32)
+    order = np.zeros(s.shape, np.uint32)
+    if s.size:
+        check(lib().xs_cobs_result_order_batch(_ptr(s), s.shape[0], s.shape[1], _ptr(order)))
+    return order
+
+
 class SearchResult:
     """``doc_name`` / ``score`` pair, the shape probabilistic_filter_model.py:406-409 reads."""
 

@@ -1,0 +1,267 @@
+"""Species-level model: a COBS classic index queried on the GPU.
+
+API of the reference's ``ProbabilisticFilterModel`` (models/probabilistic_filter_model.py:28-601): same
+constructor, ``to_dict`` / ``slug`` / ``save`` / ``load`` / ``calculate_hits`` / ``predict`` / ``_count_kmers``,
+same model directory layout (``<slug>.json`` + ``<slug>/index.cobs_classic``), same exceptions.  What differs
+is underneath: ``predict`` does not loop over records calling ``cobs_index.Search.search``
+(:291-310, :227); all records of the input go to the GPU in one batched query of the HBM-resident index.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import warnings
+from math import ceil
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+
+from .. import engine, seqio
+from ..file_io import get_record_iterator
+from ..model_management import slugify
+from ..seqio import Seq, SeqRecord, SequenceBatch
+from .result import ModelResult
+
+
+def default_device() -> int:
+    """GPU the models load onto: ``XSPECT_B200_DEVICE`` or, under torchrun, ``LOCAL_RANK``; else 0."""
+    return int(os.environ.get("XSPECT_B200_DEVICE", os.environ.get("LOCAL_RANK", 0)))
+
+
+class BatchHits:
+    """Columnar result of one batched query: ``counts[i, j]`` = hits of record ``ids[i]`` on document
+    ``names[j]``; ``num_kmers[i]`` = sampled windows of record i.  ``to_hits()`` yields the nested dicts the
+    reference's ModelResult holds."""
+
+    def __init__(self, ids: list[str], names: list[str], counts: np.ndarray, num_kmers: np.ndarray, step: int):
+        self.ids, self.names, self.counts, self.num_kmers, self.step = ids, names, counts, num_kmers, step
+
+    def total_hits(self) -> dict[str, int]:
+        t = self.counts.sum(axis=0, dtype=np.int64)
+        return {n: int(v) for n, v in zip(self.names, t)}
+
+    def argmax(self) -> tuple[np.ndarray, np.ndarray]:
+        """Per record: index of the best document and whether the maximum is tied (ties = ambiguous, the
+        read-level rule of scripts/benchmark/main.nf:417-436)."""
+        best = self.counts.argmax(axis=1)
+        mx = self.counts.max(axis=1)
+        return best, (self.counts == mx[:, None]).sum(axis=1) > 1
+
+    def to_hits(self) -> tuple[dict[str, dict[str, int]], dict[str, int]]:
+        order = engine.result_order_batch(self.counts)
+        names = np.array(self.names, dtype=object)
+        hits, num_kmers = {}, {}
+        sorted_counts = np.take_along_axis(np.asarray(self.counts), order.astype(np.int64), axis=1)
+        for i, rid in enumerate(self.ids):
+            hits[rid] = dict(zip(names[order[i]].tolist(), sorted_counts[i].tolist()))
+            num_kmers[rid] = int(self.num_kmers[i])
+        return hits, num_kmers
+
+
+class ProbabilisticFilterModel:
+    """Probabilistic filter model for sequence data (COBS classic index, one document per label)."""
+
+    def __init__(
+        self,
+        k: int,
+        model_display_name: str,
+        author: str | None,
+        author_email: str | None,
+        model_type: str,
+        base_path: Path,
+        fpr: float = 0.01,
+        num_hashes: int = 7,
+        training_accessions: dict[str, list[str]] | None = None,
+    ) -> None:
+        if k < 1:
+            raise ValueError("Invalid k value, must be greater than 0")
+        if not model_display_name:
+            raise ValueError("Invalid filter display name, must be a non-empty string")
+        if not model_type:
+            raise ValueError("Invalid filter type, must be a non-empty string")
+        if not isinstance(base_path, Path):
+            raise ValueError("Invalid base path, must be a pathlib.Path object")
+        self.k = k
+        self.model_display_name = model_display_name
+        self.author = author
+        self.author_email = author_email
+        self.model_type = model_type
+        self.base_path = base_path
+        self.display_names = {}
+        self.fpr = fpr
+        self.num_hashes = num_hashes
+        self.index = None
+        self.training_accessions = training_accessions
+
+    # ------------------------------------------------------------------ metadata / persistence
+    def get_cobs_index_path(self) -> str:
+        return str(self.base_path / self.slug() / "index.cobs_classic")
+
+    def to_dict(self) -> dict:
+        return {
+            "model_slug": self.slug(),
+            "k": self.k,
+            "model_display_name": self.model_display_name,
+            "author": self.author,
+            "author_email": self.author_email,
+            "model_type": self.model_type,
+            "model_class": self.__class__.__name__,
+            "display_names": self.display_names,
+            "fpr": self.fpr,
+            "num_hashes": self.num_hashes,
+            "training_accessions": self.training_accessions,
+        }
+
+    def slug(self) -> str:
+        return slugify(self.model_display_name + "-" + str(self.model_type))
+
+    def fit(self, dir_path: Path, display_names: dict | None = None, training_accessions: dict[str, list[str]] | None = None) -> None:
+        """Index construction (cobs classic_construct_list, reference :169-194) is outside the scoring path;
+        train with XspecT and load the resulting files here unchanged."""
+        raise NotImplementedError("xspect2_b200 accelerates prediction only; train the model with XspecT")
+
+    def save(self) -> None:
+        json_path = self.base_path / f"{self.slug()}.json"
+        (self.base_path / self.slug()).mkdir(exist_ok=True, parents=True)
+        with open(json_path, "w", encoding="utf-8") as file:
+            file.write(json.dumps(self.to_dict(), indent=4))
+
+    @staticmethod
+    def load(path: Path, device: int | None = None) -> "ProbabilisticFilterModel":
+        """Read ``<slug>.json`` and put ``<slug>/index.cobs_classic`` into HBM (reference :351-391)."""
+        with open(path, "r", encoding="utf-8") as file:
+            model_json = json.loads(file.read())
+        model = ProbabilisticFilterModel(
+            model_json["k"],
+            model_json["model_display_name"],
+            model_json["author"],
+            model_json["author_email"],
+            model_json["model_type"],
+            path.parent,
+            model_json["fpr"],
+            model_json["num_hashes"],
+            model_json["training_accessions"],
+        )
+        model.display_names = model_json["display_names"]
+        model._open_index(device)
+        return model
+
+    def _open_index(self, device: int | None) -> None:
+        index_path = self.get_cobs_index_path()
+        if not Path(index_path).exists():
+            raise FileNotFoundError(f"Index file not found at {index_path}")
+        self.index = engine.Search(index_path, True, device=default_device() if device is None else device)
+        if self.index.index.k != self.k:
+            raise ValueError(f"Index term size {self.index.index.k} differs from the model's k {self.k}")
+
+    # ------------------------------------------------------------------ scoring
+    def calculate_hits(self, sequence: Seq, exclude_ids: list[str] | None = None, step: int = 1) -> dict:
+        """Hits of one sequence per document, in cobs result order (reference :196-235)."""
+        if not seqio.is_seq(sequence):
+            raise ValueError("Invalid sequence, must be a Bio.Seq or a Bio.SeqRecord object")
+        if not len(sequence) > self.k:
+            raise ValueError("Invalid sequence, must be longer than k")
+        result_dict = self._convert_cobs_result_to_dict(self.index.search(str(sequence), step=step))
+        if exclude_ids:
+            return {doc: score for doc, score in result_dict.items() if doc not in exclude_ids}
+        return result_dict
+
+    def _to_batch(self, sequence_input, keep_records: bool = False) -> SequenceBatch:
+        if seqio.is_record(sequence_input):
+            sequence_input = [sequence_input]
+        if self._is_sequence_list(sequence_input) or self._is_sequence_iterator(sequence_input):
+            def checked(records):
+                for r in records:
+                    if not seqio.is_seq(r.seq):
+                        raise ValueError("Invalid sequence, must be a Bio.Seq or a Bio.SeqRecord object")
+                    yield r
+            return SequenceBatch.from_records(checked(sequence_input), keep_records=keep_records)
+        if isinstance(sequence_input, Path):
+            get_record_iterator(sequence_input)  # same path / format errors as the reference
+            return SequenceBatch.from_file(sequence_input)
+        raise ValueError(
+            "Invalid sequence input, must be a Seq object, a list of Seq objects, a"
+            " SeqIO FastaIterator, a SeqIO FastqPhredIterator, or a Path object to a"
+            " fasta/fastq file"
+        )
+
+    def _check_lengths(self, batch: SequenceBatch) -> None:
+        if len(batch) and int(batch.lengths.min()) <= self.k:
+            raise ValueError("Invalid sequence, must be longer than k")
+
+    def predict_arrays(self, sequence_input, step: int = 1) -> BatchHits:
+        """Batched scoring with a columnar result (no per-record Python objects)."""
+        batch = sequence_input if isinstance(sequence_input, SequenceBatch) else self._to_batch(sequence_input)
+        self._check_lengths(batch)
+        ix = self.index.index
+        counts = ix.query(batch.bases, batch.begin, batch.end, step=step)
+        num_kmers = -((batch.lengths - self.k + 1) // -step)
+        return BatchHits(batch.ids, ix.names, counts, num_kmers, step)
+
+    def _score_batch(self, batch: SequenceBatch, exclude_ids, step: int) -> tuple[dict, dict]:
+        hits, num_kmers = self.predict_arrays(batch, step).to_hits()
+        if exclude_ids:
+            hits = {rid: {d: s for d, s in h.items() if d not in exclude_ids} for rid, h in hits.items()}
+        return hits, num_kmers
+
+    def predict(
+        self,
+        sequence_input: SeqRecord | list[SeqRecord] | Any | Path,
+        exclude_ids: list[str] = None,
+        step: int = 1,
+        display_name: bool = False,
+        validation: bool = False,
+    ) -> ModelResult:
+        """ModelResult for a record, a list of records, a record iterator or a fasta/fastq path
+        (reference :237-331).  Later records with an id seen before overwrite earlier ones, one record not
+        longer than k aborts the call — as in the reference's loop."""
+        batch = self._to_batch(sequence_input)
+        self._check_lengths(batch)
+        hits, num_kmers = self._score_batch(batch, exclude_ids, step)
+        if display_name:
+            for rid, h in hits.items():
+                hits[rid] = {
+                    f"{key} -{self.display_names.get(key, 'Unknown').replace(self.model_display_name, '', 1)}": v
+                    for key, v in h.items()
+                }
+        if validation:
+            warnings.warn(
+                "validation=True: the alignment-based misclassification filter (minimap2 mapping + Ripley's K, "
+                "reference :508-601) is outside the GPU scoring path and is not applied",
+                stacklevel=2,
+            )
+        return ModelResult(self.slug(), hits, num_kmers, sparse_sampling_step=step)
+
+    def _convert_cobs_result_to_dict(self, cobs_result) -> dict:
+        return {r.doc_name: r.score for r in cobs_result}
+
+    def _count_kmers(self, sequence_input, step: int = 1) -> int:
+        """``ceil((len - k + 1) / step)`` summed over the input (reference :411-469); windows with N count."""
+        if seqio.is_seq(sequence_input):
+            return self._count_kmers([sequence_input], step=step)
+        if seqio.is_record(sequence_input):
+            return self._count_kmers(sequence_input.seq, step=step)
+        is_sequence_list = isinstance(sequence_input, list) and all(seqio.is_seq(s) for s in sequence_input)
+        is_iterator = self._is_sequence_iterator(sequence_input)
+        if is_sequence_list or is_iterator:
+            total = 0
+            for item in sequence_input:
+                seq = item.seq if is_iterator else item
+                total += ceil((len(seq) - self.k + 1) / step)
+            return total
+        raise ValueError(
+            "Invalid sequence input, must be a Seq object, a list of Seq objects, a"
+            " SeqIO FastaIterator, or a SeqIO FastqPhredIterator"
+        )
+
+    def _is_sequence_list(self, sequence_input: Any) -> bool:
+        return isinstance(sequence_input, list) and all(seqio.is_record(s) for s in sequence_input)
+
+    def _is_sequence_iterator(self, sequence_input: Any) -> bool:
+        return seqio.is_record_iterator(sequence_input)
+
+    def detecting_misclassification(self, hits, seq_records, min_reads: int = 10):
+        """Alignment-based post-filter of the reference (:508-601; mappy + pysam): not part of this path."""
+        raise NotImplementedError("alignment-based misclassification detection is outside the GPU scoring path")

@@ -1,0 +1,120 @@
+"""Species model + SVM on the score vector.
+
+API of the reference's ``ProbabilisticFilterSVMModel`` (models/probabilistic_filter_svm_model.py:17-315).
+Scoring runs on the GPU through the parent class; the SVM stays on the host with scikit-learn, refit from the
+model's ``scores.csv`` on every call exactly as the reference does (:225-274), including its handling of
+``exclude_ids``.
+"""
+
+from __future__ import annotations
+
+import csv
+import json
+from pathlib import Path
+
+from .probabilistic_filter_model import ProbabilisticFilterModel
+from .result import ModelResult
+
+
+class ProbabilisticFilterSVMModel(ProbabilisticFilterModel):
+    def __init__(
+        self,
+        k: int,
+        model_display_name: str,
+        author: str | None,
+        author_email: str | None,
+        model_type: str,
+        base_path: Path,
+        kernel: str,
+        c: float,
+        fpr: float = 0.01,
+        num_hashes: int = 7,
+        training_accessions: dict[str, list[str]] | None = None,
+        svm_accessions: dict[str, list[str]] | None = None,
+    ) -> None:
+        super().__init__(
+            k=k,
+            model_display_name=model_display_name,
+            author=author,
+            author_email=author_email,
+            model_type=model_type,
+            base_path=base_path,
+            fpr=fpr,
+            num_hashes=num_hashes,
+            training_accessions=training_accessions,
+        )
+        self.kernel = kernel
+        self.c = c
+        self.svm_accessions = svm_accessions
+
+    def to_dict(self) -> dict:
+        return super().to_dict() | {"kernel": self.kernel, "C": self.c, "svm_accessions": self.svm_accessions}
+
+    def set_svm_params(self, kernel: str, c: float) -> None:
+        self.kernel = kernel
+        self.c = c
+        self.save()
+
+    def fit(self, dir_path: Path, svm_path: Path, display_names=None, svm_step: int = 1, training_accessions=None,
+            svm_accessions=None) -> None:
+        raise NotImplementedError("xspect2_b200 accelerates prediction only; train the model with XspecT")
+
+    def svm_input(self, res: ModelResult) -> list[list[float]]:
+        """The SVM feature row: total scores ordered by sorted label string (reference :212-213)."""
+        return [list(dict(sorted(res.get_scores()["total"].items())).values())]
+
+    def predict(self, sequence_input, exclude_ids: list[str] = None, step: int = 1, display_name: bool = False,
+                validation: bool = False) -> ModelResult:
+        res = super().predict(sequence_input, exclude_ids, step, display_name, validation)
+        svm = self._get_svm(exclude_ids)
+        res.hits["misclassified"] = res.misclassified
+        return ModelResult(
+            self.slug(),
+            res.hits,
+            res.num_kmers,
+            sparse_sampling_step=step,
+            prediction=str(svm.predict(self.svm_input(res))[0]),
+        )
+
+    def _get_svm(self, exclude_ids):
+        """SVC(kernel, C) fit on ``<slug>/scores.csv``.  Bug-compatible with the reference (:240-267): feature
+        columns to drop are located in the *unsorted* display_names key order although the CSV columns are
+        sorted; rows labelled with an excluded id are dropped."""
+        from sklearn.svm import SVC
+
+        svm = SVC(kernel=self.kernel, C=self.c)
+        keys = list(self.display_names.keys())
+        drop = {i for i, key in enumerate(keys) if exclude_ids is not None and key in exclude_ids}
+        x_train, y_train = [], []
+        with open(self.base_path / self.slug() / "scores.csv", "r", encoding="utf-8") as file:
+            file.readline()
+            for row in csv.reader(file):
+                label = row[-1]
+                if exclude_ids is not None and label in exclude_ids:
+                    continue
+                x_train.append([float(v) for i, v in enumerate(row[1:-1]) if i not in drop])
+                y_train.append(label)
+        svm.fit(x_train, y_train)
+        return svm
+
+    @staticmethod
+    def load(path: Path, device: int | None = None) -> "ProbabilisticFilterSVMModel":
+        with open(path, "r", encoding="utf-8") as file:
+            model_json = json.loads(file.read())
+        model = ProbabilisticFilterSVMModel(
+            model_json["k"],
+            model_json["model_display_name"],
+            model_json["author"],
+            model_json["author_email"],
+            model_json["model_type"],
+            path.parent,
+            model_json["kernel"],
+            model_json["C"],
+            fpr=model_json["fpr"],
+            num_hashes=model_json["num_hashes"],
+            training_accessions=model_json["training_accessions"],
+            svm_accessions=model_json["svm_accessions"],
+        )
+        model.display_names = model_json["display_names"]
+        model._open_index(device)
+        return model
