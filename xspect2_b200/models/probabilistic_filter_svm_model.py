@@ -66,6 +66,7 @@ class ProbabilisticFilterSVMModel(ProbabilisticFilterModel):
     def predict(self, sequence_input, exclude_ids: list[str] = None, step: int = 1, display_name: bool = False,
                 validation: bool = False) -> ModelResult:
         res = super().predict(sequence_input, exclude_ids, step, display_name, validation)
+        svm_scores = self.svm_input(res)
         svm = self._get_svm(exclude_ids)
         res.hits["misclassified"] = res.misclassified
         return ModelResult(
@@ -73,7 +74,7 @@ class ProbabilisticFilterSVMModel(ProbabilisticFilterModel):
             res.hits,
             res.num_kmers,
             sparse_sampling_step=step,
-            prediction=str(svm.predict(self.svm_input(res))[0]),
+            prediction=str(svm.predict(svm_scores)[0]),
         )
 
     def _get_svm(self, exclude_ids):
