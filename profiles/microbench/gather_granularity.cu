@@ -18,6 +18,10 @@ __device__ __forceinline__ uint4 ld16(const uint8_t* p) {
     if (MODE == 2) asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     if (MODE == 3) asm volatile("ld.global.cv.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     if (MODE == 4) asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    if (MODE == 6) asm volatile("ld.global.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    if (MODE == 7) asm volatile("ld.global.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    if (MODE == 8) asm volatile("ld.global.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    if (MODE == 9) asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     if (MODE == 5) asm volatile("ld.global.lu.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
@@ -60,10 +64,12 @@ int main(int argc, char** argv) {
     int sm = 0; cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
     for (int occ : {4, 8}) {
         int grid = sm * occ;
-        float ms[6] = {run<0>(tab, n_rows, n_items, out, grid), run<1>(tab, n_rows, n_items, out, grid), run<2>(tab, n_rows, n_items, out, grid),
-                       run<3>(tab, n_rows, n_items, out, grid), run<4>(tab, n_rows, n_items, out, grid), run<5>(tab, n_rows, n_items, out, grid)};
-        const char* names[6] = {"nc.L1::no_allocate", "plain", "cg", "cv", "L1::no_allocate (generic)", "lu"};
-        for (int m = 0; m < 6; ++m)
+        float ms[10] = {run<0>(tab, n_rows, n_items, out, grid), run<1>(tab, n_rows, n_items, out, grid), run<2>(tab, n_rows, n_items, out, grid),
+                       run<3>(tab, n_rows, n_items, out, grid), run<4>(tab, n_rows, n_items, out, grid), run<5>(tab, n_rows, n_items, out, grid),
+                       run<6>(tab, n_rows, n_items, out, grid), run<7>(tab, n_rows, n_items, out, grid), run<8>(tab, n_rows, n_items, out, grid),
+                       run<9>(tab, n_rows, n_items, out, grid)};
+        const char* names[10] = {"nc.L1::no_allocate", "plain", "cg", "cv", "L1::no_allocate (generic)", "lu", "L2::64B", "L2::128B", "L2::256B", "nc.L2::64B"};
+        for (int m = 0; m < 10; ++m)
             printf("ctas/sm=%d %-34s %8.2f ms  %7.2f Ggather/s  %7.1f GB/s @32B-sector  %7.1f GB/s @128B-line\n", occ, names[m], ms[m],
                    n_items * 7 / ms[m] / 1e6, n_items * 7 * 32 / ms[m] / 1e6, n_items * 7 * 128 / ms[m] / 1e6);
     }

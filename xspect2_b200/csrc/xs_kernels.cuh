@@ -40,6 +40,7 @@ struct SeqBatch {
     const uint64_t* seq_begin;   // [n_seq] byte offsets (minus base_shift -> index into bases)
     const uint64_t* seq_end;     // [n_seq]
     const uint64_t* win_prefix;  // [n_seq + 1] exclusive scan of windows per sequence
+    unsigned long long* tile_counter;  // [grid.y] zeroed per launch: dynamic tile / work-item hand-out
     uint64_t n_seq;
     uint64_t n_bases;
     uint64_t base_shift;
@@ -267,9 +268,15 @@ __device__ __forceinline__ void warp_walk(const SeqBatch& sb, uint64_t t0, uint6
     }
 }
 
+__device__ __forceinline__ uint64_t next_tile(unsigned long long* counter, uint32_t lane) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(counter, 1ULL);
+    return __shfl_sync(0xFFFFFFFFu, t, 0);
+}
+
 // rounds per warp tile: large enough that few sequences straddle tiles, small enough to fill the machine
 __device__ __forceinline__ uint64_t walk_tile_windows(uint64_t total, uint64_t n_warps) {
-    uint64_t r = (total + n_warps * 128 - 1) / (n_warps * 128);   // ~4 tiles per warp
+    uint64_t r = (total + n_warps * 512 - 1) / (n_warps * 512);   // >= ~16 tiles per warp
     r = r < 8 ? 8 : (r > 128 ? 128 : r);
     return r * 32;
 }
@@ -328,7 +335,6 @@ __global__ void __launch_bounds__(NARROW_NT, 4) k_cobs_narrow(const CobsParams p
     const SeqBatch& sb = p.sb;
     const PageDesc pg = p.pages[blockIdx.y];
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t warp_g = ((uint64_t)blockIdx.x * NARROW_NT + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * NARROW_NT) >> 5;
     OutT* out = reinterpret_cast<OutT*>(p.out);
 
@@ -336,7 +342,11 @@ __global__ void __launch_bounds__(NARROW_NT, 4) k_cobs_narrow(const CobsParams p
     const uint64_t W = walk_tile_windows(total, n_warps);
     const uint64_t n_tiles = (total + W - 1) / W;
 
-    for (uint64_t tile = warp_g; tile < n_tiles; tile += n_warps) {
+    // tiles are handed out dynamically: SMs do not all sustain the same gather rate (two dies, 70/78 SM
+    // split), and a static equal split runs at the pace of the slowest one (profiles/microbench)
+    for (;;) {
+        const uint64_t tile = next_tile(sb.tile_counter + blockIdx.y, lane);
+        if (tile >= n_tiles) break;
         const uint64_t t0 = tile * W, t1 = t0 + W < total ? t0 + W : total;
         uint4 m = make_uint4(0, 0, 0, 0);
         uint32_t cnt[4] = {0, 0, 0, 0};   // lane l: documents l, l+32, l+64, l+96 of the current sequence
@@ -403,7 +413,7 @@ __global__ void __launch_bounds__(WIDE_NT) k_cobs_wide(const WideParams wp) {
     const PageDesc pg = p.pages[cb.page];
     uint64_t* s_rows = reinterpret_cast<uint64_t*>(s_dyn);                    // [WIDE_CHUNK * h] byte offsets
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_dyn + (size_t)WIDE_CHUNK * h * 8);  // [n_cols * 128]
-    __shared__ uint64_t s_seq, s_chunk;
+    __shared__ uint64_t s_seq, s_chunk, s_item;
 
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31, warp = tid >> 5;
@@ -418,13 +428,18 @@ __global__ void __launch_bounds__(WIDE_NT) k_cobs_wide(const WideParams wp) {
     const uint32_t n_unit = n_round * wsplit;
 
     const uint64_t total_items = __ldg(wp.chunk_prefix + sb.n_seq);
-    for (uint64_t item = blockIdx.x; item < total_items; item += gridDim.x) {
+    for (;;) {
         if (tid == 0) {
-            uint64_t s = seq_of_window(wp.chunk_prefix, sb.n_seq, item);
-            s_seq = s;
-            s_chunk = item - __ldg(wp.chunk_prefix + s);
+            uint64_t item = atomicAdd(sb.tile_counter + blockIdx.y, 1ULL);
+            s_item = item;
+            if (item < total_items) {
+                uint64_t s = seq_of_window(wp.chunk_prefix, sb.n_seq, item);
+                s_seq = s;
+                s_chunk = item - __ldg(wp.chunk_prefix + s);
+            }
         }
         __syncthreads();
+        if (s_item >= total_items) break;
         const uint64_t seq = s_seq;
         const uint64_t sbeg = __ldg(sb.seq_begin + seq), send = __ldg(sb.seq_end + seq);
         const uint64_t nw_seq = windows_of(sbeg, send, sb.base_shift, sb.n_bases, k, sb.step);
@@ -561,13 +576,14 @@ __global__ void __launch_bounds__(BLOOM_NT, 4) k_bloom(const BloomParams p) {
     const SeqBatch& sb = p.sb;
     const uint32_t k = K ? K : sb.k;
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t warp_g = ((uint64_t)blockIdx.x * BLOOM_NT + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * BLOOM_NT) >> 5;
 
     const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
     const uint64_t W = walk_tile_windows(total, n_warps);
     const uint64_t n_tiles = (total + W - 1) / W;
-    for (uint64_t tile = warp_g; tile < n_tiles; tile += n_warps) {
+    for (;;) {
+        const uint64_t tile = next_tile(sb.tile_counter, lane);
+        if (tile >= n_tiles) break;
         const uint64_t t0 = tile * W, t1 = t0 + W < total ? t0 + W : total;
         uint32_t hits = 0;    // warp-uniform: hits of the current sequence inside this tile
         uint32_t bal = 0;

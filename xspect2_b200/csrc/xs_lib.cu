@@ -259,6 +259,7 @@ struct Workspace {
     uint32_t* invalid = nullptr;
     uint64_t* prefix = nullptr;
     uint64_t* prefix2 = nullptr;
+    unsigned long long* counters = nullptr;
     void* scan_tmp = nullptr;
     size_t scan_bytes = 0;
 };
@@ -276,6 +277,8 @@ static int scan_windows(const WindowCountOp& op, uint64_t* d_prefix, void* tmp, 
     return XS_OK;
 }
 
+static const size_t N_COUNTERS = 4096;   // one dynamic tile counter per grid.y slice (pages / column blocks)
+
 static int workspace_alloc(Workspace& ws, uint64_t n_bases, uint64_t n_seq, bool two_prefix, cudaStream_t s) {
     uint64_t n_words = n_bases / 32 + 2;
     size_t tb = 0;
@@ -284,15 +287,18 @@ static int workspace_alloc(Workspace& ws, uint64_t n_bases, uint64_t n_seq, bool
     size_t o_inv = o_packed + align256(n_words * 8);
     size_t o_pre = o_inv + align256(n_words * 4);
     size_t o_pre2 = o_pre + align256((n_seq + 1) * 8);
-    size_t o_tmp = o_pre2 + (two_prefix ? align256((n_seq + 1) * 8) : 0);
+    size_t o_cnt = o_pre2 + (two_prefix ? align256((n_seq + 1) * 8) : 0);
+    size_t o_tmp = o_cnt + align256(N_COUNTERS * 8);
     size_t total = o_tmp + align256(tb ? tb : 1);
     XS_CUDA(cudaMallocAsync((void**)&ws.base, total, s));
     ws.packed = reinterpret_cast<uint64_t*>(ws.base + o_packed);
     ws.invalid = reinterpret_cast<uint32_t*>(ws.base + o_inv);
     ws.prefix = reinterpret_cast<uint64_t*>(ws.base + o_pre);
     ws.prefix2 = two_prefix ? reinterpret_cast<uint64_t*>(ws.base + o_pre2) : nullptr;
+    ws.counters = reinterpret_cast<unsigned long long*>(ws.base + o_cnt);
     ws.scan_tmp = ws.base + o_tmp;
     ws.scan_bytes = tb;
+    XS_CUDA(cudaMemsetAsync(ws.counters, 0, N_COUNTERS * 8, s));
     return XS_OK;
 }
 
@@ -311,7 +317,7 @@ static int prepare_batch(Workspace& ws, SeqBatch& sb, const uint8_t* d_bases, ui
         XS_TRY(scan_windows(op, ws.prefix2, ws.scan_tmp, ws.scan_bytes, n_sm, s));
     }
     sb.packed = ws.packed; sb.invalid = ws.invalid; sb.bases = d_bases;
-    sb.seq_begin = d_begin; sb.seq_end = d_end; sb.win_prefix = ws.prefix;
+    sb.seq_begin = d_begin; sb.seq_end = d_end; sb.win_prefix = ws.prefix; sb.tile_counter = ws.counters;
     sb.n_seq = n_seq; sb.n_bases = n_bases; sb.base_shift = base_shift; sb.step = step; sb.k = k;
     return XS_OK;
 }
@@ -593,6 +599,8 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
         }
     }
     fclose(f);
+    if (rc == XS_OK && (ix->pages.size() > N_COUNTERS || ix->blocks.size() > N_COUNTERS))
+        rc = fail(XS_ERR_UNSUPPORTED, "more than 4096 pages / column blocks in one index");
     if (rc == XS_OK) {
         if (cudaMalloc((void**)&ix->d_pages, ix->pages.size() * sizeof(PageDesc)) != cudaSuccess ||
             cudaMalloc((void**)&ix->d_blocks, std::max<size_t>(1, ix->blocks.size()) * sizeof(ColBlock)) != cudaSuccess)
