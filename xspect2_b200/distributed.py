@@ -1,0 +1,132 @@
+"""Multi-GPU layouts of the scoring path (one process per GPU, ``torch.distributed``).
+
+Two ways the path shards:
+
+* **read sharding** — every rank holds the whole index in its HBM and scores a contiguous slice of the
+  records; hit counts are independent per record, so there is no collective on the data path.  Totals (one
+  value per document) are summed with one tiny all-reduce when a caller wants file-level scores.
+* **document-column sharding** — for an index that does not fit one GPU, rank g holds the byte columns of
+  its document range of every row, all ranks score all records against their columns, and the per-record
+  score tiles are combined with an all-gather along the document axis (NCCL over NVLink on GPUs; the same
+  code runs on ``gloo`` for the CPU tests).  Tiles are double-buffered: the all-gather of tile t runs on a
+  side stream while tile t+1 is being queried.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, Iterator
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def read_shard(n_records: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous slice ``[lo, hi)`` of the records scored by ``rank`` (i * N / G boundaries)."""
+    return n_records * rank // world, n_records * (rank + 1) // world
+
+
+def column_shards(n_docs: int, world: int, align: int = 128) -> list[tuple[int, int]]:
+    """Document ranges per rank, boundaries on multiples of ``align`` documents (128 documents = one 16-byte
+    column chunk of a row; xs_cobs_open needs multiples of 8).  Trailing ranks may be empty for tiny indices."""
+    units = -(-n_docs // align)
+    out = []
+    for g in range(world):
+        lo = min(n_docs, (units * g // world) * align)
+        hi = min(n_docs, (units * (g + 1) // world) * align)
+        out.append((lo, hi))
+    return out
+
+
+def allreduce_totals(local_totals: np.ndarray | torch.Tensor, group=None) -> torch.Tensor:
+    """Sum of per-document totals over read-sharded ranks (int64)."""
+    t = torch.as_tensor(local_totals).to(torch.int64).clone()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        if dist.get_backend(group) == "nccl" and not t.is_cuda:
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def allgather_columns(local: torch.Tensor, shards: list[tuple[int, int]], group=None) -> torch.Tensor:
+    """``local`` = [n, width of this rank's shard] -> [n, n_docs]: all-gather along the document axis.
+    Shards may differ in width: tiles are padded to the widest shard for the collective, then trimmed."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    if local.dtype != torch.uint8:   # collectives on the byte view: every count type travels the same way
+        item = local.element_size()
+        full = allgather_columns(local.contiguous().view(torch.uint8), [(lo * item, hi * item) for lo, hi in shards], group)
+        return full.contiguous().view(local.dtype)
+    widths = [hi - lo for lo, hi in shards]
+    wmax = max(widths)
+    n = local.shape[0]
+    send = local
+    if local.shape[1] != wmax:
+        send = torch.zeros((n, wmax), dtype=local.dtype, device=local.device)
+        send[:, : local.shape[1]] = local
+    recv = torch.empty((world * n, wmax), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    recv = recv.view(world, n, wmax)
+    return torch.cat([recv[g, :, : widths[g]] for g in range(world)], dim=1)
+
+
+class ColumnShardedIndex:
+    """This rank's document-column shard of a COBS classic index plus the score all-gather."""
+
+    def __init__(self, path, rank: int | None = None, world: int | None = None, device: int | None = None, group=None):
+        from . import engine
+
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.n_docs = _doc_count(path)
+        self.shards = column_shards(self.n_docs, self.world)
+        lo, hi = self.shards[self.rank]
+        if hi <= lo:
+            raise ValueError(f"rank {self.rank} would hold no documents: use at most {-(-self.n_docs // 128)} ranks")
+        self.index = engine.CobsIndex(path, device=self.rank if device is None else device, doc_begin=lo, doc_end=hi)
+
+    def query_tiles(self, tiles: Iterator[tuple[int, int, int, int, int]], step: int, dtype: int,
+                    consume: Callable[[int, torch.Tensor], None]) -> None:
+        """For every tile ``(d_bases, n_bases, d_begin, d_end, n_seq)`` of device pointers: query the local
+        columns, all-gather the score tile, hand ``[n_seq, n_docs]`` to ``consume(tile_index, scores)``.
+        The collective of tile t overlaps the query of tile t + 1."""
+        from ._abi import XS_U8, XS_U16
+
+        tdt = {XS_U8: torch.uint8, XS_U16: torch.uint16}.get(dtype, torch.uint32)
+        dev = torch.device("cuda", self.index.device)
+        comm = torch.cuda.Stream(device=dev)
+        compute = torch.cuda.current_stream(dev)
+        pending = None
+        for t, (d_bases, n_bases, d_begin, d_end, n_seq) in enumerate(tiles):
+            local = torch.empty((n_seq, self.index.n_docs), dtype=tdt, device=dev)
+            self.index.query_device(d_bases, n_bases, d_begin, d_end, n_seq, step, dtype, local.data_ptr(), compute.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(compute)
+            if pending is not None:
+                pt, full, ev = pending
+                ev.synchronize()
+                consume(pt, full)
+            with torch.cuda.stream(comm):
+                comm.wait_event(done)
+                full = allgather_columns(local, self.shards, self.group)
+                ev = torch.cuda.Event()
+                ev.record(comm)
+            local.record_stream(comm)
+            pending = (t, full, ev)
+        if pending is not None:
+            pt, full, ev = pending
+            ev.synchronize()
+            consume(pt, full)
+
+
+def _doc_count(path) -> int:
+    """num_documents from a COBS classic header (A.1) without loading the index."""
+    import struct
+
+    with open(path, "rb") as f:
+        head = f.read(18 + 4 + 4 + 1 + 4)
+    if head[:18] != b"COBS:CLASSIC_INDEX":
+        raise ValueError("document-column sharding needs a COBS classic index")
+    return struct.unpack_from("<I", head, 27)[0]
