@@ -49,6 +49,17 @@ WORKLOAD = (f"cfg2: {N_READS} synthetic {READ_LEN}bp reads x COBS classic index 
             f"S={SIG_SIZE} (Acinetobacter-species geometry)")
 
 
+def ncu_traffic() -> float | None:
+    """dram read+write bytes of one k_cobs_narrow launch from the committed ncu capture, if it is this workload."""
+    p = ROOT / "profiles" / "traffic.json"
+    if not p.exists():
+        return None
+    t = json.loads(p.read_text()).get("k_cobs_narrow<21,7,u8>")
+    if not t or (t["n_reads"], t["read_len"], t["sig_size"]) != (N_READS, READ_LEN, SIG_SIZE):
+        return None
+    return float(t["dram_bytes_read"] + t["dram_bytes_write"])
+
+
 def peaks() -> tuple[float, str]:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -263,7 +274,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         algo_bytes = lookups_per_step * H * ROW_BYTES + n_bases * 3 // 8 + N_READS * D
         k_ms = kernel_ms / max(kernel_launches, 1)
         achieved = algo_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else None
-        sector_bytes = lookups_per_step * H * 32 + n_bases * 3 // 8 + N_READS * D
+        gathers = lookups_per_step * H
+        traffic = ncu_traffic()
         line = {
             "metric": "kmer_lookups_per_sec", "value": value, "unit": "lookups/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -281,11 +293,15 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_cobs_narrow<21,7,u8>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": k_ms, "kernel_launches": int(kernel_launches),
                          "kernel_share_of_step": kernel_ms / ms if ms else None,
                          "algorithmic_bytes_per_launch": int(algo_bytes),
-                         "sector_granular_GBps": sector_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else None},
+                         # fetch-granular view: every 16-byte row gather costs a 128-byte DRAM fetch on B200
+                         # (ncu: traffic / gathers = 124.6 B); ceiling = best rate of profiles/microbench/*.cu
+                         "gather": {"achieved_G_per_s": gathers / (k_ms / 1e3) / 1e9 if k_ms > 0 else None,
+                                    "ceiling_G_per_s": 50.2, "dram_bytes_per_gather": (traffic / gathers) if traffic else None,
+                                    "dram_GBps": (traffic / (k_ms / 1e3) / 1e9) if (traffic and k_ms > 0) else None}},
             "checksum_first_100k_reads": checksum,
         }
         if world == 1:

@@ -1,0 +1,154 @@
+"""Side measurements of the other BASELINE.json configs (not the bench headline): genus Bloom stage (config 3,
+stage 1), MLST on assembled genomes (config 4), a wide-row index (config 5 geometry, single-GPU slice).
+Test infrastructure: fixtures are built with the oracle's writers.  Run on a GPU box:
+    python tests/perf_other_configs.py [bloom] [mlst] [wide]
+Prints one JSON line per config; numbers are recorded in profiles/."""
+import json
+import struct
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import oracle  # noqa: E402
+from tests import model_fixtures as mf, synth as tsynth  # noqa: E402
+from xspect2_b200 import engine, synth  # noqa: E402
+from xspect2_b200._abi import XS_U8  # noqa: E402
+
+PEAK = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+dev = torch.device("cuda", 0)
+
+
+def timed(fn, steps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def bloom(td: Path):
+    n_reads, L, k = 10_000_000, 150, 21
+    n_bytes = 13_800_000_008 // 8
+    genome = synth.synth_genome(4_060_000, seed=1, n_rate=0.0001)
+    gen = torch.Generator(device=dev).manual_seed(11)
+    bits = torch.randint(0, 256, (n_bytes,), generator=gen, device=dev, dtype=torch.uint8).cpu().numpy()
+    bt = oracle._BloomT(bits.ctypes.data, n_bytes * 8, 6, k)
+    oracle.lib().xso_bloom_insert(oracle.C.byref(bt), bits.ctypes.data, genome.ctypes.data, genome.size)
+    p = td / "filter.bloom"
+    with open(p, "wb") as f:
+        f.write(struct.pack("<Q", 6))
+        f.write(bits.tobytes())
+    del bits
+    bf = engine.BloomFilter(p, k)
+    reads = synth.synth_reads(genome, n_reads, L, seed=4, device=dev)
+    hb, he = synth.fixed_offsets(n_reads, L)
+    d_b = torch.from_numpy(hb.view(np.int64)).to(dev)
+    d_e = torch.from_numpy(he.view(np.int64)).to(dev)
+    out = torch.empty(n_reads, dtype=torch.int32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    engine.profile_enable(True)
+    engine.profile_read()
+    ms = timed(lambda: bf.query_device(reads.data_ptr(), n_reads * L, d_b.data_ptr(), d_e.data_ptr(), n_reads, 1, out.data_ptr(), s))
+    kms, kn = engine.profile_read()
+    engine.profile_enable(False)
+    # parity on a sample + probe statistics
+    sample = 20000
+    exp = oracle.BloomOracle(p, k).hits_batch(reads[: sample * L].cpu().numpy(), hb[:sample], he[:sample], 1, threads=8)
+    assert np.array_equal(out[:sample].cpu().numpy().astype(np.uint32), exp)
+    lookups = n_reads * (L - k + 1)
+    frac_member = float(out.sum().item()) / lookups
+    print(json.dumps({"config": "cfg3 stage 1: genus Bloom, 13.8e9 bits, k_bloom=6, 10M x 150bp reads", "ms_per_step": ms,
+                      "kernel_ms": kms / max(kn, 1), "lookups_per_sec": lookups / ms * 1e3, "reads_per_sec": n_reads / ms * 1e3,
+                      "member_fraction": frac_member, "parity_sample_reads": sample}), flush=True)
+
+
+def mlst(td: Path):
+    rng = np.random.default_rng(5)
+    models = td / "models"
+    models.mkdir()
+    p, alleles = mf.mlst_model(oracle, models, rng, n_loci=7, n_alleles=600, k=31)
+    from xspect2_b200.models.probabilistic_filter_mlst_model import ProbabilisticFilterMlstSchemeModel
+    from xspect2_b200.seqio import Seq
+
+    class NoNet:
+        def get_strain_type_name(self, hr, url):
+            return "offline"
+
+    model = ProbabilisticFilterMlstSchemeModel.load(p)
+    model.pubmlst_handler = NoNet()
+    genomes = []
+    for g in range(4):
+        parts = [tsynth.random_dna(rng, 500_000)]
+        for locus in model.loci:
+            parts += [alleles[locus][f"Allele_ID_{1 + (g * 37) % 600}"], tsynth.random_dna(rng, 500_000)]
+        genomes.append(np.concatenate(parts).tobytes().decode())
+    model.calculate_hits(Seq(genomes[0]))
+    t0 = time.perf_counter()
+    outs = [model.calculate_hits(Seq(g)) for g in genomes]
+    dt = (time.perf_counter() - t0) / len(genomes)
+    for g, o in enumerate(outs):
+        st = o[0]["Strain type"]
+        assert all(next(iter(st[l])) == f"Allele_ID_{1 + (g * 37) % 600}" for l in model.loci), st
+    lookups = 7 * (len(genomes[0]) - 30)
+    print(json.dumps({"config": "cfg4: MLST 7 loci x 600 alleles compact k=31, 4 Mbp genomes, through calculate_hits (host API)",
+                      "s_per_genome": dt, "genome_bp": len(genomes[0]), "lookups_per_sec": lookups / dt,
+                      "note": "index ~ tens of MB: L2 resident; time includes chunk epilogue on the host"}), flush=True)
+
+
+def wide(td: Path):
+    D, h, k, S = 10_000, 7, 21, 4_000_000
+    row = D // 8
+    names = [f"d{i}" for i in range(D)]
+    gen = torch.Generator(device=dev).manual_seed(6)
+    p = td / "index.cobs_classic"
+    with open(p, "wb") as f:
+        f.write(synth.classic_header(k, 1, names, S, h))
+        for r0 in range(0, S, 1 << 19):
+            n = min(1 << 19, S - r0)
+            a = torch.randint(0, 256, (n, row), generator=gen, device=dev, dtype=torch.uint8)
+            b = torch.randint(0, 256, (n, row), generator=gen, device=dev, dtype=torch.uint8)
+            f.write((a & b).cpu().numpy().tobytes())          # fill 0.25
+    ix = engine.CobsIndex(p)
+    n_reads, L = 1_000_000, 150
+    genome = synth.synth_genome(1_000_000, seed=7)
+    reads = synth.synth_reads(genome, n_reads, L, seed=8, device=dev)
+    hb, he = synth.fixed_offsets(n_reads, L)
+    d_b = torch.from_numpy(hb.view(np.int64)).to(dev)
+    d_e = torch.from_numpy(he.view(np.int64)).to(dev)
+    out = torch.empty((n_reads, D), dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    engine.profile_enable(True)
+    engine.profile_read()
+    ms = timed(lambda: ix.query_device(reads.data_ptr(), n_reads * L, d_b.data_ptr(), d_e.data_ptr(), n_reads, 1, XS_U8, out.data_ptr(), s), steps=3, warm=1)
+    kms, kn = engine.profile_read()
+    engine.profile_enable(False)
+    sample = 300
+    exp = oracle.CobsOracle(p, load_complete=False).counts_batch(reads[: sample * L].cpu().numpy(), hb[:sample], he[:sample], 1, threads=8)
+    assert np.array_equal(out[:sample].cpu().numpy().astype(np.uint32), np.minimum(exp, 255))
+    lookups = n_reads * (L - k + 1)
+    kernel_ms = kms / max(kn, 1)
+    algo = lookups * h * row + n_reads * L * 3 // 8 + n_reads * D
+    print(json.dumps({"config": f"cfg5 geometry on one GPU: D={D} h={h} S={S} (row {row} B, stride {ix.info.row_stride} B), 1M x 150bp reads",
+                      "ms_per_step": ms, "kernel_ms": kernel_ms, "lookups_per_sec": lookups / ms * 1e3,
+                      "achieved_GBps": algo / kernel_ms / 1e6, "frac_of_hbm_peak": algo / kernel_ms / 1e6 / PEAK,
+                      "parity_sample_reads": sample}), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["bloom", "mlst", "wide"]
+    with tempfile.TemporaryDirectory() as td:
+        for w in which:
+            sub = Path(td) / w
+            sub.mkdir()
+            {"bloom": bloom, "mlst": mlst, "wide": wide}[w](sub)
