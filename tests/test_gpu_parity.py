@@ -182,6 +182,25 @@ def test_cobs_wide_reads(gpu, oracle, tmp_path, n_docs, k, h):
     _check_cobs(gpu, oracle, p, bases, b, e, step=3, dtype=1)
 
 
+@pytest.mark.parametrize("ldg", [False, True])
+def test_cobs_wide_tma_multi_column_block(gpu, oracle, tmp_path, monkeypatch, ldg):
+    """20 000 documents = 157 column chunks = two column blocks; TMA-staged kernel and (XS_WIDE_LDG=1) the LDG one."""
+    rng = np.random.default_rng(21)
+    if ldg:
+        monkeypatch.setenv("XS_WIDE_LDG", "1")
+    p, docs = _mk_classic(oracle, tmp_path, rng, 20000, 21, 7, length=150)
+    genomes = [s for v in docs.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes[:50], 60, (21, 140), n_rate=0.003)
+    long_seq = np.concatenate(genomes[:6])          # 900 bp: several 248-window work items
+    bases = np.concatenate([bases, long_seq])
+    b = np.concatenate([b, [e[-1]]]).astype(np.uint64)
+    e = np.concatenate([e, [e[-1] + long_seq.size]]).astype(np.uint64)
+    got = _check_cobs(gpu, oracle, p, bases, b, e)
+    assert got.sum() > 0
+    _check_cobs(gpu, oracle, p, bases, b, e, step=2, dtype=1)
+    _check_cobs(gpu, oracle, p, bases, b, e, doc_begin=4096, doc_end=12288)
+
+
 def test_cobs_wide_kernel_on_narrow_index(gpu, oracle, tmp_path, monkeypatch):
     rng = np.random.default_rng(15)
     p, docs = _mk_classic(oracle, tmp_path, rng, 90, 21, 7)
