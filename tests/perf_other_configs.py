@@ -122,7 +122,8 @@ def wide(td: Path):
             b = torch.randint(0, 256, (n, row), generator=gen, device=dev, dtype=torch.uint8)
             f.write((a & b).cpu().numpy().tobytes())          # fill 0.25
     ix = engine.CobsIndex(p)
-    n_reads, L = 1_000_000, 150
+    import os
+    n_reads, L = int(os.environ.get('XS_PERF_READS', 1_000_000)), 150
     genome = synth.synth_genome(1_000_000, seed=7)
     reads = synth.synth_reads(genome, n_reads, L, seed=8, device=dev)
     hb, he = synth.fixed_offsets(n_reads, L)

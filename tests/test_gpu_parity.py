@@ -182,12 +182,9 @@ def test_cobs_wide_reads(gpu, oracle, tmp_path, n_docs, k, h):
     _check_cobs(gpu, oracle, p, bases, b, e, step=3, dtype=1)
 
 
-@pytest.mark.parametrize("ldg", [False, True])
-def test_cobs_wide_tma_multi_column_block(gpu, oracle, tmp_path, monkeypatch, ldg):
-    """20 000 documents = 157 column chunks = two column blocks; TMA-staged kernel and (XS_WIDE_LDG=1) the LDG one."""
+def test_cobs_wide_multi_column_block(gpu, oracle, tmp_path):
+    """20 000 documents = 157 column chunks = two column blocks (grid.y)."""
     rng = np.random.default_rng(21)
-    if ldg:
-        monkeypatch.setenv("XS_WIDE_LDG", "1")
     p, docs = _mk_classic(oracle, tmp_path, rng, 20000, 21, 7, length=150)
     genomes = [s for v in docs.values() for s in v]
     bases, b, e = synth.sample_reads(rng, genomes[:50], 60, (21, 140), n_rate=0.003)

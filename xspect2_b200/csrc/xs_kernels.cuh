@@ -5,8 +5,8 @@
 //                     canonical -> XXH64 x h -> Barrett mod -> h x 128-bit gathers -> AND ->
 //                     per-sequence document counts by warp ballot/popcount
 //                     (cobs Search.search behind probabilistic_filter_model.py:227)
-//   k_cobs_wide       rows > 16 B: lanes own 16-byte column chunks, warp-coalesced row gathers,
-//                     bit-sliced vertical counters, shared-memory count staging
+//   k_cobs_wide       rows > 16 B: lanes own 16-byte column chunks, warp-coalesced row gathers (2h loads in
+//                     flight per lane), bit-plane counters, shared-memory count staging
 //   k_bloom           XXH3-64 -> 128-bit LCG -> bit probes with early exit
 //                     (probabilistic_single_filter_model.py:122-124,161-180)
 //   stage kernels     canonical codes / row ids / bloom hashes alone, for the parity tests
@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(WIDE_NT) k_cobs_wide(const WideParams wp) {
     uint64_t* s_rows = reinterpret_cast<uint64_t*>(s_dyn);                    // [WIDE_CHUNK * h] byte offsets
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_dyn + (size_t)WIDE_CHUNK * h * 8);  // [n_cols * 128]
     __shared__ uint64_t s_seq, s_chunk, s_item;
+    __shared__ uint32_t s_nvalid;
 
     const int tid = threadIdx.x;
     const uint32_t lane = tid & 31, warp = tid >> 5;
@@ -424,192 +425,9 @@ __global__ void __launch_bounds__(WIDE_NT) k_cobs_wide(const WideParams wp) {
     uint32_t lpw = 1; while (lpw < C && lpw < 32) lpw <<= 1;   // lanes per window
     const uint32_t slots = 32 / lpw;                           // windows a warp handles at once
     const uint32_t n_round = (C + lpw - 1) / lpw;
-    const uint32_t wsplit = NWARP / n_round > 0 ? NWARP / n_round : 1;
+    const uint32_t wsplit = NWARP;                             // window slices: every warp gets n_round units
     const uint32_t n_unit = n_round * wsplit;
 
-    const uint64_t total_items = __ldg(wp.chunk_prefix + sb.n_seq);
-    for (;;) {
-        if (tid == 0) {
-            uint64_t item = atomicAdd(sb.tile_counter + blockIdx.y, 1ULL);
-            s_item = item;
-            if (item < total_items) {
-                uint64_t s = seq_of_window(wp.chunk_prefix, sb.n_seq, item);
-                s_seq = s;
-                s_chunk = item - __ldg(wp.chunk_prefix + s);
-            }
-        }
-        __syncthreads();
-        if (s_item >= total_items) break;
-        const uint64_t seq = s_seq;
-        const uint64_t sbeg = __ldg(sb.seq_begin + seq), send = __ldg(sb.seq_end + seq);
-        const uint64_t nw_seq = windows_of(sbeg, send, sb.base_shift, sb.n_bases, k, sb.step);
-        const uint64_t w0 = s_chunk * WIDE_CHUNK;
-        const uint32_t nwin = (uint32_t)(nw_seq - w0 < (uint64_t)WIDE_CHUNK ? nw_seq - w0 : (uint64_t)WIDE_CHUNK);
-        const bool complete = nw_seq <= (uint64_t)WIDE_CHUNK;
-
-        // ---- phase 1: row byte offsets of every window of the item
-        for (uint32_t lw = tid; lw < nwin; lw += WIDE_NT) {
-            uint64_t pos = sbeg - sb.base_shift + (w0 + lw) * sb.step;
-            Term t;
-            if (cobs_term<K>(sb, pos, p.canonicalize != 0, p.policy, t)) {
-                Xxh64Pre pre;
-                xxh64_prepare(t, k, pre);
-                for (uint32_t j = 0; j < h; ++j) {
-                    uint64_t hv = xxh64_finish(pre, k, (uint64_t)j);
-                    s_rows[lw * h + j] = mod_barrett(hv, pg.sig_size, pg.magic) * pg.row_stride;
-                }
-            } else {
-                s_rows[lw * h] = ~0ULL;
-            }
-        }
-        for (uint32_t d = tid; d < C * 128; d += WIDE_NT) s_cnt[d] = 0;
-        __syncthreads();
-
-        // ---- phase 2: gather + AND + vertical counters
-        for (uint32_t u = warp; u < n_unit; u += NWARP) {
-            const uint32_t r = u % n_round, ws = u / n_round;
-            const uint32_t slot = lane / lpw, cl = lane % lpw;
-            const uint32_t col = r * lpw + cl;
-            const bool active = col < C;
-            const uint8_t* colbase = pg.data + (size_t)(cb.c0 + col) * 16;
-            uint32_t pl[8][4];
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) pl[a][b] = 0;
-            if (active) {
-                for (uint32_t w = ws * slots + slot; w < nwin; w += wsplit * slots) {
-                    uint64_t r0 = s_rows[w * h];
-                    if (r0 == ~0ULL) continue;
-                    uint4 m = ldg128(colbase + r0);
-                    if (H) {
-                        uint4 v[H ? H : 1];
-#pragma unroll
-                        for (int j = 1; j < (H ? H : 1); ++j) v[j] = ldg128(colbase + s_rows[w * h + j]);
-#pragma unroll
-                        for (int j = 1; j < (H ? H : 1); ++j) { m.x &= v[j].x; m.y &= v[j].y; m.z &= v[j].z; m.w &= v[j].w; }
-                    } else {
-                        for (uint32_t j = 1; j < h; ++j) {
-                            uint4 v = ldg128(colbase + s_rows[w * h + j]);
-                            m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
-                        }
-                    }
-                    uint32_t carry[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                    for (int a = 0; a < 8; ++a)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            uint32_t tcar = pl[a][b] & carry[b];
-                            pl[a][b] ^= carry[b];
-                            carry[b] = tcar;
-                        }
-                }
-                // expand the bit planes of this lane's 128 documents
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    uint32_t any = 0;
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) any |= pl[a][b];
-                    while (any) {
-                        uint32_t bit = __ffs(any) - 1; any &= any - 1;
-                        uint32_t c = 0;
-#pragma unroll
-                        for (int a = 0; a < 8; ++a) c |= ((pl[a][b] >> bit) & 1u) << a;
-                        atomicAdd(&s_cnt[col * 128 + b * 32 + bit], c);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- phase 3: coalesced write of the block's document counts
-        OutT* row = out + (p.seq0 + seq) * p.ld + pg.doc_off + (size_t)cb.c0 * 128;
-        for (uint32_t d = tid; d < cb.n_docs; d += WIDE_NT) {
-            uint32_t v = s_cnt[d];
-            if (complete) out_store<OutT>(row + d, v); else out_add<OutT>(row + d, v);
-        }
-        __syncthreads();
-    }
-}
-
-// ----------------------------------------------------------------------------------------
-// COBS, wide rows, TMA-staged (row blocks >= WT_MIN_COLS 16-byte chunks).  Whole rows are contiguous
-// in HBM, so one elected thread moves each row of a window into shared memory with one bulk copy
-// (cp.async.bulk, completion on an mbarrier) through a ring of stages; the bytes in flight are bounded
-// by shared memory instead of by load destination registers.  Thread t owns 16-byte column chunk t:
-// it ANDs the h staged rows, adds the mask into 4 bit planes and spills them every 15 windows into its
-// own byte counters in shared memory (no atomics: the owner is the only writer).
-// ----------------------------------------------------------------------------------------
-constexpr int WT_NT = 128;
-constexpr int WT_MAX_STAGES = 16;
-constexpr int WT_MIN_COLS = 32;      // 512-byte row blocks and wider
-constexpr int WT_MAX_COLS = 128;     // one thread per chunk: 16384 documents per column block
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-    uint32_t ok;
-    const uint32_t a = smem_u32(b);
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-struct WideTmaParams {
-    CobsParams cp;
-    const ColBlock* blocks;
-    const uint64_t* chunk_prefix;
-    uint32_t n_stages;      // ring depth (<= WT_MAX_STAGES)
-    uint32_t max_cols;      // widest column block: a stage holds h rows of max_cols * 16 bytes
-};
-
-template <int K, int H, typename OutT>
-__global__ void __launch_bounds__(WT_NT) k_cobs_wide_tma(const WideTmaParams wp) {
-    extern __shared__ __align__(128) uint8_t s_dyn[];
-    __shared__ __align__(8) uint64_t s_full[WT_MAX_STAGES], s_empty[WT_MAX_STAGES];
-    __shared__ uint64_t s_seq, s_chunk, s_item;
-    __shared__ uint32_t s_nvalid;
-
-    const CobsParams& p = wp.cp;
-    const SeqBatch& sb = p.sb;
-    const uint32_t k = K ? K : sb.k;
-    const uint32_t h = H ? H : p.num_hashes;
-    const ColBlock cb = wp.blocks[blockIdx.y];
-    const PageDesc pg = p.pages[cb.page];
-    const uint32_t n_stages = wp.n_stages;
-    const uint32_t row_bytes = cb.n_cols * 16;                 // bytes of one row inside this column block
-    const uint32_t stage_bytes = h * wp.max_cols * 16;
-    uint8_t* ring = s_dyn;
-    uint64_t* s_rows = reinterpret_cast<uint64_t*>(s_dyn + (size_t)n_stages * stage_bytes);           // [WIDE_CHUNK * h]
-    uint8_t* s_cnt = reinterpret_cast<uint8_t*>(s_rows + (size_t)WIDE_CHUNK * h);                      // [max_cols * 128]
-
-    const int tid = threadIdx.x;
-    const uint32_t lane = tid & 31;
-    constexpr uint32_t NWARP = WT_NT / 32;
-    OutT* out = reinterpret_cast<OutT*>(p.out);
-    const bool owner = (uint32_t)tid < cb.n_cols;
-    const uint8_t* colbase = pg.data + (size_t)cb.c0 * 16;
-
-    if (tid == 0) {
-        for (uint32_t s = 0; s < n_stages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], NWARP); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    uint64_t used = 0;   // windows pushed through the ring by this CTA so far (same value in every thread)
     const uint64_t total_items = __ldg(wp.chunk_prefix + sb.n_seq);
     for (;;) {
         if (tid == 0) {
@@ -631,91 +449,99 @@ __global__ void __launch_bounds__(WT_NT) k_cobs_wide_tma(const WideTmaParams wp)
         const uint32_t nwin = (uint32_t)(nw_seq - w0 < (uint64_t)WIDE_CHUNK ? nw_seq - w0 : (uint64_t)WIDE_CHUNK);
         const bool complete = nw_seq <= (uint64_t)WIDE_CHUNK;
 
-        // ---- phase 1: row byte offsets of the valid windows, compacted (order is irrelevant for counts)
-        for (uint32_t lw = tid; lw < nwin; lw += WT_NT) {
+        // ---- phase 1: row byte offsets of the valid windows of the item, compacted (order is irrelevant for counts)
+        for (uint32_t lw = tid; lw < nwin; lw += WIDE_NT) {
             uint64_t pos = sbeg - sb.base_shift + (w0 + lw) * sb.step;
             Term t;
             if (cobs_term<K>(sb, pos, p.canonicalize != 0, p.policy, t)) {
                 Xxh64Pre pre;
                 xxh64_prepare(t, k, pre);
-                uint32_t slot = atomicAdd(&s_nvalid, 1u);
+                uint32_t slot_w = atomicAdd(&s_nvalid, 1u);
                 for (uint32_t j = 0; j < h; ++j) {
                     uint64_t hv = xxh64_finish(pre, k, (uint64_t)j);
-                    s_rows[slot * h + j] = mod_barrett(hv, pg.sig_size, pg.magic) * pg.row_stride;
+                    s_rows[slot_w * h + j] = mod_barrett(hv, pg.sig_size, pg.magic) * pg.row_stride;
                 }
             }
         }
-        for (uint32_t d = tid; d < cb.n_cols * 32; d += WT_NT) reinterpret_cast<uint32_t*>(s_cnt)[d] = 0;
+        for (uint32_t d = tid; d < C * 128; d += WIDE_NT) s_cnt[d] = 0;
         __syncthreads();
         const uint32_t nv = s_nvalid;
 
-        // ---- phase 2: ring of bulk copies
-        auto issue = [&](uint32_t i) {   // thread 0 only: window i of this item into its ring stage
-            uint64_t g = used + i;
-            uint32_t st = (uint32_t)(g % n_stages);
-            uint32_t use = (uint32_t)(g / n_stages);
-            mbar_wait(&s_empty[st], (use & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&s_full[st], h * row_bytes);
-            uint8_t* dst = ring + (size_t)st * stage_bytes;
-            for (uint32_t j = 0; j < h; ++j) bulk_g2s(dst + (size_t)j * row_bytes, colbase + s_rows[i * h + j], row_bytes, &s_full[st]);
-        };
-        if (tid == 0) {
-            uint32_t pre = nv < n_stages ? nv : n_stages;
-            for (uint32_t i = 0; i < pre; ++i) issue(i);
-        }
-        uint32_t pl[4][4];
+        // ---- phase 2: gather + AND + bit-plane counters.  Unit = (column round, window slice); every warp gets
+        // n_round units.  Two windows (2h loads) are in flight per lane; all-zero masks (the common case) skip
+        // the counter update; 4 bit planes are spilled into the shared counters every 15 updates.
+        for (uint32_t u = warp; u < n_unit; u += NWARP) {
+            const uint32_t r = u % n_round, ws = u / n_round;
+            const uint32_t slot = lane / lpw, cl = lane % lpw;
+            const uint32_t col = r * lpw + cl;
+            const bool active = col < C;
+            const uint8_t* colbase = pg.data + (size_t)(cb.c0 + col) * 16;
+            uint32_t pl[4][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) pl[a][b] = 0;
-        auto spill = [&]() {   // planes -> this thread's byte counters
+                for (int b = 0; b < 4; ++b) pl[a][b] = 0;
+            uint32_t pending = 0;
+            auto spill = [&]() {
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                uint32_t any = pl[0][b] | pl[1][b] | pl[2][b] | pl[3][b];
-                while (any) {
-                    uint32_t bit = __ffs(any) - 1; any &= any - 1;
-                    uint32_t c = ((pl[0][b] >> bit) & 1u) | (((pl[1][b] >> bit) & 1u) << 1) | (((pl[2][b] >> bit) & 1u) << 2) |
-                                 (((pl[3][b] >> bit) & 1u) << 3);
-                    s_cnt[tid * 128 + b * 32 + bit] += (uint8_t)c;
+                for (int b = 0; b < 4; ++b) {
+                    uint32_t any = pl[0][b] | pl[1][b] | pl[2][b] | pl[3][b];
+                    while (any) {
+                        uint32_t bit = __ffs(any) - 1; any &= any - 1;
+                        uint32_t c = ((pl[0][b] >> bit) & 1u) | (((pl[1][b] >> bit) & 1u) << 1) |
+                                     (((pl[2][b] >> bit) & 1u) << 2) | (((pl[3][b] >> bit) & 1u) << 3);
+                        atomicAdd(&s_cnt[col * 128 + b * 32 + bit], c);
+                    }
+                    pl[0][b] = pl[1][b] = pl[2][b] = pl[3][b] = 0;
                 }
-                pl[0][b] = pl[1][b] = pl[2][b] = pl[3][b] = 0;
-            }
-        };
-        uint32_t since_spill = 0;
-        for (uint32_t i = 0; i < nv; ++i) {
-            uint64_t g = used + i;
-            uint32_t st = (uint32_t)(g % n_stages);
-            uint32_t use = (uint32_t)(g / n_stages);
-            mbar_wait(&s_full[st], use & 1u);
-            if (owner) {
-                const uint8_t* src = ring + (size_t)st * stage_bytes + (size_t)tid * 16;
-                uint4 m = *reinterpret_cast<const uint4*>(src);
-                for (uint32_t j = 1; j < h; ++j) {
-                    uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)j * row_bytes);
-                    m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
-                }
+                pending = 0;
+            };
+            auto add_mask = [&](const uint4& m) {
+                if ((m.x | m.y | m.z | m.w) == 0) return;
                 uint32_t carry[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        uint32_t tc = pl[a][b] & carry[b];
+                        uint32_t tcar = pl[a][b] & carry[b];
                         pl[a][b] ^= carry[b];
-                        carry[b] = tc;
+                        carry[b] = tcar;
                     }
-                if (++since_spill == 15) { spill(); since_spill = 0; }
+                if (++pending == 15) spill();
+            };
+            auto gather = [&](uint32_t w) -> uint4 {     // AND of the h rows of window w (this lane's 16-byte column)
+                uint4 m = ldg128(colbase + s_rows[w * h]);
+                if (H) {
+                    uint4 v[H ? H : 1];
+#pragma unroll
+                    for (int j = 1; j < (H ? H : 1); ++j) v[j] = ldg128(colbase + s_rows[w * h + j]);
+#pragma unroll
+                    for (int j = 1; j < (H ? H : 1); ++j) { m.x &= v[j].x; m.y &= v[j].y; m.z &= v[j].z; m.w &= v[j].w; }
+                } else {
+                    for (uint32_t j = 1; j < h; ++j) {
+                        uint4 v = ldg128(colbase + s_rows[w * h + j]);
+                        m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
+                    }
+                }
+                return m;
+            };
+            if (active) {
+                const uint32_t stride = wsplit * slots;
+                uint32_t w = ws * slots + slot;
+                for (; w + stride < nv; w += 2 * stride) {
+                    uint4 m0 = gather(w), m1 = gather(w + stride);
+                    add_mask(m0);
+                    add_mask(m1);
+                }
+                if (w < nv) add_mask(gather(w));
+                spill();
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[st]);
-            if (tid == 0 && i + n_stages < nv) issue(i + n_stages);
         }
-        if (owner) spill();
-        used += nv;
         __syncthreads();
 
         // ---- phase 3: coalesced write of the block's document counts
         OutT* row = out + (p.seq0 + seq) * p.ld + pg.doc_off + (size_t)cb.c0 * 128;
-        for (uint32_t d = tid; d < cb.n_docs; d += WT_NT) {
+        for (uint32_t d = tid; d < cb.n_docs; d += WIDE_NT) {
             uint32_t v = s_cnt[d];
             if (complete) out_store<OutT>(row + d, v); else out_add<OutT>(row + d, v);
         }

@@ -86,7 +86,6 @@ struct xs_cobs {
     PageDesc* d_pages = nullptr;
     ColBlock* d_blocks = nullptr;
     bool narrow = true;
-    bool tma = false;       // wide rows staged through shared memory with bulk copies
     int n_sm = 148;
     int force_wide = 0;
 };
@@ -342,6 +341,11 @@ template <int K, int H, typename T>
 static cudaError_t launch_wide_tt(const WideParams& p, dim3 grid, size_t smem, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(k_cobs_wide<K, H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cobs_wide<K, H, T>, WIDE_NT, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+    grid.x *= (unsigned)occ;     // grid.x arrives as the SM count
     k_cobs_wide<K, H, T><<<grid, WIDE_NT, smem, s>>>(p);
     return cudaSuccess;
 }
@@ -355,29 +359,6 @@ static cudaError_t launch_wide(const WideParams& p, dim3 grid, size_t smem, int 
     if (p.cp.sb.k == 21 && p.cp.num_hashes == 7) return launch_wide_t<21, 7>(p, grid, smem, dt, s);
     if (p.cp.sb.k == 31 && p.cp.num_hashes == 1) return launch_wide_t<31, 1>(p, grid, smem, dt, s);
     return launch_wide_t<0, 0>(p, grid, smem, dt, s);
-}
-
-template <int K, int H, typename T>
-static cudaError_t launch_tma_tt(const WideTmaParams& p, int n_sm, unsigned ny, size_t smem, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(k_cobs_wide_tma<K, H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cobs_wide_tma<K, H, T>, WT_NT, smem);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorInvalidConfiguration;
-    k_cobs_wide_tma<K, H, T><<<dim3((unsigned)(n_sm * occ), ny), WT_NT, smem, s>>>(p);
-    return cudaSuccess;
-}
-template <int K, int H>
-static cudaError_t launch_tma_t(const WideTmaParams& p, int n_sm, unsigned ny, size_t smem, int dt, cudaStream_t s) {
-    if (dt == XS_U8) return launch_tma_tt<K, H, uint8_t>(p, n_sm, ny, smem, s);
-    if (dt == XS_U16) return launch_tma_tt<K, H, uint16_t>(p, n_sm, ny, smem, s);
-    return launch_tma_tt<K, H, uint32_t>(p, n_sm, ny, smem, s);
-}
-static cudaError_t launch_tma(const WideTmaParams& p, int n_sm, unsigned ny, size_t smem, int dt, cudaStream_t s) {
-    if (p.cp.sb.k == 21 && p.cp.num_hashes == 7) return launch_tma_t<21, 7>(p, n_sm, ny, smem, dt, s);
-    if (p.cp.sb.k == 31 && p.cp.num_hashes == 1) return launch_tma_t<31, 1>(p, n_sm, ny, smem, dt, s);
-    return launch_tma_t<0, 0>(p, n_sm, ny, smem, dt, s);
 }
 
 static int dtype_size(int dt) { return (dt == XS_U8 || dt == XS_U16 || dt == XS_U32) ? dt : 0; }
@@ -403,29 +384,13 @@ static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
         KernelTimer kt(s);
         launch_narrow(p, grid, dt, s);
         XS_TRY(launch_ok("k_cobs_narrow"));
-    } else if (ix->tma && !ix->force_wide) {
-        WideTmaParams wp{};
-        wp.cp = p; wp.blocks = ix->d_blocks; wp.chunk_prefix = ws.prefix2;
-        uint32_t max_cols = 0;
-        for (const ColBlock& b : ix->blocks) max_cols = std::max(max_cols, b.n_cols);
-        const size_t stage = (size_t)ix->info.num_hashes * max_cols * 16;
-        const size_t fixed = (size_t)WIDE_CHUNK * ix->info.num_hashes * 8 + (size_t)max_cols * 128;
-        const size_t budget = 100 * 1024;   // two CTAs per SM
-        size_t ns = fixed + 2 * stage < budget ? (budget - fixed) / stage : 2;
-        ns = std::max<size_t>(2, std::min<size_t>(ns, WT_MAX_STAGES));
-        wp.n_stages = (uint32_t)ns; wp.max_cols = max_cols;
-        size_t smem = ns * stage + fixed;
-        KernelTimer kt(s);
-        cudaError_t e = launch_tma(wp, ix->n_sm, (unsigned)ix->blocks.size(), smem, dt, s);
-        if (e != cudaSuccess) return fail(XS_ERR_CUDA, std::string("k_cobs_wide_tma: ") + cudaGetErrorString(e));
-        XS_TRY(launch_ok("k_cobs_wide_tma"));
     } else {
         WideParams wp{};
         wp.cp = p; wp.blocks = ix->d_blocks; wp.chunk_prefix = ws.prefix2;
         uint32_t max_cols = 0;
         for (const ColBlock& b : ix->blocks) max_cols = std::max(max_cols, b.n_cols);
         size_t smem = (size_t)WIDE_CHUNK * ix->info.num_hashes * 8 + (size_t)max_cols * 128 * 4;
-        dim3 grid((unsigned)(ix->n_sm * 2), (unsigned)ix->blocks.size());
+        dim3 grid((unsigned)ix->n_sm, (unsigned)ix->blocks.size());
         KernelTimer kt(s);
         cudaError_t e = launch_wide(wp, grid, smem, dt, s);
         if (e != cudaSuccess) return fail(XS_ERR_CUDA, std::string("k_cobs_wide: ") + cudaGetErrorString(e));
@@ -608,8 +573,7 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
     if (n_col > 128) stride = (n_col + 127) & ~127u;
     ix->narrow = stride == 16;
     const uint32_t n_chunks = (n_col + 15) / 16;     // 16-byte chunks that hold documents
-    const char* ldg = getenv("XS_WIDE_LDG");
-    ix->tma = n_chunks >= (uint32_t)WT_MIN_COLS && !(ldg && ldg[0] == '1');
+
     uint64_t total = 0;
     std::vector<uint64_t> offs;
     for (uint64_t s : cf.sig) { offs.push_back(total); total += s * stride; }
