@@ -136,6 +136,16 @@ int xs_cobs_result_order(const uint32_t* scores, uint32_t n_docs, uint32_t* orde
 /* the same for n_seq rows of a [n_seq x n_docs] uint32 count matrix (one call per predict batch) */
 int xs_cobs_result_order_batch(const uint32_t* scores, uint64_t n_seq, uint32_t n_docs, uint32_t* order);
 
+/* Score epilogue on the device, for callers that want read-level calls and file-level totals instead of the
+ * whole count matrix: for every record the first document holding the maximum count (best), that count
+ * (best_count) and the number of documents sharing it (n_best > 1 = the "ambiguous" tie rule of
+ * scripts/benchmark/main.nf:417-436), and totals[d] += sum over records (ModelResult.get_total_hits,
+ * models/result.py:76-90; the caller zeroes totals).  Any output pointer may be NULL.  All pointers are device
+ * memory on `device`; asynchronous on `stream`. */
+int xs_scores_reduce_device(const void* d_counts, uint64_t n_seq, uint32_t n_docs, int dtype, int device,
+                            uint32_t* d_best, uint32_t* d_best_count, uint32_t* d_n_best, uint64_t* d_totals,
+                            void* stream);
+
 /* ---- Bloom filter ------------------------------------------------------------------------
  * Replaces rbloom.Bloom.load(path, hash_func=xxh3_64_intdigest)
  *   probabilistic_single_filter_model.py:155-158

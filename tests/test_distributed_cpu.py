@@ -44,6 +44,18 @@ def _worker(rank: int, world: int, port: int, tmp: str, mode: str):
             assert shards[0][0] == 0 and shards[-1][1] == orc.n_docs
             assert all(a[1] == bb[0] for a, bb in zip(shards, shards[1:]))
             lo, hi = shards[rank]
+            # reduced exchange: each rank's local (best, count, multiplicity) -> global best / tie flag
+            loc = full[:, lo:hi].astype(np.int64)
+            if hi > lo:
+                lb, lc = loc.argmax(axis=1), loc.max(axis=1)
+                ln = (loc == lc[:, None]).sum(axis=1)
+            else:
+                lb = lc = ln = np.zeros(full.shape[0], np.int64)
+            gb, gc, gt = xd.merge_local_best(torch.from_numpy(lb), torch.from_numpy(lc), torch.from_numpy(ln), shards, rank)
+            f = full.astype(np.int64)
+            assert np.array_equal(gc.numpy(), f.max(axis=1))
+            assert np.array_equal(gb.numpy(), f.argmax(axis=1))
+            assert np.array_equal(gt.numpy(), (f == f.max(axis=1)[:, None]).sum(axis=1) > 1)
             for dt in (np.uint8, np.uint16, np.uint32):
                 local = torch.from_numpy(np.ascontiguousarray(np.minimum(full[:, lo:hi], np.iinfo(dt).max).astype(dt)))
                 got = xd.allgather_columns(local, shards)

@@ -216,6 +216,36 @@ def test_cobs_document_column_shards(gpu, oracle, tmp_path, n_docs, lo, hi):
     _check_cobs(gpu, oracle, p, bases, b, e, doc_begin=lo, doc_end=hi)
 
 
+@pytest.mark.parametrize("n_docs", [5, 90, 1000])
+@pytest.mark.parametrize("dtype", [1, 2, 4])
+def test_scores_reduce_epilogue(gpu, n_docs, dtype):
+    """Device argmax / tie multiplicity / totals equal NumPy on random count matrices (incl. all-zero rows)."""
+    import torch
+    rng = np.random.default_rng(n_docs + dtype)
+    npdt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[dtype]
+    n = 3001
+    counts = rng.integers(0, 6, size=(n, n_docs)).astype(npdt)
+    counts[::7] = 0
+    counts[5, n_docs - 1] = np.iinfo(npdt).max
+    dev = torch.device("cuda", 0)
+    tdt = {1: torch.uint8, 2: torch.uint16, 4: torch.uint32}[dtype]
+    d_counts = torch.from_numpy(counts).to(dev)
+    assert d_counts.dtype == tdt
+    best = torch.empty(n, dtype=torch.int32, device=dev)
+    cnt = torch.empty(n, dtype=torch.int32, device=dev)
+    nb = torch.empty(n, dtype=torch.int32, device=dev)
+    tot = torch.zeros(n_docs, dtype=torch.int64, device=dev)
+    gpu.scores_reduce_device(d_counts.data_ptr(), n, n_docs, dtype, 0, best.data_ptr(), cnt.data_ptr(), nb.data_ptr(),
+                             tot.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    c64 = counts.astype(np.int64)
+    mx = c64.max(axis=1)
+    assert np.array_equal(best.cpu().numpy().view(np.uint32), c64.argmax(axis=1).astype(np.uint32))
+    assert np.array_equal(cnt.cpu().numpy().view(np.uint32).astype(np.int64), mx)
+    assert np.array_equal(nb.cpu().numpy(), (c64 == mx[:, None]).sum(axis=1))
+    assert np.array_equal(tot.cpu().numpy(), c64.sum(axis=0))
+
+
 # ------------------------------------------------------------------------------------------ compact (MLST)
 @pytest.mark.parametrize("n_alleles,k,page_size", [(40, 21, None), (600, 31, None), (600, 21, 4), (3000, 31, 32)])
 def test_cobs_compact(gpu, oracle, tmp_path, n_alleles, k, page_size):

@@ -46,6 +46,18 @@ def _worker(rank: int, world: int, port: int, tmp: str):
             allrows = np.concatenate([got[t] for t in range(4)])
             assert np.array_equal(allrows, np.minimum(full, np.iinfo(npdt).max).astype(npdt)), f"rank {rank} dtype {dt}"
 
+        # ---- reduced exchange: local argmax per rank, 3 integers per record travel
+        calls = {}
+        totals = sh.classify_tiles(iter(tiles), 1, XS_U8, lambda t, bst, c, tie: calls.__setitem__(t, (bst.cpu().numpy(), c.cpu().numpy(), tie.cpu().numpy())))
+        f8 = np.minimum(full, 255).astype(np.int64)
+        gb = np.concatenate([calls[t][0] for t in range(4)])
+        gc = np.concatenate([calls[t][1] for t in range(4)])
+        gt = np.concatenate([calls[t][2] for t in range(4)])
+        assert np.array_equal(gb, f8.argmax(axis=1)) and np.array_equal(gc, f8.max(axis=1))
+        assert np.array_equal(gt, (f8 == f8.max(axis=1)[:, None]).sum(axis=1) > 1)
+        lo_d, hi_d = sh.shards[rank]
+        assert np.array_equal(totals.cpu().numpy(), f8[:, lo_d:hi_d].sum(axis=0))
+
         # ---- read sharding: whole index per GPU, a slice of the records per rank, totals all-reduced
         ix = engine.CobsIndex(path, device=rank)
         lo, hi = xd.read_shard(b.size, rank, world)

@@ -627,6 +627,58 @@ __global__ void __launch_bounds__(BLOOM_NT, 4) k_bloom(const BloomParams p) {
 }
 
 // ----------------------------------------------------------------------------------------
+// score epilogue: per record the best document (first index of the maximum), the maximum and how many
+// documents share it (ties = "ambiguous", scripts/benchmark/main.nf:417-436), plus per-document totals
+// (ModelResult.get_total_hits, result.py:76-90).  Streams the count matrix once; saves the
+// [n_seq x n_docs] device->host transfer when only read-level calls and file-level totals are wanted.
+// ----------------------------------------------------------------------------------------
+constexpr int REDUCE_NT = 256;
+constexpr int REDUCE_ROWS = 256;   // records per CTA pass
+
+template <typename OutT>
+__global__ void __launch_bounds__(REDUCE_NT) k_scores_reduce(const OutT* __restrict__ counts, uint64_t n_seq, uint32_t n_docs,
+                                                             uint32_t* __restrict__ best, uint32_t* __restrict__ best_count,
+                                                             uint32_t* __restrict__ n_best, unsigned long long* __restrict__ totals) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint32_t NWARP = REDUCE_NT / 32;
+    for (uint64_t r0 = (uint64_t)blockIdx.x * REDUCE_ROWS; r0 < n_seq; r0 += (uint64_t)gridDim.x * REDUCE_ROWS) {
+        const uint32_t rows = (uint32_t)(n_seq - r0 < REDUCE_ROWS ? n_seq - r0 : REDUCE_ROWS);
+        if (best || best_count || n_best) {
+            for (uint32_t r = warp; r < rows; r += NWARP) {
+                const OutT* row = counts + (r0 + r) * n_docs;
+                uint32_t mx = 0, idx = 0xFFFFFFFFu, cnt = 0;
+                for (uint32_t d = lane; d < n_docs; d += 32) {
+                    uint32_t v = row[d];
+                    if (idx == 0xFFFFFFFFu || v > mx) { mx = v; idx = d; cnt = 1; }
+                    else if (v == mx) ++cnt;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    uint32_t omx = __shfl_xor_sync(0xFFFFFFFFu, mx, o), oidx = __shfl_xor_sync(0xFFFFFFFFu, idx, o),
+                             ocnt = __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+                    if (oidx != 0xFFFFFFFFu) {
+                        if (idx == 0xFFFFFFFFu || omx > mx) { mx = omx; idx = oidx; cnt = ocnt; }
+                        else if (omx == mx) { cnt += ocnt; idx = oidx < idx ? oidx : idx; }
+                    }
+                }
+                if (lane == 0) {
+                    if (best) best[r0 + r] = idx;
+                    if (best_count) best_count[r0 + r] = mx;
+                    if (n_best) n_best[r0 + r] = cnt;
+                }
+            }
+        }
+        if (totals) {
+            for (uint32_t d = threadIdx.x; d < n_docs; d += REDUCE_NT) {
+                unsigned long long sum = 0;
+                for (uint32_t r = 0; r < rows; ++r) sum += counts[(r0 + r) * n_docs + d];
+                if (sum) atomicAdd(totals + d, sum);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // stage kernels (parity tests pin each stage on its own)
 // ----------------------------------------------------------------------------------------
 __global__ void k_stage_canonical(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ invalid,

@@ -718,6 +718,25 @@ int xs_cobs_result_order_batch(const uint32_t* scores, uint64_t n_seq, uint32_t 
     return XS_OK;
 }
 
+int xs_scores_reduce_device(const void* d_counts, uint64_t n_seq, uint32_t n_docs, int dtype, int device,
+                            uint32_t* d_best, uint32_t* d_best_count, uint32_t* d_n_best, uint64_t* d_totals,
+                            void* stream) {
+    if (!dtype_size(dtype)) return fail(XS_ERR_ARG, "dtype must be XS_U8, XS_U16 or XS_U32");
+    if (n_seq == 0 || n_docs == 0) return XS_OK;
+    if (!d_counts) return fail(XS_ERR_ARG, "NULL count matrix");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the device");
+    int n_sm = 0;
+    XS_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned grid = (unsigned)std::min<uint64_t>((n_seq + REDUCE_ROWS - 1) / REDUCE_ROWS, (uint64_t)n_sm * 8);
+    unsigned long long* tot = reinterpret_cast<unsigned long long*>(d_totals);
+    if (dtype == XS_U8) k_scores_reduce<uint8_t><<<grid, REDUCE_NT, 0, s>>>((const uint8_t*)d_counts, n_seq, n_docs, d_best, d_best_count, d_n_best, tot);
+    else if (dtype == XS_U16) k_scores_reduce<uint16_t><<<grid, REDUCE_NT, 0, s>>>((const uint16_t*)d_counts, n_seq, n_docs, d_best, d_best_count, d_n_best, tot);
+    else k_scores_reduce<uint32_t><<<grid, REDUCE_NT, 0, s>>>((const uint32_t*)d_counts, n_seq, n_docs, d_best, d_best_count, d_n_best, tot);
+    return launch_ok("k_scores_reduce");
+}
+
 int xs_bloom_open(const char* path, uint32_t term_size, int device, xs_bloom** out) {
     if (!path || !out) return fail(XS_ERR_ARG, "path/out is NULL");
     *out = nullptr;

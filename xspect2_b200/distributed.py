@@ -71,6 +71,28 @@ def allgather_columns(local: torch.Tensor, shards: list[tuple[int, int]], group=
     return torch.cat([recv[g, :, : widths[g]] for g in range(world)], dim=1)
 
 
+def merge_local_best(best: torch.Tensor, count: torch.Tensor, n_best: torch.Tensor, shards: list[tuple[int, int]],
+                     rank: int, group=None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Combine per-rank (best local document, its count, tie multiplicity) of column-sharded scoring into the
+    global best document index, its count and the tie flag — an all-gather of 3 integers per record instead of
+    the whole score row.  Ranks hold ascending document ranges, so the first rank reaching the maximum owns the
+    first best document."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    local = torch.stack([best.to(torch.int64) + shards[rank][0], count.to(torch.int64), n_best.to(torch.int64)], dim=1).contiguous()
+    if world == 1:
+        return local[:, 0], local[:, 1], local[:, 2] > 1
+    n = local.shape[0]
+    recv = torch.empty((world * n, 3), dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(recv, local, group=group)
+    recv = recv.view(world, n, 3)
+    counts = recv[:, :, 1]
+    mx, first_rank = counts.max(dim=0)                  # torch returns the first maximal rank
+    at_max = counts == mx.unsqueeze(0)
+    multiplicity = (recv[:, :, 2] * at_max).sum(dim=0)
+    gbest = recv[:, :, 0].gather(0, first_rank.unsqueeze(0)).squeeze(0)
+    return gbest, mx, multiplicity > 1
+
+
 class ColumnShardedIndex:
     """This rank's document-column shard of a COBS classic index plus the score all-gather."""
 
@@ -119,6 +141,30 @@ class ColumnShardedIndex:
             pt, full, ev = pending
             ev.synchronize()
             consume(pt, full)
+
+
+    def classify_tiles(self, tiles: Iterator[tuple[int, int, int, int, int]], step: int, dtype: int,
+                       consume: Callable[[int, torch.Tensor, torch.Tensor, torch.Tensor], None]) -> torch.Tensor:
+        """Like ``query_tiles`` but the exchange is reduced first: every rank takes the per-record maximum over its
+        own columns on the device (xs_scores_reduce_device), and only (best, count, multiplicity) travel.
+        ``consume(tile, best_doc_index, best_count, is_tie)``; returns this rank's per-document totals (uint64)."""
+        from . import engine
+        from ._abi import XS_U8, XS_U16
+
+        tdt = {XS_U8: torch.uint8, XS_U16: torch.uint16}.get(dtype, torch.uint32)
+        dev = torch.device("cuda", self.index.device)
+        stream = torch.cuda.current_stream(dev)
+        totals = torch.zeros(self.index.n_docs, dtype=torch.int64, device=dev)
+        for t, (d_bases, n_bases, d_begin, d_end, n_seq) in enumerate(tiles):
+            local = torch.empty((n_seq, self.index.n_docs), dtype=tdt, device=dev)
+            best = torch.empty(n_seq, dtype=torch.int32, device=dev)
+            cnt = torch.empty(n_seq, dtype=torch.int32, device=dev)
+            nb = torch.empty(n_seq, dtype=torch.int32, device=dev)
+            self.index.query_device(d_bases, n_bases, d_begin, d_end, n_seq, step, dtype, local.data_ptr(), stream.cuda_stream)
+            engine.scores_reduce_device(local.data_ptr(), n_seq, self.index.n_docs, dtype, self.index.device, best.data_ptr(),
+                                        cnt.data_ptr(), nb.data_ptr(), totals.data_ptr(), stream.cuda_stream)
+            consume(t, *merge_local_best(best, cnt, nb, self.shards, self.rank, self.group))
+        return totals
 
 
 def _doc_count(path) -> int:

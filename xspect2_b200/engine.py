@@ -310,6 +310,14 @@ def kmer_rows(bases, k: int, num_hashes: int, sig_size: int, canonicalize: int =
     return rows, valid
 
 
+def scores_reduce_device(d_counts: int, n_seq: int, n_docs: int, dtype: int, device: int, d_best: int = 0,
+                         d_best_count: int = 0, d_n_best: int = 0, d_totals: int = 0, stream: int = 0) -> None:
+    """Device epilogue over a [n_seq, n_docs] count matrix: best document / its count / tie multiplicity per record
+    (uint32 each) and per-document totals (uint64, accumulated).  Raw device pointers; 0 = not wanted."""
+    check(lib().xs_scores_reduce_device(d_counts, n_seq, n_docs, int(dtype), int(device), d_best or None, d_best_count or None,
+                                        d_n_best or None, d_totals or None, stream or None))
+
+
 def device_count() -> int:
     n = C.c_int()
     rc = lib().xs_device_count(C.byref(n))
