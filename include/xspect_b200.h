@@ -164,6 +164,21 @@ int xs_bloom_query_device(xs_bloom* bf, const uint8_t* d_bases, uint64_t n_bases
                           const uint64_t* d_seq_begin, const uint64_t* d_seq_end, uint64_t n_seq,
                           uint32_t step, uint32_t* d_out_hits, void* stream);
 
+/* ---- FASTA / FASTQ ingest (host only) -----------------------------------------------------------
+ * Replaces the Biopython record iteration that feeds the path (SeqIO.parse behind
+ * file_io.get_record_iterator, file_io.py:47-79; consumed at probabilistic_filter_model.py:291-310) with one
+ * pass that lays a whole file out as query input.  format: 1 = fasta, 2 = fastq (chosen by file extension on the
+ * Python side, like the reference).  xs_fastx_open parses once to size the buffers; xs_fastx_read fills
+ *   bases[n_bases], seq_begin/seq_end[n_records] (offsets into bases), ids[n_id_bytes] (record ids back to back:
+ *   the first whitespace-delimited word of each title line, Biopython's record.id) and id_end[n_records].
+ * Sequence bytes are kept as they are; FASTA line breaks, '\r' and blanks are removed; wrapped FASTQ is accepted;
+ * malformed FASTQ -> XS_ERR_FORMAT with Biopython's message. */
+typedef struct xs_fastx xs_fastx;
+int xs_fastx_open(const char* path, int format, xs_fastx** out);
+int xs_fastx_stats(const xs_fastx* fx, uint64_t* n_records, uint64_t* n_bases, uint64_t* n_id_bytes);
+int xs_fastx_read(const xs_fastx* fx, uint8_t* bases, uint64_t* seq_begin, uint64_t* seq_end, char* ids, uint64_t* id_end);
+int xs_fastx_close(xs_fastx* fx);
+
 /* ---- single stages (host buffers; used by the parity tests to pin each kernel alone) ----- */
 /* 2-bit packing: packed[w] holds bases [32w, 32w+32), base j in bits [2j, 2j+1], A=0 C=1 G=2 T=3;
  * invalid[w] bit j = 1 when the byte is not one of upper-case ACGT.  n_words = n_bases/32 + 1. */

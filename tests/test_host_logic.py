@@ -226,3 +226,51 @@ def test_seq_semantics_used_by_the_bloom_path(oracle):
         kmer = Seq(s)
         assert str(min(kmer, str(kmer.reverse_complement()))).encode() == oracle.bloom_term(s.encode())
     assert seqio.is_seq(Seq("A")) and not seqio.is_seq("A") and seqio.is_record(SeqRecord("ACGT", "i"))
+
+
+def test_native_reader_many_records_matches_iterators(tmp_path):
+    """> 2 checkpoint segments (parallel fill pass), ragged reads, '@' and '+' opening quality lines, CRLF."""
+    rng = np.random.default_rng(17)
+    n = 70_001
+    lens = rng.integers(0, 90, size=n)
+    lens[::501] = 0
+    allb = np.frombuffer(b"ACGTNacgt", np.uint8)[rng.integers(0, 9, size=int(lens.sum()))]
+    ends = np.cumsum(lens)
+    starts = ends - lens
+    fq = tmp_path / "many.fq"
+    with open(fq, "wb") as f:
+        for i in range(n):
+            s = allb[starts[i]:ends[i]].tobytes()
+            q = (b"@" if i % 3 == 0 else b"+") * len(s)
+            nl = b"\r\n" if i % 5 == 0 else b"\n"
+            f.write(b"@r%d\tpair=%d" % (i, i % 2) + nl + s + nl + b"+" + nl + q + nl)
+    b = SequenceBatch.from_file(fq)
+    assert len(b) == n and np.array_equal(b.bases, allb)
+    assert np.array_equal(b.begin, starts.astype(np.uint64)) and np.array_equal(b.end, ends.astype(np.uint64))
+    assert b.ids == [f"r{i}" for i in range(n)]
+    it = list(get_record_iterator(fq))
+    assert [r.id for r in it[:2000]] == b.ids[:2000]
+    assert [str(r.seq) for r in it[40000:41000]] == [b.sequence(i) for i in range(40000, 41000)]
+    fa = tmp_path / "many.fna"
+    with open(fa, "wb") as f:
+        f.write(b"; comment before the first record\n")
+        for i in range(n):
+            s = allb[starts[i]:ends[i]].tobytes()
+            f.write(b">c%d some description\n" % i)
+            for j in range(0, len(s), 40):
+                f.write(s[j:j + 40][:20] + b" " + s[j:j + 40][20:] + (b"\r\n" if i % 2 else b"\n"))
+    b2 = SequenceBatch.from_file(fa)
+    assert np.array_equal(b2.bases, allb) and np.array_equal(b2.end, ends.astype(np.uint64))
+    assert b2.ids[0] == "c0" and b2.ids[-1] == f"c{n - 1}"
+    empty = tmp_path / "empty.fasta"
+    empty.write_text("")
+    assert len(SequenceBatch.from_file(empty)) == 0
+    with pytest.raises(ValueError):
+        SequenceBatch.from_file(tmp_path / "x.txt")
+    bad = tmp_path / "bad2.fastq"
+    bad.write_text("@a\nAC GT\n+\nIIIII\n")
+    with pytest.raises(ValueError, match="Whitespace"):
+        SequenceBatch.from_file(bad)
+    bad.write_text("ACGT\n")
+    with pytest.raises(ValueError, match="should start with '@'"):
+        SequenceBatch.from_file(bad)

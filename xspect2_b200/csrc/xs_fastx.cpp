@@ -1,0 +1,241 @@
+// xs_fastx.cpp — native FASTA / FASTQ ingest for the batched scoring path (host only, no CUDA).
+//
+// Replaces the record iteration the reference does with Biopython (SeqIO.parse behind
+// file_io.get_record_iterator, file_io.py:47-79, consumed record by record at
+// probabilistic_filter_model.py:291-310) by one pass that lays all records out as the C ABI's query input:
+// one contiguous base buffer + seq_begin/seq_end offsets, plus the record ids (first word of the title line,
+// Biopython's `record.id`).  Sequence bytes are copied as they are (case, N, IUPAC preserved); FASTA line
+// breaks, '\r' and blanks are removed like Bio.SeqIO.FastaIO does; FASTQ may be wrapped.
+#include <algorithm>
+#include <cerrno>
+#include <cstdint>
+#include <cstring>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "../../include/xspect_b200.h"
+
+int xs_set_error(int code, const std::string& msg);   // xs_lib.cu
+
+struct Checkpoint { uint64_t off, rec, base, id; };   // a record start: file offset and output cursors there
+
+struct xs_fastx {
+    const uint8_t* data = nullptr;
+    uint64_t size = 0;
+    int fd = -1;
+    int format = 0;          // 1 fasta, 2 fastq
+    uint64_t n_records = 0, n_bases = 0, n_id_bytes = 0;
+    std::vector<Checkpoint> cps;   // every CP_EVERY records (sizing pass) -> segments the fill pass runs in parallel
+};
+static const uint64_t CP_EVERY = 1 << 15;
+
+namespace {
+
+inline const uint8_t* find_nl(const uint8_t* p, const uint8_t* end) {
+    const void* q = memchr(p, '\n', (size_t)(end - p));
+    return q ? (const uint8_t*)q : end;
+}
+inline bool is_space(uint8_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+// first whitespace-delimited word of [p, e)
+inline void first_word(const uint8_t* p, const uint8_t* e, const uint8_t** wb, const uint8_t** we) {
+    while (p < e && is_space(*p)) ++p;
+    const uint8_t* q = p;
+    while (q < e && !is_space(*q)) ++q;
+    *wb = p; *we = q;
+}
+
+struct Sink {   // pass 1 counts, pass 2 writes
+    uint8_t* bases = nullptr;
+    uint64_t* seq_begin = nullptr;
+    uint64_t* seq_end = nullptr;
+    char* ids = nullptr;
+    uint64_t* id_end = nullptr;
+    uint64_t n_rec = 0, n_bases = 0, n_id = 0;
+    bool write = false;
+    std::vector<Checkpoint>* cps = nullptr;
+    const uint8_t* file_base = nullptr;
+
+    inline void begin_record(const uint8_t* rec_start, const uint8_t* title_b, const uint8_t* title_e) {
+        if (cps && (n_rec % CP_EVERY) == 0) cps->push_back({(uint64_t)(rec_start - file_base), n_rec, n_bases, n_id});
+        const uint8_t *wb, *we;
+        first_word(title_b, title_e, &wb, &we);
+        if (write) {
+            memcpy(ids + n_id, wb, (size_t)(we - wb));
+            seq_begin[n_rec] = n_bases;
+        }
+        n_id += (uint64_t)(we - wb);
+        if (write) id_end[n_rec] = n_id;
+    }
+    inline void end_record() {
+        if (write) seq_end[n_rec] = n_bases;
+        ++n_rec;
+    }
+    // append a FASTA line: drop ' ' and '\r' (Bio.SeqIO.FastaIO: "".join(lines).replace(" ", "").replace("\r", ""))
+    inline void append_fasta(const uint8_t* p, const uint8_t* e) {
+        if (!memchr(p, ' ', (size_t)(e - p)) && !memchr(p, '\r', (size_t)(e - p))) {
+            if (write) memcpy(bases + n_bases, p, (size_t)(e - p));
+            n_bases += (uint64_t)(e - p);
+            return;
+        }
+        for (; p < e; ++p)
+            if (*p != ' ' && *p != '\r') { if (write) bases[n_bases] = *p; ++n_bases; }
+    }
+    inline void append_raw(const uint8_t* p, const uint8_t* e) {
+        if (write) memcpy(bases + n_bases, p, (size_t)(e - p));
+        n_bases += (uint64_t)(e - p);
+    }
+};
+
+int parse_fasta(const uint8_t* p, const uint8_t* end, Sink& sk) {
+    bool in_record = false;
+    while (p < end) {
+        const uint8_t* nl = find_nl(p, end);
+        if (*p == '>') {
+            if (in_record) sk.end_record();
+            const uint8_t* te = nl;
+            if (te > p + 1 && te[-1] == '\r') --te;
+            sk.begin_record(p, p + 1, te);
+            in_record = true;
+        } else if (in_record) {
+            sk.append_fasta(p, nl);
+        }
+        p = nl + 1;
+    }
+    if (in_record) sk.end_record();
+    return XS_OK;
+}
+
+inline const uint8_t* rstrip(const uint8_t* p, const uint8_t* e) {
+    while (e > p && is_space(e[-1])) --e;
+    return e;
+}
+
+int parse_fastq(const uint8_t* p, const uint8_t* end, Sink& sk) {
+    while (p < end) {
+        const uint8_t* nl = find_nl(p, end);
+        if (rstrip(p, nl) == p) { p = nl + 1; continue; }           // blank line between records
+        if (*p != '@') return xs_set_error(XS_ERR_FORMAT, "Records in Fastq files should start with '@' character");
+        sk.begin_record(p, p + 1, rstrip(p + 1, nl));
+        p = nl + 1;
+        uint64_t seq_len = 0;
+        bool plus = false;
+        while (p < end) {
+            nl = find_nl(p, end);
+            if (*p == '+') { plus = true; p = nl + 1; break; }
+            const uint8_t* e = rstrip(p, nl);
+            if (memchr(p, ' ', (size_t)(e - p)) || memchr(p, '\t', (size_t)(e - p)))
+                return xs_set_error(XS_ERR_FORMAT, "Whitespace is not allowed in the sequence.");
+            sk.append_raw(p, e);
+            seq_len += (uint64_t)(e - p);
+            p = nl + 1;
+        }
+        if (!plus) return xs_set_error(XS_ERR_FORMAT, "End of file without quality information.");
+        uint64_t qual_len = 0;
+        while (p < end && qual_len < seq_len) {
+            nl = find_nl(p, end);
+            qual_len += (uint64_t)(rstrip(p, nl) - p);
+            p = nl + 1;
+        }
+        if (seq_len == 0 && p < end) {                                // empty record: one (empty) quality line
+            nl = find_nl(p, end);
+            if (rstrip(p, nl) == p) p = nl + 1;
+        }
+        if (qual_len != seq_len)
+            return xs_set_error(XS_ERR_FORMAT, "Lengths of sequence and quality values differs (" + std::to_string(seq_len) + " and " +
+                                                   std::to_string(qual_len) + ").");
+        sk.end_record();
+    }
+    return XS_OK;
+}
+
+int run(const xs_fastx* fx, const uint8_t* p, const uint8_t* end, Sink& sk) {
+    return fx->format == 2 ? parse_fastq(p, end, sk) : parse_fasta(p, end, sk);
+}
+
+}  // namespace
+
+extern "C" {
+
+int xs_fastx_open(const char* path, int format, xs_fastx** out) {
+    if (!path || !out) return xs_set_error(XS_ERR_ARG, "path/out is NULL");
+    *out = nullptr;
+    if (format != 1 && format != 2) return xs_set_error(XS_ERR_ARG, "format must be 1 (fasta) or 2 (fastq)");
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return xs_set_error(XS_ERR_IO, std::string(path) + ": " + strerror(errno));
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return xs_set_error(XS_ERR_IO, std::string(path) + ": " + strerror(errno)); }
+    xs_fastx* fx = new xs_fastx();
+    fx->fd = fd; fx->size = (uint64_t)st.st_size; fx->format = format;
+    if (fx->size) {
+        void* m = mmap(nullptr, fx->size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { close(fd); delete fx; return xs_set_error(XS_ERR_IO, std::string(path) + ": mmap failed"); }
+        madvise(m, fx->size, MADV_SEQUENTIAL);
+        fx->data = (const uint8_t*)m;
+    }
+    Sink sk;
+    sk.cps = &fx->cps; sk.file_base = fx->data;
+    int rc = run(fx, fx->data, fx->data + fx->size, sk);
+    if (rc != XS_OK) { xs_fastx_close(fx); return rc; }
+    fx->n_records = sk.n_rec; fx->n_bases = sk.n_bases; fx->n_id_bytes = sk.n_id;
+    *out = fx;
+    return XS_OK;
+}
+
+int xs_fastx_stats(const xs_fastx* fx, uint64_t* n_records, uint64_t* n_bases, uint64_t* n_id_bytes) {
+    if (!fx) return xs_set_error(XS_ERR_ARG, "NULL reader");
+    if (n_records) *n_records = fx->n_records;
+    if (n_bases) *n_bases = fx->n_bases;
+    if (n_id_bytes) *n_id_bytes = fx->n_id_bytes;
+    return XS_OK;
+}
+
+int xs_fastx_read(const xs_fastx* fx, uint8_t* bases, uint64_t* seq_begin, uint64_t* seq_end, char* ids, uint64_t* id_end) {
+    if (!fx) return xs_set_error(XS_ERR_ARG, "NULL reader");
+    if ((fx->n_bases && !bases) || (fx->n_records && (!seq_begin || !seq_end || !id_end)) || (fx->n_id_bytes && !ids))
+        return xs_set_error(XS_ERR_ARG, "NULL output buffer");
+    // fill pass: the segments between checkpoints are independent, run them on a few host threads
+    const size_t n_seg = fx->cps.size();
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t n_thr = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(hw ? hw : 1, 16), n_seg));
+    std::atomic<size_t> next(0);
+    std::atomic<int> status(XS_OK);
+    auto work = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n_seg) break;
+            const Checkpoint& c = fx->cps[i];
+            const uint8_t* b = fx->data + c.off;
+            const uint8_t* e = i + 1 < n_seg ? fx->data + fx->cps[i + 1].off : fx->data + fx->size;
+            Sink sk;
+            sk.bases = bases; sk.seq_begin = seq_begin; sk.seq_end = seq_end; sk.ids = ids; sk.id_end = id_end; sk.write = true;
+            sk.n_rec = c.rec; sk.n_bases = c.base; sk.n_id = c.id;
+            int rc = run(fx, b, e, sk);
+            if (rc != XS_OK) status.store(rc);
+        }
+    };
+    if (n_thr <= 1) work();
+    else {
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < n_thr; ++t) th.emplace_back(work);
+        for (auto& t : th) t.join();
+    }
+    return status.load();
+}
+
+int xs_fastx_close(xs_fastx* fx) {
+    if (!fx) return XS_OK;
+    if (fx->data) munmap((void*)fx->data, fx->size);
+    if (fx->fd >= 0) close(fx->fd);
+    delete fx;
+    return XS_OK;
+}
+
+}  // extern "C"

@@ -29,6 +29,7 @@ static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+int xs_set_error(int code, const std::string& msg) { return fail(code, msg); }   // for xs_fastx.cpp
 #define XS_CUDA(expr)                                                                              \
     do {                                                                                           \
         cudaError_t e__ = (expr);                                                                  \

@@ -243,19 +243,30 @@ def write_fasta(records: Iterable, handle, wrap: int = 60) -> int:
 # contiguous batches for the C ABI
 # --------------------------------------------------------------------------------------
 class SequenceBatch:
-    """All records of an input as one byte buffer + offsets: ``bases[begin[i]:end[i]]`` is record i."""
+    """All records of an input as one byte buffer + offsets: ``bases[begin[i]:end[i]]`` is record i.
+    Record ids are decoded lazily (a 10 M-read FASTQ should not pay for 10 M Python strings unless asked)."""
 
-    __slots__ = ("ids", "bases", "begin", "end", "records")
+    __slots__ = ("_ids", "_id_buf", "_id_end", "bases", "begin", "end", "records")
 
-    def __init__(self, ids: list[str], bases: np.ndarray, begin: np.ndarray, end: np.ndarray, records=None):
-        self.ids = ids
+    def __init__(self, ids, bases: np.ndarray, begin: np.ndarray, end: np.ndarray, records=None, id_buf=None, id_end=None):
+        self._ids = ids
+        self._id_buf = id_buf
+        self._id_end = id_end
         self.bases = bases
         self.begin = begin
         self.end = end
         self.records = records
 
+    @property
+    def ids(self) -> list[str]:
+        if self._ids is None:
+            text = self._id_buf.tobytes().decode("ascii", "replace")
+            ends = self._id_end.tolist()
+            self._ids = [text[a:b] for a, b in zip([0] + ends[:-1], ends)]
+        return self._ids
+
     def __len__(self) -> int:
-        return len(self.ids)
+        return int(self.begin.size)
 
     @property
     def lengths(self) -> np.ndarray:
@@ -281,88 +292,45 @@ class SequenceBatch:
 
     @classmethod
     def from_file(cls, path: Path) -> "SequenceBatch":
-        """Vectorised FASTA / FASTQ reader (format by extension, like file_io.get_record_iterator)."""
+        """Native FASTA / FASTQ reader (xs_fastx_*; format by extension, like file_io.get_record_iterator).  The
+        base buffer is page-locked when a GPU is present so the query's host-to-device copy is asynchronous."""
+        import ctypes as C
+
+        from . import _abi
         from .definitions import fasta_endings, fastq_endings
 
         path = Path(path)
         suffix = path.suffix[1:]
-        raw = np.fromfile(path, dtype=np.uint8)
         if suffix in fastq_endings:
-            got = _fastq_fast(raw)
-            if got is not None:
-                return got
-            return cls.from_records(FastqPhredIterator(path))
-        if suffix in fasta_endings:
-            return _fasta_fast(raw)
-        raise ValueError("Invalid file format, must be a fasta or fastq file")
+            fmt = 2
+        elif suffix in fasta_endings:
+            fmt = 1
+        else:
+            raise ValueError("Invalid file format, must be a fasta or fastq file")
+        L = _abi.lib()
+        h = C.c_void_p()
+        _abi.check(L.xs_fastx_open(str(path).encode(), fmt, C.byref(h)))
+        try:
+            n_rec, n_bases, n_id = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            _abi.check(L.xs_fastx_stats(h, C.byref(n_rec), C.byref(n_bases), C.byref(n_id)))
+            bases = _host_buffer(n_bases.value)
+            begin = np.empty(n_rec.value, np.uint64)
+            end = np.empty(n_rec.value, np.uint64)
+            id_buf = np.empty(n_id.value, np.uint8)
+            id_end = np.empty(n_rec.value, np.uint64)
+            _abi.check(L.xs_fastx_read(h, bases.ctypes.data, begin.ctypes.data, end.ctypes.data, id_buf.ctypes.data, id_end.ctypes.data))
+        finally:
+            L.xs_fastx_close(h)
+        return cls(None, bases, begin, end, None, id_buf, id_end)
 
 
-def _first_words(raw: np.ndarray, starts: np.ndarray, ends: np.ndarray) -> list[str]:
-    """First whitespace-delimited word of each title line raw[starts[i]:ends[i]] (marker already skipped)."""
-    buf = raw.tobytes()
-    out = []
-    for s, e in zip(starts.tolist(), ends.tolist()):
-        w = buf[s:e].split(None, 1)
-        out.append(w[0].decode("ascii", "replace") if w else "")
-    return out
+def _host_buffer(n: int) -> np.ndarray:
+    """Page-locked uint8 buffer when CUDA is available (large inputs only), ordinary memory otherwise."""
+    if n >= (1 << 20):
+        try:
+            from .engine import pinned_empty
 
-
-def _line_bounds(raw: np.ndarray):
-    nl = np.flatnonzero(raw == 10)
-    starts = np.concatenate(([0], nl + 1))
-    ends = np.concatenate((nl, [raw.size]))
-    if starts[-1] >= raw.size:          # file ends with '\n'
-        starts, ends = starts[:-1], ends[:-1]
-    # strip '\r'
-    has_cr = (ends > starts) & (raw[np.maximum(ends - 1, 0)] == 13)
-    ends = ends - has_cr.astype(ends.dtype)
-    return starts.astype(np.int64), ends.astype(np.int64)
-
-
-def _fastq_fast(raw: np.ndarray):
-    """Strict 4-line FASTQ: sequences are used in place (offsets into the file buffer).  Returns None when the
-    file is not in that shape (wrapped records, blank lines) so that the general parser takes over."""
-    if raw.size == 0:
-        return SequenceBatch([], raw, np.zeros(0, np.uint64), np.zeros(0, np.uint64))
-    starts, ends = _line_bounds(raw)
-    # drop trailing blank lines
-    n = starts.size
-    while n and ends[n - 1] == starts[n - 1]:
-        n -= 1
-    starts, ends = starts[:n], ends[:n]
-    if n == 0 or n % 4:
-        return None
-    t, s, p, q = (slice(i, None, 4) for i in range(4))
-    if not (np.all(raw[starts[t]] == ord("@")) and np.all(ends[p] > starts[p]) and np.all(raw[starts[p]] == ord("+"))):
-        return None
-    if not np.array_equal(ends[s] - starts[s], ends[q] - starts[q]):
-        return None
-    seq_b, seq_e = starts[s], ends[s]
-    # embedded blanks inside a sequence line are rare; the general parser handles them
-    ids = _first_words(raw, starts[t] + 1, ends[t])
-    return SequenceBatch(ids, raw, seq_b.astype(np.uint64), seq_e.astype(np.uint64))
-
-
-def _fasta_fast(raw: np.ndarray) -> SequenceBatch:
-    """FASTA with wrapped lines: sequence bytes are compacted into one buffer (newlines, '\\r', blanks removed)."""
-    if raw.size == 0:
-        return SequenceBatch([], raw, np.zeros(0, np.uint64), np.zeros(0, np.uint64))
-    starts, ends = _line_bounds(raw)
-    is_title = (ends > starts) & (raw[np.minimum(starts, raw.size - 1)] == ord(">"))
-    title_idx = np.flatnonzero(is_title)
-    if title_idx.size == 0:
-        return SequenceBatch([], np.zeros(0, np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint64))
-    # bytes that belong to sequences: not in a title line, after the first title, not whitespace
-    keep = np.ones(raw.size, dtype=bool)
-    keep[: starts[title_idx[0]]] = False
-    title_mark = np.zeros(raw.size + 1, dtype=np.int32)
-    np.add.at(title_mark, starts[title_idx], 1)
-    np.add.at(title_mark, np.minimum(ends[title_idx] + 1, raw.size), -1)
-    keep &= np.cumsum(title_mark[:-1]) == 0
-    keep &= (raw != 10) & (raw != 13) & (raw != 32)
-    bases = raw[keep]
-    kept_before = np.concatenate(([0], np.cumsum(keep, dtype=np.int64)))
-    rec_start = kept_before[starts[title_idx]]
-    rec_end = np.concatenate((rec_start[1:], [bases.size]))
-    ids = _first_words(raw, starts[title_idx] + 1, ends[title_idx])
-    return SequenceBatch(ids, np.ascontiguousarray(bases), rec_start.astype(np.uint64), rec_end.astype(np.uint64))
+            return pinned_empty(n, np.uint8)
+        except Exception:
+            pass
+    return np.empty(n, np.uint8)
