@@ -129,6 +129,15 @@ int xs_cobs_query_device(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
                          const uint64_t* d_seq_begin, const uint64_t* d_seq_end, uint64_t n_seq,
                          uint32_t step, int out_dtype, void* d_out, void* stream);
 
+/* The same query with the score epilogue applied on the device (host buffers in and out): per record the first
+ * document holding the maximum count, that count and how many documents share it, plus totals[d] = sum of the
+ * counts of document d over all records (uint64 [n_local]).  Counts are kept as uint32 on the device; only 12
+ * bytes per record come back instead of the count matrix.  Replaces the host loops that derive read-level
+ * calls (scripts/benchmark/main.nf:417-436) and ModelResult.get_total_hits (models/result.py:76-90). */
+int xs_cobs_classify(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const uint64_t* seq_begin,
+                     const uint64_t* seq_end, uint64_t n_seq, uint32_t step, uint32_t* best, uint32_t* best_count,
+                     uint32_t* n_best, uint64_t* totals);
+
 /* Result order of cobs Search.search (what _convert_cobs_result_to_dict iterates,
  * probabilistic_filter_model.py:393-409; MLST tie-breaks, probabilistic_filter_mlst_model.py:254-256,284):
  * all documents, std::partial_sort by score descending.  Host-only helper. */

@@ -174,13 +174,17 @@ def api(td: Path):
     best, tie = res.argmax()
     totals = res.total_hits()
     t3 = time.perf_counter()
+    summ = model.predict_summary(batch)
+    t4 = time.perf_counter()
+    assert np.array_equal(np.asarray(summ["best"]), best.astype(np.uint32)) and summ["total_hits"] == totals
     sample = 5000
     hb, he = batch.begin[:sample], batch.end[:sample]
     exp = oracle.CobsOracle(model.get_cobs_index_path()).counts_batch(batch.bases, hb, he, 1, threads=8)
     assert np.array_equal(np.asarray(res.counts[:sample]).astype(np.uint32), exp)
     print(json.dumps({"config": "API: 2M-read FASTQ file -> ProbabilisticFilterModel.predict_arrays (D=90 test model)",
                       "file_MB": fq.stat().st_size / 1e6, "parse_s": t1 - t0, "query_s": t2 - t1, "argmax_totals_host_s": t3 - t2,
-                      "reads_per_sec_file_to_counts": n_reads / (t2 - t0), "parity_sample_reads": sample}), flush=True)
+                      "reads_per_sec_file_to_counts": n_reads / (t2 - t0),
+                      "summary_on_device_s": t4 - t3, "reads_per_sec_file_to_calls": n_reads / ((t1 - t0) + (t4 - t3)), "parity_sample_reads": sample}), flush=True)
 
 
 if __name__ == "__main__":

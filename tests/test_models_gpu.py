@@ -114,6 +114,27 @@ def test_species_predict_arrays(world, oracle, tmp_path):
     assert best.shape == tie.shape == (len(recs),)
 
 
+def test_species_predict_summary_matches_predict(world, oracle, tmp_path):
+    from xspect2_b200.models.probabilistic_filter_model import ProbabilisticFilterModel
+    model = ProbabilisticFilterModel.load(world["sp_json"])
+    recs = [r for r in _records(world, 300) if r[0] != "read3"]          # unique ids: totals comparable
+    fq = tmp_path / "in.fq"
+    mf.write_fastq(fq, recs)
+    for step in (1, 2):
+        summ = model.predict_summary(fq, step=step)
+        res = model.predict(fq, step=step)
+        assert summ["batch"].ids == [r[0] for r in recs] and summ["labels"] == model.index.index.names
+        assert summ["total_hits"] == {lab: res.get_total_hits()[lab] for lab in summ["labels"]}
+        assert summ["total_scores"] == {lab: res.get_scores()["total"][lab] for lab in summ["labels"]}
+        for i, (rid, _) in enumerate(recs):
+            h = res.hits[rid]
+            mx = max(h.values())
+            winners = [lab for lab in summ["labels"] if h[lab] == mx]
+            assert summ["labels"][int(summ["best"][i])] == winners[0]
+            assert int(summ["best_hits"][i]) == mx and bool(summ["ambiguous"][i]) == (len(winners) > 1)
+            assert int(summ["num_kmers"][i]) == res.num_kmers[rid]
+
+
 # ------------------------------------------------------------------------------ SVM model
 def test_svm_prediction_matches_reference_flow(world, oracle, tmp_path):
     from sklearn.svm import SVC

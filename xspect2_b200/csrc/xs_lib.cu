@@ -447,7 +447,9 @@ static HostBatchPlan plan_batch(const uint64_t* b, const uint64_t* e, uint64_t n
 
 template <typename QueryFn>
 static int host_pipeline(const uint8_t* bases, uint64_t n_bases, const uint64_t* seq_begin, const uint64_t* seq_end,
-                         uint64_t n_seq, uint64_t out_row_bytes, uint8_t* out, QueryFn query) {
+                         uint64_t n_seq, uint64_t out_row_bytes, QueryFn query) {
+    // query(d_bases, span, d_begin, d_end, n, base_shift, d_out /* n * out_row_bytes */, first_seq, stream) enqueues the
+    // kernels of one batch and the device->host copies of its results
     const int NS = 3;
     const uint64_t MAX_SPAN = 64ULL << 20;
     const uint64_t MAX_OUT = 256ULL << 20;
@@ -472,11 +474,10 @@ static int host_pipeline(const uint8_t* bases, uint64_t n_bases, const uint64_t*
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, seq_begin + pl.i0, ns * 8, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_e, seq_end + pl.i0, ns * 8, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e)); break; }
-        rc = query(d + o_b, span, d_b, d_e, ns, pl.lo, d + o_o, s);
+        rc = query(d + o_b, span, d_b, d_e, ns, pl.lo, d + o_o, pl.i0, s);
         if (rc != XS_OK) break;
-        e = cudaMemcpyAsync(out + pl.i0 * out_row_bytes, d + o_o, ns * out_row_bytes, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaFreeAsync(d, s);
-        if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, std::string("D2H copy: ") + cudaGetErrorString(e)); break; }
+        e = cudaFreeAsync(d, s);
+        if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, std::string("batch buffers: ") + cudaGetErrorString(e)); break; }
         i0 = pl.i1; ++bi;
     }
     for (int i = 0; i < NS; ++i) {
@@ -692,11 +693,53 @@ int xs_cobs_query(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const uin
     DeviceGuard guard(ix->info.device);
     if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the index's device");
     const uint64_t ld = ix->info.doc_end - ix->info.doc_begin;
-    return host_pipeline(bases, n_bases, seq_begin, seq_end, n_seq, ld * (uint64_t)out_dtype, (uint8_t*)out,
+    const uint64_t row = ld * (uint64_t)out_dtype;
+    return host_pipeline(bases, n_bases, seq_begin, seq_end, n_seq, row,
                          [&](const uint8_t* db, uint64_t span, const uint64_t* d_b, const uint64_t* d_e, uint64_t ns,
-                             uint64_t shift, uint8_t* d_o, cudaStream_t s) {
-                             return cobs_query_dev(ix, db, span, d_b, d_e, ns, shift, step, out_dtype, d_o, s);
+                             uint64_t shift, uint8_t* d_o, uint64_t i0, cudaStream_t s) {
+                             XS_TRY(cobs_query_dev(ix, db, span, d_b, d_e, ns, shift, step, out_dtype, d_o, s));
+                             XS_CUDA(cudaMemcpyAsync((uint8_t*)out + i0 * row, d_o, ns * row, cudaMemcpyDeviceToHost, s));
+                             return (int)XS_OK;
                          });
+}
+
+int xs_cobs_classify(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const uint64_t* seq_begin,
+                     const uint64_t* seq_end, uint64_t n_seq, uint32_t step, uint32_t* best, uint32_t* best_count,
+                     uint32_t* n_best, uint64_t* totals) {
+    if (!ix || (n_seq && (!seq_begin || !seq_end || !best || !best_count || !n_best)) || (n_bases && !bases) || !totals)
+        return fail(XS_ERR_ARG, "NULL argument");
+    if (step == 0) return fail(XS_ERR_ARG, "step must be >= 1");
+    DeviceGuard guard(ix->info.device);
+    if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the index's device");
+    const uint64_t ld = ix->info.doc_end - ix->info.doc_begin;
+    // counts stay on the device as uint32 (no saturation whatever the record length); only 12 bytes per record
+    // and the per-document totals come back
+    uint64_t* d_tot = nullptr;
+    XS_CUDA(cudaMalloc((void**)&d_tot, ld * 8));
+    XS_CUDA(cudaMemset(d_tot, 0, ld * 8));
+    const uint64_t row = ld * 4 + 12;
+    int rc = host_pipeline(bases, n_bases, seq_begin, seq_end, n_seq, row,
+                           [&](const uint8_t* db, uint64_t span, const uint64_t* d_b, const uint64_t* d_e, uint64_t ns,
+                               uint64_t shift, uint8_t* d_o, uint64_t i0, cudaStream_t s) {
+                               uint32_t* d_best = reinterpret_cast<uint32_t*>(d_o + ns * ld * 4);
+                               uint32_t* d_cnt = d_best + ns;
+                               uint32_t* d_nb = d_cnt + ns;
+                               XS_TRY(cobs_query_dev(ix, db, span, d_b, d_e, ns, shift, step, XS_U32, d_o, s));
+                               unsigned grid = (unsigned)std::min<uint64_t>((ns + REDUCE_ROWS - 1) / REDUCE_ROWS, (uint64_t)ix->n_sm * 8);
+                               k_scores_reduce<uint32_t><<<grid, REDUCE_NT, 0, s>>>((const uint32_t*)d_o, ns, (uint32_t)ld, d_best, d_cnt, d_nb,
+                                                                                    reinterpret_cast<unsigned long long*>(d_tot));
+                               XS_TRY(launch_ok("k_scores_reduce"));
+                               XS_CUDA(cudaMemcpyAsync(best + i0, d_best, ns * 4, cudaMemcpyDeviceToHost, s));
+                               XS_CUDA(cudaMemcpyAsync(best_count + i0, d_cnt, ns * 4, cudaMemcpyDeviceToHost, s));
+                               XS_CUDA(cudaMemcpyAsync(n_best + i0, d_nb, ns * 4, cudaMemcpyDeviceToHost, s));
+                               return (int)XS_OK;
+                           });
+    if (rc == XS_OK) {
+        cudaError_t e = cudaMemcpy(totals, d_tot, ld * 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("totals copy: ") + cudaGetErrorString(e));
+    }
+    cudaFree(d_tot);
+    return rc;
 }
 
 int xs_cobs_result_order(const uint32_t* scores, uint32_t n_docs, uint32_t* order) {
@@ -803,10 +846,12 @@ int xs_bloom_query(xs_bloom* bf, const uint8_t* bases, uint64_t n_bases, const u
     if (step == 0) return fail(XS_ERR_ARG, "step must be >= 1");
     DeviceGuard guard(bf->info.device);
     if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the filter's device");
-    return host_pipeline(bases, n_bases, seq_begin, seq_end, n_seq, 4, (uint8_t*)out_hits,
+    return host_pipeline(bases, n_bases, seq_begin, seq_end, n_seq, 4,
                          [&](const uint8_t* db, uint64_t span, const uint64_t* d_b, const uint64_t* d_e, uint64_t ns,
-                             uint64_t shift, uint8_t* d_o, cudaStream_t s) {
-                             return bloom_query_dev(bf, db, span, d_b, d_e, ns, shift, step, (uint32_t*)d_o, s);
+                             uint64_t shift, uint8_t* d_o, uint64_t i0, cudaStream_t s) {
+                             XS_TRY(bloom_query_dev(bf, db, span, d_b, d_e, ns, shift, step, (uint32_t*)d_o, s));
+                             XS_CUDA(cudaMemcpyAsync(out_hits + i0, d_o, ns * 4, cudaMemcpyDeviceToHost, s));
+                             return (int)XS_OK;
                          });
 }
 

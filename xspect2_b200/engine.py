@@ -23,13 +23,33 @@ _DT = {XS_U8: np.uint8, XS_U16: np.uint16, XS_U32: np.uint32}
 # --------------------------------------------------------------------------------------
 # pinned host memory
 # --------------------------------------------------------------------------------------
+_POOL: dict[int, list[int]] = {}      # capacity -> free page-locked pointers (cudaMallocHost costs ~0.5 ms per MB)
+_POOL_BYTES = [0]
+_POOL_LIMIT = 8 << 30
+
+
+def _capacity(nbytes: int) -> int:
+    n = max(int(nbytes), 1)
+    if n <= (1 << 20):
+        return 1 << 20
+    step = 1 << (n.bit_length() - 3)      # 8 size classes per power of two: at most 12.5 % slack
+    return -(-n // step) * step
+
+
 class _PinnedBlock:
-    """Page-locked host allocation (xs_host_alloc) exposed through the array interface."""
+    """Page-locked host allocation (xs_host_alloc) exposed through the array interface; recycled through a small
+    pool when the array that owns it is collected."""
 
     def __init__(self, nbytes: int):
-        p = C.c_void_p()
-        check(lib().xs_host_alloc(max(int(nbytes), 1), C.byref(p)))
-        self.ptr = p.value
+        self.cap = _capacity(nbytes)
+        free = _POOL.get(self.cap)
+        if free:
+            self.ptr = free.pop()
+            _POOL_BYTES[0] -= self.cap
+        else:
+            p = C.c_void_p()
+            check(lib().xs_host_alloc(self.cap, C.byref(p)))
+            self.ptr = p.value
         self.nbytes = int(nbytes)
         self.__array_interface__ = {"shape": (max(self.nbytes, 1),), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
 
@@ -37,7 +57,11 @@ class _PinnedBlock:
         ptr, self.ptr = getattr(self, "ptr", None), None
         if ptr:
             try:
-                lib().xs_host_free(ptr)
+                if _POOL_BYTES[0] + self.cap <= _POOL_LIMIT:
+                    _POOL.setdefault(self.cap, []).append(ptr)
+                    _POOL_BYTES[0] += self.cap
+                else:
+                    lib().xs_host_free(ptr)
             except Exception:  # interpreter shutdown
                 pass
 
@@ -139,6 +163,19 @@ class CobsIndex:
             raise ValueError("out has the wrong dtype/shape")
         check(lib().xs_cobs_query(self._h, _ptr(bases), bases.size, _ptr(b), _ptr(e), n, int(step), int(dtype), _ptr(out)))
         return out
+
+    def classify(self, bases, seq_begin, seq_end, step: int = 1):
+        """Read-level calls without the count matrix: ``(best, best_count, n_best, totals)`` — first document with
+        the maximum count per record, that count, how many documents share it (> 1 = ambiguous), and per-document
+        totals over all records.  The epilogue runs on the device; 12 bytes per record come back."""
+        bases = _as_bases(bases)
+        b, e = _as_u64(seq_begin), _as_u64(seq_end)
+        n = b.size
+        best, cnt, nb = (pinned_empty((n,), np.uint32) for _ in range(3))
+        totals = np.zeros(self.n_docs, np.uint64)
+        check(lib().xs_cobs_classify(self._h, _ptr(bases), bases.size, _ptr(b), _ptr(e), n, int(step), _ptr(best), _ptr(cnt),
+                                     _ptr(nb), _ptr(totals)))
+        return best, cnt, nb, totals
 
     def query_device(self, d_bases: int, n_bases: int, d_begin: int, d_end: int, n_seq: int, step: int, dtype: int,
                      d_out: int, stream: int = 0) -> None:

@@ -200,6 +200,25 @@ class ProbabilisticFilterModel:
         num_kmers = -((batch.lengths - self.k + 1) // -step)
         return BatchHits(batch.ids, ix.names, counts, num_kmers, step)
 
+    def predict_summary(self, sequence_input, step: int = 1) -> dict:
+        """Read-level calls and file-level scores without the per-record dictionaries: the device takes the argmax
+        per record (ties flagged, the rule of scripts/benchmark/main.nf:417-436) and the per-document totals.
+        Returns ``{"batch", "labels", "best", "best_hits", "ambiguous", "num_kmers", "total_hits", "total_scores"}``
+        (record ids are ``result["batch"].ids``, decoded on first use);
+        ``total_scores`` equals ``ModelResult.get_scores()["total"]`` for input without duplicate ids."""
+        batch = sequence_input if isinstance(sequence_input, SequenceBatch) else self._to_batch(sequence_input)
+        self._check_lengths(batch)
+        ix = self.index.index
+        best, cnt, nb, totals = ix.classify(batch.bases, batch.begin, batch.end, step)
+        num_kmers = -((batch.lengths - self.k + 1) // -step)
+        total_kmers = int(num_kmers.sum())
+        total_hits = {n: int(v) for n, v in zip(ix.names, totals)}
+        return {
+            "batch": batch, "labels": ix.names, "best": best, "best_hits": cnt, "ambiguous": nb > 1, "num_kmers": num_kmers,
+            "total_hits": total_hits,
+            "total_scores": {n: round(v / total_kmers, 2) for n, v in total_hits.items()} if total_kmers else {},
+        }
+
     def _score_batch(self, batch: SequenceBatch, exclude_ids, step: int) -> tuple[dict, dict]:
         hits, num_kmers = self.predict_arrays(batch, step).to_hits()
         if exclude_ids:
