@@ -274,3 +274,13 @@ def test_native_reader_many_records_matches_iterators(tmp_path):
     bad.write_text("ACGT\n")
     with pytest.raises(ValueError, match="should start with '@'"):
         SequenceBatch.from_file(bad)
+
+
+def test_min_hits_table_is_exact():
+    """The integer threshold table reproduces `round(hits / num_kmers, 2) >= threshold` (result.py:59,92-123)."""
+    from xspect2_b200.pipeline import min_hits_table
+    for thr in (0.0, 0.005, 0.01, 0.5, 0.7, 0.85, 0.995, 1.0):
+        t = min_hits_table(400, thr)
+        for n in list(range(1, 140)) + [150, 199, 200, 399, 400]:
+            for h in range(n + 1):
+                assert (h >= t[n]) == (round(h / n, 2) >= thr), (thr, n, h)

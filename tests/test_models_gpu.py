@@ -190,6 +190,50 @@ def test_genus_predict_matches_reference_loop(world, oracle, tmp_path):
         model.calculate_hits(Seq("ACGT"))
 
 
+# ------------------------------------------------------------------------------ fused two-stage pipeline
+def test_genus_then_species_matches_the_file_based_stages(world, oracle, tmp_path):
+    """pipeline.genus_then_species == filter_genus (threshold on rounded scores) followed by species predict on
+    the kept records (main.py:108-145), without writing the filtered FASTA."""
+    from xspect2_b200.models.probabilistic_filter_svm_model import ProbabilisticFilterSVMModel
+    from xspect2_b200.models.probabilistic_single_filter_model import ProbabilisticSingleFilterModel
+    from xspect2_b200.pipeline import genus_then_species
+    from xspect2_b200.seqio import Seq, SeqRecord
+    genus = ProbabilisticSingleFilterModel.load(world["ge_json"])
+    species = ProbabilisticFilterSVMModel.load(world["sp_json"])
+    rng = np.random.default_rng(4)
+    gl = list(world["genomes"].values())
+    recs = []
+    for i in range(400):
+        L = int(rng.integers(40, 300))
+        if i % 3 == 0:
+            s = synth.random_dna(rng, L)
+        else:
+            g = gl[1]
+            st = int(rng.integers(0, g.size - L))
+            s = synth.mutate(rng, g[st:st + L], sub=float(rng.choice([0.0, 0.01, 0.03, 0.06])))
+        recs.append((f"r{i}", s.tobytes().decode()))
+    fq = tmp_path / "in.fastq"
+    mf.write_fastq(fq, recs)
+    for thr, step in ((0.7, 1), (0.3, 2), (1.0, 1)):
+        out = genus_then_species(genus, species, fq, threshold=thr, step=step)
+        gres = genus.predict(fq, step=step)
+        kept_ids = gres.get_filtered_subsequence_labels("Testgenus", thr)
+        assert [rid for rid, keep in zip(out["batch"].ids, out["kept"]) if keep] == kept_ids
+        assert {rid: {"Testgenus": int(h)} for rid, h in zip(out["batch"].ids, out["genus_hits"])} == gres.hits
+        if not kept_ids:
+            assert out["prediction"] is None
+            continue
+        kept_recs = [SeqRecord(Seq(s), rid) for rid, s in recs if rid in set(kept_ids)]
+        sres = species.predict(kept_recs, step=step)
+        assert out["total_hits"] == {lab: sres.get_total_hits()[lab] for lab in out["labels"]}
+        assert out["total_scores"] == {lab: sres.get_scores()["total"][lab] for lab in out["labels"]}
+        assert out["prediction"] == sres.prediction
+        for j, rid in enumerate(kept_ids[:100]):
+            h = sres.hits[rid]
+            assert int(out["best_hits"][j]) == max(h.values())
+    assert len(kept_ids) == 0 or thr < 1.0 or all(gres.get_scores()[r]["Testgenus"] == 1.0 for r in kept_ids)
+
+
 # ------------------------------------------------------------------------------ MLST model
 class FakePubMLST:
     def __init__(self):
