@@ -148,6 +148,74 @@ def wide(td: Path):
                       "parity_sample_reads": sample}), flush=True)
 
 
+def twostage(td: Path):
+    """Config 3 on one GPU: genus Bloom -> threshold 0.7 -> species COBS (+SVM) on 10 M reads, fused on the device."""
+    import bench
+    from xspect2_b200.models.probabilistic_filter_svm_model import ProbabilisticFilterSVMModel
+    from xspect2_b200.models.probabilistic_single_filter_model import ProbabilisticSingleFilterModel
+    from xspect2_b200.pipeline import genus_then_species
+    from xspect2_b200.seqio import SequenceBatch
+    n_reads, L, k = 10_000_000, 150, 21
+    models = td / "models"
+    (models / "synth-species").mkdir(parents=True)
+    (models / "synth-genus").mkdir(parents=True)
+    genome = synth.synth_genome(bench.GENOME_LEN, seed=1, n_rate=0.0001)
+    rows, valid = engine.kmer_rows(genome, bench.K, bench.H, bench.SIG_SIZE)
+    rows = rows[valid.astype(bool)]
+    names = synth.write_classic_index(models / "synth-species" / "index.cobs_classic", n_docs=bench.D, k=k, num_hashes=bench.H,
+                                      sig_size=bench.SIG_SIZE, seed=2, plant={0: rows.reshape(-1), 1: rows[: int(rows.shape[0] * 0.63)].reshape(-1)},
+                                      device=dev)
+    rng = np.random.default_rng(3)
+    with open(models / "synth-species" / "scores.csv", "w") as f:
+        f.write("file," + ",".join(sorted(names)) + ",label_id\n")
+        for i, lab in enumerate(sorted(names)):
+            for rep in range(4):
+                x = np.round(rng.uniform(0, 0.2, size=len(names)), 2)
+                x[i] = round(1.0 - 0.05 * rep, 2)
+                f.write(f"acc{i}_{rep}," + ",".join(str(v) for v in x) + f",{lab}\n")
+    meta = {"model_slug": "synth-species", "k": k, "model_display_name": "Synth", "author": None, "author_email": None,
+            "model_type": "Species", "model_class": "ProbabilisticFilterSVMModel", "display_names": {n: f"Synth sp{n}" for n in names},
+            "fpr": 0.01, "num_hashes": 7, "training_accessions": None, "kernel": "rbf", "C": 1.0, "svm_accessions": None}
+    (models / "synth-species.json").write_text(json.dumps(meta))
+    n_bytes = 13_800_000_008 // 8
+    gen = torch.Generator(device=dev).manual_seed(11)
+    bits = torch.randint(0, 256, (n_bytes,), generator=gen, device=dev, dtype=torch.uint8).cpu().numpy()
+    bt = oracle._BloomT(bits.ctypes.data, n_bytes * 8, 6, k)
+    oracle.lib().xso_bloom_insert(oracle.C.byref(bt), bits.ctypes.data, genome.ctypes.data, genome.size)
+    with open(models / "synth-genus" / "filter.bloom", "wb") as f:
+        f.write(struct.pack("<Q", 6))
+        f.write(bits.tobytes())
+    del bits
+    gmeta = {"model_slug": "synth-genus", "k": k, "model_display_name": "Synth", "author": None, "author_email": None,
+             "model_type": "Genus", "model_class": "ProbabilisticSingleFilterModel", "display_names": {"Synth": "Synth"},
+             "fpr": 0.01, "num_hashes": 1, "training_accessions": None}
+    (models / "synth-genus.json").write_text(json.dumps(gmeta))
+    genus = ProbabilisticSingleFilterModel.load(models / "synth-genus.json")
+    species = ProbabilisticFilterSVMModel.load(models / "synth-species.json")
+    reads = synth.synth_reads(genome, n_reads, L, seed=4, device=dev)
+    h_bases = engine.pinned_empty(n_reads * L, np.uint8)
+    torch.from_numpy(h_bases).copy_(reads)
+    del reads
+    hb, he = synth.fixed_offsets(n_reads, L)
+    batch = SequenceBatch(None, h_bases, hb, he, None, np.zeros(0, np.uint8), np.zeros(n_reads, np.uint64))
+    genus_then_species(genus, species, batch, 0.7, 1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = genus_then_species(genus, species, batch, 0.7, 1)
+    dt = time.perf_counter() - t0
+    kept = int(out["kept"].sum())
+    # parity of both stages on a sample
+    sample = 20000
+    eg = oracle.BloomOracle(models / "synth-genus" / "filter.bloom", k).hits_batch(h_bases, hb[:sample], he[:sample], 1, threads=8)
+    assert np.array_equal(out["genus_hits"][:sample], eg)
+    ki = out["kept_index"][:2000]
+    es = oracle.CobsOracle(models / "synth-species" / "index.cobs_classic").counts_batch(h_bases, hb[ki], he[ki], 1, threads=8)
+    assert np.array_equal(out["best_hits"][:2000], es.max(axis=1)) and np.array_equal(out["best"][:2000], es.argmax(axis=1))
+    print(json.dumps({"config": "cfg3 on one GPU: 10M x 150bp reads, genus Bloom (13.8e9 bits) -> keep score >= 0.7 -> species COBS D=90 + SVM, fused",
+                      "s_per_pass": dt, "reads_per_sec": n_reads / dt, "kept_reads": kept, "prediction": out["prediction"],
+                      "lookups_per_sec": (n_reads + kept) * (L - k + 1) / dt, "note": "host (pinned) reads in, calls/totals/prediction out"}), flush=True)
+
+
 def api(td: Path):
     """FASTQ on disk -> per-read counts through the model API (native reader + batched query), vs the numbers above."""
     rng = np.random.default_rng(9)
@@ -188,9 +256,9 @@ def api(td: Path):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["bloom", "mlst", "wide", "api"]
+    which = sys.argv[1:] or ["bloom", "mlst", "wide", "api", "twostage"]
     with tempfile.TemporaryDirectory() as td:
         for w in which:
             sub = Path(td) / w
             sub.mkdir()
-            {"bloom": bloom, "mlst": mlst, "wide": wide, "api": api}[w](sub)
+            {"bloom": bloom, "mlst": mlst, "wide": wide, "api": api, "twostage": twostage}[w](sub)
