@@ -167,7 +167,7 @@ def run_reference(args, rank: int, world: int) -> None:
         line = {
             "impl": "reference", "metric": "kmer_lookups_per_sec", "value": v, "unit": "lookups/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64 hash / u8 rows", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "reads_per_sec": n_sample * args.steps / dt,
             "config": {"workload": WORKLOAD, "step": f"bounded sample: first {n_sample} reads per step on the host cores"},
             "cpu_baseline": {"value": v, "unit": "lookups/s", "cores": threads, "kind": "port",
@@ -280,7 +280,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             "metric": "kmer_lookups_per_sec", "value": value, "unit": "lookups/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64 hash / u8 rows", "data": "synthetic",
+            "dtype": "u64", "data": "synthetic",
             "reads_per_sec": world * N_READS * args.steps / (ms / 1e3),
             "config": {"workload": WORKLOAD, "reads_per_gpu": N_READS, "index": "replicated per GPU",
                        "parallelism": f"read-sharded x{world}, no data-path collective",
