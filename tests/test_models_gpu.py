@@ -308,6 +308,52 @@ def test_mlst_calculate_hits_matches_reference_flow(world, oracle):
         model.predict("x")
 
 
+def test_mlst_predict_file_batches_records(world, oracle, tmp_path):
+    """predict(Path) scores all records of a file in one query per locus; per-record results equal the
+    single-record path and the oracle's chunk loop."""
+    from xspect2_b200.models.probabilistic_filter_mlst_model import ProbabilisticFilterMlstSchemeModel
+    from xspect2_b200.seqio import Seq
+    model = ProbabilisticFilterMlstSchemeModel.load(world["ml_json"])
+    model.pubmlst_handler = FakePubMLST()
+    rng = np.random.default_rng(77)
+    loci = list(model.loci)
+    al = world["alleles"]
+    a1 = al[loci[1]]["Allele_ID_2"]
+
+    def contig(ids, pads):
+        parts = [synth.random_dna(rng, pads[0])]
+        for locus, aid, pad in zip(loci, ids, pads[1:]):
+            parts += [al[locus][f"Allele_ID_{aid}"], synth.random_dna(rng, pad)]
+        return np.concatenate(parts).tobytes().decode()
+
+    recs = [
+        ("contig1", contig((9, 3, 17), (6000, 2500, 1800, 8000))),
+        ("allele_only", a1.tobytes().decode()),
+        ("contig2", contig((30, 2, 5), (11000, 700, 5000, 3003))),
+        ("short_random", synth.random_dna(rng, 900).tobytes().decode()),
+    ]
+    fa = tmp_path / "asm.fna"
+    mf.write_fasta(fa, recs)
+    res = model.predict(fa)
+    assert list(res.hits) == [r[0] for r in recs] and res.to_dict()["Scheme"] == "Oxford"
+    for rid, s in recs:
+        single = model.calculate_hits(Seq(s))
+        assert res.hits[rid] == single
+        highest, allres = _mlst_reference(oracle, model, s)
+        got_high = {key: v for key, v in res.hits[rid][0]["Strain type"].items() if key not in ("ST_Name", "Attention:")}
+        assert got_high == highest and list(got_high.items()) == list(highest.items())
+        assert res.hits[rid][1]["All results"] == allres
+    with pytest.raises(ValueError, match="longer than k"):
+        bad = tmp_path / "bad.fna"
+        mf.write_fasta(bad, recs[:1] + [("tiny", "ACGTACGT")])
+        model.predict(bad)
+    # bug-compatible: a long record that matches one locus well and another not at all makes the reference's
+    # ST lookup fail on int("N/A") (probabilistic_filter_mlst_model.py:259-260,296-299)
+    lonely = np.concatenate([synth.random_dna(rng, 9000), al[loci[0]]["Allele_ID_9"], synth.random_dna(rng, 9000)]).tobytes().decode()
+    with pytest.raises(ValueError, match="invalid literal"):
+        model.calculate_hits(Seq(lonely))
+
+
 # ------------------------------------------------------------------------------ workflows + CLI
 def test_workflows_and_cli(world, oracle, tmp_path, monkeypatch):
     monkeypatch.setenv("HOME", str(world["root"].parent))

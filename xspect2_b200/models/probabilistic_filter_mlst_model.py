@@ -150,45 +150,60 @@ class ProbabilisticFilterMlstSchemeModel(ProbabilisticFilterModel):
         """Allele -> score of one search, keeping scores > 50 only when ``kmer_threshold`` (reference :362-380)."""
         return {r.doc_name: r.score for r in cobs_result if not kmer_threshold or r.score > 50}
 
-    def _locus_long(self, search: "engine.Search", seq_bytes: np.ndarray, allele_len: int, step: int) -> dict:
-        """Per-allele sum over chunks of the chunk scores > 50, ordered like the reference's dict: first
-        appearance (chunk order, cobs result order inside a chunk), then a stable sort by -score."""
-        ix = search.index
-        bases, begin, end = self._chunk_segments(seq_bytes, allele_len)
-        counts = ix.query(bases, begin, end, step=step)
-        keep = counts > 50
-        rows = np.flatnonzero(keep.any(axis=1))
-        all_counts: dict[str, int] = {}
-        if rows.size:
-            sub = np.ascontiguousarray(counts[rows]).astype(np.uint32)
-            order = engine.result_order_batch(sub)
+    def _score_records(self, seqs: list[np.ndarray], step: int) -> list[list[dict]]:
+        """``out[record][locus]`` = allele -> score in the reference's dict order, for all records at once: one
+        batched query per locus over every chunk of every record (records >= 10000 bp are chunked, :236-256;
+        shorter ones are searched whole, :272-286)."""
+        out = [[None] * len(self.indices) for _ in seqs]
+        for li, search in enumerate(self.indices):
+            ix = search.index
             names = ix.names
-            for r in range(rows.size):
-                row = sub[r]
-                for j in order[r].tolist():
-                    v = int(row[j])
-                    if v > 50:
-                        all_counts[names[j]] = all_counts.get(names[j], 0) + v
-        return dict(sorted(all_counts.items(), key=lambda item: -item[1]))
+            parts, begins, ends, owner = [], [], [], []
+            off = 0
+            for ri, sb in enumerate(seqs):
+                if sb.size >= 10000:
+                    bases, b, e = self._chunk_segments(sb, self.avg_locus_bp_size[li])
+                else:
+                    bases, b, e = sb, np.zeros(1, np.uint64), np.array([sb.size], np.uint64)
+                parts.append(bases)
+                begins.append(b + np.uint64(off))
+                ends.append(e + np.uint64(off))
+                owner.append(np.full(b.size, ri, dtype=np.int64))
+                off += bases.size
+            counts = ix.query(np.concatenate(parts), np.concatenate(begins), np.concatenate(ends), step=step)
+            owner = np.concatenate(owner)
+            first = np.searchsorted(owner, np.arange(len(seqs)), side="left")
+            last = np.searchsorted(owner, np.arange(len(seqs)), side="right")
+            for ri, sb in enumerate(seqs):
+                rows = np.asarray(counts[first[ri]:last[ri]])
+                if sb.size >= 10000:
+                    # per-allele sum over chunks of the chunk scores > 50; dict order = first appearance (chunk order,
+                    # cobs result order inside a chunk), then a stable sort by -score
+                    all_counts: dict[str, int] = {}
+                    hot = np.flatnonzero((rows > 50).any(axis=1))
+                    if hot.size:
+                        sub = np.ascontiguousarray(rows[hot]).astype(np.uint32)
+                        order = engine.result_order_batch(sub)
+                        for r in range(hot.size):
+                            row = sub[r]
+                            for j in order[r].tolist():
+                                v = int(row[j])
+                                if v > 50:
+                                    all_counts[names[j]] = all_counts.get(names[j], 0) + v
+                    out[ri][li] = dict(sorted(all_counts.items(), key=lambda item: -item[1]))
+                else:
+                    row = rows[0].astype(np.uint32)
+                    out[ri][li] = {names[j]: int(row[j]) for j in engine.CobsIndex.result_order(row).tolist()}
+        return out
 
-    def calculate_hits(self, sequence: Seq, step: int = 1, limit: bool = False, limit_number: int = 5) -> list[dict]:
-        """Best allele per locus and all allele scores for one sequence (reference :192-303)."""
-        if not seqio.is_seq(sequence):
-            raise ValueError("Invalid sequence, must be a Bio.Seq object")
-        if not len(sequence) > self.k:
-            raise ValueError("Invalid sequence, must be longer than k")
-        if not self.indices:
-            raise ValueError("The model has not been trained yet")
-
+    def _assemble(self, seq_len: int, per_locus: list[dict], limit: bool, limit_number: int) -> list[dict]:
+        """The result structure of calculate_hits from per-locus allele scores (reference :257-303)."""
         loci = list(self.loci.keys())
         result_dict = {}
         highest_results = {}
-        if len(sequence) >= 10000:
-            seq_bytes = np.frombuffer(str(sequence).encode("ascii", "replace"), dtype=np.uint8)
-            for counter, search in enumerate(self.indices):
-                sorted_counts = self._locus_long(search, seq_bytes, self.avg_locus_bp_size[counter], step)
-                if limit:
-                    sorted_counts = dict(list(sorted_counts.items())[:limit_number])
+        for counter, scores in enumerate(per_locus):
+            if seq_len >= 10000:
+                sorted_counts = dict(list(scores.items())[:limit_number]) if limit else scores
                 if not sorted_counts:
                     # the reference replaces the whole result dict by this message (:259-260)
                     result_dict = "A Strain type could not be detected because of no kmer matches!"
@@ -197,15 +212,11 @@ class ProbabilisticFilterMlstSchemeModel(ProbabilisticFilterModel):
                     first_key = next(iter(sorted_counts))
                     result_dict[loci[counter]] = sorted_counts
                     highest_results[loci[counter]] = {first_key: sorted_counts[first_key]}
-        else:
-            for counter, search in enumerate(self.indices):
-                result = self.get_cobs_result(search.search(str(sequence), step=step), False)
-                if limit:
-                    result = dict(sorted(result.items(), key=lambda x: -x[1])[:limit_number])
+            else:
+                result = dict(sorted(scores.items(), key=lambda x: -x[1])[:limit_number]) if limit else scores
                 result_dict[loci[counter]] = result
                 first_key, highest_result = next(iter(result.items()))
                 highest_results[loci[counter]] = {first_key: highest_result}
-
         if not self.has_sufficient_score(highest_results, self.avg_locus_bp_size):
             highest_results["Attention:"] = "This strain type is not reliable due to low kmer hit rates!"
         else:
@@ -213,6 +224,35 @@ class ProbabilisticFilterMlstSchemeModel(ProbabilisticFilterModel):
             flattened = {locus: int(list(allele_id.keys())[0].split("_")[-1]) for locus, allele_id in highest_results.items()}
             highest_results["ST_Name"] = handler.get_strain_type_name(flattened, self.scheme_url)
         return [{"Strain type": highest_results}, {"All results": result_dict}]
+
+    def _check_sequence(self, sequence) -> None:
+        if not seqio.is_seq(sequence):
+            raise ValueError("Invalid sequence, must be a Bio.Seq object")
+        if not len(sequence) > self.k:
+            raise ValueError("Invalid sequence, must be longer than k")
+        if not self.indices:
+            raise ValueError("The model has not been trained yet")
+
+    def calculate_hits(self, sequence: Seq, step: int = 1, limit: bool = False, limit_number: int = 5) -> list[dict]:
+        """Best allele per locus and all allele scores for one sequence (reference :192-303)."""
+        self._check_sequence(sequence)
+        seq_bytes = np.frombuffer(str(sequence).encode("ascii", "replace"), dtype=np.uint8)
+        return self._assemble(len(sequence), self._score_records([seq_bytes], step)[0], limit, limit_number)
+
+    def _predict_records(self, records, step: int, limit: bool) -> dict:
+        """All records of an input in one batched query per locus; same per-record results and dict order as the
+        reference's record loop (:353-355), the first invalid record raises like there."""
+        ids, seqs = [], []
+        for record in records:
+            self._check_sequence(record.seq)
+            ids.append(record.id)
+            seqs.append(np.frombuffer(str(record.seq).encode("ascii", "replace"), dtype=np.uint8))
+        hits = {}
+        if seqs:
+            scored = self._score_records(seqs, step)
+            for rid, sb, per_locus in zip(ids, seqs, scored):
+                hits[rid] = self._assemble(int(sb.size), per_locus, limit, 5)
+        return hits
 
     def predict(self, sequence_input, step: int = 1, limit: bool = False) -> MlstResult:
         """MlstResult for one record, a record iterator or a fasta/fastq path (reference :305-360)."""
@@ -224,10 +264,7 @@ class ProbabilisticFilterMlstSchemeModel(ProbabilisticFilterModel):
         if isinstance(sequence_input, Path):
             return ProbabilisticFilterMlstSchemeModel.predict(self, get_record_iterator(sequence_input), step=step, limit=limit)
         if seqio.is_record_iterator(sequence_input):
-            hits = {}
-            for record in sequence_input:
-                hits[record.id] = self.calculate_hits(record.seq, step, limit)
-            return MlstResult(self.model_display_name, step, hits, None)
+            return MlstResult(self.model_display_name, step, self._predict_records(sequence_input, step, limit), None)
         raise ValueError(
             "Invalid sequence input, must be a Seq object, a list of Seq objects, a"
             " SeqIO FastaIterator, or a SeqIO FastqPhredIterator"
