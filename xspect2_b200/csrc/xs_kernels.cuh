@@ -422,10 +422,12 @@ __global__ void __launch_bounds__(WIDE_NT) k_cobs_wide(const WideParams wp) {
     OutT* out = reinterpret_cast<OutT*>(p.out);
 
     const uint32_t C = cb.n_cols;
-    uint32_t lpw = 1; while (lpw < C && lpw < 32) lpw <<= 1;   // lanes per window
-    const uint32_t slots = 32 / lpw;                           // windows a warp handles at once
-    const uint32_t n_round = (C + lpw - 1) / lpw;
-    const uint32_t wsplit = NWARP;                             // window slices: every warp gets n_round units
+    // column rounds: full rounds of 32 chunks (one window per warp pass) and a tail round of C % 32 chunks in which
+    // the warp handles 32 / pow2ceil(tail) windows at once, so lanes stay busy when C is not a multiple of 32
+    const uint32_t n_full = C / 32, tail = C % 32;
+    uint32_t lpw_tail = 1; while (lpw_tail < tail) lpw_tail <<= 1;
+    const uint32_t n_round = n_full + (tail ? 1u : 0u);
+    const uint32_t wsplit = NWARP;                             // window slices: every warp gets one unit per round
     const uint32_t n_unit = n_round * wsplit;
 
     const uint64_t total_items = __ldg(wp.chunk_prefix + sb.n_seq);
@@ -471,9 +473,11 @@ __global__ void __launch_bounds__(WIDE_NT) k_cobs_wide(const WideParams wp) {
         // n_round units.  Two windows (2h loads) are in flight per lane; all-zero masks (the common case) skip
         // the counter update; 4 bit planes are spilled into the shared counters every 15 updates.
         for (uint32_t u = warp; u < n_unit; u += NWARP) {
-            const uint32_t r = u % n_round, ws = u / n_round;
+            const uint32_t r = u / wsplit, ws = u % wsplit;
+            const uint32_t lpw = r < n_full ? 32u : lpw_tail;     // lanes per window in this round
+            const uint32_t slots = 32 / lpw;                      // windows the warp handles at once
             const uint32_t slot = lane / lpw, cl = lane % lpw;
-            const uint32_t col = r * lpw + cl;
+            const uint32_t col = r * 32 + cl;
             const bool active = col < C;
             const uint8_t* colbase = pg.data + (size_t)(cb.c0 + col) * 16;
             uint32_t pl[4][4];
