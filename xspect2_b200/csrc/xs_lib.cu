@@ -255,6 +255,8 @@ static int upload_rows(FILE* f, uint64_t file_off, uint64_t n_rows, uint32_t src
 // workspace of one device-side query: 2-bit stream, bitmap, window prefix, scan temp
 // ----------------------------------------------------------------------------------------
 struct Workspace {
+    cudaStream_t stream = nullptr;
+    ~Workspace() { if (base) cudaFreeAsync(base, stream); }   // also on the error paths
     uint8_t* base = nullptr;
     uint64_t* packed = nullptr;
     uint32_t* invalid = nullptr;
@@ -292,6 +294,7 @@ static int workspace_alloc(Workspace& ws, uint64_t n_bases, uint64_t n_seq, bool
     size_t o_tmp = o_cnt + align256(N_COUNTERS * 8);
     size_t total = o_tmp + align256(tb ? tb : 1);
     XS_CUDA(cudaMallocAsync((void**)&ws.base, total, s));
+    ws.stream = s;
     ws.packed = reinterpret_cast<uint64_t*>(ws.base + o_packed);
     ws.invalid = reinterpret_cast<uint32_t*>(ws.base + o_inv);
     ws.prefix = reinterpret_cast<uint64_t*>(ws.base + o_pre);
@@ -397,8 +400,7 @@ static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
         if (e != cudaSuccess) return fail(XS_ERR_CUDA, std::string("k_cobs_wide: ") + cudaGetErrorString(e));
         XS_TRY(launch_ok("k_cobs_wide"));
     }
-    XS_CUDA(cudaFreeAsync(ws.base, s));
-    return XS_OK;
+    return XS_OK;   // the workspace goes back to the stream-ordered pool when ws leaves scope
 }
 
 static int bloom_query_dev(xs_bloom* bf, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_begin,
@@ -418,7 +420,6 @@ static int bloom_query_dev(xs_bloom* bf, const uint8_t* d_bases, uint64_t n_base
     else if (bf->info.term_size == 31) k_bloom<31><<<grid, BLOOM_NT, 0, s>>>(p);
     else k_bloom<0><<<grid, BLOOM_NT, 0, s>>>(p);
     XS_TRY(launch_ok("k_bloom"));
-    XS_CUDA(cudaFreeAsync(ws.base, s));
     return XS_OK;
 }
 
@@ -473,9 +474,9 @@ static int host_pipeline(const uint8_t* bases, uint64_t n_bases, const uint64_t*
         if (span) e = cudaMemcpyAsync(d + o_b, bases + pl.lo, span, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, seq_begin + pl.i0, ns * 8, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_e, seq_end + pl.i0, ns * 8, cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e)); break; }
+        if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e)); cudaFreeAsync(d, s); break; }
         rc = query(d + o_b, span, d_b, d_e, ns, pl.lo, d + o_o, pl.i0, s);
-        if (rc != XS_OK) break;
+        if (rc != XS_OK) { cudaFreeAsync(d, s); break; }
         e = cudaFreeAsync(d, s);
         if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, std::string("batch buffers: ") + cudaGetErrorString(e)); break; }
         i0 = pl.i1; ++bi;
