@@ -195,7 +195,9 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         t_setup = time.perf_counter()
         path, d_bases = build_workload(workdir, dev,
                                        lambda g: engine.kmer_rows(g, K, H, SIG_SIZE, device=local_rank), seed_shift=rank)
+        t_open = time.perf_counter()
         ix = engine.CobsIndex(path, device=local_rank)
+        open_s = time.perf_counter() - t_open
         assert ix.n_docs == D and ix.k == K and ix.num_hashes == H
         from xspect2_b200.synth import fixed_offsets
         hb_np, he_np = fixed_offsets(N_READS, READ_LEN)
@@ -285,7 +287,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             "config": {"workload": WORKLOAD, "reads_per_gpu": N_READS, "index": "replicated per GPU",
                        "parallelism": f"read-sharded x{world}, no data-path collective",
                        "l2": "inputs (1.5 GB reads + 2.4 GB index per step) far exceed the 126 MB L2; no flush needed",
-                       "out_dtype": "u8", "setup_s": round(setup_s, 1)},
+                       "out_dtype": "u8", "setup_s": round(setup_s, 1),
+                       "index_open_s": round(open_s, 2), "index_file_GB": round(path.stat().st_size / 1e9, 2)},
             "e2e": {"value": world * lookups_per_step * e2e_steps / e2e_s, "unit": "lookups/s",
                     "reads_per_sec": world * N_READS * e2e_steps / e2e_s, "ms_per_step": e2e_s / e2e_steps * 1e3,
                     "h2d_bytes_per_step": int(n_bases + 16 * N_READS), "d2h_bytes_per_step": int(N_READS * D),
