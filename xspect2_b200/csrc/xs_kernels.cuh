@@ -297,6 +297,9 @@ struct CobsParams {
 };
 
 constexpr int NARROW_NT = 256;
+#ifndef XS_EARLY_EXIT_AFTER
+#define XS_EARLY_EXIT_AFTER 5
+#endif
 
 // 128-bit document mask of one window: h row gathers ANDed
 template <int K, int H>
@@ -309,6 +312,9 @@ __device__ __forceinline__ uint4 cobs_mask16(const CobsParams& p, const PageDesc
     xxh64_prepare(t, k, pre);
     uint4 m = make_uint4(~0u, ~0u, ~0u, ~0u);
     if (H) {
+        // the first H1 rows go out together; when their AND is already empty the remaining gathers cannot change
+        // the result and are skipped (every gather is a 128-byte DRAM fetch)
+        constexpr int H1 = (H ? H : 1) > 5 ? (XS_EARLY_EXIT_AFTER) : (H ? H : 1);
         const uint8_t* addr[H ? H : 1];
 #pragma unroll
         for (int j = 0; j < (H ? H : 1); ++j) {
@@ -316,9 +322,16 @@ __device__ __forceinline__ uint4 cobs_mask16(const CobsParams& p, const PageDesc
             addr[j] = pg.data + mod_barrett(hv, pg.sig_size, pg.magic) * 16;
         }
 #pragma unroll
-        for (int j = 0; j < (H ? H : 1); ++j) {
+        for (int j = 0; j < H1; ++j) {
             uint4 v = ldg128(addr[j]);
             m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
+        }
+        if (H1 < (H ? H : 1) && (m.x | m.y | m.z | m.w) != 0) {
+#pragma unroll
+            for (int j = H1; j < (H ? H : 1); ++j) {
+                uint4 v = ldg128(addr[j]);
+                m.x &= v.x; m.y &= v.y; m.z &= v.z; m.w &= v.w;
+            }
         }
     } else {
         for (uint32_t j = 0; j < p.num_hashes; ++j) {
