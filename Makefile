@@ -2,7 +2,7 @@
 NVCC ?= nvcc
 NVCCFLAGS ?= -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared
 LIB := xspect2_b200/libxspect_b200.so
-SRC := xspect2_b200/csrc/xs_lib.cu xspect2_b200/csrc/xs_fastx.cpp
+SRC := xspect2_b200/csrc/xs_lib.cu xspect2_b200/csrc/xs_fastx.cpp xspect2_b200/csrc/xs_result.cpp
 HDR := xspect2_b200/csrc/xs_kernels.cuh xspect2_b200/csrc/xs_device.cuh include/xspect_b200.h
 
 all: $(LIB) oracle hostcheck

@@ -188,6 +188,18 @@ int xs_fastx_stats(const xs_fastx* fx, uint64_t* n_records, uint64_t* n_bases, u
 int xs_fastx_read(const xs_fastx* fx, uint8_t* bases, uint64_t* seq_begin, uint64_t* seq_end, char* ids, uint64_t* id_end);
 int xs_fastx_close(xs_fastx* fx);
 
+/* ---- result writer (host only) -------------------------------------------------------------------
+ * Replaces ModelResult.save = json.dumps(self.to_dict(), indent=4) (models/result.py:151-189) for results held as
+ * a count matrix: writes byte-identical JSON without building the nested dictionaries.  counts is [* x n_docs]
+ * uint32; rec_index[i] is the matrix row of the i-th emitted record (dict semantics for duplicate ids are resolved
+ * by the caller); rec_keys / doc_keys are the JSON-escaped keys back to back with their end offsets; documents
+ * with doc_include[d] == 0 are left out (exclude_ids); per record the documents appear in cobs result order;
+ * prefix / suffix are the JSON text before "hits" and after "num_kmers". */
+int xs_result_write_json(const char* path, const char* prefix, const char* suffix, const uint32_t* counts,
+                         uint32_t n_docs, const uint64_t* rec_index, uint64_t n_emit, const char* rec_keys,
+                         const uint64_t* rec_key_end, const uint64_t* num_kmers, const char* doc_keys,
+                         const uint64_t* doc_key_end, const uint8_t* doc_include);
+
 /* ---- single stages (host buffers; used by the parity tests to pin each kernel alone) ----- */
 /* 2-bit packing: packed[w] holds bases [32w, 32w+32), base j in bits [2j, 2j+1], A=0 C=1 G=2 T=3;
  * invalid[w] bit j = 1 when the byte is not one of upper-case ACGT.  n_words = n_bases/32 + 1. */

@@ -284,3 +284,45 @@ def test_min_hits_table_is_exact():
         for n in list(range(1, 140)) + [150, 199, 200, 399, 400]:
             for h in range(n + 1):
                 assert (h >= t[n]) == (round(h / n, 2) >= thr), (thr, n, h)
+
+
+def test_columnar_result_json_is_byte_identical(tmp_path):
+    """ColumnarModelResult.save (native writer) == json.dumps(ModelResult.to_dict(), indent=4), incl. duplicate ids,
+    excluded documents, rewritten keys, ids that need escaping, score rounding for many (hits, num_kmers) pairs."""
+    import json
+    from xspect2_b200.engine import CobsIndex
+    from xspect2_b200.models.result import ColumnarModelResult
+    rng = np.random.default_rng(23)
+    for case in range(6):
+        n, d = (1, 3) if case == 0 else (int(rng.integers(2, 400)), int(rng.integers(1, 130)))
+        nk = rng.integers(1, 5000 if case % 2 else 131, size=n).astype(np.int64)
+        counts = np.minimum(rng.integers(0, 9000, size=(n, d)) * (rng.random((n, d)) < 0.4), nk[:, None]).astype(np.uint32)
+        ids = [f"read{i}/1" for i in range(n)]
+        if n > 5:
+            ids[3] = ids[1]                       # duplicate id: first position, last values
+            ids[4] = 'we"ird\\\\id\tx'
+        names = [str(470 + 3 * j) for j in range(d)]
+        keys = [f"{nm} - species {nm}" for nm in names] if case % 3 == 0 else list(names)
+        include = np.ones(d, bool)
+        if d > 2 and case % 2:
+            include[[0, d - 1]] = False
+        pred = None if case < 2 else "471"
+        col = ColumnarModelResult("test-slug", ids, names, keys, include, counts, nk, sparse_sampling_step=1 + case % 3, prediction=pred,
+                                  input_source=None if case == 1 else "in.fq")
+        out = tmp_path / f"col{case}.json"
+        col.save(out)
+        # the reference's dict-based construction of the same result
+        hits, num_kmers = {}, {}
+        for i, rid in enumerate(ids):
+            order = CobsIndex.result_order(counts[i])
+            hits[rid] = {keys[j]: int(counts[i, j]) for j in order.tolist() if include[j]}
+            num_kmers[rid] = int(nk[i])
+        ref = ModelResult("test-slug", hits, num_kmers, 1 + case % 3, pred, None if case == 1 else "in.fq")
+        assert out.read_text() == json.dumps(ref.to_dict(), indent=4)
+        assert col.get_total_hits() == ref.get_total_hits() and list(col.get_total_hits()) == list(ref.get_total_hits())
+        assert col.get_total_scores() == ref.get_scores()["total"]
+        assert col.hits == ref.hits and col.num_kmers == ref.num_kmers and col.to_dict() == ref.to_dict()
+        assert col.get_filtered_subsequence_labels(keys[1 if d > 2 else 0] if include[1 if d > 2 else 0] else keys[1], 0.3) == \
+            ref.get_filtered_subsequence_labels(keys[1 if d > 2 else 0] if include[1 if d > 2 else 0] else keys[1], 0.3)
+    with pytest.raises(ValueError):
+        ColumnarModelResult("s", ["total"], ["a"], ["a"], np.ones(1, bool), np.zeros((1, 1), np.uint32), np.ones(1, np.int64))

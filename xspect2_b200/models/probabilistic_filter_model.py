@@ -22,7 +22,7 @@ from .. import engine, seqio
 from ..file_io import get_record_iterator
 from ..model_management import slugify
 from ..seqio import Seq, SeqRecord, SequenceBatch
-from .result import ModelResult
+from .result import ColumnarModelResult, ModelResult
 
 
 def default_device() -> int:
@@ -62,6 +62,8 @@ class BatchHits:
 
 class ProbabilisticFilterModel:
     """Probabilistic filter model for sequence data (COBS classic index, one document per label)."""
+
+    _exclude_ids_apply = True   # the single-filter model ignores exclude_ids (probabilistic_single_filter_model.py:98-125)
 
     def __init__(
         self,
@@ -219,12 +221,6 @@ class ProbabilisticFilterModel:
             "total_scores": {n: round(v / total_kmers, 2) for n, v in total_hits.items()} if total_kmers else {},
         }
 
-    def _score_batch(self, batch: SequenceBatch, exclude_ids, step: int) -> tuple[dict, dict]:
-        hits, num_kmers = self.predict_arrays(batch, step).to_hits()
-        if exclude_ids:
-            hits = {rid: {d: s for d, s in h.items() if d not in exclude_ids} for rid, h in hits.items()}
-        return hits, num_kmers
-
     def predict(
         self,
         sequence_input: SeqRecord | list[SeqRecord] | Any | Path,
@@ -238,20 +234,21 @@ class ProbabilisticFilterModel:
         longer than k aborts the call — as in the reference's loop."""
         batch = self._to_batch(sequence_input)
         self._check_lengths(batch)
-        hits, num_kmers = self._score_batch(batch, exclude_ids, step)
+        cols = self.predict_arrays(batch, step)
         if display_name:
-            for rid, h in hits.items():
-                hits[rid] = {
-                    f"{key} -{self.display_names.get(key, 'Unknown').replace(self.model_display_name, '', 1)}": v
-                    for key, v in h.items()
-                }
+            doc_keys = [f"{key} -{self.display_names.get(key, 'Unknown').replace(self.model_display_name, '', 1)}" for key in cols.names]
+        else:
+            doc_keys = list(cols.names)
+        drop = exclude_ids if (exclude_ids and self._exclude_ids_apply) else ()
+        include = np.array([name not in drop for name in cols.names], dtype=bool)
         if validation:
             warnings.warn(
                 "validation=True: the alignment-based misclassification filter (minimap2 mapping + Ripley's K, "
                 "reference :508-601) is outside the GPU scoring path and is not applied",
                 stacklevel=2,
             )
-        return ModelResult(self.slug(), hits, num_kmers, sparse_sampling_step=step)
+        return ColumnarModelResult(self.slug(), batch.ids, cols.names, doc_keys, include, cols.counts, cols.num_kmers,
+                                   sparse_sampling_step=step)
 
     def _convert_cobs_result_to_dict(self, cobs_result) -> dict:
         return {r.doc_name: r.score for r in cobs_result}

@@ -61,21 +61,16 @@ class ProbabilisticFilterSVMModel(ProbabilisticFilterModel):
 
     def svm_input(self, res: ModelResult) -> list[list[float]]:
         """The SVM feature row: total scores ordered by sorted label string (reference :212-213)."""
-        return [list(dict(sorted(res.get_scores()["total"].items())).values())]
+        total = res.get_total_scores() if hasattr(res, "get_total_scores") else res.get_scores()["total"]
+        return [list(dict(sorted(total.items())).values())]
 
     def predict(self, sequence_input, exclude_ids: list[str] = None, step: int = 1, display_name: bool = False,
                 validation: bool = False) -> ModelResult:
         res = super().predict(sequence_input, exclude_ids, step, display_name, validation)
         svm_scores = self.svm_input(res)
         svm = self._get_svm(exclude_ids)
-        res.hits["misclassified"] = res.misclassified
-        return ModelResult(
-            self.slug(),
-            res.hits,
-            res.num_kmers,
-            sparse_sampling_step=step,
-            prediction=str(svm.predict(svm_scores)[0]),
-        )
+        res.prediction = str(svm.predict(svm_scores)[0])     # same fields as the reference's re-wrapped ModelResult
+        return res
 
     def _get_svm(self, exclude_ids):
         """SVC(kernel, C) fit on ``<slug>/scores.csv``.  Bug-compatible with the reference (:240-267): feature

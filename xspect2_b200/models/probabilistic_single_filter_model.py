@@ -21,6 +21,8 @@ from .probabilistic_filter_model import BatchHits, ProbabilisticFilterModel, def
 class ProbabilisticSingleFilterModel(ProbabilisticFilterModel):
     """Probabilistic filter model with a single Bloom filter (e.g. genus membership)."""
 
+    _exclude_ids_apply = False
+
     def __init__(
         self,
         k: int,
@@ -64,14 +66,6 @@ class ProbabilisticSingleFilterModel(ProbabilisticFilterModel):
         hits = self.bf.filter.query(batch.bases, batch.begin, batch.end, step)
         num_kmers = -((batch.lengths - self.k + 1) // -step)
         return BatchHits(batch.ids, [next(iter(self.display_names))], np.asarray(hits).reshape(-1, 1), num_kmers, step)
-
-    def _score_batch(self, batch: SequenceBatch, exclude_ids, step: int) -> tuple[dict, dict]:
-        res = self.predict_arrays(batch, step)
-        key = res.names[0]
-        col = res.counts[:, 0].tolist()
-        hits = {rid: {key: col[i]} for i, rid in enumerate(batch.ids)}
-        num_kmers = {rid: int(res.num_kmers[i]) for i, rid in enumerate(batch.ids)}
-        return hits, num_kmers
 
     @staticmethod
     def load(path: Path, device: int | None = None) -> "ProbabilisticSingleFilterModel":

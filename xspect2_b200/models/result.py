@@ -77,3 +77,131 @@ class ModelResult:
         path.parent.mkdir(exist_ok=True, parents=True)
         with open(path, "w", encoding="utf-8") as f:
             f.write(dumps(self.to_dict(), indent=4))
+
+
+class ColumnarModelResult(ModelResult):
+    """A ModelResult backed by the count matrix of a batched query.
+
+    Same attributes, methods and JSON as ``ModelResult``; the nested ``hits`` / ``num_kmers`` dictionaries are only
+    built when somebody reads them.  ``get_total_hits`` and the total scores work on the matrix, and ``save``
+    streams the JSON through the native writer (``xs_result_write_json``), byte for byte what
+    ``json.dumps(self.to_dict(), indent=4)`` produces.  Dictionary semantics are kept: a record id that occurs
+    twice keeps its first position and its last values (probabilistic_filter_model.py:295-310)."""
+
+    def __init__(self, model_slug, ids, doc_names, doc_keys, doc_include, counts, num_kmers, sparse_sampling_step=1,
+                 prediction=None, input_source=None):
+        if "total" in ids:
+            raise ValueError("'total' is a reserved key and cannot be used as a subsequence")
+        self.model_slug = model_slug
+        self.sparse_sampling_step = sparse_sampling_step
+        self.prediction = prediction
+        self.input_source = input_source
+        self.misclassified = None
+        self._ids = ids
+        self._doc_names = doc_names          # index document names (matrix columns)
+        self._doc_keys = doc_keys            # dictionary key per column (display-name rewrite applied)
+        self._doc_include = doc_include      # bool per column (exclude_ids applied)
+        self._counts = counts                # [n_records, n_docs]
+        self._nk = num_kmers                 # [n_records]
+        self._hits = None
+        self._num_kmers = None
+        self._emit = None
+
+    # ---- dictionary views, built on demand
+    def _emit_index(self):
+        """Rows that survive dict insertion: last occurrence of every id, in first-occurrence order."""
+        if self._emit is None:
+            import numpy as np
+            last = {}
+            for i, rid in enumerate(self._ids):
+                last[rid] = i
+            self._emit = np.fromiter(last.values(), dtype=np.uint64, count=len(last))
+        return self._emit
+
+    def _materialize(self):
+        if self._hits is not None:
+            return
+        import numpy as np
+        from .. import engine
+        emit = self._emit_index()
+        rows = np.ascontiguousarray(np.asarray(self._counts)[emit.astype(np.int64)]).astype(np.uint32)
+        order = engine.result_order_batch(rows)
+        keys = np.array(self._doc_keys, dtype=object)
+        inc = np.asarray(self._doc_include, dtype=bool)
+        sorted_counts = np.take_along_axis(rows, order.astype(np.int64), axis=1)
+        hits, num_kmers = {}, {}
+        all_in = bool(inc.all())
+        for j, i in enumerate(emit.tolist()):
+            o = order[j]
+            if all_in:
+                hits[self._ids[i]] = dict(zip(keys[o].tolist(), sorted_counts[j].tolist()))
+            else:
+                m = inc[o]
+                hits[self._ids[i]] = dict(zip(keys[o][m].tolist(), sorted_counts[j][m].tolist()))
+            num_kmers[self._ids[i]] = int(self._nk[i])
+        self._hits, self._num_kmers = hits, num_kmers
+
+    @property
+    def hits(self):
+        self._materialize()
+        return self._hits
+
+    @hits.setter
+    def hits(self, value):
+        self._hits = value
+
+    @property
+    def num_kmers(self):
+        self._materialize()
+        return self._num_kmers
+
+    @num_kmers.setter
+    def num_kmers(self, value):
+        self._num_kmers = value
+
+    # ---- matrix-side shortcuts
+    def get_total_hits(self) -> dict[str, int]:
+        if self._hits is not None:
+            return super().get_total_hits()
+        import numpy as np
+        from .. import engine
+        emit = self._emit_index().astype(np.int64)
+        counts = np.asarray(self._counts)
+        totals = counts[emit].sum(axis=0, dtype=np.int64)
+        first = engine.CobsIndex.result_order(counts[emit[0]].astype(np.uint32))   # IndexError without records, like the reference
+        return {self._doc_keys[d]: int(totals[d]) for d in first.tolist() if self._doc_include[d]}
+
+    def get_total_scores(self) -> dict[str, float]:
+        """``get_scores()["total"]`` without the per-record rows."""
+        import numpy as np
+        total_kmers = int(np.asarray(self._nk)[self._emit_index().astype(np.int64)].sum()) if self._hits is None else sum(self.num_kmers.values())
+        return {label: round(h / total_kmers, 2) for label, h in self.get_total_hits().items()}
+
+    def save(self, path: Path) -> None:
+        if self._hits is not None or len(self._ids) == 0 or self.misclassified is not None:
+            return super().save(path)
+        import ctypes as C
+        import json
+        import numpy as np
+        from .. import _abi
+        path.parent.mkdir(exist_ok=True, parents=True)
+        emit = self._emit_index()
+        counts = np.ascontiguousarray(self._counts, dtype=np.uint32)
+        nk = np.ascontiguousarray(np.asarray(self._nk)[emit.astype(np.int64)], dtype=np.uint64)
+
+        def blob(strings):
+            enc = [json.dumps(s).encode("ascii") for s in strings]
+            ends = np.cumsum([len(e) for e in enc], dtype=np.uint64) if enc else np.zeros(0, np.uint64)
+            return b"".join(enc), np.ascontiguousarray(ends, dtype=np.uint64)
+
+        rec_blob, rec_end = blob([self._ids[i] for i in emit.tolist()])
+        doc_blob, doc_end = blob(self._doc_keys)
+        inc = np.ascontiguousarray(self._doc_include, dtype=np.uint8)
+        prefix = "{\n    \"model_slug\": %s,\n    \"sparse_sampling_step\": %s,\n" % (json.dumps(self.model_slug), json.dumps(self.sparse_sampling_step))
+        suffix = "    \"misclassified\": null,\n    \"input_source\": %s" % json.dumps(self.input_source)
+        if self.prediction is not None:
+            suffix += ",\n    \"prediction\": %s" % json.dumps(self.prediction)
+        suffix += "\n}"
+        _abi.check(_abi.lib().xs_result_write_json(
+            str(path).encode(), prefix.encode("ascii"), suffix.encode("ascii"), counts.ctypes.data, counts.shape[1],
+            emit.ctypes.data, emit.size, rec_blob, rec_end.ctypes.data, nk.ctypes.data, doc_blob, doc_end.ctypes.data, inc.ctypes.data))
