@@ -245,6 +245,16 @@ def api(td: Path):
     summ = model.predict_summary(batch)
     t4 = time.perf_counter()
     assert np.array_equal(np.asarray(summ["best"]), best.astype(np.uint32)) and summ["total_hits"] == totals
+    t5 = time.perf_counter()
+    full = model.predict(fq)                      # the reference's API call: file -> ModelResult
+    t6 = time.perf_counter()
+    full.input_source = fq.name
+    full.save(td / "result.json")                 # ... -> the reference's JSON, through the native writer
+    t7 = time.perf_counter()
+    import json as _json
+    with open(td / "result.json") as fh:
+        head = fh.read(400)
+    assert head.startswith('{\n    "model_slug": "testgenus-species"')
     sample = 5000
     hb, he = batch.begin[:sample], batch.end[:sample]
     exp = oracle.CobsOracle(model.get_cobs_index_path()).counts_batch(batch.bases, hb, he, 1, threads=8)
@@ -252,7 +262,8 @@ def api(td: Path):
     print(json.dumps({"config": "API: 2M-read FASTQ file -> ProbabilisticFilterModel.predict_arrays (D=90 test model)",
                       "file_MB": fq.stat().st_size / 1e6, "parse_s": t1 - t0, "query_s": t2 - t1, "argmax_totals_host_s": t3 - t2,
                       "reads_per_sec_file_to_counts": n_reads / (t2 - t0),
-                      "summary_on_device_s": t4 - t3, "reads_per_sec_file_to_calls": n_reads / ((t1 - t0) + (t4 - t3)), "parity_sample_reads": sample}), flush=True)
+                      "summary_on_device_s": t4 - t3, "predict_s": t6 - t5, "save_json_s": t7 - t6,
+                      "json_MB": (td / "result.json").stat().st_size / 1e6, "reads_per_sec_file_to_json": n_reads / (t7 - t5), "reads_per_sec_file_to_calls": n_reads / ((t1 - t0) + (t4 - t3)), "parity_sample_reads": sample}), flush=True)
 
 
 if __name__ == "__main__":
