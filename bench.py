@@ -49,15 +49,16 @@ WORKLOAD = (f"cfg2: {N_READS} synthetic {READ_LEN}bp reads x COBS classic index 
             f"S={SIG_SIZE} (Acinetobacter-species geometry)")
 
 
-def ncu_traffic() -> float | None:
-    """dram read+write bytes of one k_cobs_narrow launch from the committed ncu capture, if it is this workload."""
+def ncu_traffic() -> tuple[float | None, float | None]:
+    """(dram read+write bytes, global load sectors) of one k_cobs_narrow launch from the committed ncu capture, if it
+    is this workload."""
     p = ROOT / "profiles" / "traffic.json"
     if not p.exists():
-        return None
+        return None, None
     t = json.loads(p.read_text()).get("k_cobs_narrow<21,7,u8>")
     if not t or (t["n_reads"], t["read_len"], t["sig_size"]) != (N_READS, READ_LEN, SIG_SIZE):
-        return None
-    return float(t["dram_bytes_read"] + t["dram_bytes_write"])
+        return None, None
+    return float(t["dram_bytes_read"] + t["dram_bytes_write"]), float(t.get("global_load_sectors") or 0) or None
 
 
 def peaks() -> tuple[float, str]:
@@ -276,8 +277,10 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         algo_bytes = lookups_per_step * H * ROW_BYTES + n_bases * 3 // 8 + N_READS * D
         k_ms = kernel_ms / max(kernel_launches, 1)
         achieved = algo_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else None
-        gathers = lookups_per_step * H
-        traffic = ncu_traffic()
+        traffic, load_sectors = ncu_traffic()
+        # row gathers issued per launch: h per lookup, minus the last two when the first five rows AND to zero;
+        # ncu's global-load sector count (each row gather is one sector; ~1 % of it is the packed read stream)
+        gathers = load_sectors or lookups_per_step * H
         line = {
             "metric": "kmer_lookups_per_sec", "value": value, "unit": "lookups/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -303,6 +306,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                          # fetch-granular view: every 16-byte row gather costs a 128-byte DRAM fetch on B200
                          # (ncu: traffic / gathers = 124.6 B); ceiling = best rate of profiles/microbench/*.cu
                          "gather": {"achieved_G_per_s": gathers / (k_ms / 1e3) / 1e9 if k_ms > 0 else None,
+                                    "gathers_per_launch": int(gathers), "nominal_gathers_per_launch": int(lookups_per_step * H),
                                     "ceiling_G_per_s": 50.2, "dram_bytes_per_gather": (traffic / gathers) if traffic else None,
                                     "dram_GBps": (traffic / (k_ms / 1e3) / 1e9) if (traffic and k_ms > 0) else None}},
             "checksum_first_100k_reads": checksum,

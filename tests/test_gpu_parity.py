@@ -330,3 +330,36 @@ def test_single_record_shims(gpu, oracle, tmp_path):
     assert km in bf
     assert (oracle.bloom_term(b"ACGTTGCATGCATGCATGCAA").decode() in bf) == (
         oracle.bloom_term(b"ACGTTGCATGCATGCATGCAA").decode() in oracle.BloomOracle(pb, 21))
+
+
+def test_concurrent_queries_on_one_handle(gpu, oracle, tmp_path):
+    """Handles are immutable after open: several host threads may query the same index / filter at once
+    (include/xspect_b200.h conventions; the reference's web app runs background tasks in threads, web.py:73-90)."""
+    import threading
+    rng = np.random.default_rng(31)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 90, 21, 7, length=2000)
+    genomes = [s for v in docs.values() for s in v]
+    pb, g, _ = _mk_bloom(oracle, tmp_path, rng, 21)
+    ix = gpu.CobsIndex(p)
+    bf = gpu.BloomFilter(pb, 21)
+    jobs = []
+    for t in range(6):
+        bases, b, e = synth.sample_reads(np.random.default_rng(100 + t), genomes + [g], 3000, (21, 300), n_rate=0.002)
+        jobs.append((bases, b, e))
+    expected = [(oracle.CobsOracle(p).counts_batch(*j, 1, threads=4), oracle.BloomOracle(pb, 21).hits_batch(*j, 1, threads=4)) for j in jobs]
+    got = [None] * len(jobs)
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got[i] = (np.asarray(ix.query(*jobs[i], 1)).astype(np.uint32), np.asarray(bf.query(*jobs[i], 1)).copy())
+        except Exception as exc:   # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for (gc, gb), (ec, eb) in zip(got, expected):
+        assert np.array_equal(gc, ec) and np.array_equal(gb, eb)
