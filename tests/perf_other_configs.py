@@ -216,6 +216,48 @@ def twostage(td: Path):
                       "lookups_per_sec": (n_reads + kept) * (L - k + 1) / dt, "note": "host (pinned) reads in, calls/totals/prediction out"}), flush=True)
 
 
+def assembly(td: Path):
+    """Config 1: one ~4 Mbp assembly (4 contigs, FASTA on disk) through the species model's predict, next to the CPU
+    oracle driven like the reference (one search per contig, one host thread)."""
+    import bench
+    from tests import model_fixtures as mfx
+    from xspect2_b200.models.probabilistic_filter_model import ProbabilisticFilterModel
+    models = td / "models"
+    (models / "synth-species").mkdir(parents=True)
+    genome = synth.synth_genome(bench.GENOME_LEN, seed=1, n_rate=0.0001)
+    rows, valid = engine.kmer_rows(genome, bench.K, bench.H, bench.SIG_SIZE)
+    rows = rows[valid.astype(bool)]
+    names = synth.write_classic_index(models / "synth-species" / "index.cobs_classic", n_docs=bench.D, k=bench.K, num_hashes=bench.H,
+                                      sig_size=bench.SIG_SIZE, seed=2, plant={0: rows[: int(rows.shape[0] * 0.3)].reshape(-1)}, device=dev)
+    meta = {"model_slug": "synth-species", "k": bench.K, "model_display_name": "Synth", "author": None, "author_email": None,
+            "model_type": "Species", "model_class": "ProbabilisticFilterModel", "display_names": {n: f"Synth sp{n}" for n in names},
+            "fpr": 0.01, "num_hashes": 7, "training_accessions": None}
+    (models / "synth-species.json").write_text(json.dumps(meta))
+    cuts = [0, 3_900_000, 4_000_000, 4_050_000, bench.GENOME_LEN]
+    recs = [(f"contig_{i + 1}", genome[a:b]) for i, (a, b) in enumerate(zip(cuts, cuts[1:]))]
+    fa = td / "assembly.fna"
+    mfx.write_fasta(fa, recs)
+    t0 = time.perf_counter()
+    model = ProbabilisticFilterModel.load(models / "synth-species.json")
+    t_load = time.perf_counter() - t0
+    model.predict(fa)
+    t0 = time.perf_counter()
+    res = model.predict(fa)
+    res.input_source = fa.name
+    res.save(td / "assembly.json")
+    t_gpu = time.perf_counter() - t0
+    orc = oracle.CobsOracle(models / "synth-species" / "index.cobs_classic")
+    t0 = time.perf_counter()
+    ref_hits, ref_nk = oracle.reference_predict(orc, [(rid, s.tobytes().decode()) for rid, s in recs], bench.K)
+    t_cpu = time.perf_counter() - t0
+    assert res.hits == ref_hits and res.num_kmers == ref_nk
+    lookups = sum(ref_nk.values())
+    print(json.dumps({"config": "cfg1: one ~4 Mbp assembly (4 contigs) x D=90 index (S=150000001), predict + save JSON",
+                      "model_load_s": t_load, "gpu_predict_save_s": t_gpu, "gpu_lookups_per_sec": lookups / t_gpu,
+                      "cpu_oracle_1thread_s": t_cpu, "cpu_lookups_per_sec": lookups / t_cpu, "lookups": lookups,
+                      "parity": "hits and num_kmers of all contigs equal the oracle (dict order included)"}), flush=True)
+
+
 def api(td: Path):
     """FASTQ on disk -> per-read counts through the model API (native reader + batched query), vs the numbers above."""
     rng = np.random.default_rng(9)
@@ -267,9 +309,9 @@ def api(td: Path):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["bloom", "mlst", "wide", "api", "twostage"]
+    which = sys.argv[1:] or ["bloom", "mlst", "wide", "api", "twostage", "assembly"]
     with tempfile.TemporaryDirectory() as td:
         for w in which:
             sub = Path(td) / w
             sub.mkdir()
-            {"bloom": bloom, "mlst": mlst, "wide": wide, "api": api, "twostage": twostage}[w](sub)
+            {"bloom": bloom, "mlst": mlst, "wide": wide, "api": api, "twostage": twostage, "assembly": assembly}[w](sub)
