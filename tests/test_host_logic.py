@@ -326,3 +326,51 @@ def test_columnar_result_json_is_byte_identical(tmp_path):
             ref.get_filtered_subsequence_labels(keys[1 if d > 2 else 0] if include[1 if d > 2 else 0] else keys[1], 0.3)
     with pytest.raises(ValueError):
         ColumnarModelResult("s", ["total"], ["a"], ["a"], np.ones(1, bool), np.zeros((1, 1), np.uint32), np.ones(1, np.int64))
+
+
+def test_native_reader_fuzz_against_python_iterators(tmp_path):
+    """Randomised FASTA / FASTQ texts (blank lines, CRLF, wrapped records, odd characters, missing final newline):
+    the native reader and the pure-Python iterators agree on ids and sequences, and fail on the same inputs."""
+    from hypothesis import given, settings, strategies as st
+    from xspect2_b200.seqio import FastaIterator, FastqPhredIterator
+
+    seq_chars = "ACGTNacgtnRYKM*-"
+    word = st.text(alphabet="abcXYZ019_./|:=", min_size=0, max_size=8)
+    title = st.builds(lambda w, rest: (w + (" " + rest if rest else "")), word, st.text(alphabet="abc =;,", max_size=10))
+    seq = st.text(alphabet=seq_chars, min_size=0, max_size=70)
+    nl = st.sampled_from(["\n", "\r\n"])
+
+    fasta_rec = st.builds(lambda t, s, w, e: ">" + t + e + "".join(s[i:i + w] + e for i in range(0, len(s), w)) + (e if len(s) % 7 == 0 else ""),
+                          title, seq, st.integers(5, 40), nl)
+    fasta_text = st.builds(lambda recs, cut: ("".join(recs))[: None if not cut else -1] if recs else "", st.lists(fasta_rec, max_size=8), st.booleans())
+
+    @settings(max_examples=150, deadline=None)
+    @given(fasta_text)
+    def check_fasta(text):
+        p = tmp_path / "h.fasta"
+        p.write_bytes(text.encode())
+        exp = [(r.id, str(r.seq)) for r in FastaIterator(p)]
+        b = SequenceBatch.from_file(p)
+        assert [(b.ids[i], b.sequence(i)) for i in range(len(b))] == exp
+
+    fastq_rec = st.builds(lambda t, s, w, e, qc: "@" + t + e + ("".join(s[i:i + w] + e for i in range(0, len(s), w)) if s else e) + "+" + e +
+                          ("".join((qc * len(s))[i:i + w] + e for i in range(0, len(s), w)) if s else e),
+                          title, st.text(alphabet="ACGTNacgt", min_size=0, max_size=60), st.integers(4, 80), nl, st.sampled_from("I@+#5"))
+    fastq_text = st.builds(lambda recs, junk: "".join(recs) + junk, st.lists(fastq_rec, max_size=8), st.sampled_from(["", "\n", "@x\nAC\n+\nI\n", "ACGT\n"]))
+
+    @settings(max_examples=150, deadline=None)
+    @given(fastq_text)
+    def check_fastq(text):
+        p = tmp_path / "h.fastq"
+        p.write_bytes(text.encode())
+        try:
+            exp = [(r.id, str(r.seq)) for r in FastqPhredIterator(p)]
+        except ValueError:
+            with pytest.raises(ValueError):
+                SequenceBatch.from_file(p)
+            return
+        b = SequenceBatch.from_file(p)
+        assert [(b.ids[i], b.sequence(i)) for i in range(len(b))] == exp
+
+    check_fasta()
+    check_fastq()

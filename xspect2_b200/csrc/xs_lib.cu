@@ -564,6 +564,7 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
     if (rc != XS_OK) { fclose(f); return rc; }
 
     xs_cobs* ix = new xs_cobs();
+    ix->info.device = device;
     ix->n_sm = n_sm;
     ix->names = cf.names;
     const char* fw = getenv("XS_FORCE_WIDE");
