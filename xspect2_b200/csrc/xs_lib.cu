@@ -368,17 +368,10 @@ static cudaError_t launch_wide(const WideParams& p, dim3 grid, size_t smem, int 
 static int dtype_size(int dt) { return (dt == XS_U8 || dt == XS_U16 || dt == XS_U32) ? dt : 0; }
 
 // all pointers device; asynchronous on s
-static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_begin,
-                          const uint64_t* d_end, uint64_t n_seq, uint64_t base_shift, uint32_t step, int dt,
-                          void* d_out, cudaStream_t s) {
+// the scoring kernel of a prepared batch (narrow or wide rows)
+static int cobs_launch(xs_cobs* ix, const SeqBatch& sb, const uint64_t* chunk_prefix, int dt, void* d_out, cudaStream_t s) {
     const uint64_t ld = ix->info.doc_end - ix->info.doc_begin;
-    XS_CUDA(cudaMemsetAsync(d_out, 0, n_seq * ld * (uint64_t)dt, s));
-    if (n_seq == 0) return XS_OK;
-    Workspace ws;
-    SeqBatch sb{};
     const bool wide = !ix->narrow || ix->force_wide;
-    XS_TRY(prepare_batch(ws, sb, d_bases, n_bases, d_begin, d_end, n_seq, base_shift, ix->info.term_size, step,
-                         wide ? WIDE_CHUNK : 0, ix->n_sm, s));
     CobsParams p{};
     p.sb = sb; p.pages = ix->d_pages; p.n_pages = (uint32_t)ix->pages.size();
     p.num_hashes = ix->info.num_hashes; p.canonicalize = ix->info.canonicalize; p.policy = ix->info.policy;
@@ -390,7 +383,7 @@ static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
         XS_TRY(launch_ok("k_cobs_narrow"));
     } else {
         WideParams wp{};
-        wp.cp = p; wp.blocks = ix->d_blocks; wp.chunk_prefix = ws.prefix2;
+        wp.cp = p; wp.blocks = ix->d_blocks; wp.chunk_prefix = chunk_prefix;
         uint32_t max_cols = 0;
         for (const ColBlock& b : ix->blocks) max_cols = std::max(max_cols, b.n_cols);
         size_t smem = (size_t)WIDE_CHUNK * ix->info.num_hashes * 8 + (size_t)max_cols * 128 * 4;
@@ -400,18 +393,26 @@ static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
         if (e != cudaSuccess) return fail(XS_ERR_CUDA, std::string("k_cobs_wide: ") + cudaGetErrorString(e));
         XS_TRY(launch_ok("k_cobs_wide"));
     }
-    return XS_OK;   // the workspace goes back to the stream-ordered pool when ws leaves scope
+    return XS_OK;
 }
 
-static int bloom_query_dev(xs_bloom* bf, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_begin,
-                           const uint64_t* d_end, uint64_t n_seq, uint64_t base_shift, uint32_t step,
-                           uint32_t* d_out, cudaStream_t s) {
-    XS_CUDA(cudaMemsetAsync(d_out, 0, n_seq * 4, s));
+static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_begin,
+                          const uint64_t* d_end, uint64_t n_seq, uint64_t base_shift, uint32_t step, int dt,
+                          void* d_out, cudaStream_t s) {
+    const uint64_t ld = ix->info.doc_end - ix->info.doc_begin;
+    XS_CUDA(cudaMemsetAsync(d_out, 0, n_seq * ld * (uint64_t)dt, s));
     if (n_seq == 0) return XS_OK;
     Workspace ws;
+    SeqBatch sb{};
+    const bool wide = !ix->narrow || ix->force_wide;
+    XS_TRY(prepare_batch(ws, sb, d_bases, n_bases, d_begin, d_end, n_seq, base_shift, ix->info.term_size, step,
+                         wide ? WIDE_CHUNK : 0, ix->n_sm, s));
+    return cobs_launch(ix, sb, ws.prefix2, dt, d_out, s);   // ws goes back to the stream-ordered pool on scope exit
+}
+
+static int bloom_launch(xs_bloom* bf, const SeqBatch& sb, uint32_t* d_out, cudaStream_t s) {
     BloomParams p{};
-    XS_TRY(prepare_batch(ws, p.sb, d_bases, n_bases, d_begin, d_end, n_seq, base_shift, bf->info.term_size, step, 0,
-                         bf->n_sm, s));
+    p.sb = sb;
     p.bits = bf->d_bits; p.n_bits = bf->info.n_bits; p.magic = magic_of(bf->info.n_bits);
     p.k_hashes = (uint32_t)bf->info.k_hashes; p.out = d_out; p.seq0 = 0;
     dim3 grid((unsigned)(bf->n_sm * 4));
@@ -420,6 +421,125 @@ static int bloom_query_dev(xs_bloom* bf, const uint8_t* d_bases, uint64_t n_base
     else if (bf->info.term_size == 31) k_bloom<31><<<grid, BLOOM_NT, 0, s>>>(p);
     else k_bloom<0><<<grid, BLOOM_NT, 0, s>>>(p);
     XS_TRY(launch_ok("k_bloom"));
+    return XS_OK;
+}
+
+static int bloom_query_dev(xs_bloom* bf, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_begin,
+                           const uint64_t* d_end, uint64_t n_seq, uint64_t base_shift, uint32_t step,
+                           uint32_t* d_out, cudaStream_t s) {
+    XS_CUDA(cudaMemsetAsync(d_out, 0, n_seq * 4, s));
+    if (n_seq == 0) return XS_OK;
+    Workspace ws;
+    SeqBatch sb{};
+    XS_TRY(prepare_batch(ws, sb, d_bases, n_bases, d_begin, d_end, n_seq, base_shift, bf->info.term_size, step, 0, bf->n_sm, s));
+    return bloom_launch(bf, sb, d_out, s);
+}
+
+// ----------------------------------------------------------------------------------------
+// low-latency path for small host batches (single records through the Search / Bloom shims, MLST chunk sets):
+// one pinned staging buffer, one H2D copy (offsets + host-computed window prefix + bases), one memset, the
+// packing kernel, the scoring kernel, one D2H copy — on a stream and buffers cached per host thread and device.
+// ----------------------------------------------------------------------------------------
+static const uint64_t SMALL_MAX_SEQ = 4096, SMALL_MAX_SPAN = 1 << 20, SMALL_MAX_OUT = 1 << 20;
+
+struct SmallCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    uint8_t* h = nullptr;   // pinned staging
+    uint8_t* d = nullptr;   // device mirror + workspace
+    size_t h_bytes = 0, d_bytes = 0;
+    ~SmallCtx() {
+        if (device < 0) return;
+        int prev = -1;
+        if (cudaGetDevice(&prev) != cudaSuccess) return;    // runtime already shut down
+        if (cudaSetDevice(device) == cudaSuccess) {
+            if (h) cudaFreeHost(h);
+            if (d) cudaFree(d);
+            if (stream) cudaStreamDestroy(stream);
+        }
+        cudaSetDevice(prev);
+    }
+};
+
+static SmallCtx* small_ctx(int device) {
+    static thread_local std::vector<SmallCtx*> ctxs;   // leaked on purpose at thread exit only if CUDA is gone
+    for (SmallCtx* c : ctxs) if (c->device == device) return c;
+    SmallCtx* c = new SmallCtx();
+    c->h_bytes = 2 * SMALL_MAX_SEQ * 8 * 2 + SMALL_MAX_SPAN + SMALL_MAX_OUT + 4096;
+    c->d_bytes = c->h_bytes + SMALL_MAX_SPAN / 2 + N_COUNTERS * 8 + 8192;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMallocHost((void**)&c->h, c->h_bytes) != cudaSuccess ||
+        cudaMalloc((void**)&c->d, c->d_bytes) != cudaSuccess) {
+        if (c->h) cudaFreeHost(c->h);
+        if (c->d) cudaFree(c->d);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+        return nullptr;
+    }
+    c->device = device;
+    ctxs.push_back(c);
+    return c;
+}
+
+// returns XS_OK and *handled = true when the batch went through the small path
+template <typename LaunchFn>
+static int small_query(int device, int n_sm, uint32_t k, uint32_t step, uint32_t chunk, uint32_t n_counters, const uint8_t* bases,
+                       uint64_t n_bases, const uint64_t* seq_begin, const uint64_t* seq_end, uint64_t n_seq, uint64_t out_row_bytes,
+                       void* out, bool* handled, LaunchFn launch) {
+    *handled = false;
+    if (n_seq == 0 || n_seq > SMALL_MAX_SEQ || n_seq * out_row_bytes > SMALL_MAX_OUT) return XS_OK;
+    uint64_t lo = ~0ULL, hi = 0;
+    for (uint64_t i = 0; i < n_seq; ++i) {
+        if (seq_end[i] < seq_begin[i]) continue;
+        lo = std::min(lo, seq_begin[i]); hi = std::max(hi, seq_end[i]);
+    }
+    if (lo == ~0ULL) { lo = 0; hi = 0; }
+    if (hi > n_bases) return fail(XS_ERR_ARG, "sequence offsets exceed n_bases");
+    const uint64_t span = hi - lo;
+    if (span > SMALL_MAX_SPAN) return XS_OK;
+    SmallCtx* c = small_ctx(device);
+    if (!c) return XS_OK;   // fall through to the pipelined path, which reports allocation problems
+    cudaStream_t s = c->stream;
+    // staging layout (host and device identical): begin | end | prefix | prefix2 | bases
+    const size_t o_b = 0, o_e = align256(n_seq * 8), o_p = o_e + align256(n_seq * 8), o_p2 = o_p + align256((n_seq + 1) * 8);
+    const size_t o_bases = o_p2 + align256((n_seq + 1) * 8);
+    const size_t up_bytes = o_bases + align256(span + 64);
+    uint64_t* hb = reinterpret_cast<uint64_t*>(c->h + o_b);
+    uint64_t* he = reinterpret_cast<uint64_t*>(c->h + o_e);
+    uint64_t* hp = reinterpret_cast<uint64_t*>(c->h + o_p);
+    uint64_t* hp2 = reinterpret_cast<uint64_t*>(c->h + o_p2);
+    uint64_t acc = 0, acc2 = 0;
+    for (uint64_t i = 0; i < n_seq; ++i) {
+        hb[i] = seq_begin[i]; he[i] = seq_end[i];
+        uint64_t nw = windows_of(seq_begin[i], seq_end[i], lo, span, k, step);
+        hp[i] = acc; acc += nw;
+        hp2[i] = acc2; acc2 += chunk ? (nw + chunk - 1) / chunk : 0;
+    }
+    hp[n_seq] = acc; hp2[n_seq] = acc2;
+    if (span) memcpy(c->h + o_bases, bases + lo, span);
+    // device-only regions: 2-bit stream | bitmap | counters | out   (counters and out are cleared by one memset)
+    const uint64_t n_words = span / 32 + 2;
+    const size_t o_packed = up_bytes, o_inv = o_packed + align256(n_words * 8), o_cnt = o_inv + align256(n_words * 4);
+    const size_t o_out = o_cnt + align256((size_t)n_counters * 8);
+    const size_t out_bytes = n_seq * out_row_bytes;
+    if (o_out + out_bytes > c->d_bytes || up_bytes + out_bytes > c->h_bytes) return XS_OK;
+    XS_CUDA(cudaMemcpyAsync(c->d, c->h, up_bytes, cudaMemcpyHostToDevice, s));
+    XS_CUDA(cudaMemsetAsync(c->d + o_cnt, 0, (o_out - o_cnt) + out_bytes, s));
+    uint64_t grid = std::max<uint64_t>(1, std::min<uint64_t>((n_words + 255) / 256, (uint64_t)n_sm * 16));
+    k_pack2bit<<<(unsigned)grid, 256, 0, s>>>(c->d + o_bases, span, reinterpret_cast<uint64_t*>(c->d + o_packed),
+                                              reinterpret_cast<uint32_t*>(c->d + o_inv), n_words);
+    XS_TRY(launch_ok("k_pack2bit"));
+    SeqBatch sb{};
+    sb.packed = reinterpret_cast<const uint64_t*>(c->d + o_packed); sb.invalid = reinterpret_cast<const uint32_t*>(c->d + o_inv);
+    sb.bases = c->d + o_bases; sb.seq_begin = reinterpret_cast<const uint64_t*>(c->d + o_b);
+    sb.seq_end = reinterpret_cast<const uint64_t*>(c->d + o_e); sb.win_prefix = reinterpret_cast<const uint64_t*>(c->d + o_p);
+    sb.tile_counter = reinterpret_cast<unsigned long long*>(c->d + o_cnt);
+    sb.n_seq = n_seq; sb.n_bases = span; sb.base_shift = lo; sb.step = step; sb.k = k;
+    XS_TRY(launch(sb, reinterpret_cast<const uint64_t*>(c->d + o_p2), c->d + o_out, s));
+    uint8_t* h_out = c->h + up_bytes;
+    XS_CUDA(cudaMemcpyAsync(h_out, c->d + o_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    XS_CUDA(cudaStreamSynchronize(s));
+    memcpy(out, h_out, out_bytes);
+    *handled = true;
     return XS_OK;
 }
 
@@ -696,6 +816,17 @@ int xs_cobs_query(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const uin
     if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the index's device");
     const uint64_t ld = ix->info.doc_end - ix->info.doc_begin;
     const uint64_t row = ld * (uint64_t)out_dtype;
+    {
+        bool handled = false;
+        const bool wide = !ix->narrow || ix->force_wide;
+        const uint32_t n_counters = (uint32_t)std::max(ix->pages.size(), ix->blocks.size());
+        XS_TRY(small_query(ix->info.device, ix->n_sm, ix->info.term_size, step, wide ? WIDE_CHUNK : 0, n_counters, bases, n_bases,
+                           seq_begin, seq_end, n_seq, row, out, &handled,
+                           [&](const SeqBatch& sb, const uint64_t* chunk_prefix, uint8_t* d_o, cudaStream_t s) {
+                               return cobs_launch(ix, sb, chunk_prefix, out_dtype, d_o, s);
+                           }));
+        if (handled) return XS_OK;
+    }
     return host_pipeline(bases, n_bases, seq_begin, seq_end, n_seq, row,
                          [&](const uint8_t* db, uint64_t span, const uint64_t* d_b, const uint64_t* d_e, uint64_t ns,
                              uint64_t shift, uint8_t* d_o, uint64_t i0, cudaStream_t s) {
@@ -848,6 +979,14 @@ int xs_bloom_query(xs_bloom* bf, const uint8_t* bases, uint64_t n_bases, const u
     if (step == 0) return fail(XS_ERR_ARG, "step must be >= 1");
     DeviceGuard guard(bf->info.device);
     if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the filter's device");
+    {
+        bool handled = false;
+        XS_TRY(small_query(bf->info.device, bf->n_sm, bf->info.term_size, step, 0, 1, bases, n_bases, seq_begin, seq_end, n_seq, 4,
+                           out_hits, &handled, [&](const SeqBatch& sb, const uint64_t*, uint8_t* d_o, cudaStream_t s) {
+                               return bloom_launch(bf, sb, reinterpret_cast<uint32_t*>(d_o), s);
+                           }));
+        if (handled) return XS_OK;
+    }
     return host_pipeline(bases, n_bases, seq_begin, seq_end, n_seq, 4,
                          [&](const uint8_t* db, uint64_t span, const uint64_t* d_b, const uint64_t* d_e, uint64_t ns,
                              uint64_t shift, uint8_t* d_o, uint64_t i0, cudaStream_t s) {

@@ -158,7 +158,8 @@ class CobsIndex:
             mx = int((e - b).max()) if n else 0
             dtype = pick_dtype(max(0, (mx - self.k) // step + 1))
         if out is None:
-            out = pinned_empty((n, self.n_docs), _DT[dtype])
+            small = n * self.n_docs * int(dtype) < (1 << 20)      # small results come back through the library's own staging
+            out = np.empty((n, self.n_docs), _DT[dtype]) if small else pinned_empty((n, self.n_docs), _DT[dtype])
         elif out.dtype != _DT[dtype] or out.shape != (n, self.n_docs) or not out.flags.c_contiguous:
             raise ValueError("out has the wrong dtype/shape")
         check(lib().xs_cobs_query(self._h, _ptr(bases), bases.size, _ptr(b), _ptr(e), n, int(step), int(dtype), _ptr(out)))
@@ -275,7 +276,7 @@ class BloomFilter:
         bases = _as_bases(bases)
         b, e = _as_u64(seq_begin), _as_u64(seq_end)
         if out is None:
-            out = pinned_empty((b.size,), np.uint32)
+            out = np.empty(b.size, np.uint32) if b.size < (1 << 18) else pinned_empty((b.size,), np.uint32)
         check(lib().xs_bloom_query(self._h, _ptr(bases), bases.size, _ptr(b), _ptr(e), b.size, int(step), _ptr(out)))
         return out
 
