@@ -30,7 +30,7 @@ class ModelResult:
 
     def get_total_hits(self) -> dict[str, int]:
         """Hits summed over subsequences; label set and order come from the first subsequence."""
-        totals = dict.fromkeys(next(iter(self.hits.values())), 0)
+        totals = dict.fromkeys(list(self.hits.values())[0], 0)   # IndexError on an empty result, like the reference
         for per_label in self.hits.values():
             for label, n in per_label.items():
                 totals[label] += n
