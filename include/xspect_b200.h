@@ -186,6 +186,9 @@ typedef struct xs_fastx xs_fastx;
 int xs_fastx_open(const char* path, int format, xs_fastx** out);
 int xs_fastx_stats(const xs_fastx* fx, uint64_t* n_records, uint64_t* n_bases, uint64_t* n_id_bytes);
 int xs_fastx_read(const xs_fastx* fx, uint8_t* bases, uint64_t* seq_begin, uint64_t* seq_end, char* ids, uint64_t* id_end);
+/* file_io.filter_sequences (file_io.py:166-191): write the records with keep[i] != 0 to out_path as FASTA the way
+ * Bio.SeqIO.write does for parsed records ('>' + title line, sequence wrapped at 60 columns). */
+int xs_fastx_filter_fasta(const xs_fastx* fx, const uint8_t* keep, const char* out_path);
 int xs_fastx_close(xs_fastx* fx);
 
 /* ---- result writer (host only) -------------------------------------------------------------------

@@ -374,3 +374,25 @@ def test_native_reader_fuzz_against_python_iterators(tmp_path):
 
     check_fasta()
     check_fastq()
+
+
+def test_native_filtered_fasta_equals_python_writer(tmp_path):
+    """filter_sequences through the native writer == SeqIO.write-style output of the kept parsed records."""
+    import io
+    rng = np.random.default_rng(41)
+    recs = []
+    for i in range(300):
+        s = "".join(rng.choice(list("ACGTNacgt"), size=int(rng.integers(0, 250))))
+        recs.append((f"r{i} sample={i % 7} len={len(s)}" if i % 4 else f"r{i}", s))
+    fq = tmp_path / "in.fastq"
+    fq.write_text("".join(f"@{t}\n{s}\n+\n{'I' * len(s)}\n" for t, s in recs))
+    fa = tmp_path / "in.fasta"
+    fa.write_text("".join(f">{t}\r\n" + "".join(s[j:j + 70] + "\r\n" for j in range(0, len(s), 70)) for t, s in recs))
+    wanted = [f"r{i}" for i in range(0, 300, 3)]
+    for src in (fq, fa):
+        out = tmp_path / f"kept_{src.suffix[1:]}.fasta"
+        filter_sequences(src, out, wanted)
+        buf = io.StringIO()
+        seqio.write_fasta((r for r in get_record_iterator(src) if r.id in set(wanted)), buf)
+        assert out.read_text() == buf.getvalue()
+        assert [r.id for r in get_record_iterator(out)] == wanted

@@ -66,6 +66,7 @@ SYMBOLS = {
     "xs_fastx_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
     "xs_fastx_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "xs_fastx_read": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "xs_fastx_filter_fasta": (C.c_int, [_P, _P, C.c_char_p]),
     "xs_fastx_close": (C.c_int, [_P]),
     "xs_result_write_json": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, _P, C.c_uint32, _P, C.c_uint64, _P, _P, _P, _P, _P, _P]),
     "xs_pack_2bit": (C.c_int, [_P, C.c_uint64, C.c_int, _P, _P]),

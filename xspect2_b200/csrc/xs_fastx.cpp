@@ -62,9 +62,23 @@ struct Sink {   // pass 1 counts, pass 2 writes
     bool write = false;
     std::vector<Checkpoint>* cps = nullptr;
     const uint8_t* file_base = nullptr;
+    // filter mode: write the kept records as FASTA (title line as read, sequence wrapped at 60 columns)
+    FILE* filter_out = nullptr;
+    const uint8_t* keep = nullptr;
+    bool keeping = false;
+    std::string seq_buf;
 
     inline void begin_record(const uint8_t* rec_start, const uint8_t* title_b, const uint8_t* title_e) {
         if (cps && (n_rec % CP_EVERY) == 0) cps->push_back({(uint64_t)(rec_start - file_base), n_rec, n_bases, n_id});
+        if (filter_out) {
+            keeping = keep[n_rec] != 0;
+            if (keeping) {
+                seq_buf.clear();
+                fputc('>', filter_out);
+                fwrite(title_b, 1, (size_t)(title_e - title_b), filter_out);
+                fputc('\n', filter_out);
+            }
+        }
         const uint8_t *wb, *we;
         first_word(title_b, title_e, &wb, &we);
         if (write) {
@@ -76,20 +90,30 @@ struct Sink {   // pass 1 counts, pass 2 writes
     }
     inline void end_record() {
         if (write) seq_end[n_rec] = n_bases;
+        if (filter_out && keeping) {
+            for (size_t i = 0; i < seq_buf.size(); i += 60) {
+                fwrite(seq_buf.data() + i, 1, std::min<size_t>(60, seq_buf.size() - i), filter_out);
+                fputc('\n', filter_out);
+            }
+        }
         ++n_rec;
     }
     // append a FASTA line: drop ' ' and '\r' (Bio.SeqIO.FastaIO: "".join(lines).replace(" ", "").replace("\r", ""))
     inline void append_fasta(const uint8_t* p, const uint8_t* e) {
         if (!memchr(p, ' ', (size_t)(e - p)) && !memchr(p, '\r', (size_t)(e - p))) {
-            if (write) memcpy(bases + n_bases, p, (size_t)(e - p));
-            n_bases += (uint64_t)(e - p);
+            append_raw(p, e);
             return;
         }
         for (; p < e; ++p)
-            if (*p != ' ' && *p != '\r') { if (write) bases[n_bases] = *p; ++n_bases; }
+            if (*p != ' ' && *p != '\r') {
+                if (write) bases[n_bases] = *p;
+                if (filter_out && keeping) seq_buf.push_back((char)*p);
+                ++n_bases;
+            }
     }
     inline void append_raw(const uint8_t* p, const uint8_t* e) {
         if (write) memcpy(bases + n_bases, p, (size_t)(e - p));
+        if (filter_out && keeping) seq_buf.append((const char*)p, (size_t)(e - p));
         n_bases += (uint64_t)(e - p);
     }
 };
@@ -228,6 +252,19 @@ int xs_fastx_read(const xs_fastx* fx, uint8_t* bases, uint64_t* seq_begin, uint6
         for (auto& t : th) t.join();
     }
     return status.load();
+}
+
+int xs_fastx_filter_fasta(const xs_fastx* fx, const uint8_t* keep, const char* out_path) {
+    if (!fx || !out_path || (fx->n_records && !keep)) return xs_set_error(XS_ERR_ARG, "NULL argument");
+    FILE* f = fopen(out_path, "wb");
+    if (!f) return xs_set_error(XS_ERR_IO, std::string(out_path) + ": " + strerror(errno));
+    std::vector<char> big(8 << 20);
+    setvbuf(f, big.data(), _IOFBF, big.size());
+    Sink sk;
+    sk.filter_out = f; sk.keep = keep;
+    int rc = run(fx, fx->data, fx->data + fx->size, sk);
+    if (fclose(f) != 0 && rc == XS_OK) rc = xs_set_error(XS_ERR_IO, std::string(out_path) + ": write failed");
+    return rc;
 }
 
 int xs_fastx_close(xs_fastx* fx) {

@@ -27,11 +27,25 @@ def filter_sequences(input_file: Path, output_file: Path, included_ids: list[str
     if not included_ids:
         print("No IDs provided, no output file will be created.")
         return
+    import ctypes as C
+
+    import numpy as np
+
+    from . import _abi
+    from .seqio import SequenceBatch
+
+    get_record_iterator(input_file)          # same path / format errors as the reference
     wanted = set(included_ids)
-    with open(output_file, "w", encoding="utf-8") as out_f:
-        for record in get_record_iterator(input_file):
-            if record.id in wanted:
-                seqio.write_fasta(record, out_f)
+    ids = SequenceBatch.from_file(input_file).ids
+    keep = np.fromiter((rid in wanted for rid in ids), dtype=np.uint8, count=len(ids))
+    L = _abi.lib()
+    h = C.c_void_p()
+    fmt = 2 if input_file.suffix[1:] in fastq_endings else 1
+    _abi.check(L.xs_fastx_open(str(input_file).encode(), fmt, C.byref(h)))
+    try:
+        _abi.check(L.xs_fastx_filter_fasta(h, keep.ctypes.data, str(output_file).encode()))
+    finally:
+        L.xs_fastx_close(h)
 
 
 def prepare_input_output_paths(input_path: Path) -> tuple[list[Path], Callable[[int, Path], Path]]:
