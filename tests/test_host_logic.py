@@ -321,6 +321,12 @@ def test_columnar_result_json_is_byte_identical(tmp_path):
         assert out.read_text() == json.dumps(ref.to_dict(), indent=4)
         assert col.get_total_hits() == ref.get_total_hits() and list(col.get_total_hits()) == list(ref.get_total_hits())
         assert col.get_total_scores() == ref.get_scores()["total"]
+        for lab in [key for key, keep in zip(keys, include) if keep][:3]:
+            for thr in (0.0, 0.01, 0.3, 0.7, 1.0, -1):
+                assert col.get_filter_mask(lab, thr) == ref.get_filter_mask(lab, thr), (case, lab, thr)
+        assert col._hits is None                  # all of the above without building the nested dictionaries
+        with pytest.raises(ValueError):
+            col.get_filter_mask(keys[0], 1.5)
         assert col.hits == ref.hits and col.num_kmers == ref.num_kmers and col.to_dict() == ref.to_dict()
         assert col.get_filtered_subsequence_labels(keys[1 if d > 2 else 0] if include[1 if d > 2 else 0] else keys[1], 0.3) == \
             ref.get_filtered_subsequence_labels(keys[1 if d > 2 else 0] if include[1 if d > 2 else 0] else keys[1], 0.3)

@@ -171,6 +171,36 @@ class ColumnarModelResult(ModelResult):
         first = engine.CobsIndex.result_order(counts[emit[0]].astype(np.uint32))   # IndexError without records, like the reference
         return {self._doc_keys[d]: int(totals[d]) for d in first.tolist() if self._doc_include[d]}
 
+    def get_filter_mask(self, label: str, filter_threshold: float) -> dict[str, bool]:
+        """Same mask as ModelResult.get_filter_mask (result.py:92-123), taken on the matrix: the rounded score
+        ``round(hits / num_kmers, 2)`` is evaluated with Python's own ``round`` once per distinct
+        (hits, num_kmers) pair instead of once per record and label."""
+        if self._hits is not None:
+            return super().get_filter_mask(label, filter_threshold)
+        if filter_threshold < 0 and not filter_threshold == -1 or filter_threshold > 1:
+            raise ValueError("The filter threshold must be between 0 and 1.")
+        import numpy as np
+        inc = np.asarray(self._doc_include, dtype=bool)
+        cols = [d for d, key in enumerate(self._doc_keys) if key == label and inc[d]]
+        if not cols:
+            raise KeyError(label)
+        emit = self._emit_index().astype(np.int64)
+        counts = np.asarray(self._counts)
+        h = counts[emit, cols[-1]].astype(np.int64)
+        n = np.asarray(self._nk)[emit].astype(np.int64)
+
+        def rounded(hits, kmers):      # round(h / n, 2) with Python semantics, one evaluation per distinct pair
+            pairs, inverse = np.unique(np.stack([hits, kmers], axis=1), axis=0, return_inverse=True)
+            vals = np.array([round(int(a) / int(b), 2) for a, b in pairs], dtype=np.float64)
+            return vals[inverse.reshape(-1)]
+
+        if filter_threshold != -1:
+            mask = rounded(h, n) >= filter_threshold
+        else:
+            hmax = counts[emit][:, inc].max(axis=1).astype(np.int64)
+            mask = rounded(h, n) == rounded(hmax, n)
+        return {self._ids[i]: bool(m) for i, m in zip(emit.tolist(), mask.tolist())}
+
     def get_total_scores(self) -> dict[str, float]:
         """``get_scores()["total"]`` without the per-record rows."""
         import numpy as np
