@@ -258,6 +258,42 @@ def assembly(td: Path):
                       "parity": "hits and num_kmers of all contigs equal the oracle (dict order included)"}), flush=True)
 
 
+def workflow(td: Path):
+    """The reference's `xspect all` stages through the workflow functions (files between stages, main.py:108-145):
+    filter_genus (genus JSON + filtered FASTA) -> classify_species (species JSON) on a 1 M-read FASTQ."""
+    import os
+    rng = np.random.default_rng(12)
+    root = td / "home" / "xspect-data" / "models"
+    root.mkdir(parents=True)
+    sp_json, genomes, _ = mf.species_model(oracle, root, rng, n_species=90, genome_len=20000, svm=True)
+    mf.genus_model(oracle, root, list(genomes.values())[:60])
+    os.environ["HOME"] = str(td / "home")
+    from xspect2_b200 import classify, filter_sequences
+    n_reads, L = 1_000_000, 150
+    g = np.concatenate(list(genomes.values()))
+    reads = synth.synth_reads(g, n_reads, L, seed=13, device=dev).cpu().numpy().reshape(n_reads, L)
+    fq = td / "reads.fastq"
+    qual = b"I" * L
+    with open(fq, "wb") as f:
+        for c0 in range(0, n_reads, 50000):
+            f.write(b"".join(b"@read%d/1\n" % i + reads[i].tobytes() + b"\n+\n" + qual + b"\n" for i in range(c0, min(n_reads, c0 + 50000))))
+    out = td / "out"
+    (out / "filtered_sequences").mkdir(parents=True)
+    t0 = time.perf_counter()
+    filter_sequences.filter_genus("Testgenus", fq, out / "filtered_sequences" / "genus_filtered.fasta", 0.7, out / "genus.json")
+    t1 = time.perf_counter()
+    classify.classify_species("Testgenus", out / "filtered_sequences", out / "species.json")
+    t2 = time.perf_counter()
+    kept = sum(1 for line in open(out / "filtered_sequences" / "genus_filtered.fasta", "rb") if line.startswith(b">"))
+    with open(out / "species_1.json") as fh:
+        head = fh.read(200)
+    assert "testgenus-species" in head
+    print(json.dumps({"config": "workflow: filter_genus + classify_species (SVM) on a 1M-read FASTQ, files between the stages",
+                      "filter_genus_s": t1 - t0, "classify_species_s": t2 - t1, "kept_reads": kept,
+                      "genus_json_MB": (out / "genus.json").stat().st_size / 1e6, "species_json_MB": (out / "species_1.json").stat().st_size / 1e6,
+                      "reads_per_sec_overall": n_reads / (t2 - t0)}), flush=True)
+
+
 def api(td: Path):
     """FASTQ on disk -> per-read counts through the model API (native reader + batched query), vs the numbers above."""
     rng = np.random.default_rng(9)
@@ -314,4 +350,4 @@ if __name__ == "__main__":
         for w in which:
             sub = Path(td) / w
             sub.mkdir()
-            {"bloom": bloom, "mlst": mlst, "wide": wide, "api": api, "twostage": twostage, "assembly": assembly}[w](sub)
+            {"bloom": bloom, "mlst": mlst, "wide": wide, "api": api, "twostage": twostage, "assembly": assembly, "workflow": workflow}[w](sub)
