@@ -173,6 +173,24 @@ int xs_bloom_query_device(xs_bloom* bf, const uint8_t* d_bases, uint64_t n_bases
                           const uint64_t* d_seq_begin, const uint64_t* d_seq_end, uint64_t n_seq,
                           uint32_t step, uint32_t* d_out_hits, void* stream);
 
+/* ---- construction (training side) ------------------------------------------------------------------
+ * xs_cobs_build replaces cobs.classic_construct_list / cobs.compact_construct_list
+ *   (probabilistic_filter_model.py:186-192; probabilistic_filter_mlst_model.py:132-141): every sequence i
+ *   (bases[seq_begin[i]:seq_end[i]]) belongs to document seq_doc[i]; all windows of a document are hashed like the
+ *   query does and OR-ed into its column.  sig_size = 0 derives the signature size from fpr
+ *   (ceil(max k-mers per document * -h / ln(1 - fpr^(1/h)))); compact: documents sorted by size, 8 * page_size
+ *   per page (page_size = 0 -> floor(sqrt(n_docs / 8)), at least 1).  Writes the index file in the layout of
+ *   SURVEY.md A.1 / A.3 ([UNVERIFIED-3P] like the reader).
+ * xs_bloom_build replaces Bloom(expected_items, fpr, hash_func=xxh3_64_intdigest) + add per k-mer + save
+ *   (probabilistic_single_filter_model.py:83-96). */
+int xs_cobs_build(const char* out_path, int device, int kind, uint32_t k, uint32_t num_hashes, double fpr,
+                  uint32_t canonicalize, uint64_t sig_size, uint64_t page_size, const char* names, uint32_t n_docs,
+                  const uint8_t* bases, uint64_t n_bases, const uint64_t* seq_begin, const uint64_t* seq_end,
+                  const uint32_t* seq_doc, uint64_t n_seq);
+int xs_bloom_build(const char* out_path, int device, uint32_t k, uint64_t expected_items, double fpr,
+                   const uint8_t* bases, uint64_t n_bases, const uint64_t* seq_begin, const uint64_t* seq_end,
+                   uint64_t n_seq);
+
 /* ---- FASTA / FASTQ ingest (host only) -----------------------------------------------------------
  * Replaces the Biopython record iteration that feeds the path (SeqIO.parse behind
  * file_io.get_record_iterator, file_io.py:47-79; consumed at probabilistic_filter_model.py:291-310) with one

@@ -696,6 +696,69 @@ __global__ void __launch_bounds__(REDUCE_NT) k_scores_reduce(const OutT* __restr
 }
 
 // ----------------------------------------------------------------------------------------
+// construction (training side; probabilistic_filter_model.py:169-194, probabilistic_single_filter_model.py:63-96,
+// probabilistic_filter_mlst_model.py:100-142): the query kernels' hashing with an atomic OR instead of a gather
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_or_bit(uint8_t* data, uint64_t byte, uint32_t bit) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(data + byte);
+    unsigned int* w = reinterpret_cast<unsigned int*>(a & ~(uintptr_t)3);
+    atomicOr(w, 1u << ((uint32_t)(a & 3) * 8 + bit));
+}
+
+struct CobsBuildParams {
+    SeqBatch sb;
+    const uint32_t* seq_doc;   // [n_seq] document (after page ordering) of every sequence
+    uint8_t* data;             // [sig_size x row_bytes] of this page, zeroed, 4-byte aligned
+    uint64_t sig_size, magic;
+    uint32_t row_bytes, num_hashes, canonicalize;
+    int32_t policy;
+    uint32_t doc_lo, doc_hi;   // documents of this page
+};
+
+__global__ void __launch_bounds__(256) k_cobs_build(const CobsBuildParams p) {
+    const SeqBatch& sb = p.sb;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t s = seq_of_window(sb.win_prefix, sb.n_seq, g);
+        uint32_t doc = __ldg(p.seq_doc + s);
+        if (doc < p.doc_lo || doc >= p.doc_hi) continue;
+        uint64_t pos = __ldg(sb.seq_begin + s) - sb.base_shift + (g - __ldg(sb.win_prefix + s)) * sb.step;
+        Term t;
+        if (!cobs_term<0>(sb, pos, p.canonicalize != 0, p.policy, t)) continue;
+        Xxh64Pre pre;
+        xxh64_prepare(t, sb.k, pre);
+        const uint32_t within = doc - p.doc_lo;
+        for (uint32_t j = 0; j < p.num_hashes; ++j) {
+            uint64_t row = mod_barrett(xxh64_finish(pre, sb.k, (uint64_t)j), p.sig_size, p.magic);
+            atomic_or_bit(p.data, row * p.row_bytes + within / 8, within % 8);
+        }
+    }
+}
+
+struct BloomBuildParams {
+    SeqBatch sb;
+    uint8_t* bits;
+    uint64_t n_bits, magic;
+    uint32_t k_hashes;
+};
+
+__global__ void __launch_bounds__(256) k_bloom_build(const BloomBuildParams p) {
+    const SeqBatch& sb = p.sb;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t s = seq_of_window(sb.win_prefix, sb.n_seq, g);
+        uint64_t pos = __ldg(sb.seq_begin + s) - sb.base_shift + (g - __ldg(sb.win_prefix + s)) * sb.step;
+        Term t;
+        bloom_term<0>(sb, pos, t);
+        uint64_t hi = 0, lo = xxh3_64(t, sb.k);
+        for (uint32_t j = 0; j < p.k_hashes; ++j) {
+            uint64_t ix = mod_barrett(lcg_next(hi, lo), p.n_bits, p.magic);
+            atomic_or_bit(p.bits, ix >> 3, (uint32_t)(ix & 7));
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // stage kernels (parity tests pin each stage on its own)
 // ----------------------------------------------------------------------------------------
 __global__ void k_stage_canonical(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ invalid,

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cerrno>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
@@ -996,7 +997,7 @@ int xs_bloom_query(xs_bloom* bf, const uint8_t* bases, uint64_t n_bases, const u
                          });
 }
 
-// ---- single stages -----------------------------------------------------------------------
+// ---- construction ---------------------------------------------------------------------------
 struct DevBuf {
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
@@ -1006,6 +1007,161 @@ struct DevBuf {
     }
 };
 
+static uint64_t cobs_signature_size(uint64_t max_doc_kmers, uint32_t num_hashes, double fpr) {
+    double ratio = -(double)num_hashes / std::log(1.0 - std::pow(fpr, 1.0 / (double)num_hashes));
+    double v = std::ceil((double)std::max<uint64_t>(max_doc_kmers, 1) * ratio);
+    return v < 1.0 ? 1 : (uint64_t)v;
+}
+
+static bool put_all(FILE* f, const void* p, size_t n) { return n == 0 || fwrite(p, 1, n, f) == n; }
+
+int xs_cobs_build(const char* out_path, int device, int kind, uint32_t k, uint32_t num_hashes, double fpr, uint32_t canonicalize,
+                  uint64_t sig_size, uint64_t page_size, const char* names, uint32_t n_docs, const uint8_t* bases, uint64_t n_bases,
+                  const uint64_t* seq_begin, const uint64_t* seq_end, const uint32_t* seq_doc, uint64_t n_seq) {
+    if (!out_path || !names || n_docs == 0 || (n_seq && (!seq_begin || !seq_end || !seq_doc)) || (n_bases && !bases))
+        return fail(XS_ERR_ARG, "NULL argument");
+    if (kind != XS_COBS_CLASSIC && kind != XS_COBS_COMPACT) return fail(XS_ERR_ARG, "kind must be classic or compact");
+    if (k == 0 || k > 32) return fail(XS_ERR_UNSUPPORTED, "term_size must be in 1..32");
+    if (num_hashes == 0 || num_hashes > 64) return fail(XS_ERR_UNSUPPORTED, "num_hashes must be in 1..64");
+    if (!(fpr > 0.0 && fpr < 1.0) && sig_size == 0) return fail(XS_ERR_ARG, "false positive rate must be in (0, 1)");
+    // document names and sizes (k-mers per document)
+    std::vector<std::string> name(n_docs);
+    {
+        const char* p = names;
+        for (uint32_t d = 0; d < n_docs; ++d) {
+            const char* e = strchr(p, '\n');
+            if (!e) { name[d] = p; p += name[d].size(); } else { name[d].assign(p, e); p = e + 1; }
+        }
+    }
+    std::vector<uint64_t> size(n_docs, 0);
+    for (uint64_t i = 0; i < n_seq; ++i) {
+        if (seq_doc[i] >= n_docs || seq_end[i] < seq_begin[i] || seq_end[i] > n_bases) return fail(XS_ERR_ARG, "bad sequence / document table");
+        uint64_t len = seq_end[i] - seq_begin[i];
+        if (len >= k) size[seq_doc[i]] += len - k + 1;
+    }
+    // page layout: classic = one page of all documents; compact = documents sorted by size, 8 * page_size per page
+    std::vector<uint32_t> order(n_docs);
+    std::iota(order.begin(), order.end(), 0u);
+    uint64_t row_bytes, n_pages;
+    if (kind == XS_COBS_CLASSIC) {
+        row_bytes = ((uint64_t)n_docs + 7) / 8; n_pages = 1;
+    } else {
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return size[a] < size[b]; });
+        if (page_size == 0) page_size = std::max<uint64_t>(1, (uint64_t)std::sqrt((double)n_docs / 8.0));
+        row_bytes = page_size; n_pages = ((uint64_t)n_docs + 8 * page_size - 1) / (8 * page_size);
+    }
+    std::vector<uint32_t> rank(n_docs);
+    for (uint32_t r = 0; r < n_docs; ++r) rank[order[r]] = r;
+    const uint64_t per_page = kind == XS_COBS_CLASSIC ? n_docs : 8 * row_bytes;
+    std::vector<uint64_t> sig(n_pages);
+    for (uint64_t pg = 0; pg < n_pages; ++pg) {
+        uint64_t mx = 0;
+        for (uint64_t r = pg * per_page; r < std::min<uint64_t>((pg + 1) * per_page, n_docs); ++r) mx = std::max(mx, size[order[r]]);
+        sig[pg] = (sig_size && kind == XS_COBS_CLASSIC) ? sig_size : cobs_signature_size(mx, num_hashes, fpr);
+    }
+    // header
+    std::string head = std::string("COBS:") + (kind == XS_COBS_CLASSIC ? "CLASSIC_INDEX" : "COMPACT_INDEX");
+    auto pod = [&](const void* p, size_t n) { head.append((const char*)p, n); };
+    uint32_t version = 1; uint8_t canon = (uint8_t)(canonicalize != 0);
+    pod(&version, 4); pod(&k, 4); pod(&canon, 1);
+    if (kind == XS_COBS_CLASSIC) {
+        uint64_t nh = num_hashes;
+        pod(&n_docs, 4); pod(&sig[0], 8); pod(&nh, 8);
+    } else {
+        uint32_t np = (uint32_t)n_pages;
+        pod(&np, 4); pod(&n_docs, 4); pod(&row_bytes, 8);
+        for (uint64_t pg = 0; pg < n_pages; ++pg) { uint64_t nh = num_hashes; pod(&sig[pg], 8); pod(&nh, 8); }
+    }
+    for (uint32_t r = 0; r < n_docs; ++r) { head += name[order[r]]; head += '\n'; }
+    if (kind == XS_COBS_COMPACT) head.append((row_bytes - ((head.size() + 13) % row_bytes)) % row_bytes, '\0');
+    head += kind == XS_COBS_CLASSIC ? "CLASSIC_INDEX" : "COMPACT_INDEX";
+
+    DeviceGuard guard(device);
+    int n_sm = 0;
+    XS_TRY(device_setup(device, &n_sm));
+    cudaStream_t s = nullptr;
+    DevBuf d_bases, d_b, d_e, d_doc, d_data;
+    XS_TRY(d_bases.alloc(n_bases + 64));
+    XS_TRY(d_b.alloc(n_seq * 8)); XS_TRY(d_e.alloc(n_seq * 8)); XS_TRY(d_doc.alloc(n_seq * 4));
+    std::vector<uint32_t> doc_rank(n_seq);
+    for (uint64_t i = 0; i < n_seq; ++i) doc_rank[i] = rank[seq_doc[i]];
+    if (n_bases) XS_CUDA(cudaMemcpy(d_bases.p, bases, n_bases, cudaMemcpyHostToDevice));
+    if (n_seq) {
+        XS_CUDA(cudaMemcpy(d_b.p, seq_begin, n_seq * 8, cudaMemcpyHostToDevice));
+        XS_CUDA(cudaMemcpy(d_e.p, seq_end, n_seq * 8, cudaMemcpyHostToDevice));
+        XS_CUDA(cudaMemcpy(d_doc.p, doc_rank.data(), n_seq * 4, cudaMemcpyHostToDevice));
+    }
+    Workspace ws;
+    SeqBatch sb{};
+    XS_TRY(prepare_batch(ws, sb, (const uint8_t*)d_bases.p, n_bases, (const uint64_t*)d_b.p, (const uint64_t*)d_e.p, n_seq, 0, k, 1, 0, n_sm, s));
+    FILE* f = fopen(out_path, "wb");
+    if (!f) return fail(XS_ERR_IO, std::string(out_path) + ": " + strerror(errno));
+    int rc = put_all(f, head.data(), head.size()) ? XS_OK : fail(XS_ERR_IO, "write failed");
+    std::vector<uint8_t> host;
+    for (uint64_t pg = 0; pg < n_pages && rc == XS_OK; ++pg) {
+        uint64_t bytes = sig[pg] * row_bytes;
+        DevBuf d_page;
+        rc = d_page.alloc(bytes + 8);
+        if (rc != XS_OK) break;
+        cudaMemsetAsync(d_page.p, 0, bytes + 8, s);
+        CobsBuildParams bp{};
+        bp.sb = sb; bp.seq_doc = (const uint32_t*)d_doc.p; bp.data = (uint8_t*)d_page.p; bp.sig_size = sig[pg]; bp.magic = magic_of(sig[pg]);
+        bp.row_bytes = (uint32_t)row_bytes; bp.num_hashes = num_hashes; bp.canonicalize = canonicalize; bp.policy = XS_NONACGT_SKIP;
+        bp.doc_lo = (uint32_t)(pg * per_page); bp.doc_hi = (uint32_t)std::min<uint64_t>((pg + 1) * per_page, n_docs);
+        k_cobs_build<<<n_sm * 8, 256, 0, s>>>(bp);
+        rc = launch_ok("k_cobs_build");
+        if (rc != XS_OK) break;
+        host.resize(bytes);
+        cudaError_t e = cudaMemcpyAsync(host.data(), d_page.p, bytes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { rc = fail(XS_ERR_CUDA, std::string("index build: ") + cudaGetErrorString(e)); break; }
+        if (!put_all(f, host.data(), bytes)) rc = fail(XS_ERR_IO, "write failed");
+    }
+    if (fclose(f) != 0 && rc == XS_OK) rc = fail(XS_ERR_IO, "write failed");
+    cudaStreamSynchronize(s);
+    return rc;
+}
+
+int xs_bloom_build(const char* out_path, int device, uint32_t k, uint64_t expected_items, double fpr, const uint8_t* bases,
+                   uint64_t n_bases, const uint64_t* seq_begin, const uint64_t* seq_end, uint64_t n_seq) {
+    if (!out_path || (n_seq && (!seq_begin || !seq_end)) || (n_bases && !bases)) return fail(XS_ERR_ARG, "NULL argument");
+    if (k == 0 || k > 32) return fail(XS_ERR_UNSUPPORTED, "term_size must be in 1..32");
+    if (expected_items == 0 || !(fpr > 0.0 && fpr < 1.0)) return fail(XS_ERR_ARG, "expected_items must be > 0 and the false positive rate in (0, 1)");
+    // rbloom.Bloom(expected_items, fpr): bits = -n ln(fpr) / ln(2)^2 (truncated), k = trunc(bits / n * ln 2)
+    double size_in_bits = -1.0 * (double)expected_items * std::log(fpr) / std::pow(std::log(2.0), 2.0);
+    uint64_t k_hashes = (uint64_t)((size_in_bits / (double)expected_items) * std::log(2.0));
+    uint64_t n_bytes = ((uint64_t)size_in_bits + 7) / 8;
+    if (n_bytes == 0) return fail(XS_ERR_ARG, "filter would be empty");
+    DeviceGuard guard(device);
+    int n_sm = 0;
+    XS_TRY(device_setup(device, &n_sm));
+    cudaStream_t s = nullptr;
+    DevBuf d_bases, d_b, d_e, d_bits;
+    XS_TRY(d_bases.alloc(n_bases + 64));
+    XS_TRY(d_b.alloc(n_seq * 8)); XS_TRY(d_e.alloc(n_seq * 8)); XS_TRY(d_bits.alloc(n_bytes + 8));
+    if (n_bases) XS_CUDA(cudaMemcpy(d_bases.p, bases, n_bases, cudaMemcpyHostToDevice));
+    if (n_seq) {
+        XS_CUDA(cudaMemcpy(d_b.p, seq_begin, n_seq * 8, cudaMemcpyHostToDevice));
+        XS_CUDA(cudaMemcpy(d_e.p, seq_end, n_seq * 8, cudaMemcpyHostToDevice));
+    }
+    XS_CUDA(cudaMemsetAsync(d_bits.p, 0, n_bytes + 8, s));
+    Workspace ws;
+    BloomBuildParams bp{};
+    XS_TRY(prepare_batch(ws, bp.sb, (const uint8_t*)d_bases.p, n_bases, (const uint64_t*)d_b.p, (const uint64_t*)d_e.p, n_seq, 0, k, 1, 0, n_sm, s));
+    bp.bits = (uint8_t*)d_bits.p; bp.n_bits = n_bytes * 8; bp.magic = magic_of(n_bytes * 8); bp.k_hashes = (uint32_t)k_hashes;
+    k_bloom_build<<<n_sm * 8, 256, 0, s>>>(bp);
+    XS_TRY(launch_ok("k_bloom_build"));
+    std::vector<uint8_t> host(n_bytes);
+    XS_CUDA(cudaMemcpyAsync(host.data(), d_bits.p, n_bytes, cudaMemcpyDeviceToHost, s));
+    XS_CUDA(cudaStreamSynchronize(s));
+    FILE* f = fopen(out_path, "wb");
+    if (!f) return fail(XS_ERR_IO, std::string(out_path) + ": " + strerror(errno));
+    bool ok = put_all(f, &k_hashes, 8) && put_all(f, host.data(), n_bytes);
+    if (fclose(f) != 0) ok = false;
+    return ok ? XS_OK : fail(XS_ERR_IO, std::string(out_path) + ": write failed");
+}
+
+// ---- single stages -----------------------------------------------------------------------
 static int stage_pack(const uint8_t* bases, uint64_t n_bases, int n_sm, DevBuf& d_bases, DevBuf& d_packed, DevBuf& d_inv) {
     uint64_t n_words = n_bases / 32 + 2;
     XS_TRY(d_bases.alloc(n_bases + 64));

@@ -356,6 +356,28 @@ def scores_reduce_device(d_counts: int, n_seq: int, n_docs: int, dtype: int, dev
                                         d_n_best or None, d_totals or None, stream or None))
 
 
+def build_cobs(path, kind: int, k: int, num_hashes: int, fpr: float, names: list[str], bases, seq_begin, seq_end, seq_doc,
+               canonicalize: int = 1, sig_size: int = 0, page_size: int = 0, device: int = 0) -> None:
+    """Construct a COBS classic (kind 1) / compact (kind 2) index file on the GPU: sequence i belongs to document
+    ``seq_doc[i]`` (index into ``names``)."""
+    bases = _as_bases(bases)
+    b, e = _as_u64(seq_begin), _as_u64(seq_end)
+    doc = np.ascontiguousarray(seq_doc, dtype=np.uint32)
+    if any("\n" in n for n in names):
+        raise ValueError("document names must not contain line breaks")
+    blob = ("\n".join(names) + "\n").encode("utf-8")
+    check(lib().xs_cobs_build(str(path).encode(), int(device), int(kind), int(k), int(num_hashes), float(fpr), int(canonicalize),
+                              int(sig_size), int(page_size), blob, len(names), _ptr(bases), bases.size, _ptr(b), _ptr(e), _ptr(doc), b.size))
+
+
+def build_bloom(path, k: int, expected_items: int, fpr: float, bases, seq_begin, seq_end, device: int = 0) -> None:
+    """Construct an rbloom filter file on the GPU from every k-mer of the given sequences."""
+    bases = _as_bases(bases)
+    b, e = _as_u64(seq_begin), _as_u64(seq_end)
+    check(lib().xs_bloom_build(str(path).encode(), int(device), int(k), int(expected_items), float(fpr), _ptr(bases), bases.size,
+                               _ptr(b), _ptr(e), b.size))
+
+
 def device_count() -> int:
     n = C.c_int()
     rc = lib().xs_device_count(C.byref(n))

@@ -61,8 +61,32 @@ class ProbabilisticFilterMlstSchemeModel(ProbabilisticFilterModel):
     def get_cobs_index_path(self, locus: str) -> Path:
         return self.base_path / self.slug() / f"{locus}.cobs_compact"
 
-    def fit(self, scheme_path: Path) -> None:
-        raise NotImplementedError("xspect2_b200 accelerates prediction only; train the model with XspecT")
+    def fit(self, scheme_path: Path, device: int | None = None) -> None:
+        """One compact index per locus directory of ``scheme_path``, one document per allele file (reference
+        :100-142 via cobs compact_construct_list), constructed on the GPU.  ``avg_locus_bp_size`` is, like there, the
+        length of the first allele file's record; loci and files are taken in sorted order."""
+        if not scheme_path.exists():
+            raise ValueError("Scheme not found. Please make sure to download the schemes prior!")
+        from ..definitions import fasta_endings, fastq_endings
+        from ..seqio import SequenceBatch
+        from .probabilistic_filter_model import _abi_kind
+        dev = default_device() if device is None else device
+        for locus_path in sorted(scheme_path.iterdir()):
+            if not locus_path.is_dir():
+                continue
+            locus = locus_path.name
+            files = [p for p in sorted(locus_path.iterdir()) if p.is_file() and p.suffix[1:] in fasta_endings + fastq_endings]
+            self.loci[locus] = sum(1 for p in files if p.suffix == ".fasta")
+            first = next((p for p in files if p.suffix == ".fasta"), None)
+            if first is None:
+                raise ValueError(f"No allele fasta files found for locus {locus}")
+            self.avg_locus_bp_size.append(int(SequenceBatch.from_file(first).lengths[0]))
+            names = [p.stem.split(".")[0] for p in files]
+            bases, begin, end, seq_doc = self._gather_documents(files)
+            cobs_path = self.get_cobs_index_path(locus)
+            cobs_path.parent.mkdir(exist_ok=True, parents=True)
+            engine.build_cobs(cobs_path, _abi_kind("compact"), self.k, self.num_hashes, self.fpr, names, bases, begin, end, seq_doc, device=dev)
+            self.indices.append(engine.Search(str(cobs_path), False, device=dev))
 
     def save(self) -> None:
         json_path = self.base_path / f"{self.slug()}.json"

@@ -25,6 +25,11 @@ from ..seqio import Seq, SeqRecord, SequenceBatch
 from .result import ColumnarModelResult, ModelResult
 
 
+def _abi_kind(kind: str) -> int:
+    from .._abi import XS_COBS_CLASSIC, XS_COBS_COMPACT
+    return XS_COBS_CLASSIC if kind == "classic" else XS_COBS_COMPACT
+
+
 def default_device() -> int:
     """GPU the models load onto: ``XSPECT_B200_DEVICE`` or, under torchrun, ``LOCAL_RANK``; else 0."""
     return int(os.environ.get("XSPECT_B200_DEVICE", os.environ.get("LOCAL_RANK", 0)))
@@ -119,10 +124,51 @@ class ProbabilisticFilterModel:
     def slug(self) -> str:
         return slugify(self.model_display_name + "-" + str(self.model_type))
 
-    def fit(self, dir_path: Path, display_names: dict | None = None, training_accessions: dict[str, list[str]] | None = None) -> None:
-        """Index construction (cobs classic_construct_list, reference :169-194) is outside the scoring path;
-        train with XspecT and load the resulting files here unchanged."""
-        raise NotImplementedError("xspect2_b200 accelerates prediction only; train the model with XspecT")
+    @staticmethod
+    def _gather_documents(files: list[Path]):
+        """All records of the given files as one buffer; sequence i belongs to document ``seq_doc[i]`` = its file."""
+        parts, begins, ends, docs = [], [], [], []
+        off = 0
+        for d, file in enumerate(files):
+            b = SequenceBatch.from_file(file)
+            parts.append(b.bases)
+            begins.append(b.begin + np.uint64(off))
+            ends.append(b.end + np.uint64(off))
+            docs.append(np.full(len(b), d, dtype=np.uint32))
+            off += b.bases.size
+        cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dt)   # noqa: E731
+        return cat(parts, np.uint8), cat(begins, np.uint64), cat(ends, np.uint64), cat(docs, np.uint32)
+
+    def fit(self, dir_path: Path, display_names: dict | None = None, training_accessions: dict[str, list[str]] | None = None,
+            device: int | None = None) -> None:
+        """Build ``<slug>/index.cobs_classic`` from the fasta/fastq files of a directory, one document per file
+        (reference :138-194, which hands the files to cobs classic_construct_list) — here the construction runs on
+        the GPU (xs_cobs_build).  Document names are the file names up to the first '.', as cobs derives them;
+        files are taken in sorted order."""
+        if display_names is None:
+            display_names = {}
+        if not isinstance(dir_path, Path):
+            raise ValueError("Invalid directory path, must be a pathlib.Path object")
+        if not dir_path.exists():
+            raise ValueError("Directory path does not exist")
+        if not dir_path.is_dir():
+            raise ValueError("Directory path must be a directory")
+        self.training_accessions = training_accessions
+        from ..definitions import fasta_endings, fastq_endings
+        files = [f for f in sorted(dir_path.iterdir()) if f.is_file() and f.suffix[1:] in fasta_endings + fastq_endings]
+        if not files:
+            raise ValueError("No valid files found in directory. Must be fasta or fastq")
+        names = []
+        for file in files:
+            doc_name = file.stem.split(".")[0]
+            self.display_names[doc_name] = display_names.get(file.stem, file.stem)
+            names.append(doc_name)
+        bases, begin, end, seq_doc = self._gather_documents(files)
+        index_path = Path(self.get_cobs_index_path())
+        index_path.parent.mkdir(exist_ok=True, parents=True)
+        dev = default_device() if device is None else device
+        engine.build_cobs(index_path, _abi_kind("classic"), self.k, self.num_hashes, self.fpr, names, bases, begin, end, seq_doc, device=dev)
+        self._open_index(dev)
 
     def save(self) -> None:
         json_path = self.base_path / f"{self.slug()}.json"

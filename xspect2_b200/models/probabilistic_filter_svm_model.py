@@ -55,9 +55,29 @@ class ProbabilisticFilterSVMModel(ProbabilisticFilterModel):
         self.c = c
         self.save()
 
-    def fit(self, dir_path: Path, svm_path: Path, display_names=None, svm_step: int = 1, training_accessions=None,
-            svm_accessions=None) -> None:
-        raise NotImplementedError("xspect2_b200 accelerates prediction only; train the model with XspecT")
+    def fit(self, dir_path: Path, svm_path: Path, display_names: dict[str, str] | None = None, svm_step: int = 1,
+            training_accessions=None, svm_accessions=None, device: int | None = None) -> None:
+        """Build the index (parent ``fit``), then score every file of ``svm_path/<label>/`` and write
+        ``<slug>/scores.csv`` — rows ``accession,<total score per sorted document id>,label`` under the header
+        ``file,<sorted ids>,label_id`` (reference :112-173)."""
+        from ..definitions import fasta_endings, fastq_endings
+        super().fit(dir_path, display_names=display_names, training_accessions=training_accessions, device=device)
+        self.svm_accessions = svm_accessions
+        score_list = []
+        for species_folder in sorted(svm_path.iterdir()):
+            if not species_folder.is_dir():
+                continue
+            for file in sorted(species_folder.iterdir()):
+                if file.suffix[1:] not in fasta_endings + fastq_endings:
+                    continue
+                print(f"Calculating {file.name} scores for SVM training...")
+                res = ProbabilisticFilterModel.predict(self, file, step=svm_step)
+                scores = dict(sorted(res.get_total_scores().items()))
+                score_list.append(f"{file.stem},{','.join(str(v) for v in scores.values())},{species_folder.name}")
+        keys = sorted(self.display_names.keys())
+        score_list.insert(0, f"file,{','.join(keys)},label_id")
+        with open(self.base_path / self.slug() / "scores.csv", "w", encoding="utf-8") as file:
+            file.write("\n".join(score_list))
 
     def svm_input(self, res: ModelResult) -> list[list[float]]:
         """The SVM feature row: total scores ordered by sorted label string (reference :212-213)."""

@@ -47,8 +47,21 @@ class ProbabilisticSingleFilterModel(ProbabilisticFilterModel):
         )
         self.bf = None
 
-    def fit(self, file_path: Path, display_name: str, training_accessions: list[str] | None = None) -> None:
-        raise NotImplementedError("xspect2_b200 accelerates prediction only; train the model with XspecT")
+    def fit(self, file_path: Path, display_name: str, training_accessions: list[str] | None = None, device: int | None = None) -> None:
+        """Build ``<slug>/filter.bloom`` from every k-mer of the records of ``file_path`` (reference :63-96: a
+        per-k-mer Python loop around rbloom.add) with one kernel launch; sized like the reference:
+        ``Bloom(total_length - k + 1, fpr)``."""
+        from ..file_io import get_record_iterator
+        self.training_accessions = training_accessions
+        get_record_iterator(file_path)     # same path / format errors as the reference
+        batch = SequenceBatch.from_file(file_path)
+        num_kmers = int(batch.lengths.sum()) - self.k + 1
+        bloom_path = self.base_path / self.slug() / "filter.bloom"
+        bloom_path.parent.mkdir(parents=True, exist_ok=True)
+        dev = default_device() if device is None else device
+        engine.build_bloom(bloom_path, self.k, num_kmers, self.fpr, batch.bases, batch.begin, batch.end, device=dev)
+        self.display_names[file_path.stem] = display_name
+        self.bf = engine.Bloom.load(str(bloom_path), self.k, device=dev)
 
     def calculate_hits(self, sequence: Seq | SeqRecord, exclude_ids=None, step: int = 1) -> dict:
         """``{first display name key: number of sampled k-mers found in the filter}`` (reference :98-125)."""
