@@ -294,6 +294,35 @@ def workflow(td: Path):
                       "reads_per_sec_overall": n_reads / (t2 - t0)}), flush=True)
 
 
+def train(td: Path):
+    """Construction on the GPU at a fraction of the real model sizes: classic index of 90 documents x 4 Mbp
+    (S = 38.4 M rows) and a genus Bloom filter over 360 Mbp."""
+    n_docs, doc_len, k = 90, 4_000_000, 21
+    gen = torch.Generator(device=dev).manual_seed(21)
+    acgt = torch.from_numpy(synth.ACGT.copy()).to(dev)
+    bases = acgt[torch.randint(0, 4, (n_docs * doc_len,), generator=gen, device=dev)].cpu().numpy()
+    begin = np.arange(n_docs, dtype=np.uint64) * np.uint64(doc_len)
+    end = begin + np.uint64(doc_len)
+    names = [str(1000 + d) for d in range(n_docs)]
+    t0 = time.perf_counter()
+    engine.build_cobs(td / "index.cobs_classic", 1, k, 7, 0.01, names, bases, begin, end, np.arange(n_docs, dtype=np.uint32))
+    t_cobs = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    engine.build_bloom(td / "filter.bloom", k, n_docs * doc_len - k + 1, 0.01, bases, begin, end)
+    t_bloom = time.perf_counter() - t0
+    # self-check: every document scores 100 % on its own column, members are found
+    ix = engine.CobsIndex(td / "index.cobs_classic")
+    c = ix.counts(bases[5 * doc_len: 5 * doc_len + 100_000])
+    assert int(c[5]) == 100_000 - k + 1 and int(np.delete(c, 5).max()) < 3000
+    bf = engine.BloomFilter(td / "filter.bloom", k)
+    assert bf.hits(bases[7 * doc_len: 7 * doc_len + 50_000]) == 50_000 - k + 1
+    print(json.dumps({"config": "training: classic index 90 docs x 4 Mbp (h=7, fpr=0.01) and genus Bloom over 360 Mbp, host arrays -> files",
+                      "cobs_build_s": t_cobs, "cobs_file_GB": (td / "index.cobs_classic").stat().st_size / 1e9,
+                      "cobs_kmers_per_sec": n_docs * (doc_len - k + 1) / t_cobs,
+                      "bloom_build_s": t_bloom, "bloom_file_GB": (td / "filter.bloom").stat().st_size / 1e9,
+                      "bloom_kmers_per_sec": n_docs * (doc_len - k + 1) / t_bloom}), flush=True)
+
+
 def api(td: Path):
     """FASTQ on disk -> per-read counts through the model API (native reader + batched query), vs the numbers above."""
     rng = np.random.default_rng(9)
@@ -350,4 +379,4 @@ if __name__ == "__main__":
         for w in which:
             sub = Path(td) / w
             sub.mkdir()
-            {"bloom": bloom, "mlst": mlst, "wide": wide, "api": api, "twostage": twostage, "assembly": assembly, "workflow": workflow}[w](sub)
+            {"bloom": bloom, "mlst": mlst, "wide": wide, "api": api, "twostage": twostage, "assembly": assembly, "workflow": workflow, "train": train}[w](sub)
