@@ -77,3 +77,27 @@ def test_totals_epilogue_shards_and_dtypes_agree(big, gpu):
     joined = np.concatenate([np.asarray(lo.query(big["reads"][: n * L], big["b"][:n], big["e"][:n], 1)),
                              np.asarray(hi.query(big["reads"][: n * L], big["b"][:n], big["e"][:n], 1))], axis=1)
     assert np.array_equal(joined, fwd[:n])
+
+
+def test_one_very_long_sequence_through_the_host_pipeline(big):
+    """A single 70 Mbp record (larger than one pipeline batch) equals the sum of its two overlapping halves, and a
+    mixed batch with records before and after it keeps every row where it belongs."""
+    ix = big["ix"]
+    rng = np.random.default_rng(5)
+    n = 70_000_000
+    seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, size=n)]
+    seq[10_000_000:10_600_000] = big["genome"][:600_000]              # a stretch of the planted genome
+    whole = ix.counts(seq, 1).astype(np.int64)
+    half = n // 2
+    a = ix.counts(seq[: half + K - 1], 1).astype(np.int64)
+    b = ix.counts(seq[half:], 1).astype(np.int64)
+    assert np.array_equal(a + b, whole) and whole[0] >= 600_000 - K + 1
+    small = big["reads"][: 1000 * L]
+    bases = np.concatenate([small, seq, small])
+    begin = np.concatenate([big["b"][:1000], [1000 * L], big["b"][:1000] + np.uint64(1000 * L + n)]).astype(np.uint64)
+    end = np.concatenate([big["e"][:1000], [1000 * L + n], big["e"][:1000] + np.uint64(1000 * L + n)]).astype(np.uint64)
+    mixed = np.asarray(ix.query(bases, begin, end, 1, dtype=4)).astype(np.int64)
+    assert np.array_equal(mixed[1000], whole)
+    assert np.array_equal(mixed[:1000], mixed[1001:])
+    ref = np.asarray(ix.query(small, big["b"][:1000], big["e"][:1000], 1, dtype=4)).astype(np.int64)
+    assert np.array_equal(mixed[:1000], ref)
