@@ -164,3 +164,48 @@ def test_mlst_fit_builds_compact_indices(gpu, oracle, tmp_path):
     best = res.hits["a4"][0]["Strain type"]["Oxf_cpn60"]
     assert list(best.values()) == [a4.size - 21 + 1]                      # G9 shape: every k-mer of the allele hits
     assert res.hits["a4"][1]["All results"]["Oxf_cpn60"]["Allele_ID_4"] == a4.size - 21 + 1
+
+
+def test_train_from_directory_and_cli(gpu, oracle, tmp_path, monkeypatch):
+    """train.train_from_directory (train.py:28-184 of the reference) on local data, then the trained models through
+    the CLI: `models train directory`, `models list`, `classify species`, `classify genus`."""
+    import importlib
+    import json
+    from click.testing import CliRunner
+    monkeypatch.setenv("HOME", str(tmp_path / "home"))
+    (tmp_path / "home" / "xspect-data").mkdir(parents=True)
+    rng = np.random.default_rng(6)
+    data = tmp_path / "training"
+    anc = synth.random_dna(rng, 9000)
+    genomes = {}
+    for sp in ("470", "471", "48296"):
+        g = anc.copy()
+        m = rng.random(g.size) < 0.4
+        g[m] = synth.ACGT[rng.integers(0, 4, size=int(m.sum()))]
+        genomes[sp] = g
+        for part, folder in (("cobs", data / "cobs" / sp), ("svm", data / "svm" / sp)):
+            folder.mkdir(parents=True)
+            for rep in range(2):
+                seq = g if part == "cobs" else synth.mutate(rng, g, sub=0.01 * (rep + 1))
+                mf.write_fasta(folder / f"GCF_{sp}_{rep}.fna", [(f"{sp}_{rep}_c{c}", seq[c * 3000:(c + 1) * 3000]) for c in range(3)])
+    import xspect2_b200.main as main
+    main = importlib.reload(main)
+    runner = CliRunner()
+    r = runner.invoke(main.cli, ["models", "train", "directory", "-g", "Trained", "-i", str(data), "--svm-steps", "2"])
+    assert r.exit_code == 0, r.output
+    models = tmp_path / "home" / "xspect-data" / "models"
+    assert (models / "trained-species.json").is_file() and (models / "trained-species" / "index.cobs_classic").is_file()
+    assert (models / "trained-species" / "scores.csv").is_file() and (models / "trained-genus" / "filter.bloom").is_file()
+    meta = json.loads((models / "trained-species.json").read_text())
+    assert meta["model_class"] == "ProbabilisticFilterSVMModel" and sorted(meta["display_names"]) == ["470", "471", "48296"]
+    main = importlib.reload(main)        # click choices are read at import
+    r = runner.invoke(main.cli, ["models", "list"])
+    assert "Trained" in r.output and "Genus:" in r.output and "Species:" in r.output
+    sample = tmp_path / "sample.fna"
+    mf.write_fasta(sample, [("contig1", synth.mutate(rng, genomes["471"], sub=0.005))])
+    r = runner.invoke(main.cli, ["classify", "species", "-g", "Trained", "-i", str(sample), "-o", str(tmp_path / "sp.json")])
+    assert r.exit_code == 0, r.output
+    assert json.loads((tmp_path / "sp.json").read_text())["prediction"] == "471"
+    r = runner.invoke(main.cli, ["classify", "genus", "-g", "Trained", "-i", str(sample), "-o", str(tmp_path / "ge.json")])
+    assert r.exit_code == 0, r.output
+    assert json.loads((tmp_path / "ge.json").read_text())["scores"]["total"]["Trained"] >= 0.8

@@ -64,3 +64,23 @@ def prepare_input_output_paths(input_path: Path) -> tuple[list[Path], Callable[[
         return output_path
 
     return input_paths, get_output_path
+
+
+def concatenate_species_fasta_files(input_folders: list[Path], output_directory: Path) -> None:
+    """One ``<species>.fasta`` per species folder, the folder's fasta files appended one after another
+    (file_io.py:82-109 of the reference; files in sorted order here)."""
+    for species_folder in input_folders:
+        fasta_files = sorted(f for ending in fasta_endings for f in species_folder.glob(f"*.{ending}"))
+        if len(fasta_files) == 0:
+            raise ValueError(f"no fasta files found in {species_folder}")
+        with open(output_directory / f"{species_folder.name}.fasta", "wb") as out:
+            for fasta_file in fasta_files:
+                out.write(fasta_file.read_bytes())
+
+
+def concatenate_metagenome(fasta_dir: Path, meta_path: Path) -> None:
+    """All fasta files of a directory appended into one file (file_io.py:112-132 of the reference)."""
+    fasta_files = sorted(f for ending in fasta_endings for f in fasta_dir.glob(f"*.{ending}"))
+    with open(meta_path, "wb") as meta_file:
+        for fasta_file in fasta_files:
+            meta_file.write(fasta_file.read_bytes())
