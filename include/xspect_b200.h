@@ -169,6 +169,10 @@ int xs_bloom_close(xs_bloom* bf);
  * bytes, no filtering) passes all k_hashes LCG probes seeded by XXH3-64}. */
 int xs_bloom_query(xs_bloom* bf, const uint8_t* bases, uint64_t n_bases, const uint64_t* seq_begin,
                    const uint64_t* seq_end, uint64_t n_seq, uint32_t step, uint32_t* out_hits);
+/* Replaces `obj in bf` (rbloom.Bloom.__contains__) on caller-supplied terms: terms holds n_terms strings of term_size
+ * bytes back to back, each hashed as it is (no canonicalisation — the reference canonicalises in _generate_kmers,
+ * probabilistic_single_filter_model.py:175-180, before it asks the filter); out[i] = 1 for members. */
+int xs_bloom_contains(xs_bloom* bf, const uint8_t* terms, uint64_t n_terms, uint8_t* out);
 int xs_bloom_query_device(xs_bloom* bf, const uint8_t* d_bases, uint64_t n_bases,
                           const uint64_t* d_seq_begin, const uint64_t* d_seq_end, uint64_t n_seq,
                           uint32_t step, uint32_t* d_out_hits, void* stream);

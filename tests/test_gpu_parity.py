@@ -328,6 +328,11 @@ def test_single_record_shims(gpu, oracle, tmp_path):
     bf = gpu.Bloom.load(str(pb), 21)
     km = oracle.bloom_term(g[50:71].tobytes()).decode()
     assert km in bf
+    # `in` hashes the k-mer as given, canonical or not (rbloom does not canonicalise)
+    orc_bf = oracle.BloomOracle(pb, 21)
+    probes = [g[i:i + 21].tobytes().decode() for i in range(0, 2000, 37)] + ["TTGCAACCAGACGTAATCTCT", "acgtnACGTNacgtnACGTNa"]
+    assert [p in bf for p in probes] == [p in orc_bf for p in probes]
+    assert np.array_equal(bf.filter.contains(probes), np.array([p in orc_bf for p in probes]))
     assert (oracle.bloom_term(b"ACGTTGCATGCATGCATGCAA").decode() in bf) == (
         oracle.bloom_term(b"ACGTTGCATGCATGCATGCAA").decode() in oracle.BloomOracle(pb, 21))
 

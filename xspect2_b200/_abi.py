@@ -62,6 +62,7 @@ SYMBOLS = {
     "xs_bloom_info": (C.c_int, [_P, C.POINTER(BloomInfo)]),
     "xs_bloom_close": (C.c_int, [_P]),
     "xs_bloom_query": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, _P]),
+    "xs_bloom_contains": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "xs_bloom_query_device": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, _P, _P]),
     "xs_cobs_build": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32, C.c_uint64, C.c_uint64,
                                 C.c_char_p, C.c_uint32, _P, C.c_uint64, _P, _P, _P, C.c_uint64]),

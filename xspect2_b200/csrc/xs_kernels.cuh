@@ -575,7 +575,7 @@ struct BloomParams {
     uint64_t n_bits;
     uint64_t magic;      // floor(2^64 / n_bits)
     uint32_t k_hashes;
-    uint32_t pad;
+    uint32_t literal;    // 1: hash the window bytes as they are (rbloom's `obj in bf` on a caller-supplied k-mer)
     uint32_t* out;       // [n_seq]
     uint64_t seq0;
 };
@@ -627,7 +627,8 @@ __global__ void __launch_bounds__(BLOOM_NT, 4) k_bloom(const BloomParams p) {
                 bool hit = false;
                 if (has) {
                     Term t;
-                    bloom_term<K>(sb, pos, t);
+                    if (p.literal) literal_term(sb.bases, pos, k, BioComp(), false, t);
+                    else bloom_term<K>(sb, pos, t);
                     hit = bloom_member(p, xxh3_64(t, k));
                 }
                 bal = __ballot_sync(0xFFFFFFFFu, hit);

@@ -411,9 +411,10 @@ static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
     return cobs_launch(ix, sb, ws.prefix2, dt, d_out, s);   // ws goes back to the stream-ordered pool on scope exit
 }
 
-static int bloom_launch(xs_bloom* bf, const SeqBatch& sb, uint32_t* d_out, cudaStream_t s) {
+static int bloom_launch(xs_bloom* bf, const SeqBatch& sb, uint32_t* d_out, cudaStream_t s, bool literal = false) {
     BloomParams p{};
     p.sb = sb;
+    p.literal = literal ? 1u : 0u;
     p.bits = bf->d_bits; p.n_bits = bf->info.n_bits; p.magic = magic_of(bf->info.n_bits);
     p.k_hashes = (uint32_t)bf->info.k_hashes; p.out = d_out; p.seq0 = 0;
     dim3 grid((unsigned)(bf->n_sm * 4));
@@ -961,6 +962,29 @@ int xs_bloom_close(xs_bloom* bf) {
     DeviceGuard guard(bf->info.device);
     if (bf->d_bits) cudaFree(bf->d_bits);
     delete bf;
+    return XS_OK;
+}
+
+int xs_bloom_contains(xs_bloom* bf, const uint8_t* terms, uint64_t n_terms, uint8_t* out) {
+    if (!bf || (n_terms && (!terms || !out))) return fail(XS_ERR_ARG, "NULL argument");
+    DeviceGuard guard(bf->info.device);
+    if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the filter's device");
+    const uint32_t k = bf->info.term_size;
+    // every term is one sequence of exactly k bytes = one window, hashed without canonicalisation
+    const uint64_t CH = SMALL_MAX_SEQ;
+    std::vector<uint64_t> b(std::min(n_terms, CH)), e(b.size());
+    std::vector<uint32_t> hits(b.size());
+    for (uint64_t i0 = 0; i0 < n_terms; i0 += CH) {
+        uint64_t n = std::min(CH, n_terms - i0);
+        for (uint64_t i = 0; i < n; ++i) { b[i] = (i0 + i) * k; e[i] = b[i] + k; }
+        bool handled = false;
+        XS_TRY(small_query(bf->info.device, bf->n_sm, k, 1, 0, 1, terms, n_terms * k, b.data(), e.data(), n, 4, hits.data(), &handled,
+                           [&](const SeqBatch& sb, const uint64_t*, uint8_t* d_o, cudaStream_t s) {
+                               return bloom_launch(bf, sb, reinterpret_cast<uint32_t*>(d_o), s, true);
+                           }));
+        if (!handled) return fail(XS_ERR_NOMEM, "membership batch could not be staged");
+        for (uint64_t i = 0; i < n; ++i) out[i0 + i] = (uint8_t)(hits[i] != 0);
+    }
     return XS_OK;
 }
 

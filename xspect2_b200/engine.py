@@ -288,6 +288,20 @@ class BloomFilter:
         a = _as_bases(sequence)
         return int(self.query(a, np.array([0], np.uint64), np.array([a.size], np.uint64), step)[0])
 
+    def contains(self, terms) -> np.ndarray:
+        """Membership of k-mers exactly as given (no canonicalisation): ``terms`` is a list of str/bytes of length k
+        or a uint8 array [n, k]; returns bool [n]."""
+        if isinstance(terms, np.ndarray):
+            arr = np.ascontiguousarray(terms, dtype=np.uint8).reshape(-1, self.k)
+        else:
+            enc = [t.encode("utf-8") if isinstance(t, str) else bytes(t) for t in terms]
+            if any(len(t) != self.k for t in enc):
+                raise ValueError("k-mer length differs from the model's k")
+            arr = np.frombuffer(b"".join(enc), dtype=np.uint8).reshape(-1, self.k) if enc else np.zeros((0, self.k), np.uint8)
+        out = np.zeros(arr.shape[0], np.uint8)
+        check(lib().xs_bloom_contains(self._h, _ptr(arr), arr.shape[0], _ptr(out)))
+        return out.astype(bool)
+
     def hashes(self, sequence, step: int = 1) -> np.ndarray:
         a = _as_bases(sequence)
         n_w = (a.size - self.k) // step + 1 if a.size >= self.k else 0
@@ -298,9 +312,8 @@ class BloomFilter:
 
 
 class Bloom:
-    """Drop-in for the loaded ``rbloom.Bloom``: ``kmer in bf`` for a k-mer string of the model's k.
-    The k-mer is taken as given (the caller has already canonicalised it, like _generate_kmers does),
-    so membership is evaluated on ``min(kmer, revcomp(kmer))`` == kmer for canonical input."""
+    """Drop-in for the loaded ``rbloom.Bloom``: ``kmer in bf`` for a k-mer string of the model's k, hashed exactly
+    as given (the caller canonicalises, like _generate_kmers does)."""
 
     def __init__(self, path, k: int, device: int = 0):
         self.filter = BloomFilter(path, k, device)
@@ -310,10 +323,7 @@ class Bloom:
         return cls(path, k, device)
 
     def __contains__(self, kmer) -> bool:
-        s = str(kmer)
-        if len(s) != self.filter.k:
-            raise ValueError("k-mer length differs from the model's k")
-        return self.filter.hits(s, 1) == 1
+        return bool(self.filter.contains([str(kmer)])[0])
 
 
 # --------------------------------------------------------------------------------------

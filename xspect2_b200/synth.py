@@ -69,24 +69,6 @@ def write_classic_index(path, *, n_docs: int, k: int, num_hashes: int, sig_size:
     return names
 
 
-def write_bloom_filter(path, *, n_bytes: int, k_hashes: int, seed: int, fill: float = 0.5, device=None,
-                       chunk: int = 1 << 28) -> None:
-    """Write an rbloom ``filter.bloom``: u64 LE hash count, then the bit array (iid bits)."""
-    dev = _dev(device)
-    gen = torch.Generator(device=dev).manual_seed(seed)
-    weights = (2 ** torch.arange(8, device=dev)).to(torch.int32)
-    with open(path, "wb") as f:
-        f.write(struct.pack("<Q", k_hashes))
-        for b0 in range(0, n_bytes, chunk):
-            n = min(chunk, n_bytes - b0)
-            if abs(fill - 0.5) < 1e-9:
-                data = torch.randint(0, 256, (n,), generator=gen, device=dev, dtype=torch.uint8)
-            else:
-                bits = (torch.rand((n, 8), generator=gen, device=dev) < fill).to(torch.int32)
-                data = (bits * weights).sum(dim=1).to(torch.uint8)
-            f.write(data.cpu().numpy().tobytes())
-
-
 def synth_reads(genome: np.ndarray, n_reads: int, read_len: int, seed: int, *, frac_genome: float = 0.6,
                 sub_rate: float = 0.001, n_rate: float = 0.0005, device=None, chunk: int = 1 << 20) -> torch.Tensor:
     """``n_reads`` reads of ``read_len`` bases, concatenated (uint8 ASCII) on ``device``: ``frac_genome`` sampled
