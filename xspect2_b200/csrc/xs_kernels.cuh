@@ -9,12 +9,17 @@
 //                     flight per lane), bit-plane counters, shared-memory count staging
 //   k_bloom           XXH3-64 -> 128-bit LCG -> bit probes with early exit
 //                     (probabilistic_single_filter_model.py:122-124,161-180)
+//   k_scores_reduce   per-record best document / tie multiplicity and per-document totals over a count matrix
+//   k_cobs_build,     construction: the query hashing with an atomic OR instead of a gather
+//   k_bloom_build       (probabilistic_filter_model.py:169-194, probabilistic_single_filter_model.py:63-96)
 //   stage kernels     canonical codes / row ids / bloom hashes alone, for the parity tests
 //
 // Work decomposition.  The sampled windows of all sequences of a batch form one flat index
 // space (win_prefix = exclusive scan of windows per sequence).  Persistent warps walk tiles of
 // that space (warp_walk), so lanes stay dense whatever the read lengths are; all bookkeeping
-// is warp-uniform (no shared memory, no CTA barrier on the narrow and Bloom paths).
+// is warp-uniform (no shared memory, no CTA barrier on the narrow and Bloom paths).  Tiles and work
+// items are handed out through an atomic counter: a static equal split runs at the pace of the
+// slowest SM (profiles/microbench/gather_concurrent.cu).
 #pragma once
 #include "xs_device.cuh"
 
