@@ -92,6 +92,9 @@ uint64_t xs_launch_count(void);
  * the last read, and clears them. */
 int xs_profile_enable(int on);
 int xs_profile_read(double* kernel_ms, uint64_t* launches);
+/* the same, split by kernel: [0] k_cobs_narrow / k_cobs_wide / k_bloom, [1] k_bucket_emit, [2] k_bucket_fetch,
+ * [3] k_bucket_reduce (four entries each) */
+int xs_profile_read_phases(double* kernel_ms, uint64_t* launches);
 /* pinned host memory for the host-buffer query entry points (pageable memory also works,
  * but is copied through the driver's bounce buffer) */
 int xs_host_alloc(uint64_t bytes, void** out);
@@ -109,6 +112,15 @@ int xs_cobs_info(const xs_cobs* ix, xs_cobs_info_t* info);
 /* document names of the whole file, '\n'-separated, no trailing NUL counted in *needed */
 int xs_cobs_doc_names(const xs_cobs* ix, char* buf, uint64_t cap, uint64_t* needed);
 int xs_cobs_set_policy(xs_cobs* ix, int policy);
+/* Large batches against a large narrow-row classic index (16-byte rows, 256 MB .. 8.6 GB in HBM) are scored by the
+ * bucketed kernels: probe records grouped by L2-sized row ranges, rows fetched from L2, ANDed per window in shared
+ * memory.  Results are identical to the direct-gather kernel's.  enabled: 0/1; min_windows: smallest batch (sampled
+ * windows) that takes this path (0 = keep); scratch_bytes: upper bound of the per-query device scratch (0 = keep);
+ * bucket_shift: log2 rows per bucket, 0 = automatic (test hook: lets small indices exercise the path).
+ * Defaults: enabled, 16 Mi windows, 24 GiB (never more than half of the free device memory). */
+int xs_cobs_set_bucketed(xs_cobs* ix, int enabled, uint64_t min_windows, uint64_t scratch_bytes, uint32_t bucket_shift);
+/* number of queries (device batches) of this handle that went through the bucketed kernels */
+int xs_cobs_bucketed_queries(const xs_cobs* ix, uint64_t* n);
 int xs_cobs_close(xs_cobs* ix);
 
 /* Replaces the per-record loop around cobs Search.search(str(sequence), step=step)

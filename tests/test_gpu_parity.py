@@ -73,6 +73,95 @@ def test_cobs_row_ids(gpu, oracle, tmp_path, k, h, step):
     assert np.array_equal(rows, erows)
 
 
+# ------------------------------------------------------------------------------------------ bucketed probing
+def _bucket_shift(path, gpu):
+    """Rows per bucket (log2) that gives a small test index 100-250 buckets (the shipped geometry has 144)."""
+    ix = gpu.CobsIndex(path)
+    s = int(ix.info.sig_size_max)
+    ix.close()
+    shift = 1
+    while ((s - 1) >> shift) + 1 > 250:
+        shift += 1
+    return shift
+
+
+def _check_bucketed(gpu, oracle, path, bases, b, e, step=1, dtype=None, policy=0, scratch=0, shift=None):
+    ix = gpu.CobsIndex(path)
+    ix.set_policy(policy)
+    ix.set_bucketed(True, min_windows=1, scratch_bytes=scratch, bucket_shift=shift or _bucket_shift(path, gpu))
+    got = ix.query(bases, b, e, step=step, dtype=dtype)
+    assert ix.bucketed_queries >= 1, "the bucketed kernels did not run"
+    exp = oracle.CobsOracle(path, policy=policy).counts_batch(bases, b, e, step=step, threads=4)
+    if dtype in (1, 2):
+        exp = np.minimum(exp, 255 if dtype == 1 else 65535)
+    bad = np.argwhere(got.astype(np.uint32) != exp)
+    assert bad.size == 0, f"{bad.shape[0]} mismatches, first {bad[:5].tolist()}: got {got[tuple(bad[0])]} exp {exp[tuple(bad[0])]}"
+    # and the direct-gather kernel agrees
+    ix.set_bucketed(False)
+    n0 = ix.bucketed_queries
+    assert np.array_equal(ix.query(bases, b, e, step=step, dtype=dtype), got)
+    assert ix.bucketed_queries == n0
+    ix.close()
+    return got
+
+
+@pytest.mark.parametrize("n_docs", [8, 90, 97, 128])
+@pytest.mark.parametrize("k,h", [(21, 7), (31, 1), (15, 3)])
+def test_cobs_bucketed_reads(gpu, oracle, tmp_path, n_docs, k, h):
+    """Ragged reads with N / substitutions through k_bucket_emit / fetch / reduce (both row packings: <= 96 and
+    > 96 documents), several chunks, records straddling chunk and warp boundaries."""
+    rng = np.random.default_rng(300 + n_docs)
+    p, docs = _mk_classic(oracle, tmp_path, rng, n_docs, k, h)
+    genomes = [s for v in docs.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes, 700, (k, 300), sub=0.01, n_rate=0.003)
+    got = _check_bucketed(gpu, oracle, p, bases, b, e)
+    assert got.sum() > 0
+
+
+@pytest.mark.parametrize("step", [1, 3, 500])
+@pytest.mark.parametrize("dtype", [None, 1])
+def test_cobs_bucketed_long_and_low_complexity(gpu, oracle, tmp_path, step, dtype):
+    """Contigs spanning many chunks, homopolymer / short-period runs that overflow single blocks (direct-gather
+    windows), empty and short records in between, saturating uint8 counts on long records."""
+    rng = np.random.default_rng(17)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 12, 21, 7, length=20000)
+    g = docs["doc00003"][0]
+    rep = np.tile(np.frombuffer(b"ACGTTGCA", np.uint8), 900)
+    parts = [synth.mutate(rng, g, n_rate=0.0005), np.full(6000, ord("A"), np.uint8), g[:0], g[:20], g[:21], rep, g[100:250],
+             np.full(300, ord("N"), np.uint8), g[:5000] | 0x20, synth.random_dna(rng, 2500), g[::-1].copy()]
+    bases = np.concatenate(parts)
+    lens = np.array([x.size for x in parts], np.uint64)
+    e = np.cumsum(lens, dtype=np.uint64)
+    b = e - lens
+    _check_bucketed(gpu, oracle, p, bases, b, e, step=step, dtype=dtype)
+    if step == 1:
+        _check_bucketed(gpu, oracle, p, bases, b, e, step=step, dtype=dtype, policy=1)
+
+
+def test_cobs_bucketed_sub_batches_and_overlaps(gpu, oracle, tmp_path):
+    """A scratch budget of a few chunks (many sub-batches) and overlapping / unordered segments (MLST-style)."""
+    rng = np.random.default_rng(19)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 90, 21, 7, length=4000)
+    genomes = [s for v in docs.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes, 900, 150, sub=0.002, n_rate=0.0005)
+    _check_bucketed(gpu, oracle, p, bases, b, e, scratch=3 << 20)
+    g = np.concatenate(genomes[:3])
+    n = 400
+    bb = rng.integers(0, g.size - 600, n).astype(np.uint64)
+    ee = bb + rng.integers(0, 600, n).astype(np.uint64)
+    _check_bucketed(gpu, oracle, p, g, bb, ee, scratch=3 << 20)
+
+
+def test_cobs_bucketed_shift_21_and_few_buckets(gpu, oracle, tmp_path):
+    """Other geometries of the record word: 2^21 rows per bucket (one bucket here) and 2 rows per bucket."""
+    rng = np.random.default_rng(23)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 30, 21, 7, length=40)     # tiny signature: a few hundred rows
+    genomes = [s for v in docs.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes, 300, (21, 40), frac_random=0.1)
+    _check_bucketed(gpu, oracle, p, bases, b, e, shift=21)
+    _check_bucketed(gpu, oracle, p, bases, b, e, shift=_bucket_shift(p, gpu))
+
+
 # ------------------------------------------------------------------------------------------ narrow rows
 @pytest.mark.parametrize("n_docs", [1, 7, 8, 9, 90, 128])
 @pytest.mark.parametrize("k,h", [(21, 7), (31, 1), (15, 3)])

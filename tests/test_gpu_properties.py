@@ -43,6 +43,30 @@ def test_reverse_complement_invariance(big):
     big["fwd"] = fwd
 
 
+def test_bucketed_and_direct_kernels_agree(big):
+    """The 1 M-read batch is large enough for the bucketed kernels (probe records grouped by L2-sized row ranges);
+    the direct-gather kernel must give the same matrix, and so must a run with a scratch budget of a few hundred
+    chunks (many sub-batches) and one with uint32 counts."""
+    ix = big["ix"]
+    fwd = big.get("fwd")
+    n0 = ix.bucketed_queries
+    if fwd is None:
+        fwd = np.asarray(ix.query(big["reads"], big["b"], big["e"], 1)).copy()
+        big["fwd"] = fwd
+    assert ix.bucketed_queries > 0, "large batches should take the bucketed path by default"
+    ix.set_bucketed(False)
+    n0 = ix.bucketed_queries
+    direct = np.asarray(ix.query(big["reads"], big["b"], big["e"], 1))
+    assert ix.bucketed_queries == n0
+    assert np.array_equal(direct, fwd)
+    ix.set_bucketed(True, min_windows=1 << 20, scratch_bytes=256 << 20)
+    n = 400_000
+    small = np.asarray(ix.query(big["reads"][: n * L], big["b"][:n], big["e"][:n], 1, dtype=4))
+    assert ix.bucketed_queries > n0
+    assert np.array_equal(small, fwd[:n])
+    ix.set_bucketed(True, min_windows=16 << 20, scratch_bytes=24 << 30)
+
+
 def test_additivity_over_overlapping_chunks_and_steps(big):
     """Counts are additive over windows: a long sequence equals the sum of its chunks overlapping by k-1 bases
     (what the MLST splitter relies on), and step-s sampling at the s offsets partitions the step-1 windows."""

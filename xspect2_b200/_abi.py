@@ -45,12 +45,15 @@ SYMBOLS = {
     "xs_launch_count": (C.c_uint64, []),
     "xs_profile_enable": (C.c_int, [C.c_int]),
     "xs_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "xs_profile_read_phases": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "xs_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P)]),
     "xs_host_free": (C.c_int, [_P]),
     "xs_cobs_open": (C.c_int, [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "xs_cobs_info": (C.c_int, [_P, C.POINTER(CobsInfo)]),
     "xs_cobs_doc_names": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "xs_cobs_set_policy": (C.c_int, [_P, C.c_int]),
+    "xs_cobs_set_bucketed": (C.c_int, [_P, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32]),
+    "xs_cobs_bucketed_queries": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "xs_cobs_close": (C.c_int, [_P]),
     "xs_cobs_query": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, C.c_int, _P]),
     "xs_cobs_query_device": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, C.c_int, _P, _P]),

@@ -100,9 +100,10 @@ template <typename OutT>
 __device__ __forceinline__ void out_store(OutT* p, uint32_t v) {
     *p = (OutT)(v > out_max<OutT>() ? out_max<OutT>() : v);
 }
-// saturating add into an element other CTAs may add to as well
+// saturating add into an element other CTAs may add to as well.  nosat: the record has no more windows than OutT
+// can hold, so no partial sum can carry into the neighbouring element and a plain word atomic is exact
 template <typename OutT>
-__device__ __forceinline__ void out_add(OutT* p, uint32_t v) {
+__device__ __forceinline__ void out_add(OutT* p, uint32_t v, bool nosat) {
     if (v == 0) return;
     if (sizeof(OutT) == 4) {
         atomicAdd(reinterpret_cast<unsigned int*>(p), v);
@@ -110,6 +111,7 @@ __device__ __forceinline__ void out_add(OutT* p, uint32_t v) {
         uintptr_t a = reinterpret_cast<uintptr_t>(p);
         unsigned int* w = reinterpret_cast<unsigned int*>(a & ~(uintptr_t)3);
         uint32_t sh = (uint32_t)(a & 3) * 8;
+        if (nosat) { atomicAdd(w, v << sh); return; }
         uint32_t mx = out_max<OutT>();
         unsigned int old = *w, assumed;
         do {
@@ -206,9 +208,9 @@ __device__ __forceinline__ void bloom_term(const SeqBatch& sb, uint64_t pos, Ter
 // ----------------------------------------------------------------------------------------
 // warp walk: one warp owns a tile [t0, t1) of the flat window space and walks the sequences it
 // touches.  Each round packs the next 32 windows into the lanes (a round may span several
-// sequences); `compute(has, pos)` is called once per lane with the base position of its window,
-// `accum(segmask)` once per (round, sequence) with the lanes of that sequence, `flush(seq, complete)`
-// when a sequence (or the tile) ends.  All bookkeeping is warp-uniform: no shared memory, no CTA
+// sequences); `compute(has, pos, g)` is called once per lane with the base position and the flat index of
+// its window, `accum(segmask)` once per (round, sequence) with the lanes of that sequence,
+// `flush(seq, complete, nwin)` when a sequence (or the tile) ends (nwin = all windows of the sequence).  All bookkeeping is warp-uniform: no shared memory, no CTA
 // barrier, lanes stay dense whatever the read lengths are.
 // ----------------------------------------------------------------------------------------
 struct WalkBatch {           // 32 consecutive sequences, one per lane
@@ -240,7 +242,7 @@ __device__ __forceinline__ void warp_walk(const SeqBatch& sb, uint64_t t0, uint6
         // ---- pack up to 32 windows into the lanes
         uint32_t fill = 0;
         bool has = false;
-        uint64_t pos = 0;
+        uint64_t pos = 0, gidx = 0;
         while (fill < 32 && f < t1 && cur < 32) {
             uint64_t s_start = __shfl_sync(FULL, wb.pre, cur), s_end = __shfl_sync(FULL, wb.pre_next, cur);
             uint64_t lim = s_end < t1 ? s_end : t1;
@@ -249,13 +251,14 @@ __device__ __forceinline__ void warp_walk(const SeqBatch& sb, uint64_t t0, uint6
             uint32_t take = avail < 32 - fill ? avail : 32 - fill;
             uint64_t b = __shfl_sync(FULL, wb.beg, cur);
             if (lane >= fill && lane < fill + take) {
-                pos = b + (f - s_start + (lane - fill)) * sb.step;
+                gidx = f + (lane - fill);
+                pos = b + (gidx - s_start) * sb.step;
                 has = true;
             }
             fill += take; f += take;
             if (f == s_end) ++cur;
         }
-        compute(has, pos);
+        compute(has, pos, gidx);
         // ---- replay the packing to attribute lanes to sequences
         cur = cur0; f = f0; fill = 0;
         while (fill < 32 && f < t1 && cur < 32) {
@@ -267,7 +270,7 @@ __device__ __forceinline__ void warp_walk(const SeqBatch& sb, uint64_t t0, uint6
             uint32_t segmask = (take == 32 ? FULL : ((1u << take) - 1u)) << fill;
             accum(segmask);
             fill += take; f += take;
-            if (f == s_end || f == t1) flush(base + cur, s_start >= t0 && s_end <= t1);
+            if (f == s_end || f == t1) flush(base + cur, s_start >= t0 && s_end <= t1, s_end - s_start);
             if (f == s_end) ++cur;
         }
     }
@@ -348,13 +351,44 @@ __device__ __forceinline__ uint4 cobs_mask16(const CobsParams& p, const PageDesc
     return m;
 }
 
+// per-sequence document counts of the masks held by the lanes in `segmask`: lane l keeps the counts of documents
+// l, l+32, l+64, l+96
+__device__ __forceinline__ void narrow_accum(uint32_t lane, uint32_t segmask, const uint4& m, uint32_t (&cnt)[4]) {
+    const bool mine = (segmask >> lane) & 1u;
+    uint32_t mw[4] = {mine ? m.x : 0u, mine ? m.y : 0u, mine ? m.z : 0u, mine ? m.w : 0u};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        uint32_t u = __reduce_or_sync(0xFFFFFFFFu, mw[w]);
+        while (u) {
+            uint32_t b = __ffs(u) - 1;
+            u &= u - 1;
+            uint32_t v = __popc(__ballot_sync(0xFFFFFFFFu, (mw[w] >> b) & 1u));
+            if (lane == b) cnt[w] += v;
+        }
+    }
+}
+
+template <typename OutT>
+__device__ __forceinline__ void narrow_flush(const CobsParams& p, const PageDesc& pg, uint32_t lane, uint64_t seq, bool complete,
+                                             uint64_t nwin, uint32_t (&cnt)[4]) {
+    OutT* row = reinterpret_cast<OutT*>(p.out) + (p.seq0 + seq) * p.ld + pg.doc_off;
+    const bool nosat = nwin <= (uint64_t)out_max<OutT>();
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        uint32_t d = w * 32 + lane;
+        if (d < pg.n_docs) {
+            if (complete) out_store<OutT>(row + d, cnt[w]); else out_add<OutT>(row + d, cnt[w], nosat);
+        }
+        cnt[w] = 0;
+    }
+}
+
 template <int K, int H, typename OutT>
 __global__ void __launch_bounds__(NARROW_NT, 4) k_cobs_narrow(const CobsParams p) {
     const SeqBatch& sb = p.sb;
     const PageDesc pg = p.pages[blockIdx.y];
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t n_warps = ((uint64_t)gridDim.x * NARROW_NT) >> 5;
-    OutT* out = reinterpret_cast<OutT*>(p.out);
 
     const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
     const uint64_t W = walk_tile_windows(total, n_warps);
@@ -370,32 +404,291 @@ __global__ void __launch_bounds__(NARROW_NT, 4) k_cobs_narrow(const CobsParams p
         uint32_t cnt[4] = {0, 0, 0, 0};   // lane l: documents l, l+32, l+64, l+96 of the current sequence
         warp_walk(
             sb, t0, t1, lane,
-            [&](bool has, uint64_t pos) { m = has ? cobs_mask16<K, H>(p, pg, pos) : make_uint4(0, 0, 0, 0); },
-            [&](uint32_t segmask) {
-                const bool mine = (segmask >> lane) & 1u;
-                uint32_t mw[4] = {mine ? m.x : 0u, mine ? m.y : 0u, mine ? m.z : 0u, mine ? m.w : 0u};
+            [&](bool has, uint64_t pos, uint64_t) { m = has ? cobs_mask16<K, H>(p, pg, pos) : make_uint4(0, 0, 0, 0); },
+            [&](uint32_t segmask) { narrow_accum(lane, segmask, m, cnt); },
+            [&](uint64_t seq, bool complete, uint64_t nwin) { narrow_flush<OutT>(p, pg, lane, seq, complete, nwin, cnt); });
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// COBS, narrow rows, bucketed probing (large batches against an index much larger than L2).
+//
+// A random 16-byte row gather costs a 128-byte DRAM fetch, so k_cobs_narrow moves ~10x the bytes it uses.  For large
+// batches every index row is probed many times; the three kernels below turn those re-reads into L2 hits:
+//
+//   k_bucket_emit     window -> canonical -> XXH64 x h -> row ids; probe record (local window, row in bucket) appended
+//                     to the block of (chunk of BK_CH windows, bucket of 2^bshift rows), staged in shared memory and
+//                     written out in whole sectors
+//   k_bucket_fetch    bucket by bucket (all warps sweep one bucket's blocks at a time, its 16-32 MB of rows stay in
+//                     L2): row gather per record, written next to the chunk it belongs to
+//   k_bucket_reduce   CTA per chunk: AND of the fetched rows into per-window masks in shared memory, then the
+//                     per-sequence document counts exactly as k_cobs_narrow does
+//
+// Blocks have a fixed capacity (mean + ~3 sigma); a window with a probe that does not fit (low-complexity reads put
+// thousands of identical k-mers into one block) is flagged and scored with direct gathers by k_bucket_reduce.
+// Results are identical to k_cobs_narrow's whatever the record order inside a block.
+// ----------------------------------------------------------------------------------------
+constexpr int BK_CH = 2048;            // windows per chunk (11-bit local window index)
+constexpr int BK_NT = 256;
+constexpr int BK_WARP_WIN = BK_CH / (BK_NT / 32);
+constexpr uint32_t BK_MAX_BUCKETS = 256;
+constexpr uint32_t BK_MAX_SHIFT = 21;  // 11 + 21 = 32 bits per probe record
+
+struct BucketParams {
+    CobsParams cp;
+    uint32_t* rec;        // [n_buckets][nc][cap]  (local window << bshift) | (row & (2^bshift - 1))
+    uint4* rows;          // [nc][n_buckets][cap]  fetched rows; .w = local window when pack_id
+    uint16_t* cnt_bc;     // [n_buckets][nc]       records per block
+    uint16_t* cnt_cb;     // [nc][n_buckets]
+    uint32_t* ovf;        // [nc][BK_CH / 32]      windows to score with direct gathers
+    unsigned long long* counter;   // [3] work hand-out of the three kernels, zeroed
+    uint64_t chunk0;      // first chunk of this sub-batch in the flat window space
+    uint32_t nc;          // chunks of this sub-batch
+    uint32_t n_buckets, bshift, cap;
+    uint32_t pack_id;     // rows hold <= 96 documents: the fourth word is free for the local window
+};
+
+__device__ __forceinline__ uint32_t ld_stream32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_stream128(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream128(uint4* p, const uint4& v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// chunks of the sub-batch that hold windows
+__device__ __forceinline__ uint32_t bucket_live_chunks(const BucketParams& bp, uint64_t total) {
+    const uint64_t first = bp.chunk0 * BK_CH;
+    if (total <= first) return 0;
+    const uint64_t n = (total - first + BK_CH - 1) / BK_CH;
+    return n < bp.nc ? (uint32_t)n : bp.nc;
+}
+
+template <int K, int H>
+__global__ void __launch_bounds__(BK_NT) k_bucket_emit(const BucketParams bp) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    const CobsParams& p = bp.cp;
+    const SeqBatch& sb = p.sb;
+    const PageDesc pg = p.pages[0];
+    const uint32_t k = K ? K : sb.k;
+    const uint32_t h = H ? H : p.num_hashes;
+    uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_dyn);     // [n_buckets][cap]
+    uint32_t* s_cnt = s_rec + (size_t)bp.n_buckets * bp.cap;  // [n_buckets] records offered (may exceed cap)
+    uint32_t* s_ovf = s_cnt + bp.n_buckets;                   // [BK_CH / 32]
+    __shared__ unsigned long long s_chunk;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    const uint32_t nc_live = bucket_live_chunks(bp, total);
+    const uint32_t rmask = (1u << bp.bshift) - 1u;
+    const uint32_t cap = bp.cap, nb = bp.n_buckets;
+
+    for (;;) {
+        if (tid == 0) s_chunk = atomicAdd(bp.counter + 0, 1ULL);
+        for (uint32_t i = tid; i < nb + BK_CH / 32; i += BK_NT) s_cnt[i] = 0;   // s_cnt and s_ovf are contiguous
+        __syncthreads();
+        const uint64_t c = s_chunk;
+        if (c >= nc_live) break;
+        const uint64_t g0 = (bp.chunk0 + c) * BK_CH;
+        const uint64_t g1 = g0 + BK_CH < total ? g0 + BK_CH : total;
+        const uint64_t t0 = g0 + (uint64_t)warp * BK_WARP_WIN;
+        const uint64_t t1 = t0 + BK_WARP_WIN < g1 ? t0 + BK_WARP_WIN : g1;
+        if (t0 < t1) {
+            warp_walk(
+                sb, t0, t1, lane,
+                [&](bool has, uint64_t pos, uint64_t g) {
+                    if (!has) return;
+                    Term t;
+                    if (!cobs_term<K>(sb, pos, p.canonicalize != 0, p.policy, t)) return;
+                    Xxh64Pre pre;
+                    xxh64_prepare(t, k, pre);
+                    const uint32_t lid = (uint32_t)(g - g0);
+                    bool over = false;
+                    auto emit = [&](uint32_t j) {
+                        const uint64_t row = mod_barrett(xxh64_finish(pre, k, (uint64_t)j), pg.sig_size, pg.magic);
+                        const uint32_t b = (uint32_t)(row >> bp.bshift);
+                        const uint32_t slot = atomicAdd(&s_cnt[b], 1u);
+                        if (slot < cap) s_rec[b * cap + slot] = (lid << bp.bshift) | ((uint32_t)row & rmask);
+                        else over = true;
+                    };
+                    if (H) {
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    uint32_t u = __reduce_or_sync(0xFFFFFFFFu, mw[w]);
-                    while (u) {
-                        uint32_t b = __ffs(u) - 1;
-                        u &= u - 1;
-                        uint32_t v = __popc(__ballot_sync(0xFFFFFFFFu, (mw[w] >> b) & 1u));
-                        if (lane == b) cnt[w] += v;
+                        for (int j = 0; j < (H ? H : 1); ++j) emit((uint32_t)j);
+                    } else {
+                        for (uint32_t j = 0; j < h; ++j) emit(j);
+                    }
+                    if (over) atomicOr(&s_ovf[lid >> 5], 1u << (lid & 31));
+                },
+                [&](uint32_t) {}, [&](uint64_t, bool, uint64_t) {});
+        }
+        __syncthreads();
+        // blocks go out in whole 32-byte sectors (cap is a multiple of 8; the slack words are never read)
+        for (uint32_t b = warp; b < nb; b += BK_NT / 32) {
+            const uint32_t n = s_cnt[b] < cap ? s_cnt[b] : cap;
+            const uint32_t n4 = ((n + 7) & ~7u) / 4;
+            const uint4* src = reinterpret_cast<const uint4*>(s_rec + b * cap);
+            uint4* dst = reinterpret_cast<uint4*>(bp.rec + ((uint64_t)b * bp.nc + c) * cap);
+            for (uint32_t i = lane; i < n4; i += 32) dst[i] = src[i];
+        }
+        for (uint32_t b = tid; b < nb; b += BK_NT) {
+            const uint16_t n = (uint16_t)(s_cnt[b] < cap ? s_cnt[b] : cap);
+            bp.cnt_bc[(uint64_t)b * bp.nc + c] = n;
+            bp.cnt_cb[c * nb + b] = n;
+        }
+        for (uint32_t i = tid; i < BK_CH / 32; i += BK_NT) bp.ovf[c * (BK_CH / 32) + i] = s_ovf[i];
+        __syncthreads();
+    }
+}
+
+constexpr uint32_t BK_FETCH_SPAN = 8;   // consecutive (bucket, chunk) blocks per warp hand-out
+
+__global__ void __launch_bounds__(BK_NT) k_bucket_fetch(const BucketParams bp) {
+    const SeqBatch& sb = bp.cp.sb;
+    const PageDesc pg = bp.cp.pages[0];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    const uint32_t nc_live = bucket_live_chunks(bp, total);
+    const uint64_t n_units = (uint64_t)bp.n_buckets * nc_live;    // unit = bucket * nc_live + chunk: bucket-major sweep
+    const uint32_t rmask = (1u << bp.bshift) - 1u;
+    const uint32_t cap = bp.cap;
+    for (;;) {
+        const uint64_t u0 = next_tile(bp.counter + 1, lane) * BK_FETCH_SPAN;
+        if (u0 >= n_units) break;
+        const uint64_t u1 = u0 + BK_FETCH_SPAN < n_units ? u0 + BK_FETCH_SPAN : n_units;
+        for (uint64_t u = u0; u < u1; ++u) {
+            const uint32_t b = (uint32_t)(u / nc_live), c = (uint32_t)(u % nc_live);
+            const uint32_t n = __ldg(bp.cnt_bc + (uint64_t)b * bp.nc + c);
+            const uint32_t* src = bp.rec + ((uint64_t)b * bp.nc + c) * cap;
+            uint4* dst = bp.rows + ((uint64_t)c * bp.n_buckets + b) * cap;
+            const uint8_t* base = pg.data + (((uint64_t)b << bp.bshift) * 16);
+            for (uint32_t i0 = 0; i0 < n; i0 += 128) {
+                uint32_t r[4];
+                uint4 v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t i = i0 + q * 32 + lane;
+                    r[q] = i < n ? ld_stream32(src + i) : 0u;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t i = i0 + q * 32 + lane;
+                    if (i < n) v[q] = ldg128(base + (uint64_t)(r[q] & rmask) * 16);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t i = i0 + q * 32 + lane;
+                    if (i < n) {
+                        if (bp.pack_id) v[q].w = r[q] >> bp.bshift;
+                        st_stream128(dst + i, v[q]);
                     }
                 }
-            },
-            [&](uint64_t seq, bool complete) {
-                OutT* row = out + (p.seq0 + seq) * p.ld + pg.doc_off;
+            }
+        }
+    }
+}
+
+template <int K>
+__device__ __forceinline__ bool cobs_window_skipped(const SeqBatch& sb, uint64_t pos, bool canonicalize, int policy) {
+    const uint32_t k = K ? K : sb.k;
+    return policy == POLICY_SKIP && canonicalize && window_invalid(sb.invalid, pos, k);   // cobs_term() == false
+}
+
+// the rare flagged window: direct gathers, kept out of line so the streaming path stays lean
+template <int K, int H>
+__device__ __noinline__ void cobs_mask16_outline(const CobsParams* p, const PageDesc* pg, uint64_t pos, uint4* m) {
+    *m = cobs_mask16<K, H>(*p, *pg, pos);
+}
+
+template <int K, int H, typename OutT>
+__global__ void __launch_bounds__(BK_NT, 4) k_bucket_reduce(const __grid_constant__ BucketParams bp) {
+    __shared__ __align__(16) uint32_t s_m[4][BK_CH];   // window masks, one array per 32 documents
+    __shared__ uint32_t s_ovf[BK_CH / 32];
+    __shared__ unsigned long long s_chunk;
+    const CobsParams& p = bp.cp;
+    const SeqBatch& sb = p.sb;
+    const PageDesc pg = p.pages[0];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    const uint32_t nc_live = bucket_live_chunks(bp, total);
+    const uint32_t cap = bp.cap, nb = bp.n_buckets;
+    const bool pack = bp.pack_id != 0;
+
+    for (;;) {
+        if (tid == 0) s_chunk = atomicAdd(bp.counter + 2, 1ULL);
+        {
+            uint4* z = reinterpret_cast<uint4*>(&s_m[0][0]);
+            const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+            for (uint32_t i = tid; i < 4 * BK_CH / 4; i += BK_NT) z[i] = ones;
+        }
+        __syncthreads();
+        const uint64_t c = s_chunk;
+        if (c >= nc_live) break;
+        const uint64_t g0 = (bp.chunk0 + c) * BK_CH;
+        const uint64_t g1 = g0 + BK_CH < total ? g0 + BK_CH : total;
+        if (tid < BK_CH / 32) s_ovf[tid] = __ldg(bp.ovf + c * (BK_CH / 32) + tid);
+
+        // ---- AND of the fetched rows into the window masks (warp w takes buckets w, w + 8, ...)
+        uint32_t myn = 0;
+        {
+            const uint32_t b = lane * (BK_NT / 32) + warp;
+            if (b < nb) myn = __ldg(bp.cnt_cb + c * nb + b);
+        }
+        for (uint32_t t = 0; t * (BK_NT / 32) + warp < nb; ++t) {
+            const uint32_t b = t * (BK_NT / 32) + warp;
+            const uint32_t n = __shfl_sync(0xFFFFFFFFu, myn, t);
+            const uint4* src = bp.rows + (c * nb + b) * (uint64_t)cap;
+            const uint32_t* rsrc = bp.rec + ((uint64_t)b * bp.nc + c) * cap;
+            for (uint32_t i0 = 0; i0 < n; i0 += 128) {
+                uint4 v[4];
+                uint32_t id[4];
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    uint32_t d = w * 32 + lane;
-                    if (d < pg.n_docs) {
-                        if (complete) out_store<OutT>(row + d, cnt[w]); else out_add<OutT>(row + d, cnt[w]);
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t i = i0 + q * 32 + lane;
+                    if (i < n) {
+                        v[q] = ld_stream128(src + i);
+                        id[q] = pack ? 0u : (ld_stream32(rsrc + i) >> bp.bshift);
                     }
-                    cnt[w] = 0;
                 }
-            });
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t i = i0 + q * 32 + lane;
+                    if (i < n) {
+                        const uint32_t w = (pack ? v[q].w : id[q]) & (BK_CH - 1);
+                        atomicAnd(&s_m[0][w], v[q].x);
+                        atomicAnd(&s_m[1][w], v[q].y);
+                        atomicAnd(&s_m[2][w], v[q].z);
+                        if (!pack) atomicAnd(&s_m[3][w], v[q].w);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- per-sequence document counts of the chunk's windows
+        const uint64_t t0 = g0 + (uint64_t)warp * BK_WARP_WIN;
+        const uint64_t t1 = t0 + BK_WARP_WIN < g1 ? t0 + BK_WARP_WIN : g1;
+        if (t0 < t1) {
+            uint4 m = make_uint4(0, 0, 0, 0);
+            uint32_t cnt[4] = {0, 0, 0, 0};
+            warp_walk(
+                sb, t0, t1, lane,
+                [&](bool has, uint64_t pos, uint64_t g) {
+                    m = make_uint4(0, 0, 0, 0);
+                    if (!has) return;
+                    const uint32_t lid = (uint32_t)(g - g0);
+                    if ((s_ovf[lid >> 5] >> (lid & 31)) & 1u) cobs_mask16_outline<K, H>(&bp.cp, bp.cp.pages, pos, &m);
+                    else if (!cobs_window_skipped<K>(sb, pos, p.canonicalize != 0, p.policy))
+                        m = make_uint4(s_m[0][lid], s_m[1][lid], s_m[2][lid], pack ? 0u : s_m[3][lid]);
+                },
+                [&](uint32_t segmask) { narrow_accum(lane, segmask, m, cnt); },
+                [&](uint64_t seq, bool complete, uint64_t nwin) { narrow_flush<OutT>(p, pg, lane, seq, complete, nwin, cnt); });
+        }
+        __syncthreads();
     }
 }
 
@@ -468,6 +761,7 @@ __global__ void __launch_bounds__(WIDE_NT) k_cobs_wide(const WideParams wp) {
         const uint64_t w0 = s_chunk * WIDE_CHUNK;
         const uint32_t nwin = (uint32_t)(nw_seq - w0 < (uint64_t)WIDE_CHUNK ? nw_seq - w0 : (uint64_t)WIDE_CHUNK);
         const bool complete = nw_seq <= (uint64_t)WIDE_CHUNK;
+        const bool nosat = nw_seq <= (uint64_t)out_max<OutT>();
 
         // ---- phase 1: row byte offsets of the valid windows of the item, compacted (order is irrelevant for counts)
         for (uint32_t lw = tid; lw < nwin; lw += WIDE_NT) {
@@ -565,7 +859,7 @@ __global__ void __launch_bounds__(WIDE_NT) k_cobs_wide(const WideParams wp) {
         OutT* row = out + (p.seq0 + seq) * p.ld + pg.doc_off + (size_t)cb.c0 * 128;
         for (uint32_t d = tid; d < cb.n_docs; d += WIDE_NT) {
             uint32_t v = s_cnt[d];
-            if (complete) out_store<OutT>(row + d, v); else out_add<OutT>(row + d, v);
+            if (complete) out_store<OutT>(row + d, v); else out_add<OutT>(row + d, v, nosat);
         }
         __syncthreads();
     }
@@ -628,7 +922,7 @@ __global__ void __launch_bounds__(BLOOM_NT, 4) k_bloom(const BloomParams p) {
         uint32_t bal = 0;
         warp_walk(
             sb, t0, t1, lane,
-            [&](bool has, uint64_t pos) {
+            [&](bool has, uint64_t pos, uint64_t) {
                 bool hit = false;
                 if (has) {
                     Term t;
@@ -639,7 +933,7 @@ __global__ void __launch_bounds__(BLOOM_NT, 4) k_bloom(const BloomParams p) {
                 bal = __ballot_sync(0xFFFFFFFFu, hit);
             },
             [&](uint32_t segmask) { hits += __popc(bal & segmask); },
-            [&](uint64_t seq, bool complete) {
+            [&](uint64_t seq, bool complete, uint64_t) {
                 if (lane == 0 && hits) {
                     uint32_t* o = p.out + p.seq0 + seq;
                     if (complete) *o = hits; else atomicAdd(o, hits);

@@ -55,11 +55,14 @@ static int launch_ok(const char* what) {
 #include <mutex>
 static std::atomic<int> g_profile{0};
 static std::mutex g_prof_mu;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+struct ProfEvent { cudaEvent_t a, b; int tag; };
+static std::vector<ProfEvent> g_prof_events;
+enum { PROF_DIRECT = 0, PROF_EMIT = 1, PROF_FETCH = 2, PROF_REDUCE = 3, PROF_TAGS = 4 };
 struct KernelTimer {
     cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t s;
-    explicit KernelTimer(cudaStream_t st) : s(st) {
+    int tag;
+    explicit KernelTimer(cudaStream_t st, int tg = PROF_DIRECT) : s(st), tag(tg) {
         if (!g_profile.load(std::memory_order_relaxed)) return;
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
         cudaEventRecord(a, s);
@@ -68,7 +71,7 @@ struct KernelTimer {
         if (!a) return;
         cudaEventRecord(b, s);
         std::lock_guard<std::mutex> lk(g_prof_mu);
-        g_prof_events.emplace_back(a, b);
+        g_prof_events.push_back(ProfEvent{a, b, tag});
     }
 };
 
@@ -90,6 +93,11 @@ struct xs_cobs {
     bool narrow = true;
     int n_sm = 148;
     int force_wide = 0;
+    int bucketed = 1;                 // large batches against a large narrow index go through the bucketed kernels
+    uint64_t bucket_min_windows = 16ULL << 20;
+    uint64_t bucket_scratch_bytes = 24ULL << 30;
+    uint32_t bucket_shift = 0;        // 0 = automatic
+    std::atomic<uint64_t> bucketed_queries{0};
 };
 
 struct xs_bloom {
@@ -366,6 +374,117 @@ static cudaError_t launch_wide(const WideParams& p, dim3 grid, size_t smem, int 
     return launch_wide_t<0, 0>(p, grid, smem, dt, s);
 }
 
+// ---- bucketed probing (k_bucket_emit / k_bucket_fetch / k_bucket_reduce) -------------------------------------
+struct BucketGeom {
+    uint32_t nb = 0, bshift = 0, cap = 0;
+    size_t smem = 0;        // dynamic shared memory of k_bucket_emit
+    size_t per_chunk = 0;   // scratch bytes per chunk
+};
+
+// geometry for an index of `sig` rows probed with `h` hashes; false when the bucketed path does not apply
+static bool bucket_geometry(uint64_t sig, uint32_t h, uint32_t shift_override, BucketGeom& g) {
+    if (h == 0 || h > 16) return false;
+    if (shift_override) {
+        if (shift_override > BK_MAX_SHIFT) return false;
+        g.bshift = shift_override;
+        if (((sig - 1) >> g.bshift) + 1 > BK_MAX_BUCKETS) return false;
+        g.nb = (uint32_t)(((sig - 1) >> g.bshift) + 1);
+    } else {
+        g.bshift = 20;
+        if (((sig - 1) >> g.bshift) + 1 > BK_MAX_BUCKETS) g.bshift = BK_MAX_SHIFT;
+        if (((sig - 1) >> g.bshift) + 1 > BK_MAX_BUCKETS) return false;
+        g.nb = (uint32_t)(((sig - 1) >> g.bshift) + 1);
+        if (g.nb < 16) return false;                                  // 256 MB .. 8.6 GB of 16-byte rows
+    }
+    const double mean = (double)BK_CH * h / (double)g.nb;
+    g.cap = ((uint32_t)std::ceil(mean + 2.8 * std::sqrt(mean)) + 7) & ~7u;
+    if (g.cap > 60000) return false;       // block counts are 16-bit
+    g.smem = ((size_t)g.nb * g.cap + g.nb + BK_CH / 32) * 4;
+    if (g.smem > 200 * 1024) return false;
+    g.per_chunk = (size_t)g.nb * g.cap * 20 + (size_t)g.nb * 4 + (BK_CH / 32) * 4;
+    return true;
+}
+
+template <int K, int H>
+static cudaError_t launch_bucket_t(const BucketParams& bp, const BucketGeom& g, int n_sm, int dt, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(k_bucket_emit<K, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bucket_emit<K, H>, BK_NT, g.smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+    {
+        KernelTimer kt(s, PROF_EMIT);
+        k_bucket_emit<K, H><<<n_sm * occ, BK_NT, g.smem, s>>>(bp);
+    }
+    {
+        KernelTimer kt(s, PROF_FETCH);
+        k_bucket_fetch<<<n_sm * 8, BK_NT, 0, s>>>(bp);
+    }
+    {
+        KernelTimer kt(s, PROF_REDUCE);
+        if (dt == XS_U8) k_bucket_reduce<K, H, uint8_t><<<n_sm * 4, BK_NT, 0, s>>>(bp);
+        else if (dt == XS_U16) k_bucket_reduce<K, H, uint16_t><<<n_sm * 4, BK_NT, 0, s>>>(bp);
+        else k_bucket_reduce<K, H, uint32_t><<<n_sm * 4, BK_NT, 0, s>>>(bp);
+    }
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// returns XS_OK with *handled = false when the batch should go through k_cobs_narrow instead
+static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaStream_t s, bool* handled) {
+    *handled = false;
+    if (!ix->bucketed || !ix->narrow || ix->force_wide || ix->pages.size() != 1) return XS_OK;
+    if (p.sb.n_bases / p.sb.step < ix->bucket_min_windows) return XS_OK;
+    BucketGeom g;
+    if (!bucket_geometry(ix->pages[0].sig_size, ix->info.num_hashes, ix->bucket_shift, g)) return XS_OK;
+    // the number of sampled windows decides the chunking (the only host read of this query)
+    uint64_t total = 0;
+    XS_CUDA(cudaMemcpyAsync(&total, p.sb.win_prefix + p.sb.n_seq, 8, cudaMemcpyDeviceToHost, s));
+    XS_CUDA(cudaStreamSynchronize(s));
+    if (total < ix->bucket_min_windows) return XS_OK;
+    size_t free_b = 0, total_b = 0;
+    XS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t budget = std::min<uint64_t>(ix->bucket_scratch_bytes, free_b / 2);
+    const uint64_t nc_total = (total + BK_CH - 1) / BK_CH;
+    uint64_t nc_sub = std::min<uint64_t>(nc_total, budget / g.per_chunk);
+    if (nc_sub == 0 || nc_sub * BK_CH < ix->bucket_min_windows / 2) return XS_OK;    // not enough memory to make re-reads L2 hits
+    const uint64_t n_sub = (nc_total + nc_sub - 1) / nc_sub;
+    nc_sub = (nc_total + n_sub - 1) / n_sub;
+    nc_sub = std::min<uint64_t>(nc_sub, 0xFFFFFFFFu / BK_MAX_BUCKETS);
+
+    const size_t o_rows = 0;
+    const size_t o_rec = o_rows + align256(nc_sub * g.nb * g.cap * 16);
+    const size_t o_bc = o_rec + align256(nc_sub * g.nb * g.cap * 4);
+    const size_t o_cb = o_bc + align256(nc_sub * g.nb * 2);
+    const size_t o_ovf = o_cb + align256(nc_sub * g.nb * 2);
+    const size_t o_ctr = o_ovf + align256(nc_sub * (BK_CH / 32) * 4);
+    const size_t bytes = o_ctr + align256(n_sub * 3 * 8);
+    uint8_t* d = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&d, bytes, s);
+    if (e != cudaSuccess) { cudaGetLastError(); return XS_OK; }   // no room for the scratch: direct gathers
+    int rc = XS_OK;
+    e = cudaMemsetAsync(d + o_ctr, 0, n_sub * 3 * 8, s);
+    for (uint64_t i = 0; i < n_sub && e == cudaSuccess; ++i) {
+        BucketParams bp{};
+        bp.cp = p;
+        bp.rows = reinterpret_cast<uint4*>(d + o_rows); bp.rec = reinterpret_cast<uint32_t*>(d + o_rec);
+        bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.cnt_cb = reinterpret_cast<uint16_t*>(d + o_cb);
+        bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
+        bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
+        bp.chunk0 = i * nc_sub;
+        bp.nc = (uint32_t)std::min<uint64_t>(nc_sub, nc_total - bp.chunk0);
+        bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap;
+        bp.pack_id = ix->pages[0].n_docs <= 96 ? 1u : 0u;
+        if (p.sb.k == 21 && p.num_hashes == 7) e = launch_bucket_t<21, 7>(bp, g, ix->n_sm, dt, s);
+        else e = launch_bucket_t<0, 0>(bp, g, ix->n_sm, dt, s);
+    }
+    if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("bucketed query: ") + cudaGetErrorString(e));
+    cudaFreeAsync(d, s);
+    if (rc == XS_OK) { *handled = true; ix->bucketed_queries.fetch_add(1, std::memory_order_relaxed); }
+    return rc;
+}
+
 static int dtype_size(int dt) { return (dt == XS_U8 || dt == XS_U16 || dt == XS_U32) ? dt : 0; }
 
 // all pointers device; asynchronous on s
@@ -378,6 +497,9 @@ static int cobs_launch(xs_cobs* ix, const SeqBatch& sb, const uint64_t* chunk_pr
     p.num_hashes = ix->info.num_hashes; p.canonicalize = ix->info.canonicalize; p.policy = ix->info.policy;
     p.out = d_out; p.ld = ld; p.seq0 = 0;
     if (!wide) {
+        bool handled = false;
+        XS_TRY(cobs_launch_bucketed(ix, p, dt, s, &handled));
+        if (handled) return XS_OK;
         dim3 grid((unsigned)(ix->n_sm * 4), (unsigned)ix->pages.size());
         KernelTimer kt(s);
         launch_narrow(p, grid, dt, s);
@@ -624,25 +746,34 @@ int xs_profile_enable(int on) {
     g_profile.store(on ? 1 : 0);
     return XS_OK;
 }
-int xs_profile_read(double* kernel_ms, uint64_t* launches) {
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+static int profile_collect(double* ms, uint64_t* launches) {   // [PROF_TAGS] each
+    std::vector<ProfEvent> ev;
     {
         std::lock_guard<std::mutex> lk(g_prof_mu);
         ev.swap(g_prof_events);
     }
-    double sum = 0;
+    for (int t = 0; t < PROF_TAGS; ++t) { ms[t] = 0; launches[t] = 0; }
     int rc = XS_OK;
     for (auto& pr : ev) {
-        float ms = 0;
-        cudaError_t e = cudaEventSynchronize(pr.second);
-        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, pr.first, pr.second);
+        float t = 0;
+        cudaError_t e = cudaEventSynchronize(pr.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, pr.a, pr.b);
         if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("profile events: ") + cudaGetErrorString(e));
-        sum += ms;
-        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        ms[pr.tag] += t; launches[pr.tag] += 1;
+        cudaEventDestroy(pr.a); cudaEventDestroy(pr.b);
     }
-    if (kernel_ms) *kernel_ms = sum;
-    if (launches) *launches = ev.size();
     return rc;
+}
+int xs_profile_read(double* kernel_ms, uint64_t* launches) {
+    double ms[PROF_TAGS]; uint64_t n[PROF_TAGS];
+    int rc = profile_collect(ms, n);
+    if (kernel_ms) { *kernel_ms = 0; for (int t = 0; t < PROF_TAGS; ++t) *kernel_ms += ms[t]; }
+    if (launches) { *launches = 0; for (int t = 0; t < PROF_TAGS; ++t) *launches += n[t]; }
+    return rc;
+}
+int xs_profile_read_phases(double* kernel_ms, uint64_t* launches) {
+    if (!kernel_ms || !launches) return fail(XS_ERR_ARG, "NULL argument");
+    return profile_collect(kernel_ms, launches);
 }
 
 int xs_device_count(int* n) {
@@ -691,6 +822,9 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
     ix->names = cf.names;
     const char* fw = getenv("XS_FORCE_WIDE");
     ix->force_wide = (fw && fw[0] == '1') ? 1 : 0;
+    if (const char* v = getenv("XS_BUCKETED")) ix->bucketed = v[0] != '0';
+    if (const char* v = getenv("XS_BUCKET_MIN_WINDOWS")) ix->bucket_min_windows = std::max<uint64_t>(1, strtoull(v, nullptr, 10));
+    if (const char* v = getenv("XS_BUCKET_SCRATCH_MB")) ix->bucket_scratch_bytes = strtoull(v, nullptr, 10) << 20;
     uint32_t col0 = doc_begin / 8;
     uint32_t n_col = cf.kind == XS_COBS_CLASSIC ? (doc_end - doc_begin + 7) / 8 : (uint32_t)cf.page_bytes;
     // HBM row stride: a row never straddles a 128-byte DRAM fetch (power of two up to 128 B, then multiples of 128 B)
@@ -783,6 +917,22 @@ int xs_cobs_set_policy(xs_cobs* ix, int policy) {
     if (!ix) return fail(XS_ERR_ARG, "NULL index");
     if (policy != XS_NONACGT_SKIP && policy != XS_NONACGT_LITERAL) return fail(XS_ERR_ARG, "unknown policy");
     ix->info.policy = policy;
+    return XS_OK;
+}
+
+int xs_cobs_set_bucketed(xs_cobs* ix, int enabled, uint64_t min_windows, uint64_t scratch_bytes, uint32_t bucket_shift) {
+    if (!ix) return fail(XS_ERR_ARG, "NULL index");
+    if (bucket_shift > BK_MAX_SHIFT) return fail(XS_ERR_ARG, "bucket_shift must be <= 21");
+    ix->bucketed = enabled ? 1 : 0;
+    if (min_windows) ix->bucket_min_windows = min_windows;
+    if (scratch_bytes) ix->bucket_scratch_bytes = scratch_bytes;
+    ix->bucket_shift = bucket_shift;
+    return XS_OK;
+}
+
+int xs_cobs_bucketed_queries(const xs_cobs* ix, uint64_t* n) {
+    if (!ix || !n) return fail(XS_ERR_ARG, "NULL argument");
+    *n = ix->bucketed_queries.load();
     return XS_OK;
 }
 

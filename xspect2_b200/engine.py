@@ -136,6 +136,16 @@ class CobsIndex:
         check(lib().xs_cobs_set_policy(self._h, int(policy)))
         self.info.policy = int(policy)
 
+    def set_bucketed(self, enabled: bool = True, min_windows: int = 0, scratch_bytes: int = 0, bucket_shift: int = 0) -> None:
+        """Tune the bucketed path large batches take on a large narrow-row index (see ``xs_cobs_set_bucketed``)."""
+        check(lib().xs_cobs_set_bucketed(self._h, 1 if enabled else 0, int(min_windows), int(scratch_bytes), int(bucket_shift)))
+
+    @property
+    def bucketed_queries(self) -> int:
+        n = C.c_uint64()
+        check(lib().xs_cobs_bucketed_queries(self._h, C.byref(n)))
+        return int(n.value)
+
     def close(self) -> None:
         h, self._h = self._h, C.c_void_p()
         if h:
@@ -407,3 +417,10 @@ def profile_read() -> tuple[float, int]:
     ms, n = C.c_double(), C.c_uint64()
     check(lib().xs_profile_read(C.byref(ms), C.byref(n)))
     return ms.value, n.value
+
+
+def profile_read_phases() -> tuple[list[float], list[int]]:
+    """Per-kernel split of :func:`profile_read`: [direct kernel, k_bucket_emit, k_bucket_fetch, k_bucket_reduce]."""
+    ms, n = (C.c_double * 4)(), (C.c_uint64 * 4)()
+    check(lib().xs_profile_read_phases(ms, n))
+    return list(ms), [int(x) for x in n]
