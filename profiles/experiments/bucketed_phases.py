@@ -1,8 +1,12 @@
 """Direct-gather kernel vs the bucketed kernels on the bench workload (device-resident reads), per-kernel times,
 and the sensitivity to the scratch budget (= windows per sub-batch = how often every index row is re-used from L2).
 
-    python profiles/experiments/bucketed_phases.py [scratch_GiB ...]
+    python profiles/experiments/bucketed_phases.py [scratch_GiB[:nbuf[:emit_ctas[:fetch_ctas[:reduce_ctas[:prefetch]]]]] ...]
+
+nbuf = scratch sets in flight (1 = the three kernels back to back on one stream; 3 = emit / fetch / reduce of
+neighbouring sub-batches overlap on three streams); *_ctas = CTAs per SM of each kernel when they share the SMs.
 """
+import os
 import json
 import sys
 import tempfile
@@ -21,7 +25,7 @@ from xspect2_b200.synth import fixed_offsets  # noqa: E402
 
 
 def main():
-    budgets = [float(x) for x in sys.argv[1:]] or [24.0]
+    configs = sys.argv[1:] or ["24"]
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     wd = Path(tempfile.mkdtemp(prefix="xs_bk_"))
@@ -54,12 +58,20 @@ def main():
     ix.set_bucketed(False)
     dt, ms, n = run(out_a)
     print(json.dumps({"path": "direct", "ms_per_step": dt * 1e3, "G_lookups_s": lookups / dt / 1e9, "kernel_ms": ms, "launches": n}), flush=True)
-    for gib in budgets:
+    names = ["XS_BK_NBUF", "XS_BK_EMIT_CTAS", "XS_BK_FETCH_CTAS", "XS_BK_REDUCE_CTAS", "XS_BK_PREFETCH"]
+    for cfg in configs:
+        f = cfg.split(":")
+        gib = float(f[0])
+        for name, v in zip(names, f[1:] + [""] * 5):
+            if v:
+                os.environ[name] = v
+            else:
+                os.environ.pop(name, None)
         ix.set_bucketed(True, min_windows=1 << 20, scratch_bytes=int(gib * (1 << 30)))
         out_b.zero_()
         dt, ms, n = run(out_b)
         same = bool(torch.equal(out_a, out_b))
-        print(json.dumps({"path": "bucketed", "scratch_GiB": gib, "ms_per_step": dt * 1e3, "G_lookups_s": lookups / dt / 1e9,
+        print(json.dumps({"path": "bucketed", "config": cfg, "ms_per_step": dt * 1e3, "G_lookups_s": lookups / dt / 1e9,
                           "kernel_ms[direct,emit,fetch,reduce]": ms, "launches": n, "identical_to_direct": same,
                           "mem_GB": torch.cuda.mem_get_info()[0] / 1e9}), flush=True)
 

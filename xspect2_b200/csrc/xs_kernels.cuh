@@ -446,6 +446,7 @@ struct BucketParams {
     uint32_t nc;          // chunks of this sub-batch
     uint32_t n_buckets, bshift, cap;
     uint32_t pack_id;     // rows hold <= 96 documents: the fourth word is free for the local window
+    uint32_t prefetch;    // k_bucket_fetch prefetches the next bucket's rows into L2
 };
 
 __device__ __forceinline__ uint32_t ld_stream32(const uint32_t* p) {
@@ -457,6 +458,22 @@ __device__ __forceinline__ uint4 ld_stream128(const uint4* p) {
     uint4 v;
     asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
+}
+// row gathers of the bucket being swept: keep them in L2 ahead of the record / row streams passing through
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ldg128_keep(const uint8_t* p, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2_keep(const uint8_t* p, uint64_t pol) {
+    asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(p));
+    (void)pol;
 }
 __device__ __forceinline__ void st_stream128(uint4* p, const uint4& v) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -556,6 +573,11 @@ __global__ void __launch_bounds__(BK_NT) k_bucket_fetch(const BucketParams bp) {
     const uint64_t n_units = (uint64_t)bp.n_buckets * nc_live;    // unit = bucket * nc_live + chunk: bucket-major sweep
     const uint32_t rmask = (1u << bp.bshift) - 1u;
     const uint32_t cap = bp.cap;
+    const uint64_t keep = l2_policy_evict_last();
+    // the units of bucket b prefetch the rows of bucket b + 1 between them, so a sweep does not start on cold rows
+    const uint64_t slice_lines = ((16ULL << bp.bshift) + 127) / 128;
+    const uint32_t pf_per_unit = nc_live ? (uint32_t)((slice_lines + nc_live - 1) / nc_live) : 0;
+    const uint64_t index_lines = (pg.sig_size * 16 + 127) / 128;
     for (;;) {
         const uint64_t u0 = next_tile(bp.counter + 1, lane) * BK_FETCH_SPAN;
         if (u0 >= n_units) break;
@@ -566,6 +588,13 @@ __global__ void __launch_bounds__(BK_NT) k_bucket_fetch(const BucketParams bp) {
             const uint32_t* src = bp.rec + ((uint64_t)b * bp.nc + c) * cap;
             uint4* dst = bp.rows + ((uint64_t)c * bp.n_buckets + b) * cap;
             const uint8_t* base = pg.data + (((uint64_t)b << bp.bshift) * 16);
+            if (bp.prefetch && b + 1 < bp.n_buckets) {
+                for (uint32_t l = lane; l < pf_per_unit; l += 32) {
+                    const uint64_t in_slice = (uint64_t)c * pf_per_unit + l;
+                    const uint64_t line = (uint64_t)(b + 1) * slice_lines + in_slice;
+                    if (in_slice < slice_lines && line < index_lines) prefetch_l2_keep(pg.data + line * 128, keep);
+                }
+            }
             for (uint32_t i0 = 0; i0 < n; i0 += 128) {
                 uint32_t r[4];
                 uint4 v[4];
@@ -577,7 +606,7 @@ __global__ void __launch_bounds__(BK_NT) k_bucket_fetch(const BucketParams bp) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint32_t i = i0 + q * 32 + lane;
-                    if (i < n) v[q] = ldg128(base + (uint64_t)(r[q] & rmask) * 16);
+                    if (i < n) v[q] = ldg128_keep(base + (uint64_t)(r[q] & rmask) * 16, keep);
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
