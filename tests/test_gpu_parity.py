@@ -138,11 +138,8 @@ def test_cobs_bucketed_long_and_low_complexity(gpu, oracle, tmp_path, step, dtyp
         _check_bucketed(gpu, oracle, p, bases, b, e, step=step, dtype=dtype, policy=1)
 
 
-@pytest.mark.parametrize("nbuf", [1, 2, 3])
-def test_cobs_bucketed_sub_batches_and_overlaps(gpu, oracle, tmp_path, monkeypatch, nbuf):
-    """A scratch budget of a few chunks (many sub-batches; nbuf > 1: emit / fetch / reduce of neighbouring sub-batches
-    overlap on three streams) and overlapping / unordered segments (MLST-style)."""
-    monkeypatch.setenv("XS_BK_NBUF", str(nbuf))
+def test_cobs_bucketed_sub_batches_and_overlaps(gpu, oracle, tmp_path):
+    """A scratch budget of a few chunks (many sub-batches) and overlapping / unordered segments (MLST-style)."""
     rng = np.random.default_rng(19)
     p, docs = _mk_classic(oracle, tmp_path, rng, 90, 21, 7, length=4000)
     genomes = [s for v in docs.values() for s in v]

@@ -440,7 +440,7 @@ struct BucketParams {
     uint4* rows;          // [nc][n_buckets][cap]  fetched rows; .w = local window when pack_id
     uint16_t* cnt_bc;     // [n_buckets][nc]       records per block
     uint16_t* cnt_cb;     // [nc][n_buckets]
-    uint32_t* ovf;        // [nc][BK_CH / 32]      windows to score with direct gathers
+    uint32_t* ovf;        // [nc][2][BK_CH / 32]   windows to score with direct gathers | windows that are not scored
     unsigned long long* counter;   // [3] work hand-out of the three kernels, zeroed
     uint64_t chunk0;      // first chunk of this sub-batch in the flat window space
     uint32_t nc;          // chunks of this sub-batch
@@ -487,8 +487,54 @@ __device__ __forceinline__ uint32_t bucket_live_chunks(const BucketParams& bp, u
     return n < bp.nc ? (uint32_t)n : bp.nc;
 }
 
+// Sequence of every window of the chunk [g0, g1): s_wseq[l] = (sequence of window g0 + l) - s_lo + 1, where s_lo (the
+// return value) is the sequence of window g0.  Sequences that start inside the chunk mark their first window, an
+// inclusive max-scan carries the marks forward.  CTA-wide (NT threads); ends with a barrier.  This replaces warp_walk
+// in the bucketed kernels: its 64-bit shuffle bookkeeping is hidden by DRAM latency in k_cobs_narrow but was a third
+// of k_bucket_emit's and half of k_bucket_reduce's instructions (profiles/r1_bucketed_notes.md).
+template <int NT>
+__device__ __forceinline__ uint64_t chunk_seq_table(const SeqBatch& sb, uint64_t g0, uint64_t g1, uint32_t* s_wseq,
+                                                    uint32_t* s_scan, unsigned long long* s_lo_slot) {
+    constexpr int PER = BK_CH / NT;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) *s_lo_slot = seq_of_window(sb.win_prefix, sb.n_seq, g0);
+    for (uint32_t i = tid; i < BK_CH; i += NT) s_wseq[i] = 0;
+    __syncthreads();
+    const uint64_t s_lo = *s_lo_slot;
+    for (uint64_t q = s_lo + tid; q < sb.n_seq; q += NT) {
+        const uint64_t p = __ldg(sb.win_prefix + q);
+        if (p >= g1) break;
+        const uint64_t pn = __ldg(sb.win_prefix + q + 1);
+        if (pn > p && pn > g0) s_wseq[p > g0 ? (uint32_t)(p - g0) : 0u] = (uint32_t)(q - s_lo) + 1u;
+    }
+    __syncthreads();
+    uint32_t v[PER];
+    uint32_t run = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { const uint32_t x = s_wseq[tid * PER + q]; run = x > run ? x : run; v[q] = run; }
+    uint32_t x = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= (uint32_t)o && y > x) x = y;
+    }
+    if (lane == 31) s_scan[warp] = x;
+    __syncthreads();
+    uint32_t pre = 0;
+    for (uint32_t w = 0; w < warp; ++w) { const uint32_t y = s_scan[w]; pre = y > pre ? y : pre; }
+    uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, x, 1);
+    if (lane == 0) excl = 0;
+    excl = excl > pre ? excl : pre;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) s_wseq[tid * PER + q] = v[q] > excl ? v[q] : excl;
+    __syncthreads();
+    return s_lo;
+}
+
+constexpr int BK_EMIT_NT = 512;
+
 template <int K, int H>
-__global__ void __launch_bounds__(BK_NT) k_bucket_emit(const BucketParams bp) {
+__global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bucket_emit(const BucketParams bp) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const CobsParams& p = bp.cp;
     const SeqBatch& sb = p.sb;
@@ -497,8 +543,11 @@ __global__ void __launch_bounds__(BK_NT) k_bucket_emit(const BucketParams bp) {
     const uint32_t h = H ? H : p.num_hashes;
     uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_dyn);     // [n_buckets][cap]
     uint32_t* s_cnt = s_rec + (size_t)bp.n_buckets * bp.cap;  // [n_buckets] records offered (may exceed cap)
-    uint32_t* s_ovf = s_cnt + bp.n_buckets;                   // [BK_CH / 32]
-    __shared__ unsigned long long s_chunk;
+    uint32_t* s_ovf = s_cnt + bp.n_buckets;                   // [BK_CH / 32] windows with a probe that did not fit
+    uint32_t* s_skp = s_ovf + BK_CH / 32;                     // [BK_CH / 32] windows that are not scored (non-ACGT, SKIP)
+    uint32_t* s_wseq = s_skp + BK_CH / 32;                    // [BK_CH]
+    uint32_t* s_scan = s_wseq + BK_CH;                        // [BK_EMIT_NT / 32]
+    __shared__ unsigned long long s_chunk, s_lo_slot;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
     const uint32_t nc_live = bucket_live_chunks(bp, total);
@@ -507,57 +556,56 @@ __global__ void __launch_bounds__(BK_NT) k_bucket_emit(const BucketParams bp) {
 
     for (;;) {
         if (tid == 0) s_chunk = atomicAdd(bp.counter + 0, 1ULL);
-        for (uint32_t i = tid; i < nb + BK_CH / 32; i += BK_NT) s_cnt[i] = 0;   // s_cnt and s_ovf are contiguous
+        for (uint32_t i = tid; i < nb + 2 * (BK_CH / 32); i += BK_EMIT_NT) s_cnt[i] = 0;   // s_cnt, s_ovf, s_skp are contiguous
         __syncthreads();
         const uint64_t c = s_chunk;
         if (c >= nc_live) break;
         const uint64_t g0 = (bp.chunk0 + c) * BK_CH;
         const uint64_t g1 = g0 + BK_CH < total ? g0 + BK_CH : total;
-        const uint64_t t0 = g0 + (uint64_t)warp * BK_WARP_WIN;
-        const uint64_t t1 = t0 + BK_WARP_WIN < g1 ? t0 + BK_WARP_WIN : g1;
-        if (t0 < t1) {
-            warp_walk(
-                sb, t0, t1, lane,
-                [&](bool has, uint64_t pos, uint64_t g) {
-                    if (!has) return;
-                    Term t;
-                    if (!cobs_term<K>(sb, pos, p.canonicalize != 0, p.policy, t)) return;
-                    Xxh64Pre pre;
-                    xxh64_prepare(t, k, pre);
-                    const uint32_t lid = (uint32_t)(g - g0);
-                    bool over = false;
-                    auto emit = [&](uint32_t j) {
-                        const uint64_t row = mod_barrett(xxh64_finish(pre, k, (uint64_t)j), pg.sig_size, pg.magic);
-                        const uint32_t b = (uint32_t)(row >> bp.bshift);
-                        const uint32_t slot = atomicAdd(&s_cnt[b], 1u);
-                        if (slot < cap) s_rec[b * cap + slot] = (lid << bp.bshift) | ((uint32_t)row & rmask);
-                        else over = true;
-                    };
-                    if (H) {
+        const uint32_t nwin = (uint32_t)(g1 - g0);
+        const uint64_t s_lo = chunk_seq_table<BK_EMIT_NT>(sb, g0, g1, s_wseq, s_scan, &s_lo_slot);
+#pragma unroll 1
+        for (uint32_t lid = tid; lid < nwin; lid += BK_EMIT_NT) {
+            const uint64_t seq = s_lo + s_wseq[lid] - 1;
+            const uint64_t pos = __ldg(sb.seq_begin + seq) - sb.base_shift + (g0 + lid - __ldg(sb.win_prefix + seq)) * sb.step;
+            Term t;
+            if (!cobs_term<K>(sb, pos, p.canonicalize != 0, p.policy, t)) {
+                atomicOr(&s_skp[lid >> 5], 1u << (lid & 31));
+                continue;
+            }
+            Xxh64Pre pre;
+            xxh64_prepare(t, k, pre);
+            bool over = false;
+            auto emit = [&](uint32_t j) {
+                const uint64_t row = mod_barrett(xxh64_finish(pre, k, (uint64_t)j), pg.sig_size, pg.magic);
+                const uint32_t b = (uint32_t)(row >> bp.bshift);
+                const uint32_t slot = atomicAdd(&s_cnt[b], 1u);
+                if (slot < cap) s_rec[b * cap + slot] = (lid << bp.bshift) | ((uint32_t)row & rmask);
+                else over = true;
+            };
+            if (H) {
 #pragma unroll
-                        for (int j = 0; j < (H ? H : 1); ++j) emit((uint32_t)j);
-                    } else {
-                        for (uint32_t j = 0; j < h; ++j) emit(j);
-                    }
-                    if (over) atomicOr(&s_ovf[lid >> 5], 1u << (lid & 31));
-                },
-                [&](uint32_t) {}, [&](uint64_t, bool, uint64_t) {});
+                for (int j = 0; j < (H ? H : 1); ++j) emit((uint32_t)j);
+            } else {
+                for (uint32_t j = 0; j < h; ++j) emit(j);
+            }
+            if (over) atomicOr(&s_ovf[lid >> 5], 1u << (lid & 31));
         }
         __syncthreads();
         // blocks go out in whole 32-byte sectors (cap is a multiple of 8; the slack words are never read)
-        for (uint32_t b = warp; b < nb; b += BK_NT / 32) {
+        for (uint32_t b = warp; b < nb; b += BK_EMIT_NT / 32) {
             const uint32_t n = s_cnt[b] < cap ? s_cnt[b] : cap;
             const uint32_t n4 = ((n + 7) & ~7u) / 4;
             const uint4* src = reinterpret_cast<const uint4*>(s_rec + b * cap);
             uint4* dst = reinterpret_cast<uint4*>(bp.rec + ((uint64_t)b * bp.nc + c) * cap);
             for (uint32_t i = lane; i < n4; i += 32) dst[i] = src[i];
         }
-        for (uint32_t b = tid; b < nb; b += BK_NT) {
+        for (uint32_t b = tid; b < nb; b += BK_EMIT_NT) {
             const uint16_t n = (uint16_t)(s_cnt[b] < cap ? s_cnt[b] : cap);
             bp.cnt_bc[(uint64_t)b * bp.nc + c] = n;
             bp.cnt_cb[c * nb + b] = n;
         }
-        for (uint32_t i = tid; i < BK_CH / 32; i += BK_NT) bp.ovf[c * (BK_CH / 32) + i] = s_ovf[i];
+        for (uint32_t i = tid; i < 2 * (BK_CH / 32); i += BK_EMIT_NT) bp.ovf[c * (2 * (BK_CH / 32)) + i] = s_ovf[i];   // ovf | skp
         __syncthreads();
     }
 }
@@ -621,12 +669,6 @@ __global__ void __launch_bounds__(BK_NT) k_bucket_fetch(const BucketParams bp) {
     }
 }
 
-template <int K>
-__device__ __forceinline__ bool cobs_window_skipped(const SeqBatch& sb, uint64_t pos, bool canonicalize, int policy) {
-    const uint32_t k = K ? K : sb.k;
-    return policy == POLICY_SKIP && canonicalize && window_invalid(sb.invalid, pos, k);   // cobs_term() == false
-}
-
 // the rare flagged window: direct gathers, kept out of line so the streaming path stays lean
 template <int K, int H>
 __device__ __noinline__ void cobs_mask16_outline(const CobsParams* p, const PageDesc* pg, uint64_t pos, uint4* m) {
@@ -636,8 +678,10 @@ __device__ __noinline__ void cobs_mask16_outline(const CobsParams* p, const Page
 template <int K, int H, typename OutT>
 __global__ void __launch_bounds__(BK_NT, 4) k_bucket_reduce(const __grid_constant__ BucketParams bp) {
     __shared__ __align__(16) uint32_t s_m[4][BK_CH];   // window masks, one array per 32 documents
-    __shared__ uint32_t s_ovf[BK_CH / 32];
-    __shared__ unsigned long long s_chunk;
+    __shared__ uint32_t s_wseq[BK_CH];
+    __shared__ uint32_t s_flag[2 * (BK_CH / 32)];      // ovf | skp bitmaps of the chunk
+    __shared__ uint32_t s_scan[BK_NT / 32];
+    __shared__ unsigned long long s_chunk, s_lo_slot;
     const CobsParams& p = bp.cp;
     const SeqBatch& sb = p.sb;
     const PageDesc pg = p.pages[0];
@@ -659,7 +703,9 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bucket_reduce(const __grid_constan
         if (c >= nc_live) break;
         const uint64_t g0 = (bp.chunk0 + c) * BK_CH;
         const uint64_t g1 = g0 + BK_CH < total ? g0 + BK_CH : total;
-        if (tid < BK_CH / 32) s_ovf[tid] = __ldg(bp.ovf + c * (BK_CH / 32) + tid);
+        const uint32_t nwin = (uint32_t)(g1 - g0);
+        if (tid < 2 * (BK_CH / 32)) s_flag[tid] = __ldg(bp.ovf + c * (2 * (BK_CH / 32)) + tid);
+        const uint64_t s_lo = chunk_seq_table<BK_NT>(sb, g0, g1, s_wseq, s_scan, &s_lo_slot);
 
         // ---- AND of the fetched rows into the window masks (warp w takes buckets w, w + 8, ...)
         uint32_t myn = 0;
@@ -698,24 +744,39 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bucket_reduce(const __grid_constan
         }
         __syncthreads();
 
-        // ---- per-sequence document counts of the chunk's windows
-        const uint64_t t0 = g0 + (uint64_t)warp * BK_WARP_WIN;
-        const uint64_t t1 = t0 + BK_WARP_WIN < g1 ? t0 + BK_WARP_WIN : g1;
-        if (t0 < t1) {
+        // ---- per-sequence document counts: warp w owns windows [w * BK_WARP_WIN, ...) of the chunk; the lanes of a
+        // round that belong to one sequence are counted together, a sequence is flushed after its last window here
+        const uint32_t w_lo = warp * BK_WARP_WIN;
+        const uint32_t w_hi = w_lo + BK_WARP_WIN < nwin ? w_lo + BK_WARP_WIN : nwin;
+        uint32_t cnt[4] = {0, 0, 0, 0};
+        for (uint32_t r0 = w_lo; r0 < w_hi; r0 += 32) {
+            const uint32_t lid = r0 + lane;
+            const bool has = lid < w_hi;
+            const uint32_t sq = has ? s_wseq[lid] : 0u;
             uint4 m = make_uint4(0, 0, 0, 0);
-            uint32_t cnt[4] = {0, 0, 0, 0};
-            warp_walk(
-                sb, t0, t1, lane,
-                [&](bool has, uint64_t pos, uint64_t g) {
-                    m = make_uint4(0, 0, 0, 0);
-                    if (!has) return;
-                    const uint32_t lid = (uint32_t)(g - g0);
-                    if ((s_ovf[lid >> 5] >> (lid & 31)) & 1u) cobs_mask16_outline<K, H>(&bp.cp, bp.cp.pages, pos, &m);
-                    else if (!cobs_window_skipped<K>(sb, pos, p.canonicalize != 0, p.policy))
-                        m = make_uint4(s_m[0][lid], s_m[1][lid], s_m[2][lid], pack ? 0u : s_m[3][lid]);
-                },
-                [&](uint32_t segmask) { narrow_accum(lane, segmask, m, cnt); },
-                [&](uint64_t seq, bool complete, uint64_t nwin) { narrow_flush<OutT>(p, pg, lane, seq, complete, nwin, cnt); });
+            if (has) {
+                const uint32_t bit = 1u << (lid & 31);
+                if (s_flag[lid >> 5] & bit) {
+                    const uint64_t seq = s_lo + sq - 1;
+                    const uint64_t pos = __ldg(sb.seq_begin + seq) - sb.base_shift + (g0 + lid - __ldg(sb.win_prefix + seq)) * sb.step;
+                    cobs_mask16_outline<K, H>(&bp.cp, bp.cp.pages, pos, &m);
+                } else if (!(s_flag[BK_CH / 32 + (lid >> 5)] & bit)) {
+                    m = make_uint4(s_m[0][lid], s_m[1][lid], s_m[2][lid], pack ? 0u : s_m[3][lid]);
+                }
+            }
+            uint32_t rem = __ballot_sync(0xFFFFFFFFu, has);
+            while (rem) {
+                const uint32_t cur = __shfl_sync(0xFFFFFFFFu, sq, __ffs(rem) - 1);
+                const uint32_t segmask = __ballot_sync(0xFFFFFFFFu, has && sq == cur);
+                narrow_accum(lane, segmask, m, cnt);
+                rem &= ~segmask;
+                const uint32_t nxt = r0 + (32 - __clz(segmask));   // the window after this sequence's last lane of the round
+                if (!(nxt < w_hi && s_wseq[nxt] == cur)) {
+                    const uint64_t seq = s_lo + cur - 1;
+                    const uint64_t ps = __ldg(sb.win_prefix + seq), pe = __ldg(sb.win_prefix + seq + 1);
+                    narrow_flush<OutT>(p, pg, lane, seq, ps >= g0 + w_lo && pe <= g0 + w_hi, pe - ps, cnt);
+                }
+            }
         }
         __syncthreads();
     }

@@ -400,47 +400,36 @@ static bool bucket_geometry(uint64_t sig, uint32_t h, uint32_t shift_override, B
     const double mean = (double)BK_CH * h / (double)g.nb;
     g.cap = ((uint32_t)std::ceil(mean + 2.8 * std::sqrt(mean)) + 7) & ~7u;
     if (g.cap > 60000) return false;       // block counts are 16-bit
-    g.smem = ((size_t)g.nb * g.cap + g.nb + BK_CH / 32) * 4;
+    g.smem = ((size_t)g.nb * g.cap + g.nb + 2 * (BK_CH / 32) + BK_CH + BK_EMIT_NT / 32) * 4;
     if (g.smem > 200 * 1024) return false;
-    g.per_chunk = (size_t)g.nb * g.cap * 20 + (size_t)g.nb * 4 + (BK_CH / 32) * 4;
+    g.per_chunk = (size_t)g.nb * g.cap * 20 + (size_t)g.nb * 4 + 2 * (BK_CH / 32) * 4;
     return true;
 }
 
-struct BucketGrid { int emit, fetch, reduce; };   // CTAs per kernel
-
-enum { BK_EMIT = 0, BK_FETCH = 1, BK_REDUCE = 2 };
-
 template <int K, int H>
-static cudaError_t bucket_emit_setup(const BucketGeom& g, int* occ) {
+static cudaError_t launch_bucket_t(const BucketParams& bp, const BucketGeom& g, int n_sm, int dt, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(k_bucket_emit<K, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_bucket_emit<K, H>, BK_NT, g.smem);
-    if (e == cudaSuccess && *occ < 1) e = cudaErrorInvalidConfiguration;
-    return e;
-}
-
-template <int K, int H>
-static cudaError_t launch_bucket_t(int which, const BucketParams& bp, const BucketGeom& g, const BucketGrid& grid, int dt,
-                                   cudaStream_t s) {
-    if (which == BK_EMIT) {
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bucket_emit<K, H>, BK_EMIT_NT, g.smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+    {
         KernelTimer kt(s, PROF_EMIT);
-        k_bucket_emit<K, H><<<grid.emit, BK_NT, g.smem, s>>>(bp);
-    } else if (which == BK_FETCH) {
-        KernelTimer kt(s, PROF_FETCH);
-        k_bucket_fetch<<<grid.fetch, BK_NT, 0, s>>>(bp);
-    } else {
-        KernelTimer kt(s, PROF_REDUCE);
-        if (dt == XS_U8) k_bucket_reduce<K, H, uint8_t><<<grid.reduce, BK_NT, 0, s>>>(bp);
-        else if (dt == XS_U16) k_bucket_reduce<K, H, uint16_t><<<grid.reduce, BK_NT, 0, s>>>(bp);
-        else k_bucket_reduce<K, H, uint32_t><<<grid.reduce, BK_NT, 0, s>>>(bp);
+        k_bucket_emit<K, H><<<n_sm * occ, BK_EMIT_NT, g.smem, s>>>(bp);
     }
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    {
+        KernelTimer kt(s, PROF_FETCH);
+        k_bucket_fetch<<<n_sm * 8, BK_NT, 0, s>>>(bp);
+    }
+    {
+        KernelTimer kt(s, PROF_REDUCE);
+        if (dt == XS_U8) k_bucket_reduce<K, H, uint8_t><<<n_sm * 4, BK_NT, 0, s>>>(bp);
+        else if (dt == XS_U16) k_bucket_reduce<K, H, uint16_t><<<n_sm * 4, BK_NT, 0, s>>>(bp);
+        else k_bucket_reduce<K, H, uint32_t><<<n_sm * 4, BK_NT, 0, s>>>(bp);
+    }
+    g_launches.fetch_add(3, std::memory_order_relaxed);
     return cudaGetLastError();
-}
-
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
 }
 
 // returns XS_OK with *handled = false when the batch should go through k_cobs_narrow instead
@@ -455,94 +444,47 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
     XS_CUDA(cudaMemcpyAsync(&total, p.sb.win_prefix + p.sb.n_seq, 8, cudaMemcpyDeviceToHost, s));
     XS_CUDA(cudaStreamSynchronize(s));
     if (total < ix->bucket_min_windows) return XS_OK;
-    const bool k21h7 = p.sb.k == 21 && p.num_hashes == 7;
-    int occ_emit = 0;
-    XS_CUDA((k21h7 ? bucket_emit_setup<21, 7>(g, &occ_emit) : bucket_emit_setup<0, 0>(g, &occ_emit)));
-
-    // Sub-batches of nc_sub chunks flow through emit -> fetch -> reduce on three streams with NBUF scratch sets, so the
-    // ALU-bound emit, the L2-request-bound fetch and the DRAM-bound reduce of neighbouring sub-batches overlap.
-    const uint64_t NBUF = (uint64_t)std::max(1, std::min(4, env_int("XS_BK_NBUF", 3)));
+    // Sub-batches of nc_sub chunks go through emit -> fetch -> reduce back to back on the caller's stream.  (Running the
+    // three kernels of neighbouring sub-batches concurrently on three streams was measured and lost: they compete for
+    // issue slots and L2, profiles/r1_bucketed_notes.md.)
     size_t free_b = 0, total_b = 0;
     XS_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t budget = std::min<uint64_t>(ix->bucket_scratch_bytes, free_b / 2);
     const uint64_t nc_total = (total + BK_CH - 1) / BK_CH;
-    // small batches: one set, kernels back to back on the caller's stream (XS_BK_NBUF forces a depth: tests)
-    uint64_t nbuf = getenv("XS_BK_NBUF") ? NBUF : std::min<uint64_t>(NBUF, std::max<uint64_t>(1, nc_total / 4096));
-    uint64_t nc_sub = std::min<uint64_t>((nc_total + nbuf - 1) / nbuf, budget / nbuf / g.per_chunk);
-    if (nc_sub == 0 || nc_sub * BK_CH * nbuf < ix->bucket_min_windows / 2) return XS_OK;   // too little memory for L2 re-use
+    uint64_t nc_sub = std::min<uint64_t>(nc_total, budget / g.per_chunk);
+    if (nc_sub == 0 || nc_sub * BK_CH < ix->bucket_min_windows / 2) return XS_OK;    // too little memory for L2 re-use
     const uint64_t n_sub = (nc_total + nc_sub - 1) / nc_sub;
     nc_sub = (nc_total + n_sub - 1) / n_sub;
     nc_sub = std::min<uint64_t>(nc_sub, 0xFFFFFFFFu / BK_MAX_BUCKETS);
-    nbuf = std::min(nbuf, n_sub);
 
     const size_t o_rows = 0;
     const size_t o_rec = o_rows + align256(nc_sub * g.nb * g.cap * 16);
     const size_t o_bc = o_rec + align256(nc_sub * g.nb * g.cap * 4);
     const size_t o_cb = o_bc + align256(nc_sub * g.nb * 2);
     const size_t o_ovf = o_cb + align256(nc_sub * g.nb * 2);
-    const size_t set_bytes = o_ovf + align256(nc_sub * (BK_CH / 32) * 4);
-    const size_t o_ctr = set_bytes * nbuf;
+    const size_t o_ctr = o_ovf + align256(nc_sub * 2 * (BK_CH / 32) * 4);
     const size_t bytes = o_ctr + align256(n_sub * 3 * 8);
     uint8_t* d = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&d, bytes, s);
     if (e != cudaSuccess) { cudaGetLastError(); return XS_OK; }   // no room for the scratch: direct gathers
-
-    BucketGrid grid;
-    grid.emit = ix->n_sm * std::max(1, std::min(occ_emit, env_int("XS_BK_EMIT_CTAS", nbuf > 1 ? 2 : occ_emit)));
-    grid.fetch = ix->n_sm * std::max(1, env_int("XS_BK_FETCH_CTAS", nbuf > 1 ? 1 : 8));
-    grid.reduce = ix->n_sm * std::max(1, std::min(4, env_int("XS_BK_REDUCE_CTAS", nbuf > 1 ? 1 : 4)));
-
-    cudaStream_t st[3] = {s, s, s};
-    std::vector<cudaEvent_t> ev;   // [n_sub][3] done events, pipelined mode only
-    cudaEvent_t ev_start = nullptr;
-    if (nbuf > 1) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = greatest priority (numerically lowest)
-        const int prio[3] = {lo, std::min(lo, hi + 1), hi};
-        for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&st[i], cudaStreamNonBlocking, prio[i]);
-        ev.resize(n_sub * 3, nullptr);
-        for (size_t i = 0; i < ev.size() && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
-    }
-    if (e == cudaSuccess) e = cudaMemsetAsync(d + o_ctr, 0, n_sub * 3 * 8, s);
-    if (e == cudaSuccess && nbuf > 1) {
-        e = cudaEventRecord(ev_start, s);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(st[BK_EMIT], ev_start, 0);
-    }
+    int rc = XS_OK;
+    e = cudaMemsetAsync(d + o_ctr, 0, n_sub * 3 * 8, s);
+    const bool prefetch = getenv("XS_BK_PREFETCH") ? atoi(getenv("XS_BK_PREFETCH")) != 0 : true;
     for (uint64_t i = 0; i < n_sub && e == cudaSuccess; ++i) {
-        uint8_t* set = d + (i % nbuf) * set_bytes;
         BucketParams bp{};
         bp.cp = p;
-        bp.rows = reinterpret_cast<uint4*>(set + o_rows); bp.rec = reinterpret_cast<uint32_t*>(set + o_rec);
-        bp.cnt_bc = reinterpret_cast<uint16_t*>(set + o_bc); bp.cnt_cb = reinterpret_cast<uint16_t*>(set + o_cb);
-        bp.ovf = reinterpret_cast<uint32_t*>(set + o_ovf);
+        bp.rows = reinterpret_cast<uint4*>(d + o_rows); bp.rec = reinterpret_cast<uint32_t*>(d + o_rec);
+        bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.cnt_cb = reinterpret_cast<uint16_t*>(d + o_cb);
+        bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
         bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
         bp.chunk0 = i * nc_sub;
         bp.nc = (uint32_t)std::min<uint64_t>(nc_sub, nc_total - bp.chunk0);
         bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap;
         bp.pack_id = ix->pages[0].n_docs <= 96 ? 1u : 0u;
-        bp.prefetch = env_int("XS_BK_PREFETCH", 1) ? 1u : 0u;
-        for (int ph = 0; ph < 3 && e == cudaSuccess; ++ph) {
-            if (nbuf > 1) {
-                // emit waits until the reduce that last used this scratch set is done; fetch / reduce wait for the
-                // previous phase of their own sub-batch
-                if (ph == BK_EMIT && i >= nbuf) e = cudaStreamWaitEvent(st[ph], ev[(i - nbuf) * 3 + BK_REDUCE], 0);
-                if (ph != BK_EMIT) e = cudaStreamWaitEvent(st[ph], ev[i * 3 + ph - 1], 0);
-                if (e != cudaSuccess) break;
-            }
-            e = k21h7 ? launch_bucket_t<21, 7>(ph, bp, g, grid, dt, st[ph]) : launch_bucket_t<0, 0>(ph, bp, g, grid, dt, st[ph]);
-            if (e == cudaSuccess && nbuf > 1) e = cudaEventRecord(ev[i * 3 + ph], st[ph]);
-        }
+        bp.prefetch = prefetch ? 1u : 0u;
+        if (p.sb.k == 21 && p.num_hashes == 7) e = launch_bucket_t<21, 7>(bp, g, ix->n_sm, dt, s);
+        else e = launch_bucket_t<0, 0>(bp, g, ix->n_sm, dt, s);
     }
-    if (nbuf > 1) {
-        // reduces run in order on one stream: the last one covers them all
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ev[(n_sub - 1) * 3 + BK_REDUCE], 0);
-        else cudaDeviceSynchronize();                              // do not free scratch under running kernels
-        for (cudaEvent_t x : ev) if (x) cudaEventDestroy(x);
-        if (ev_start) cudaEventDestroy(ev_start);
-        for (int i = 0; i < 3; ++i) if (st[i] != s && st[i]) cudaStreamDestroy(st[i]);
-    }
-    int rc = XS_OK;
     if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("bucketed query: ") + cudaGetErrorString(e));
     cudaFreeAsync(d, s);
     if (rc == XS_OK) { *handled = true; ix->bucketed_queries.fetch_add(1, std::memory_order_relaxed); }
