@@ -441,6 +441,7 @@ struct BucketParams {
     uint16_t* cnt_bc;     // [n_buckets][nc]       records per block
     uint16_t* cnt_cb;     // [nc][n_buckets]
     uint32_t* ovf;        // [nc][2][BK_CH / 32]   windows to score with direct gathers | windows that are not scored
+    const uint64_t* chunk_seq;   // [all chunks of the batch] sequence of each chunk's first window (k_bucket_chunk_seq)
     unsigned long long* counter;   // [3] work hand-out of the three kernels, zeroed
     uint64_t chunk0;      // first chunk of this sub-batch in the flat window space
     uint32_t nc;          // chunks of this sub-batch
@@ -487,20 +488,28 @@ __device__ __forceinline__ uint32_t bucket_live_chunks(const BucketParams& bp, u
     return n < bp.nc ? (uint32_t)n : bp.nc;
 }
 
-// Sequence of every window of the chunk [g0, g1): s_wseq[l] = (sequence of window g0 + l) - s_lo + 1, where s_lo (the
-// return value) is the sequence of window g0.  Sequences that start inside the chunk mark their first window, an
+// Sequence of every window of the chunk [g0, g1): s_wseq[l] = (sequence of window g0 + l) - s_lo + 1, where s_lo (from
+// k_bucket_chunk_seq, also the return value) is the sequence of window g0.  Sequences that start inside the chunk mark their first window, an
 // inclusive max-scan carries the marks forward.  CTA-wide (NT threads); ends with a barrier.  This replaces warp_walk
 // in the bucketed kernels: its 64-bit shuffle bookkeeping is hidden by DRAM latency in k_cobs_narrow but was a third
 // of k_bucket_emit's and half of k_bucket_reduce's instructions (profiles/r1_bucketed_notes.md).
+// sequence of the first window of every chunk: one binary search per chunk, all chunks in parallel (inside the
+// kernels below the same search by one thread per chunk stalled the other 511 for ~27 dependent loads)
+__global__ void __launch_bounds__(256) k_bucket_chunk_seq(const SeqBatch sb, uint64_t n_chunks, uint64_t* __restrict__ chunk_seq) {
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_chunks; c += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t g0 = c * BK_CH;
+        chunk_seq[c] = g0 < total ? seq_of_window(sb.win_prefix, sb.n_seq, g0) : 0;
+    }
+}
+
 template <int NT>
-__device__ __forceinline__ uint64_t chunk_seq_table(const SeqBatch& sb, uint64_t g0, uint64_t g1, uint32_t* s_wseq,
-                                                    uint32_t* s_scan, unsigned long long* s_lo_slot) {
+__device__ __forceinline__ uint64_t chunk_seq_table(const SeqBatch& sb, uint64_t s_lo, uint64_t g0, uint64_t g1, uint32_t* s_wseq,
+                                                    uint32_t* s_scan) {
     constexpr int PER = BK_CH / NT;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) *s_lo_slot = seq_of_window(sb.win_prefix, sb.n_seq, g0);
     for (uint32_t i = tid; i < BK_CH; i += NT) s_wseq[i] = 0;
     __syncthreads();
-    const uint64_t s_lo = *s_lo_slot;
     for (uint64_t q = s_lo + tid; q < sb.n_seq; q += NT) {
         const uint64_t p = __ldg(sb.win_prefix + q);
         if (p >= g1) break;
@@ -547,23 +556,26 @@ __global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bucket_emit(const BucketParam
     uint32_t* s_skp = s_ovf + BK_CH / 32;                     // [BK_CH / 32] windows that are not scored (non-ACGT, SKIP)
     uint32_t* s_wseq = s_skp + BK_CH / 32;                    // [BK_CH]
     uint32_t* s_scan = s_wseq + BK_CH;                        // [BK_EMIT_NT / 32]
-    __shared__ unsigned long long s_chunk, s_lo_slot;
+    __shared__ unsigned long long s_chunk;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
     const uint32_t nc_live = bucket_live_chunks(bp, total);
     const uint32_t rmask = (1u << bp.bshift) - 1u;
     const uint32_t cap = bp.cap, nb = bp.n_buckets;
 
+    // the next chunk is requested while the current one is processed (thread 0 keeps the pending ticket)
+    unsigned long long ticket = tid == 0 ? atomicAdd(bp.counter + 0, 1ULL) : 0ULL;
     for (;;) {
-        if (tid == 0) s_chunk = atomicAdd(bp.counter + 0, 1ULL);
+        if (tid == 0) s_chunk = ticket;
         for (uint32_t i = tid; i < nb + 2 * (BK_CH / 32); i += BK_EMIT_NT) s_cnt[i] = 0;   // s_cnt, s_ovf, s_skp are contiguous
         __syncthreads();
         const uint64_t c = s_chunk;
         if (c >= nc_live) break;
+        if (tid == 0) ticket = atomicAdd(bp.counter + 0, 1ULL);
         const uint64_t g0 = (bp.chunk0 + c) * BK_CH;
         const uint64_t g1 = g0 + BK_CH < total ? g0 + BK_CH : total;
         const uint32_t nwin = (uint32_t)(g1 - g0);
-        const uint64_t s_lo = chunk_seq_table<BK_EMIT_NT>(sb, g0, g1, s_wseq, s_scan, &s_lo_slot);
+        const uint64_t s_lo = chunk_seq_table<BK_EMIT_NT>(sb, __ldg(bp.chunk_seq + bp.chunk0 + c), g0, g1, s_wseq, s_scan);
 #pragma unroll 1
         for (uint32_t lid = tid; lid < nwin; lid += BK_EMIT_NT) {
             const uint64_t seq = s_lo + s_wseq[lid] - 1;
@@ -681,7 +693,7 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bucket_reduce(const __grid_constan
     __shared__ uint32_t s_wseq[BK_CH];
     __shared__ uint32_t s_flag[2 * (BK_CH / 32)];      // ovf | skp bitmaps of the chunk
     __shared__ uint32_t s_scan[BK_NT / 32];
-    __shared__ unsigned long long s_chunk, s_lo_slot;
+    __shared__ unsigned long long s_chunk;
     const CobsParams& p = bp.cp;
     const SeqBatch& sb = p.sb;
     const PageDesc pg = p.pages[0];
@@ -691,8 +703,9 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bucket_reduce(const __grid_constan
     const uint32_t cap = bp.cap, nb = bp.n_buckets;
     const bool pack = bp.pack_id != 0;
 
+    unsigned long long ticket = tid == 0 ? atomicAdd(bp.counter + 2, 1ULL) : 0ULL;
     for (;;) {
-        if (tid == 0) s_chunk = atomicAdd(bp.counter + 2, 1ULL);
+        if (tid == 0) s_chunk = ticket;
         {
             uint4* z = reinterpret_cast<uint4*>(&s_m[0][0]);
             const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
@@ -701,11 +714,12 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bucket_reduce(const __grid_constan
         __syncthreads();
         const uint64_t c = s_chunk;
         if (c >= nc_live) break;
+        if (tid == 0) ticket = atomicAdd(bp.counter + 2, 1ULL);
         const uint64_t g0 = (bp.chunk0 + c) * BK_CH;
         const uint64_t g1 = g0 + BK_CH < total ? g0 + BK_CH : total;
         const uint32_t nwin = (uint32_t)(g1 - g0);
         if (tid < 2 * (BK_CH / 32)) s_flag[tid] = __ldg(bp.ovf + c * (2 * (BK_CH / 32)) + tid);
-        const uint64_t s_lo = chunk_seq_table<BK_NT>(sb, g0, g1, s_wseq, s_scan, &s_lo_slot);
+        const uint64_t s_lo = chunk_seq_table<BK_NT>(sb, __ldg(bp.chunk_seq + bp.chunk0 + c), g0, g1, s_wseq, s_scan);
 
         // ---- AND of the fetched rows into the window masks (warp w takes buckets w, w + 8, ...)
         uint32_t myn = 0;

@@ -463,12 +463,16 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
     const size_t o_cb = o_bc + align256(nc_sub * g.nb * 2);
     const size_t o_ovf = o_cb + align256(nc_sub * g.nb * 2);
     const size_t o_ctr = o_ovf + align256(nc_sub * 2 * (BK_CH / 32) * 4);
-    const size_t bytes = o_ctr + align256(n_sub * 3 * 8);
+    const size_t o_seq = o_ctr + align256(n_sub * 3 * 8);
+    const size_t bytes = o_seq + align256(nc_total * 8);
     uint8_t* d = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&d, bytes, s);
     if (e != cudaSuccess) { cudaGetLastError(); return XS_OK; }   // no room for the scratch: direct gathers
     int rc = XS_OK;
     e = cudaMemsetAsync(d + o_ctr, 0, n_sub * 3 * 8, s);
+    k_bucket_chunk_seq<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nc_total + 255) / 256, (uint64_t)ix->n_sm * 8)), 256, 0, s>>>(
+        p.sb, nc_total, reinterpret_cast<uint64_t*>(d + o_seq));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     const bool prefetch = getenv("XS_BK_PREFETCH") ? atoi(getenv("XS_BK_PREFETCH")) != 0 : true;
     for (uint64_t i = 0; i < n_sub && e == cudaSuccess; ++i) {
         BucketParams bp{};
@@ -476,6 +480,7 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
         bp.rows = reinterpret_cast<uint4*>(d + o_rows); bp.rec = reinterpret_cast<uint32_t*>(d + o_rec);
         bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.cnt_cb = reinterpret_cast<uint16_t*>(d + o_cb);
         bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
+        bp.chunk_seq = reinterpret_cast<const uint64_t*>(d + o_seq);
         bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
         bp.chunk0 = i * nc_sub;
         bp.nc = (uint32_t)std::min<uint64_t>(nc_sub, nc_total - bp.chunk0);
