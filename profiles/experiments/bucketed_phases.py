@@ -1,10 +1,10 @@
 """Direct-gather kernel vs the bucketed kernels on the bench workload (device-resident reads), per-kernel times,
 and the sensitivity to the scratch budget (= windows per sub-batch = how often every index row is re-used from L2).
 
-    python profiles/experiments/bucketed_phases.py [scratch_GiB[:nbuf[:emit_ctas[:fetch_ctas[:reduce_ctas[:prefetch]]]]] ...]
+    python profiles/experiments/bucketed_phases.py [scratch_GiB[:overlap[:emit_ctas[:fetch_ctas[:prefetch]]]] ...]
 
-nbuf = scratch sets in flight (1 = the three kernels back to back on one stream; 3 = emit / fetch / reduce of
-neighbouring sub-batches overlap on three streams); *_ctas = CTAs per SM of each kernel when they share the SMs.
+overlap = 0: the three kernels back to back on one stream; 1: emit of sub-batch i + 1 next to fetch of sub-batch i on a
+second stream; *_ctas = CTAs per SM of those two kernels.
 """
 import os
 import json
@@ -58,11 +58,11 @@ def main():
     ix.set_bucketed(False)
     dt, ms, n = run(out_a)
     print(json.dumps({"path": "direct", "ms_per_step": dt * 1e3, "G_lookups_s": lookups / dt / 1e9, "kernel_ms": ms, "launches": n}), flush=True)
-    names = ["XS_BK_NBUF", "XS_BK_EMIT_CTAS", "XS_BK_FETCH_CTAS", "XS_BK_REDUCE_CTAS", "XS_BK_PREFETCH"]
+    names = ["XS_BK_OVERLAP", "XS_BK_EMIT_CTAS", "XS_BK_FETCH_CTAS", "XS_BK_PREFETCH"]
     for cfg in configs:
         f = cfg.split(":")
         gib = float(f[0])
-        for name, v in zip(names, f[1:] + [""] * 5):
+        for name, v in zip(names, f[1:] + [""] * 4):
             if v:
                 os.environ[name] = v
             else:
