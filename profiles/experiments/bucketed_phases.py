@@ -1,10 +1,11 @@
 """Direct-gather kernel vs the bucketed kernels on the bench workload (device-resident reads), per-kernel times,
 and the sensitivity to the scratch budget (= windows per sub-batch = how often every index row is re-used from L2).
 
-    python profiles/experiments/bucketed_phases.py [scratch_GiB[:overlap[:emit_ctas[:fetch_ctas[:prefetch]]]] ...]
+    python profiles/experiments/bucketed_phases.py [scratch_GiB[:prefetch] ...]
 
-overlap = 0: the three kernels back to back on one stream; 1: emit of sub-batch i + 1 next to fetch of sub-batch i on a
-second stream; *_ctas = CTAs per SM of those two kernels.
+prefetch = 0 switches the next-slice L2 prefetch of k_bucket_fetch off.  (Earlier revisions of this script also drove
+multi-stream variants — emit / fetch / reduce of neighbouring sub-batches on three streams, and fetch(i) next to
+emit(i+1) — which were measured and removed: profiles/r1_bucketed_notes.md.)
 """
 import os
 import json
@@ -58,11 +59,11 @@ def main():
     ix.set_bucketed(False)
     dt, ms, n = run(out_a)
     print(json.dumps({"path": "direct", "ms_per_step": dt * 1e3, "G_lookups_s": lookups / dt / 1e9, "kernel_ms": ms, "launches": n}), flush=True)
-    names = ["XS_BK_OVERLAP", "XS_BK_EMIT_CTAS", "XS_BK_FETCH_CTAS", "XS_BK_PREFETCH"]
+    names = ["XS_BK_PREFETCH"]
     for cfg in configs:
         f = cfg.split(":")
         gib = float(f[0])
-        for name, v in zip(names, f[1:] + [""] * 4):
+        for name, v in zip(names, f[1:] + [""]):
             if v:
                 os.environ[name] = v
             else:

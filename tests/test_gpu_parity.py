@@ -138,11 +138,8 @@ def test_cobs_bucketed_long_and_low_complexity(gpu, oracle, tmp_path, step, dtyp
         _check_bucketed(gpu, oracle, p, bases, b, e, step=step, dtype=dtype, policy=1)
 
 
-@pytest.mark.parametrize("overlap", [0, 2])
-def test_cobs_bucketed_sub_batches_and_overlaps(gpu, oracle, tmp_path, monkeypatch, overlap):
-    """A scratch budget of a few chunks (many sub-batches; overlap=2: the emit of the next sub-batch runs next to the
-    fetch of the current one on a second stream) and overlapping / unordered segments (MLST-style)."""
-    monkeypatch.setenv("XS_BK_OVERLAP", str(overlap))
+def test_cobs_bucketed_sub_batches_and_overlaps(gpu, oracle, tmp_path):
+    """A scratch budget of a few chunks (many sub-batches) and overlapping / unordered segments (MLST-style)."""
     rng = np.random.default_rng(19)
     p, docs = _mk_classic(oracle, tmp_path, rng, 90, 21, 7, length=4000)
     genomes = [s for v in docs.values() for s in v]

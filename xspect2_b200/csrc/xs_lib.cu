@@ -406,39 +406,30 @@ static bool bucket_geometry(uint64_t sig, uint32_t h, uint32_t shift_override, B
     return true;
 }
 
-enum { BK_EMIT = 0, BK_FETCH = 1, BK_REDUCE = 2 };
-struct BucketGrid { int emit, fetch, reduce; };   // CTAs of each kernel
-
 template <int K, int H>
-static cudaError_t bucket_emit_occupancy(const BucketGeom& g, int* occ) {
+static cudaError_t launch_bucket_t(const BucketParams& bp, const BucketGeom& g, int n_sm, int dt, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(k_bucket_emit<K, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_bucket_emit<K, H>, BK_EMIT_NT, g.smem);
-    if (e == cudaSuccess && *occ < 1) e = cudaErrorInvalidConfiguration;
-    return e;
-}
-
-template <int K, int H>
-static cudaError_t launch_bucket_t(int which, const BucketParams& bp, const BucketGeom& g, const BucketGrid& grid, int dt,
-                                   cudaStream_t s) {
-    if (which == BK_EMIT) {
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bucket_emit<K, H>, BK_EMIT_NT, g.smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+    {
         KernelTimer kt(s, PROF_EMIT);
-        k_bucket_emit<K, H><<<grid.emit, BK_EMIT_NT, g.smem, s>>>(bp);
-    } else if (which == BK_FETCH) {
-        KernelTimer kt(s, PROF_FETCH);
-        k_bucket_fetch<<<grid.fetch, BK_NT, 0, s>>>(bp);
-    } else {
-        KernelTimer kt(s, PROF_REDUCE);
-        if (dt == XS_U8) k_bucket_reduce<K, H, uint8_t><<<grid.reduce, BK_NT, 0, s>>>(bp);
-        else if (dt == XS_U16) k_bucket_reduce<K, H, uint16_t><<<grid.reduce, BK_NT, 0, s>>>(bp);
-        else k_bucket_reduce<K, H, uint32_t><<<grid.reduce, BK_NT, 0, s>>>(bp);
+        k_bucket_emit<K, H><<<n_sm * occ, BK_EMIT_NT, g.smem, s>>>(bp);
     }
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    {
+        KernelTimer kt(s, PROF_FETCH);
+        k_bucket_fetch<<<n_sm * 8, BK_NT, 0, s>>>(bp);
+    }
+    {
+        KernelTimer kt(s, PROF_REDUCE);
+        if (dt == XS_U8) k_bucket_reduce<K, H, uint8_t><<<n_sm * 4, BK_NT, 0, s>>>(bp);
+        else if (dt == XS_U16) k_bucket_reduce<K, H, uint16_t><<<n_sm * 4, BK_NT, 0, s>>>(bp);
+        else k_bucket_reduce<K, H, uint32_t><<<n_sm * 4, BK_NT, 0, s>>>(bp);
+    }
+    g_launches.fetch_add(3, std::memory_order_relaxed);
     return cudaGetLastError();
-}
-
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
 }
 
 // returns XS_OK with *handled = false when the batch should go through k_cobs_narrow instead
@@ -453,76 +444,42 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
     XS_CUDA(cudaMemcpyAsync(&total, p.sb.win_prefix + p.sb.n_seq, 8, cudaMemcpyDeviceToHost, s));
     XS_CUDA(cudaStreamSynchronize(s));
     if (total < ix->bucket_min_windows) return XS_OK;
-    const bool k21h7 = p.sb.k == 21 && p.num_hashes == 7;
-    int occ_emit = 0;
-    XS_CUDA((k21h7 ? bucket_emit_occupancy<21, 7>(g, &occ_emit) : bucket_emit_occupancy<0, 0>(g, &occ_emit)));
-
-    // Sub-batches of nc_sub chunks go through emit -> fetch -> reduce.  With `overlap` the emit of sub-batch i + 1 (ALU
-    // bound) runs next to the fetch of sub-batch i (L1TEX bound: one tag lookup per gathered row) on a second stream,
-    // with grids sized so that both fit on every SM; reduce runs alone.  Probe records, block counts and flags are
-    // double-buffered for that, the fetched rows are not.
+    // Sub-batches of nc_sub chunks go through emit -> fetch -> reduce back to back on the caller's stream.  (Running the
+    // three kernels of neighbouring sub-batches concurrently on three streams was measured and lost: they compete for
+    // issue slots and L2, profiles/r1_bucketed_notes.md.)
     size_t free_b = 0, total_b = 0;
     XS_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t budget = std::min<uint64_t>(ix->bucket_scratch_bytes, free_b / 2);
     const uint64_t nc_total = (total + BK_CH - 1) / BK_CH;
-    const int ov = env_int("XS_BK_OVERLAP", 1);                                 // 0 off, 1 large batches, 2 always (tests)
-    bool overlap = ov != 0 && (ov == 2 || nc_total >= 8192);
-    const size_t rec_chunk = g.per_chunk - (size_t)g.nb * g.cap * 16;          // everything but the rows
-    uint64_t nc_sub = budget / (g.per_chunk + (overlap ? rec_chunk : 0));
-    if (overlap) nc_sub = std::min<uint64_t>(nc_sub, (nc_total + 1) / 2);      // at least two sub-batches to overlap
-    nc_sub = std::min<uint64_t>(nc_sub, nc_total);
+    uint64_t nc_sub = std::min<uint64_t>(nc_total, budget / g.per_chunk);
     if (nc_sub == 0 || nc_sub * BK_CH < ix->bucket_min_windows / 2) return XS_OK;    // too little memory for L2 re-use
     const uint64_t n_sub = (nc_total + nc_sub - 1) / nc_sub;
     nc_sub = (nc_total + n_sub - 1) / n_sub;
     nc_sub = std::min<uint64_t>(nc_sub, 0xFFFFFFFFu / BK_MAX_BUCKETS);
-    if (n_sub < 2) overlap = false;
-    const uint64_t n_set = overlap ? 2 : 1;
 
-    const size_t o_rec = 0;
+    const size_t o_rows = 0;
+    const size_t o_rec = o_rows + align256(nc_sub * g.nb * g.cap * 16);
     const size_t o_bc = o_rec + align256(nc_sub * g.nb * g.cap * 4);
     const size_t o_cb = o_bc + align256(nc_sub * g.nb * 2);
     const size_t o_ovf = o_cb + align256(nc_sub * g.nb * 2);
-    const size_t set_bytes = o_ovf + align256(nc_sub * 2 * (BK_CH / 32) * 4);
-    const size_t o_rows = set_bytes * n_set;
-    const size_t o_ctr = o_rows + align256(nc_sub * g.nb * g.cap * 16);
+    const size_t o_ctr = o_ovf + align256(nc_sub * 2 * (BK_CH / 32) * 4);
     const size_t o_seq = o_ctr + align256(n_sub * 3 * 8);
     const size_t bytes = o_seq + align256(nc_total * 8);
     uint8_t* d = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&d, bytes, s);
     if (e != cudaSuccess) { cudaGetLastError(); return XS_OK; }   // no room for the scratch: direct gathers
-
-    BucketGrid grid;
-    grid.emit = ix->n_sm * std::max(1, std::min(occ_emit, env_int("XS_BK_EMIT_CTAS", overlap ? 1 : occ_emit)));
-    grid.fetch = ix->n_sm * std::max(1, env_int("XS_BK_FETCH_CTAS", overlap ? 3 : 8));
-    grid.reduce = ix->n_sm * 4;
-    const bool prefetch = env_int("XS_BK_PREFETCH", 1) != 0;
-
-    cudaStream_t s2 = nullptr;
-    std::vector<cudaEvent_t> ev_e, ev_r;    // emit / reduce done, per sub-batch (overlap only)
-    cudaEvent_t ev_start = nullptr;
-    if (overlap) {
-        e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
-        ev_e.assign(n_sub, nullptr); ev_r.assign(n_sub, nullptr);
-        for (uint64_t i = 0; i < n_sub && e == cudaSuccess; ++i) {
-            e = cudaEventCreateWithFlags(&ev_e[i], cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_r[i], cudaEventDisableTiming);
-        }
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
-    }
-    if (e == cudaSuccess) e = cudaMemsetAsync(d + o_ctr, 0, n_sub * 3 * 8, s);
-    if (e == cudaSuccess) {
-        k_bucket_chunk_seq<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nc_total + 255) / 256, (uint64_t)ix->n_sm * 8)), 256, 0, s>>>(
-            p.sb, nc_total, reinterpret_cast<uint64_t*>(d + o_seq));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        e = cudaGetLastError();
-    }
-    auto params = [&](uint64_t i) {
-        uint8_t* set = d + (i % n_set) * set_bytes;
+    int rc = XS_OK;
+    e = cudaMemsetAsync(d + o_ctr, 0, n_sub * 3 * 8, s);
+    k_bucket_chunk_seq<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nc_total + 255) / 256, (uint64_t)ix->n_sm * 8)), 256, 0, s>>>(
+        p.sb, nc_total, reinterpret_cast<uint64_t*>(d + o_seq));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const bool prefetch = getenv("XS_BK_PREFETCH") ? atoi(getenv("XS_BK_PREFETCH")) != 0 : true;
+    for (uint64_t i = 0; i < n_sub && e == cudaSuccess; ++i) {
         BucketParams bp{};
         bp.cp = p;
-        bp.rows = reinterpret_cast<uint4*>(d + o_rows); bp.rec = reinterpret_cast<uint32_t*>(set + o_rec);
-        bp.cnt_bc = reinterpret_cast<uint16_t*>(set + o_bc); bp.cnt_cb = reinterpret_cast<uint16_t*>(set + o_cb);
-        bp.ovf = reinterpret_cast<uint32_t*>(set + o_ovf);
+        bp.rows = reinterpret_cast<uint4*>(d + o_rows); bp.rec = reinterpret_cast<uint32_t*>(d + o_rec);
+        bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.cnt_cb = reinterpret_cast<uint16_t*>(d + o_cb);
+        bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
         bp.chunk_seq = reinterpret_cast<const uint64_t*>(d + o_seq);
         bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
         bp.chunk0 = i * nc_sub;
@@ -530,40 +487,9 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
         bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap;
         bp.pack_id = ix->pages[0].n_docs <= 96 ? 1u : 0u;
         bp.prefetch = prefetch ? 1u : 0u;
-        return bp;
-    };
-    auto launch = [&](int which, uint64_t i, cudaStream_t st) {
-        const BucketParams bp = params(i);
-        return k21h7 ? launch_bucket_t<21, 7>(which, bp, g, grid, dt, st) : launch_bucket_t<0, 0>(which, bp, g, grid, dt, st);
-    };
-    if (!overlap) {
-        for (uint64_t i = 0; i < n_sub && e == cudaSuccess; ++i)
-            for (int ph = 0; ph < 3 && e == cudaSuccess; ++ph) e = launch(ph, i, s);
-    } else {
-        // s:  [fetch_i] .. wait emit_{i+1} .. [reduce_i]        s2:  wait reduce_{i-1} .. [emit_{i+1}]
-        if (e == cudaSuccess) e = cudaEventRecord(ev_start, s);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, ev_start, 0);
-        if (e == cudaSuccess) e = launch(BK_EMIT, 0, s2);
-        if (e == cudaSuccess) e = cudaEventRecord(ev_e[0], s2);
-        for (uint64_t i = 0; i < n_sub && e == cudaSuccess; ++i) {
-            e = cudaStreamWaitEvent(s, ev_e[i], 0);
-            if (e == cudaSuccess) e = launch(BK_FETCH, i, s);
-            if (i + 1 < n_sub) {
-                if (e == cudaSuccess && i >= 1) e = cudaStreamWaitEvent(s2, ev_r[i - 1], 0);
-                if (e == cudaSuccess) e = launch(BK_EMIT, i + 1, s2);
-                if (e == cudaSuccess) e = cudaEventRecord(ev_e[i + 1], s2);
-                if (e == cudaSuccess) e = cudaStreamWaitEvent(s, ev_e[i + 1], 0);
-            }
-            if (e == cudaSuccess) e = launch(BK_REDUCE, i, s);
-            if (e == cudaSuccess) e = cudaEventRecord(ev_r[i], s);
-        }
-        if (e != cudaSuccess) cudaDeviceSynchronize();               // do not free scratch under running kernels
-        for (cudaEvent_t x : ev_e) if (x) cudaEventDestroy(x);
-        for (cudaEvent_t x : ev_r) if (x) cudaEventDestroy(x);
-        if (ev_start) cudaEventDestroy(ev_start);
-        if (s2) cudaStreamDestroy(s2);
+        if (p.sb.k == 21 && p.num_hashes == 7) e = launch_bucket_t<21, 7>(bp, g, ix->n_sm, dt, s);
+        else e = launch_bucket_t<0, 0>(bp, g, ix->n_sm, dt, s);
     }
-    int rc = XS_OK;
     if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("bucketed query: ") + cudaGetErrorString(e));
     cudaFreeAsync(d, s);
     if (rc == XS_OK) { *handled = true; ix->bucketed_queries.fetch_add(1, std::memory_order_relaxed); }
