@@ -13,8 +13,10 @@ the index is replicated, no data-path collective (weak scaling).
   value   whole-job lookups/s, reads resident in HBM, CUDA events on the launch stream, max over ranks
   e2e     same metric through the public API with HOST (pinned) buffers: H2D of reads + offsets and D2H of the
           uint8 count matrix inside the timed region
-  roofline  the dominant kernel (k_cobs_narrow) timed by CUDA events inside the library on its launch stream;
-            algorithmic bytes per launch over that time, against MEASURED_PEAKS.json hbm_gbs
+  roofline  the scoring kernels timed by CUDA events inside the library on their launch stream: the three bucketed
+            kernels (k_bucket_emit / k_bucket_fetch / k_bucket_reduce) that large batches take, as one unit and
+            one by one, and the direct-gather kernel k_cobs_narrow next to them; algorithmic bytes per launch over
+            that time, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the CPU oracle (restated reference algorithm; the reference's own native wheels are not
             installable offline) on all host threads over a bounded sample of the same reads
 
@@ -49,16 +51,20 @@ WORKLOAD = (f"cfg2: {N_READS} synthetic {READ_LEN}bp reads x COBS classic index 
             f"S={SIG_SIZE} (Acinetobacter-species geometry)")
 
 
-def ncu_traffic() -> tuple[float | None, float | None]:
-    """(dram read+write bytes, global load sectors) of one k_cobs_narrow launch from the committed ncu capture, if it
-    is this workload."""
+def ncu_traffic(kernel: str = "k_cobs_narrow<21,7,u8>") -> tuple[float | None, float | None]:
+    """(dram read+write bytes, global load sectors) of the launches of `kernel` in one step, from the committed ncu
+    capture scaled to this workload's read count (the capture may be of a smaller batch of the same geometry)."""
     p = ROOT / "profiles" / "traffic.json"
     if not p.exists():
         return None, None
-    t = json.loads(p.read_text()).get("k_cobs_narrow<21,7,u8>")
-    if not t or (t["n_reads"], t["read_len"], t["sig_size"]) != (N_READS, READ_LEN, SIG_SIZE):
+    t = json.loads(p.read_text()).get(kernel)
+    if not t or (t["read_len"], t["sig_size"]) != (READ_LEN, SIG_SIZE):
         return None, None
-    return float(t["dram_bytes_read"] + t["dram_bytes_write"]), float(t.get("global_load_sectors") or 0) or None
+    scale = N_READS / t["n_reads"]
+    if scale != 1 and not t.get("scales_with_reads"):
+        return None, None
+    sectors = float(t.get("global_load_sectors") or 0) * scale
+    return float(t["dram_bytes_read"] + t["dram_bytes_write"]) * scale, sectors or None
 
 
 def peaks() -> tuple[float, str]:
@@ -221,6 +227,30 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        if os.environ.get("XS_BENCH_BUCKETED", "1") == "0":
+            ix.set_bucketed(False)
+        # the direct-gather kernel on the same batch (the path small batches take), for the record
+        bucketed0 = ix.bucketed_queries
+        for _ in range(3):
+            step_device()
+        torch.cuda.synchronize()
+        uses_bucketed = ix.bucketed_queries > bucketed0
+        direct = None
+        if uses_bucketed:
+            ix.set_bucketed(False)
+            step_device()
+            torch.cuda.synchronize()
+            engine.profile_enable(True)
+            engine.profile_read()
+            for _ in range(3):
+                step_device()
+            torch.cuda.synchronize()
+            d_ms, d_n = engine.profile_read()
+            engine.profile_enable(False)
+            direct = {"kernel": "k_cobs_narrow<21,7,u8>", "kernel_ms": d_ms / max(d_n, 1), "checksum": int(d_out[:100000].to(torch.int64).sum().item())}
+            ix.set_bucketed(True)
+            step_device()
+            torch.cuda.synchronize()
         engine.profile_enable(True)
         engine.profile_read()
         launches0 = engine.launch_count()
@@ -235,7 +265,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1)
         clocks = sampler.stop()
-        kernel_ms, kernel_launches = engine.profile_read()
+        phase_ms, phase_n = engine.profile_read_phases()
+        kernel_ms, kernel_launches = sum(phase_ms), sum(phase_n)
         engine.profile_enable(False)
         launches = engine.launch_count() - launches0
         if world > 1:
@@ -275,12 +306,45 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         # algorithmic bytes of one k_cobs_narrow launch: h row reads of ceil(D/8) bytes per lookup,
         # the 2-bit stream + bitmap of the reads, the uint8 count matrix written
         algo_bytes = lookups_per_step * H * ROW_BYTES + n_bases * 3 // 8 + N_READS * D
-        k_ms = kernel_ms / max(kernel_launches, 1)
+        k_ms = kernel_ms / args.steps                      # scoring-kernel time per step (one launch, or the bucketed kernels)
         achieved = algo_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else None
-        traffic, load_sectors = ncu_traffic()
-        # row gathers issued per launch: h per lookup, minus the last two when the first five rows AND to zero;
-        # ncu's global-load sector count (each row gather is one sector; ~1 % of it is the packed read stream)
-        gathers = load_sectors or lookups_per_step * H
+        if uses_bucketed:
+            names = ["k_bucket_emit<21,7>", "k_bucket_fetch", "k_bucket_reduce<21,7,u8>"]
+            parts = [ncu_traffic(n) for n in names]
+            traffic = sum(t for t, _ in parts) if all(t is not None for t, _ in parts) else None
+            kernel_name = "bucketed probing: k_bucket_emit<21,7> + k_bucket_fetch + k_bucket_reduce<21,7,u8> (per step)"
+        else:
+            traffic, load_sectors = ncu_traffic()
+            kernel_name = "k_cobs_narrow<21,7,u8>"
+        roof = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms": k_ms, "kernel_launches": int(kernel_launches),
+                "kernel_share_of_step": kernel_ms / ms if ms else None,
+                "algorithmic_bytes_per_launch": int(algo_bytes)}
+        if uses_bucketed:
+            # what bounds each of the three kernels (ncu, profiles/r1_bucketed_ncu.txt): emit = instruction issue (XXH64),
+            # fetch = L1TEX tag stage (one lookup per gathered row; the rows come from L2), reduce = shared-memory
+            # atomics + the row stream.  Each kernel's DRAM traffic per step is in profiles/traffic.json.
+            roof["phases"] = [{"kernel": n, "ms_per_step": phase_ms[i + 1] / args.steps, "launches_per_step": phase_n[i + 1] / args.steps,
+                               "dram_bytes_per_step": parts[i][0]} for i, n in enumerate(names)]
+            roof["dominant"] = {"kernel": "k_bucket_fetch", "bound": "L1TEX tag lookups (row gathers served from L2)",
+                                "gathers_per_s_G": lookups_per_step * H / (phase_ms[2] / args.steps / 1e3) / 1e9 if phase_ms[2] else None,
+                                "algorithmic_GBps": lookups_per_step * H * ROW_BYTES / (phase_ms[2] / args.steps / 1e3) / 1e9 if phase_ms[2] else None}
+            if direct:
+                d_traffic, d_sectors = ncu_traffic()
+                d_ach = algo_bytes / (direct["kernel_ms"] / 1e3) / 1e9
+                roof["direct_kernel"] = {"kernel": direct["kernel"], "kernel_ms": direct["kernel_ms"], "achieved": d_ach,
+                                         "frac": d_ach / peak, "traffic": d_traffic,
+                                         "same_counts": direct["checksum"] == checksum,
+                                         "note": "the path of batches below 16 Mi windows; every 16-byte row gather is a 128-byte DRAM fetch"}
+        else:
+            gathers = load_sectors or lookups_per_step * H
+            # fetch-granular view: every 16-byte row gather costs a 128-byte DRAM fetch on B200
+            # (ncu: traffic / gathers = 124.6 B); ceiling = best rate of profiles/microbench/*.cu
+            roof["gather"] = {"achieved_G_per_s": gathers / (k_ms / 1e3) / 1e9 if k_ms > 0 else None,
+                              "gathers_per_launch": int(gathers), "nominal_gathers_per_launch": int(lookups_per_step * H),
+                              "ceiling_G_per_s": 50.2, "dram_bytes_per_gather": (traffic / gathers) if traffic else None,
+                              "dram_GBps": (traffic / (k_ms / 1e3) / 1e9) if (traffic and k_ms > 0) else None}
         line = {
             "metric": "kmer_lookups_per_sec", "value": value, "unit": "lookups/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -290,7 +354,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             "config": {"workload": WORKLOAD, "reads_per_gpu": N_READS, "index": "replicated per GPU",
                        "parallelism": f"read-sharded x{world}, no data-path collective",
                        "l2": "inputs (1.5 GB reads + 2.4 GB index per step) far exceed the 126 MB L2; no flush needed",
-                       "out_dtype": "u8", "setup_s": round(setup_s, 1),
+                       "out_dtype": "u8", "scoring_path": "bucketed" if uses_bucketed else "direct", "setup_s": round(setup_s, 1),
                        "index_open_s": round(open_s, 2), "index_file_GB": round(path.stat().st_size / 1e9, 2)},
             "e2e": {"value": world * lookups_per_step * e2e_steps / e2e_s, "unit": "lookups/s",
                     "reads_per_sec": world * N_READS * e2e_steps / e2e_s, "ms_per_step": e2e_s / e2e_steps * 1e3,
@@ -298,17 +362,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                     "steps": e2e_steps, "matches_device_run": same},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_cobs_narrow<21,7,u8>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "peak_source": peak_src, "kernel_ms": k_ms, "kernel_launches": int(kernel_launches),
-                         "kernel_share_of_step": kernel_ms / ms if ms else None,
-                         "algorithmic_bytes_per_launch": int(algo_bytes),
-                         # fetch-granular view: every 16-byte row gather costs a 128-byte DRAM fetch on B200
-                         # (ncu: traffic / gathers = 124.6 B); ceiling = best rate of profiles/microbench/*.cu
-                         "gather": {"achieved_G_per_s": gathers / (k_ms / 1e3) / 1e9 if k_ms > 0 else None,
-                                    "gathers_per_launch": int(gathers), "nominal_gathers_per_launch": int(lookups_per_step * H),
-                                    "ceiling_G_per_s": 50.2, "dram_bytes_per_gather": (traffic / gathers) if traffic else None,
-                                    "dram_GBps": (traffic / (k_ms / 1e3) / 1e9) if (traffic and k_ms > 0) else None}},
+            "roofline": roof,
             "checksum_first_100k_reads": checksum,
         }
         if world == 1:

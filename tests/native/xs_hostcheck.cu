@@ -62,4 +62,8 @@ uint64_t hc_mod(uint64_t x, uint64_t m) {
     uint64_t magic = m == 1 ? ~0ULL : (uint64_t)((((unsigned __int128)1) << 64) / m);
     return mod_barrett(x, m, magic);
 }
+uint32_t hc_mod_small(uint64_t x, uint32_t m) {   // m < 2^31
+    uint64_t magic = m == 1 ? ~0ULL : (uint64_t)((((unsigned __int128)1) << 64) / m);
+    return mod_barrett_small(x, m, magic);
+}
 }

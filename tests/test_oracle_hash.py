@@ -30,6 +30,8 @@ def hc():
     L.hc_lcg.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p]
     L.hc_mod.restype = C.c_uint64
     L.hc_mod.argtypes = [C.c_uint64, C.c_uint64]
+    L.hc_mod_small.restype = C.c_uint32
+    L.hc_mod_small.argtypes = [C.c_uint64, C.c_uint32]
     L.hc_biocomp.restype = C.c_uint8
     L.hc_biocomp.argtypes = [C.c_uint8]
     L.hc_cobscomp.restype = C.c_uint8
@@ -140,3 +142,11 @@ def test_device_lcg_and_barrett_on_host(hc):
     for m in (1, 2, 3, 2**32, 2**32 + 1, 150000001, 13800000008):
         for x in (0, 1, m - 1, m, m + 1, 2**64 - 1):
             assert hc.hc_mod(x, m) == x % m
+    # the 32-bit remainder variant of the bucketed kernels (signature_size < 2^31)
+    for _ in range(4000):
+        x = int(rng.integers(0, 2**63)) * 2 + int(rng.integers(0, 2))
+        m = int(rng.integers(1, 2**31)) if rng.random() < 0.7 else int(rng.integers(1, 2**12))
+        assert hc.hc_mod_small(x, m) == x % m
+    for m in (1, 2, 3, 2**31 - 1, 2**30, 150000001, 20000003):
+        for x in (0, 1, m - 1, m, m + 1, 2**32 - 1, 2**32, 2**64 - 1, 2**64 - m):
+            assert hc.hc_mod_small(x, m) == x % m

@@ -83,6 +83,13 @@ XS_HD uint64_t mod_barrett(uint64_t x, uint64_t m, uint64_t magic) {
     return r >= m ? r - m : r;
 }
 
+// the same for m < 2^31: the remainder before the correction is < 2m < 2^32, so 32-bit arithmetic is exact
+XS_HD uint32_t mod_barrett_small(uint64_t x, uint32_t m, uint64_t magic) {
+    uint32_t q = (uint32_t)umul64hi(x, magic);
+    uint32_t r = (uint32_t)x - q * m;
+    return r >= m ? r - m : r;
+}
+
 // ------------------------------------------------------------------ 2-bit windows
 // packed stream: word i covers bases [32i, 32i+32), base j at bits [2j, 2j+1] (A0 C1 G2 T3);
 // invalid stream: uint32 word i bit j = 1 for a non-ACGT byte.  Both have one spare word.

@@ -562,6 +562,7 @@ __global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bucket_emit(const BucketParam
     const uint32_t nc_live = bucket_live_chunks(bp, total);
     const uint32_t rmask = (1u << bp.bshift) - 1u;
     const uint32_t cap = bp.cap, nb = bp.n_buckets;
+    const uint32_t sig32 = (uint32_t)pg.sig_size;
 
     // the next chunk is requested while the current one is processed (thread 0 keeps the pending ticket)
     unsigned long long ticket = tid == 0 ? atomicAdd(bp.counter + 0, 1ULL) : 0ULL;
@@ -588,11 +589,11 @@ __global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bucket_emit(const BucketParam
             Xxh64Pre pre;
             xxh64_prepare(t, k, pre);
             bool over = false;
-            auto emit = [&](uint32_t j) {
-                const uint64_t row = mod_barrett(xxh64_finish(pre, k, (uint64_t)j), pg.sig_size, pg.magic);
-                const uint32_t b = (uint32_t)(row >> bp.bshift);
+            auto emit = [&](uint32_t j) {   // signature_size < 2^29 on this path (bucket_geometry)
+                const uint32_t row = mod_barrett_small(xxh64_finish(pre, k, (uint64_t)j), sig32, pg.magic);
+                const uint32_t b = row >> bp.bshift;
                 const uint32_t slot = atomicAdd(&s_cnt[b], 1u);
-                if (slot < cap) s_rec[b * cap + slot] = (lid << bp.bshift) | ((uint32_t)row & rmask);
+                if (slot < cap) s_rec[b * cap + slot] = (lid << bp.bshift) | (row & rmask);
                 else over = true;
             };
             if (H) {

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -99,6 +100,11 @@ struct xs_cobs {
     uint64_t bucket_scratch_bytes = 24ULL << 30;
     uint32_t bucket_shift = 0;        // 0 = automatic
     std::atomic<uint64_t> bucketed_queries{0};
+    // bucketed queries of one handle run one after the other even when they are enqueued on different streams (the
+    // host pipeline uses three): their kernels compete for the same L2 slice and LSU path when they overlap
+    std::mutex bucket_mu;
+    cudaEvent_t bucket_done = nullptr;
+    bool bucket_prev = false;
 };
 
 struct xs_bloom {
@@ -469,6 +475,9 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
     cudaError_t e = cudaMallocAsync((void**)&d, bytes, s);
     if (e != cudaSuccess) { cudaGetLastError(); return XS_OK; }   // no room for the scratch: direct gathers
     int rc = XS_OK;
+    std::lock_guard<std::mutex> serial(ix->bucket_mu);
+    if (!ix->bucket_done && cudaEventCreateWithFlags(&ix->bucket_done, cudaEventDisableTiming) != cudaSuccess) ix->bucket_done = nullptr;
+    if (ix->bucket_done && ix->bucket_prev) cudaStreamWaitEvent(s, ix->bucket_done, 0);
     e = cudaMemsetAsync(d + o_ctr, 0, n_sub * 3 * 8, s);
     k_bucket_chunk_seq<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nc_total + 255) / 256, (uint64_t)ix->n_sm * 8)), 256, 0, s>>>(
         p.sb, nc_total, reinterpret_cast<uint64_t*>(d + o_seq));
@@ -491,6 +500,7 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
         else e = launch_bucket_t<0, 0>(bp, g, ix->n_sm, dt, s);
     }
     if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("bucketed query: ") + cudaGetErrorString(e));
+    if (ix->bucket_done && cudaEventRecord(ix->bucket_done, s) == cudaSuccess) ix->bucket_prev = true;
     cudaFreeAsync(d, s);
     if (rc == XS_OK) { *handled = true; ix->bucketed_queries.fetch_add(1, std::memory_order_relaxed); }
     return rc;
@@ -953,6 +963,7 @@ int xs_cobs_close(xs_cobs* ix) {
     if (ix->d_data) cudaFree(ix->d_data);
     if (ix->d_pages) cudaFree(ix->d_pages);
     if (ix->d_blocks) cudaFree(ix->d_blocks);
+    if (ix->bucket_done) cudaEventDestroy(ix->bucket_done);
     delete ix;
     return XS_OK;
 }
