@@ -688,7 +688,7 @@ __device__ __noinline__ void cobs_mask16_outline(const CobsParams* p, const Page
     *m = cobs_mask16<K, H>(*p, *pg, pos);
 }
 
-template <int K, int H, typename OutT>
+template <int K, int H, typename OutT, bool PACK>
 __global__ void __launch_bounds__(BK_NT, 4) k_bucket_reduce(const __grid_constant__ BucketParams bp) {
     __shared__ __align__(16) uint32_t s_m[4][BK_CH];   // window masks, one array per 32 documents
     __shared__ uint32_t s_wseq[BK_CH];
@@ -702,7 +702,6 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bucket_reduce(const __grid_constan
     const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
     const uint32_t nc_live = bucket_live_chunks(bp, total);
     const uint32_t cap = bp.cap, nb = bp.n_buckets;
-    const bool pack = bp.pack_id != 0;
 
     unsigned long long ticket = tid == 0 ? atomicAdd(bp.counter + 2, 1ULL) : 0ULL;
     for (;;) {
@@ -728,32 +727,32 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bucket_reduce(const __grid_constan
             const uint32_t b = lane * (BK_NT / 32) + warp;
             if (b < nb) myn = __ldg(bp.cnt_cb + c * nb + b);
         }
-        for (uint32_t t = 0; t * (BK_NT / 32) + warp < nb; ++t) {
-            const uint32_t b = t * (BK_NT / 32) + warp;
-            const uint32_t n = __shfl_sync(0xFFFFFFFFu, myn, t);
-            const uint4* src = bp.rows + (c * nb + b) * (uint64_t)cap;
-            const uint32_t* rsrc = bp.rec + ((uint64_t)b * bp.nc + c) * cap;
-            for (uint32_t i0 = 0; i0 < n; i0 += 128) {
-                uint4 v[4];
-                uint32_t id[4];
+        {
+            uint32_t* const m0 = &s_m[0][0];
+            const uint4* src = bp.rows + (c * nb + warp) * (uint64_t)cap + lane;              // this lane's slot of the block
+            const uint32_t* rsrc = bp.rec + ((uint64_t)warp * bp.nc + c) * cap + lane;
+            const uint64_t src_step = (uint64_t)(BK_NT / 32) * cap, rsrc_step = (uint64_t)(BK_NT / 32) * bp.nc * cap;
+            for (uint32_t t = 0; t * (BK_NT / 32) + warp < nb; ++t, src += src_step, rsrc += rsrc_step) {
+                const uint32_t n = __shfl_sync(0xFFFFFFFFu, myn, t);
+                for (uint32_t i0 = lane; i0 < n; i0 += 128) {       // i0 = this lane's first record of the pass
+                    const uint32_t left = n - i0;                   // records from i0 on; lane takes i0, +32, +64, +96
+                    uint4 v[4];
+                    uint32_t id[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t i = i0 + q * 32 + lane;
-                    if (i < n) {
-                        v[q] = ld_stream128(src + i);
-                        id[q] = pack ? 0u : (ld_stream32(rsrc + i) >> bp.bshift);
-                    }
-                }
+                    for (int q = 0; q < 4; ++q)
+                        if ((uint32_t)(q * 32) < left) {
+                            v[q] = ld_stream128(src + (i0 - lane) + q * 32);
+                            if (!PACK) id[q] = ld_stream32(rsrc + (i0 - lane) + q * 32) >> bp.bshift;
+                        }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t i = i0 + q * 32 + lane;
-                    if (i < n) {
-                        const uint32_t w = (pack ? v[q].w : id[q]) & (BK_CH - 1);
-                        atomicAnd(&s_m[0][w], v[q].x);
-                        atomicAnd(&s_m[1][w], v[q].y);
-                        atomicAnd(&s_m[2][w], v[q].z);
-                        if (!pack) atomicAnd(&s_m[3][w], v[q].w);
-                    }
+                    for (int q = 0; q < 4; ++q)
+                        if ((uint32_t)(q * 32) < left) {
+                            uint32_t* a = m0 + ((PACK ? v[q].w : id[q]) & (BK_CH - 1));
+                            atomicAnd(a, v[q].x);
+                            atomicAnd(a + BK_CH, v[q].y);
+                            atomicAnd(a + 2 * BK_CH, v[q].z);
+                            if (!PACK) atomicAnd(a + 3 * BK_CH, v[q].w);
+                        }
                 }
             }
         }
@@ -776,7 +775,7 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bucket_reduce(const __grid_constan
                     const uint64_t pos = __ldg(sb.seq_begin + seq) - sb.base_shift + (g0 + lid - __ldg(sb.win_prefix + seq)) * sb.step;
                     cobs_mask16_outline<K, H>(&bp.cp, bp.cp.pages, pos, &m);
                 } else if (!(s_flag[BK_CH / 32 + (lid >> 5)] & bit)) {
-                    m = make_uint4(s_m[0][lid], s_m[1][lid], s_m[2][lid], pack ? 0u : s_m[3][lid]);
+                    m = make_uint4(s_m[0][lid], s_m[1][lid], s_m[2][lid], PACK ? 0u : s_m[3][lid]);
                 }
             }
             uint32_t rem = __ballot_sync(0xFFFFFFFFu, has);

@@ -430,9 +430,10 @@ static cudaError_t launch_bucket_t(const BucketParams& bp, const BucketGeom& g, 
     }
     {
         KernelTimer kt(s, PROF_REDUCE);
-        if (dt == XS_U8) k_bucket_reduce<K, H, uint8_t><<<n_sm * 4, BK_NT, 0, s>>>(bp);
-        else if (dt == XS_U16) k_bucket_reduce<K, H, uint16_t><<<n_sm * 4, BK_NT, 0, s>>>(bp);
-        else k_bucket_reduce<K, H, uint32_t><<<n_sm * 4, BK_NT, 0, s>>>(bp);
+        const bool pk = bp.pack_id != 0;
+        if (dt == XS_U8) { if (pk) k_bucket_reduce<K, H, uint8_t, true><<<n_sm * 4, BK_NT, 0, s>>>(bp); else k_bucket_reduce<K, H, uint8_t, false><<<n_sm * 4, BK_NT, 0, s>>>(bp); }
+        else if (dt == XS_U16) { if (pk) k_bucket_reduce<K, H, uint16_t, true><<<n_sm * 4, BK_NT, 0, s>>>(bp); else k_bucket_reduce<K, H, uint16_t, false><<<n_sm * 4, BK_NT, 0, s>>>(bp); }
+        else { if (pk) k_bucket_reduce<K, H, uint32_t, true><<<n_sm * 4, BK_NT, 0, s>>>(bp); else k_bucket_reduce<K, H, uint32_t, false><<<n_sm * 4, BK_NT, 0, s>>>(bp); }
     }
     g_launches.fetch_add(3, std::memory_order_relaxed);
     return cudaGetLastError();
