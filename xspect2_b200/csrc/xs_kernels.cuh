@@ -302,6 +302,7 @@ struct CobsParams {
     void* out;          // [n_seq x ld] OutT
     uint64_t ld;        // output row length (all local documents)
     uint64_t seq0;      // output row of sequence 0 of this batch
+    uint64_t win_begin; // k_cobs_narrow: first flat window to score (the bucketed path's tail launch), normally 0
 };
 
 constexpr int NARROW_NT = 256;
@@ -391,15 +392,16 @@ __global__ void __launch_bounds__(NARROW_NT, 4) k_cobs_narrow(const CobsParams p
     const uint64_t n_warps = ((uint64_t)gridDim.x * NARROW_NT) >> 5;
 
     const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
-    const uint64_t W = walk_tile_windows(total, n_warps);
-    const uint64_t n_tiles = (total + W - 1) / W;
+    const uint64_t first = p.win_begin < total ? p.win_begin : total;
+    const uint64_t W = walk_tile_windows(total - first, n_warps);
+    const uint64_t n_tiles = (total - first + W - 1) / W;
 
     // tiles are handed out dynamically: SMs do not all sustain the same gather rate (two dies, 70/78 SM
     // split), and a static equal split runs at the pace of the slowest one (profiles/microbench)
     for (;;) {
         const uint64_t tile = next_tile(sb.tile_counter + blockIdx.y, lane);
         if (tile >= n_tiles) break;
-        const uint64_t t0 = tile * W, t1 = t0 + W < total ? t0 + W : total;
+        const uint64_t t0 = first + tile * W, t1 = t0 + W < total ? t0 + W : total;
         uint4 m = make_uint4(0, 0, 0, 0);
         uint32_t cnt[4] = {0, 0, 0, 0};   // lane l: documents l, l+32, l+64, l+96 of the current sequence
         warp_walk(

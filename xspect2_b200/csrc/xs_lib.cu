@@ -100,6 +100,7 @@ struct xs_cobs {
     uint64_t bucket_scratch_bytes = 24ULL << 30;
     uint32_t bucket_shift = 0;        // 0 = automatic
     std::atomic<uint64_t> bucketed_queries{0};
+    std::atomic<uint64_t> bucket_budget{0};   // scratch bytes per query; 0 = not asked yet
     // bucketed queries of one handle run one after the other even when they are enqueued on different streams (the
     // host pipeline uses three): their kernels compete for the same L2 slice and LSU path when they overlap
     std::mutex bucket_mu;
@@ -446,17 +447,21 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
     if (p.sb.n_bases / p.sb.step < ix->bucket_min_windows) return XS_OK;
     BucketGeom g;
     if (!bucket_geometry(ix->pages[0].sig_size, ix->info.num_hashes, ix->bucket_shift, g)) return XS_OK;
-    // the number of sampled windows decides the chunking (the only host read of this query)
-    uint64_t total = 0;
-    XS_CUDA(cudaMemcpyAsync(&total, p.sb.win_prefix + p.sb.n_seq, 8, cudaMemcpyDeviceToHost, s));
-    XS_CUDA(cudaStreamSynchronize(s));
-    if (total < ix->bucket_min_windows) return XS_OK;
+    // No host read of the window count: chunking and scratch are sized from an upper bound that holds whenever the
+    // sequences do not overlap (sum of ((len - k) / step + 1) <= n_bases / step + n_seq); the kernels read the true
+    // count on the device and skip chunks beyond it, and windows beyond the bound (overlapping segments) are scored by
+    // a tail launch of k_cobs_narrow that normally finds nothing to do.
+    const uint64_t total = p.sb.n_bases / p.sb.step + p.sb.n_seq;
     // Sub-batches of nc_sub chunks go through emit -> fetch -> reduce back to back on the caller's stream.  (Running the
     // three kernels of neighbouring sub-batches concurrently on three streams was measured and lost: they compete for
     // issue slots and L2, profiles/r1_bucketed_notes.md.)
-    size_t free_b = 0, total_b = 0;
-    XS_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t budget = std::min<uint64_t>(ix->bucket_scratch_bytes, free_b / 2);
+    uint64_t budget = ix->bucket_budget.load(std::memory_order_relaxed);
+    if (budget == 0) {     // asked once per handle (and again after a failed allocation): at most half of what is free
+        size_t free_b = 0, total_b = 0;
+        XS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        budget = std::max<uint64_t>(1, std::min<uint64_t>(ix->bucket_scratch_bytes, free_b / 2));
+        ix->bucket_budget.store(budget, std::memory_order_relaxed);
+    }
     const uint64_t nc_total = (total + BK_CH - 1) / BK_CH;
     uint64_t nc_sub = std::min<uint64_t>(nc_total, budget / g.per_chunk);
     if (nc_sub == 0 || nc_sub * BK_CH < ix->bucket_min_windows / 2) return XS_OK;    // too little memory for L2 re-use
@@ -474,7 +479,11 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
     const size_t bytes = o_seq + align256(nc_total * 8);
     uint8_t* d = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&d, bytes, s);
-    if (e != cudaSuccess) { cudaGetLastError(); return XS_OK; }   // no room for the scratch: direct gathers
+    if (e != cudaSuccess) {                                       // no room for the scratch: direct gathers
+        cudaGetLastError();
+        ix->bucket_budget.store(0, std::memory_order_relaxed);
+        return XS_OK;
+    }
     int rc = XS_OK;
     std::lock_guard<std::mutex> serial(ix->bucket_mu);
     if (!ix->bucket_done && cudaEventCreateWithFlags(&ix->bucket_done, cudaEventDisableTiming) != cudaSuccess) ix->bucket_done = nullptr;
@@ -499,6 +508,14 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
         bp.prefetch = prefetch ? 1u : 0u;
         if (p.sb.k == 21 && p.num_hashes == 7) e = launch_bucket_t<21, 7>(bp, g, ix->n_sm, dt, s);
         else e = launch_bucket_t<0, 0>(bp, g, ix->n_sm, dt, s);
+    }
+    if (e == cudaSuccess) {
+        CobsParams tail = p;
+        tail.win_begin = nc_total * BK_CH;
+        KernelTimer kt(s, PROF_DIRECT);
+        launch_narrow(tail, dim3((unsigned)(ix->n_sm * 4), 1), dt, s);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
     }
     if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("bucketed query: ") + cudaGetErrorString(e));
     if (ix->bucket_done && cudaEventRecord(ix->bucket_done, s) == cudaSuccess) ix->bucket_prev = true;
@@ -948,6 +965,7 @@ int xs_cobs_set_bucketed(xs_cobs* ix, int enabled, uint64_t min_windows, uint64_
     ix->bucketed = enabled ? 1 : 0;
     if (min_windows) ix->bucket_min_windows = min_windows;
     if (scratch_bytes) ix->bucket_scratch_bytes = scratch_bytes;
+    ix->bucket_budget.store(0);
     ix->bucket_shift = bucket_shift;
     return XS_OK;
 }
