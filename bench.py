@@ -336,7 +336,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                 roof["direct_kernel"] = {"kernel": direct["kernel"], "kernel_ms": direct["kernel_ms"], "achieved": d_ach,
                                          "frac": d_ach / peak, "traffic": d_traffic,
                                          "same_counts": direct["checksum"] == checksum,
-                                         "note": "the path of batches below 16 Mi windows; every 16-byte row gather is a 128-byte DRAM fetch"}
+                                         "note": "the path of batches below 32 Mi windows; every 16-byte row gather is a 128-byte DRAM fetch"}
         else:
             gathers = load_sectors or lookups_per_step * H
             # fetch-granular view: every 16-byte row gather costs a 128-byte DRAM fetch on B200

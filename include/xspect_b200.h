@@ -117,7 +117,7 @@ int xs_cobs_set_policy(xs_cobs* ix, int policy);
  * memory.  Results are identical to the direct-gather kernel's.  enabled: 0/1; min_windows: smallest batch (sampled
  * windows) that takes this path (0 = keep); scratch_bytes: upper bound of the per-query device scratch (0 = keep);
  * bucket_shift: log2 rows per bucket, 0 = automatic (test hook: lets small indices exercise the path).
- * Defaults: enabled, 16 Mi windows, 24 GiB (never more than half of the free device memory). */
+ * Defaults: enabled, 32 Mi windows, 24 GiB (never more than half of the free device memory). */
 int xs_cobs_set_bucketed(xs_cobs* ix, int enabled, uint64_t min_windows, uint64_t scratch_bytes, uint32_t bucket_shift);
 /* number of queries (device batches) of this handle that went through the bucketed kernels */
 int xs_cobs_bucketed_queries(const xs_cobs* ix, uint64_t* n);

@@ -64,7 +64,7 @@ def test_bucketed_and_direct_kernels_agree(big):
     small = np.asarray(ix.query(big["reads"][: n * L], big["b"][:n], big["e"][:n], 1, dtype=4))
     assert ix.bucketed_queries > n0
     assert np.array_equal(small, fwd[:n])
-    ix.set_bucketed(True, min_windows=16 << 20, scratch_bytes=24 << 30)
+    ix.set_bucketed(True, min_windows=32 << 20, scratch_bytes=24 << 30)
 
 
 def test_additivity_over_overlapping_chunks_and_steps(big):

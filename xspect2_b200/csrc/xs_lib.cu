@@ -96,7 +96,7 @@ struct xs_cobs {
     int n_sm = 148;
     int force_wide = 0;
     int bucketed = 1;                 // large batches against a large narrow index go through the bucketed kernels
-    uint64_t bucket_min_windows = 16ULL << 20;
+    uint64_t bucket_min_windows = 32ULL << 20;
     uint64_t bucket_scratch_bytes = 24ULL << 30;
     uint32_t bucket_shift = 0;        // 0 = automatic
     std::atomic<uint64_t> bucketed_queries{0};
