@@ -173,6 +173,10 @@ int xs_scores_reduce_device(const void* d_counts, uint64_t n_seq, uint32_t n_doc
  * term_size is the model's k (the .bloom file does not store it). */
 int xs_bloom_open(const char* path, uint32_t term_size, int device, xs_bloom** out);
 int xs_bloom_info(const xs_bloom* bf, xs_bloom_info_t* info);
+/* The same bucketed path for the Bloom filter (probes grouped by 16 MB ranges of the bit array; all k probes of a
+ * window are made, results identical).  Arguments as xs_cobs_set_bucketed; bucket_shift = log2 bits per bucket. */
+int xs_bloom_set_bucketed(xs_bloom* bf, int enabled, uint64_t min_windows, uint64_t scratch_bytes, uint32_t bucket_shift);
+int xs_bloom_bucketed_queries(const xs_bloom* bf, uint64_t* n);
 int xs_bloom_close(xs_bloom* bf);
 
 /* Replaces sum(1 for kmer in _generate_kmers(sequence, step) if kmer in self.bf)

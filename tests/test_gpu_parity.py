@@ -152,6 +152,19 @@ def test_cobs_bucketed_sub_batches_and_overlaps(gpu, oracle, tmp_path):
     _check_bucketed(gpu, oracle, p, g, bb, ee, scratch=3 << 20)
 
 
+def test_cobs_bucketed_runs_of_empty_records(gpu, oracle, tmp_path):
+    """Thousands of zero-window records inside and between chunks (the chunk-local sequence table skips them)."""
+    rng = np.random.default_rng(29)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 10, 21, 7)
+    g = docs["doc00002"][0]
+    parts = [g[:300]] + [g[:5]] * 3000 + [g[300:2900]] + [g[:0]] * 2500 + [g[700:1000]] + [g[:20]] * 600 + [g[:2200]]
+    bases = np.concatenate(parts)
+    lens = np.array([x.size for x in parts], np.uint64)
+    e = np.cumsum(lens, dtype=np.uint64)
+    _check_bucketed(gpu, oracle, p, bases, e - lens, e)
+    _check_bucketed(gpu, oracle, p, bases, e - lens, e, dtype=1, scratch=2 << 20)
+
+
 def test_cobs_bucketed_shift_21_and_few_buckets(gpu, oracle, tmp_path):
     """Other geometries of the record word: 2^21 rows per bucket (one bucket here) and 2 rows per bucket."""
     rng = np.random.default_rng(23)
@@ -403,6 +416,54 @@ def test_bloom_hash_stage_and_long_sequence(gpu, oracle, tmp_path):
     lens = np.array([x.size for x in parts], np.uint64)
     e = np.cumsum(lens, dtype=np.uint64)
     assert np.array_equal(bf.query(bases, e - lens, e), orc.hits_batch(bases, e - lens, e))
+
+
+def _check_bloom_bucketed(gpu, oracle, path, k, bases, b, e, step=1, scratch=0):
+    bf = gpu.BloomFilter(path, k)
+    shift = 3
+    while ((int(bf.info.n_bits) - 1) >> shift) + 1 > 250:
+        shift += 1
+    bf.set_bucketed(True, min_windows=1, scratch_bytes=scratch, bucket_shift=shift)
+    got = np.asarray(bf.query(bases, b, e, step)).copy()
+    assert bf.bucketed_queries >= 1, "the bucketed Bloom kernels did not run"
+    exp = oracle.BloomOracle(path, k).hits_batch(bases, b, e, step, threads=4)
+    bad = np.flatnonzero(got != exp)
+    assert bad.size == 0, f"{bad.size} mismatches, first {bad[:5].tolist()}: got {got[bad[:5]]} exp {exp[bad[:5]]}"
+    bf.set_bucketed(False)
+    n0 = bf.bucketed_queries
+    assert np.array_equal(bf.query(bases, b, e, step), got) and bf.bucketed_queries == n0
+    bf.close()
+    return got
+
+
+@pytest.mark.parametrize("k,step", [(21, 1), (31, 1), (17, 2), (21, 500)])
+def test_bloom_bucketed_reads(gpu, oracle, tmp_path, k, step):
+    """Ragged reads with N / lower case / IUPAC (literal-byte terms) through k_bbucket_emit / fetch / reduce."""
+    rng = np.random.default_rng(500 + k)
+    p, g, meta = _mk_bloom(oracle, tmp_path, rng, k)
+    bases, b, e = synth.sample_reads(rng, [g], 800, (k, 300), sub=0.01, n_rate=0.004, lower=0.002, iupac=0.002)
+    got = _check_bloom_bucketed(gpu, oracle, p, k, bases, b, e, step)
+    assert got.sum() > 0
+
+
+def test_bloom_bucketed_long_low_complexity_and_sub_batches(gpu, oracle, tmp_path):
+    """Sequences spanning many chunks, homopolymer runs that overflow blocks (direct-probe windows), runs of empty and
+    short records, overlapping segments, and a scratch budget of a few chunks (many sub-batches)."""
+    rng = np.random.default_rng(31)
+    p, g, _ = _mk_bloom(oracle, tmp_path, rng, 21)
+    rep = np.tile(np.frombuffer(b"ACGTTGCA", np.uint8), 900)
+    parts = [g, np.full(6000, ord("A"), np.uint8), g[:0], g[:20], g[:21], rep] + [g[:5]] * 2500 + [g[100:250], np.full(300, ord("N"), np.uint8),
+             g[:5000] | 0x20, synth.random_dna(rng, 30000), g[::-1].copy()]
+    bases = np.concatenate(parts)
+    lens = np.array([x.size for x in parts], np.uint64)
+    e = np.cumsum(lens, dtype=np.uint64)
+    got = _check_bloom_bucketed(gpu, oracle, p, 21, bases, e - lens, e)
+    assert got[0] == g.size - 20
+    _check_bloom_bucketed(gpu, oracle, p, 21, bases, e - lens, e, scratch=1 << 20)
+    n = 400
+    bb = rng.integers(0, g.size - 600, n).astype(np.uint64)
+    ee = bb + rng.integers(0, 600, n).astype(np.uint64)
+    _check_bloom_bucketed(gpu, oracle, p, 21, g, bb, ee, scratch=1 << 20)     # windows beyond the bound: tail launch of k_bloom
 
 
 def test_single_record_shims(gpu, oracle, tmp_path):

@@ -983,6 +983,7 @@ struct BloomParams {
     uint32_t literal;    // 1: hash the window bytes as they are (rbloom's `obj in bf` on a caller-supplied k-mer)
     uint32_t* out;       // [n_seq]
     uint64_t seq0;
+    uint64_t win_begin;  // k_bloom: first flat window to score (the bucketed path's tail launch), normally 0
 };
 
 constexpr int BLOOM_NT = 256;
@@ -1018,12 +1019,13 @@ __global__ void __launch_bounds__(BLOOM_NT, 4) k_bloom(const BloomParams p) {
     const uint64_t n_warps = ((uint64_t)gridDim.x * BLOOM_NT) >> 5;
 
     const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
-    const uint64_t W = walk_tile_windows(total, n_warps);
-    const uint64_t n_tiles = (total + W - 1) / W;
+    const uint64_t first = p.win_begin < total ? p.win_begin : total;
+    const uint64_t W = walk_tile_windows(total - first, n_warps);
+    const uint64_t n_tiles = (total - first + W - 1) / W;
     for (;;) {
         const uint64_t tile = next_tile(sb.tile_counter, lane);
         if (tile >= n_tiles) break;
-        const uint64_t t0 = tile * W, t1 = t0 + W < total ? t0 + W : total;
+        const uint64_t t0 = first + tile * W, t1 = t0 + W < total ? t0 + W : total;
         uint32_t hits = 0;    // warp-uniform: hits of the current sequence inside this tile
         uint32_t bal = 0;
         warp_walk(
@@ -1046,6 +1048,238 @@ __global__ void __launch_bounds__(BLOOM_NT, 4) k_bloom(const BloomParams p) {
                 }
                 hits = 0;
             });
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Bloom, bucketed probing: the scheme of k_bucket_emit / fetch / reduce for the single-filter model.  A probe of
+// k_bloom costs a 128-byte DRAM fetch for one bit; here the k_hashes probes of every window are grouped by 16 MB ranges
+// of the bit array and served from L2.  All k_hashes probes are emitted (no early exit), which still wins when most
+// windows are members or the batch is large.  Record = bit index in the bucket (u32) + window in chunk (u16); fetch adds
+// one result byte; reduce marks the windows with a failed probe and counts the others per sequence.
+// ----------------------------------------------------------------------------------------
+struct BloomBucketParams {
+    BloomParams bl;
+    uint32_t* pos;        // [n_buckets][nc][cap]  bit index within the bucket
+    uint16_t* wid;        // [n_buckets][nc][cap]  window in chunk
+    uint8_t* res;         // [n_buckets][nc][cap]  the probed bit (k_bbucket_fetch)
+    uint16_t* cnt_bc;     // [n_buckets][nc]       records per block
+    uint32_t* ovf;        // [nc][BK_CH / 32]      windows to score with direct probes
+    const uint64_t* chunk_seq;
+    unsigned long long* counter;   // [3]
+    uint64_t chunk0;
+    uint32_t nc, n_buckets, bshift, cap, prefetch;   // bshift = log2 bits per bucket
+};
+
+__device__ __forceinline__ uint32_t bbucket_live_chunks(const BloomBucketParams& bp, uint64_t total) {
+    const uint64_t first = bp.chunk0 * BK_CH;
+    if (total <= first) return 0;
+    const uint64_t n = (total - first + BK_CH - 1) / BK_CH;
+    return n < bp.nc ? (uint32_t)n : bp.nc;
+}
+
+template <int K>
+__global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bbucket_emit(const BloomBucketParams bp) {
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    const BloomParams& p = bp.bl;
+    const SeqBatch& sb = p.sb;
+    const uint32_t k = K ? K : sb.k;
+    const uint32_t cap = bp.cap, nb = bp.n_buckets;
+    const uint32_t nb4 = (nb + 3) & ~3u;                                  // keeps s_wid 16-byte aligned
+    uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_dyn);                 // [nb][cap]
+    uint32_t* s_cnt = s_pos + (size_t)nb * cap;                           // [nb4]
+    uint32_t* s_ovf = s_cnt + nb4;                                        // [BK_CH / 32]
+    uint32_t* s_wseq = s_ovf + BK_CH / 32;                                // [BK_CH]
+    uint32_t* s_scan = s_wseq + BK_CH;                                    // [BK_EMIT_NT / 32]
+    uint16_t* s_wid = reinterpret_cast<uint16_t*>(s_scan + BK_EMIT_NT / 32);   // [nb][cap]
+    __shared__ unsigned long long s_chunk;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    const uint32_t nc_live = bbucket_live_chunks(bp, total);
+    const uint64_t bmask = (1ULL << bp.bshift) - 1ULL;
+
+    unsigned long long ticket = tid == 0 ? atomicAdd(bp.counter + 0, 1ULL) : 0ULL;
+    for (;;) {
+        if (tid == 0) s_chunk = ticket;
+        for (uint32_t i = tid; i < nb4 + BK_CH / 32; i += BK_EMIT_NT) s_cnt[i] = 0;   // s_cnt and s_ovf are contiguous
+        __syncthreads();
+        const uint64_t c = s_chunk;
+        if (c >= nc_live) break;
+        if (tid == 0) ticket = atomicAdd(bp.counter + 0, 1ULL);
+        const uint64_t g0 = (bp.chunk0 + c) * BK_CH;
+        const uint64_t g1 = g0 + BK_CH < total ? g0 + BK_CH : total;
+        const uint32_t nwin = (uint32_t)(g1 - g0);
+        const uint64_t s_lo = chunk_seq_table<BK_EMIT_NT>(sb, __ldg(bp.chunk_seq + bp.chunk0 + c), g0, g1, s_wseq, s_scan);
+#pragma unroll 1
+        for (uint32_t lid = tid; lid < nwin; lid += BK_EMIT_NT) {
+            const uint64_t seq = s_lo + s_wseq[lid] - 1;
+            const uint64_t pos = __ldg(sb.seq_begin + seq) - sb.base_shift + (g0 + lid - __ldg(sb.win_prefix + seq)) * sb.step;
+            Term t;
+            bloom_term<K>(sb, pos, t);
+            uint64_t hi = 0, lo = xxh3_64(t, k);
+            bool over = false;
+            for (uint32_t j = 0; j < p.k_hashes; ++j) {
+                const uint64_t ix = mod_barrett(lcg_next(hi, lo), p.n_bits, p.magic);
+                const uint32_t b = (uint32_t)(ix >> bp.bshift);
+                const uint32_t slot = atomicAdd(&s_cnt[b], 1u);
+                if (slot < cap) { s_pos[b * cap + slot] = (uint32_t)(ix & bmask); s_wid[b * cap + slot] = (uint16_t)lid; }
+                else over = true;
+            }
+            if (over) atomicOr(&s_ovf[lid >> 5], 1u << (lid & 31));
+        }
+        __syncthreads();
+        // blocks go out in whole sectors (cap is a multiple of 16: 64 bytes of positions, 32 bytes of window ids)
+        for (uint32_t b = warp; b < nb; b += BK_EMIT_NT / 32) {
+            const uint32_t n = s_cnt[b] < cap ? s_cnt[b] : cap;
+            const uint32_t n16 = (n + 15) & ~15u;
+            const uint64_t blk = ((uint64_t)b * bp.nc + c) * cap;
+            const uint4* src = reinterpret_cast<const uint4*>(s_pos + b * cap);
+            uint4* dst = reinterpret_cast<uint4*>(bp.pos + blk);
+            for (uint32_t i = lane; i < n16 / 4; i += 32) dst[i] = src[i];
+            const uint4* srcw = reinterpret_cast<const uint4*>(s_wid + b * cap);
+            uint4* dstw = reinterpret_cast<uint4*>(bp.wid + blk);
+            for (uint32_t i = lane; i < n16 / 8; i += 32) dstw[i] = srcw[i];
+        }
+        for (uint32_t b = tid; b < nb; b += BK_EMIT_NT) bp.cnt_bc[(uint64_t)b * bp.nc + c] = (uint16_t)(s_cnt[b] < cap ? s_cnt[b] : cap);
+        for (uint32_t i = tid; i < BK_CH / 32; i += BK_EMIT_NT) bp.ovf[c * (BK_CH / 32) + i] = s_ovf[i];
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ uint32_t ldg_byte_keep(const uint8_t* p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+__global__ void __launch_bounds__(BK_NT) k_bbucket_fetch(const BloomBucketParams bp) {
+    const BloomParams& p = bp.bl;
+    const SeqBatch& sb = p.sb;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    const uint32_t nc_live = bbucket_live_chunks(bp, total);
+    const uint64_t n_units = (uint64_t)bp.n_buckets * nc_live;    // unit = bucket * nc_live + chunk: bucket-major sweep
+    const uint32_t cap = bp.cap;
+    const uint64_t keep = l2_policy_evict_last();
+    const uint64_t slice_bytes = (1ULL << bp.bshift) / 8;
+    const uint64_t slice_lines = (slice_bytes + 127) / 128;
+    const uint32_t pf_per_unit = nc_live ? (uint32_t)((slice_lines + nc_live - 1) / nc_live) : 0;
+    const uint64_t array_lines = (p.n_bits / 8 + 127) / 128;
+    for (;;) {
+        const uint64_t u0 = next_tile(bp.counter + 1, lane) * BK_FETCH_SPAN;
+        if (u0 >= n_units) break;
+        const uint64_t u1 = u0 + BK_FETCH_SPAN < n_units ? u0 + BK_FETCH_SPAN : n_units;
+        for (uint64_t u = u0; u < u1; ++u) {
+            const uint32_t b = (uint32_t)(u / nc_live), c = (uint32_t)(u % nc_live);
+            const uint32_t n = __ldg(bp.cnt_bc + (uint64_t)b * bp.nc + c);
+            const uint64_t blk = ((uint64_t)b * bp.nc + c) * cap;
+            const uint32_t* src = bp.pos + blk + lane;
+            uint8_t* dst = bp.res + blk + lane;
+            const uint8_t* base = p.bits + (uint64_t)b * slice_bytes;
+            if (bp.prefetch && b + 1 < bp.n_buckets) {
+                for (uint32_t l = lane; l < pf_per_unit; l += 32) {
+                    const uint64_t in_slice = (uint64_t)c * pf_per_unit + l;
+                    const uint64_t line = (uint64_t)(b + 1) * slice_lines + in_slice;
+                    if (in_slice < slice_lines && line < array_lines) prefetch_l2_keep(p.bits + line * 128, keep);
+                }
+            }
+            for (uint32_t i0 = lane; i0 < n; i0 += 128) {
+                const uint32_t left = n - i0;
+                uint32_t r[4], v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if ((uint32_t)(q * 32) < left) r[q] = ld_stream32(src + (i0 - lane) + q * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if ((uint32_t)(q * 32) < left) v[q] = ldg_byte_keep(base + (r[q] >> 3), keep);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if ((uint32_t)(q * 32) < left) dst[(i0 - lane) + q * 32] = (uint8_t)((v[q] >> (r[q] & 7)) & 1u);
+            }
+        }
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(BK_NT, 4) k_bbucket_reduce(const BloomBucketParams bp) {
+    __shared__ uint32_t s_fail[BK_CH / 32];   // windows with a probe that found a zero bit
+    __shared__ uint32_t s_ovf[BK_CH / 32];
+    __shared__ uint32_t s_wseq[BK_CH];
+    __shared__ uint32_t s_scan[BK_NT / 32];
+    __shared__ unsigned long long s_chunk;
+    const BloomParams& p = bp.bl;
+    const SeqBatch& sb = p.sb;
+    const uint32_t k = K ? K : sb.k;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    const uint32_t nc_live = bbucket_live_chunks(bp, total);
+    const uint32_t cap = bp.cap, nb = bp.n_buckets;
+
+    unsigned long long ticket = tid == 0 ? atomicAdd(bp.counter + 2, 1ULL) : 0ULL;
+    for (;;) {
+        if (tid == 0) s_chunk = ticket;
+        if (tid < BK_CH / 32) s_fail[tid] = 0;
+        __syncthreads();
+        const uint64_t c = s_chunk;
+        if (c >= nc_live) break;
+        if (tid == 0) ticket = atomicAdd(bp.counter + 2, 1ULL);
+        const uint64_t g0 = (bp.chunk0 + c) * BK_CH;
+        const uint64_t g1 = g0 + BK_CH < total ? g0 + BK_CH : total;
+        const uint32_t nwin = (uint32_t)(g1 - g0);
+        if (tid < BK_CH / 32) s_ovf[tid] = __ldg(bp.ovf + c * (BK_CH / 32) + tid);
+        const uint64_t s_lo = chunk_seq_table<BK_NT>(sb, __ldg(bp.chunk_seq + bp.chunk0 + c), g0, g1, s_wseq, s_scan);
+
+        // ---- windows with a failed probe (warp w takes buckets w, w + 8, ...)
+        for (uint32_t b = warp; b < nb; b += BK_NT / 32) {
+            const uint32_t n = __ldg(bp.cnt_bc + (uint64_t)b * bp.nc + c);
+            const uint64_t blk = ((uint64_t)b * bp.nc + c) * cap;
+            for (uint32_t i = lane; i < n; i += 32) {
+                if (bp.res[blk + i] == 0) {
+                    const uint32_t w = bp.wid[blk + i] & (BK_CH - 1);
+                    atomicOr(&s_fail[w >> 5], 1u << (w & 31));
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- hits per sequence: warp w owns windows [w * BK_WARP_WIN, ...) of the chunk
+        const uint32_t w_lo = warp * BK_WARP_WIN;
+        const uint32_t w_hi = w_lo + BK_WARP_WIN < nwin ? w_lo + BK_WARP_WIN : nwin;
+        uint32_t hits = 0;
+        for (uint32_t r0 = w_lo; r0 < w_hi; r0 += 32) {
+            const uint32_t lid = r0 + lane;
+            const bool has = lid < w_hi;
+            const uint32_t sq = has ? s_wseq[lid] : 0u;
+            bool hit = false;
+            if (has) {
+                const uint32_t bit = 1u << (lid & 31);
+                if (s_ovf[lid >> 5] & bit) {
+                    const uint64_t seq = s_lo + sq - 1;
+                    const uint64_t pos = __ldg(sb.seq_begin + seq) - sb.base_shift + (g0 + lid - __ldg(sb.win_prefix + seq)) * sb.step;
+                    Term t;
+                    bloom_term<K>(sb, pos, t);
+                    hit = bloom_member(p, xxh3_64(t, k));
+                } else {
+                    hit = !(s_fail[lid >> 5] & bit);
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, hit);
+            uint32_t rem = __ballot_sync(0xFFFFFFFFu, has);
+            while (rem) {
+                const uint32_t cur = __shfl_sync(0xFFFFFFFFu, sq, __ffs(rem) - 1);
+                const uint32_t segmask = __ballot_sync(0xFFFFFFFFu, has && sq == cur);
+                hits += __popc(bal & segmask);
+                rem &= ~segmask;
+                const uint32_t nxt = r0 + (32 - __clz(segmask));
+                if (!(nxt < w_hi && s_wseq[nxt] == cur)) {
+                    const uint64_t seq = s_lo + cur - 1;
+                    if (lane == 0 && hits) {
+                        const uint64_t ps = __ldg(sb.win_prefix + seq), pe = __ldg(sb.win_prefix + seq + 1);
+                        uint32_t* o = p.out + p.seq0 + seq;
+                        if (ps >= g0 + w_lo && pe <= g0 + w_hi) *o = hits; else atomicAdd(o, hits);
+                    }
+                    hits = 0;
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 

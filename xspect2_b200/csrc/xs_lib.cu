@@ -112,6 +112,16 @@ struct xs_bloom {
     xs_bloom_info_t info{};
     uint8_t* d_bits = nullptr;
     int n_sm = 148;
+    // bucketed probing of large batches (k_bbucket_emit / fetch / reduce), see xs_cobs
+    int bucketed = 1;
+    uint64_t bucket_min_windows = 32ULL << 20;
+    uint64_t bucket_scratch_bytes = 24ULL << 30;
+    uint32_t bucket_shift = 0;        // log2 bits per bucket, 0 = automatic
+    std::atomic<uint64_t> bucketed_queries{0};
+    std::atomic<uint64_t> bucket_budget{0};
+    std::mutex bucket_mu;
+    cudaEvent_t bucket_done = nullptr;
+    bool bucket_prev = false;
 };
 
 struct DeviceGuard {
@@ -572,17 +582,153 @@ static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
     return cobs_launch(ix, sb, ws.prefix2, dt, d_out, s);   // ws goes back to the stream-ordered pool on scope exit
 }
 
+// ---- Bloom, bucketed probing (k_bbucket_emit / k_bbucket_fetch / k_bbucket_reduce) ---------------------------
+struct BloomBucketGeom {
+    uint32_t nb = 0, bshift = 0, cap = 0;
+    size_t smem = 0, per_chunk = 0;
+};
+
+static bool bloom_bucket_geometry(uint64_t n_bits, uint32_t k_hashes, uint32_t shift_override, BloomBucketGeom& g) {
+    if (k_hashes == 0 || k_hashes > 16 || n_bits == 0) return false;
+    if (shift_override) {
+        if (shift_override < 3 || shift_override > 31) return false;
+        g.bshift = shift_override;
+    } else {
+        g.bshift = 27;                                                   // 16 MB of the bit array per bucket
+        if (((n_bits - 1) >> g.bshift) + 1 > BK_MAX_BUCKETS) g.bshift = 28;
+    }
+    if (((n_bits - 1) >> g.bshift) + 1 > BK_MAX_BUCKETS) return false;
+    g.nb = (uint32_t)(((n_bits - 1) >> g.bshift) + 1);
+    if (!shift_override && g.nb < 16) return false;                      // 256 MB .. 8 GB filters
+    const double mean = (double)BK_CH * k_hashes / (double)g.nb;
+    g.cap = ((uint32_t)std::ceil(mean + 2.8 * std::sqrt(mean)) + 15) & ~15u;
+    if (g.cap > 60000) return false;
+    const uint32_t nb4 = (g.nb + 3) & ~3u;
+    g.smem = ((size_t)g.nb * g.cap + nb4 + BK_CH / 32 + BK_CH + BK_EMIT_NT / 32) * 4 + (size_t)g.nb * g.cap * 2;
+    if (g.smem > 200 * 1024) return false;
+    g.per_chunk = (size_t)g.nb * g.cap * 7 + (size_t)g.nb * 2 + (BK_CH / 32) * 4;
+    return true;
+}
+
+template <int K>
+static cudaError_t launch_bbucket_t(const BloomBucketParams& bp, const BloomBucketGeom& g, int n_sm, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(k_bbucket_emit<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bbucket_emit<K>, BK_EMIT_NT, g.smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+    {
+        KernelTimer kt(s, PROF_EMIT);
+        k_bbucket_emit<K><<<n_sm * occ, BK_EMIT_NT, g.smem, s>>>(bp);
+    }
+    {
+        KernelTimer kt(s, PROF_FETCH);
+        k_bbucket_fetch<<<n_sm * 8, BK_NT, 0, s>>>(bp);
+    }
+    {
+        KernelTimer kt(s, PROF_REDUCE);
+        k_bbucket_reduce<K><<<n_sm * 4, BK_NT, 0, s>>>(bp);
+    }
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+static void launch_bloom_kernel(const BloomParams& p, uint32_t k, int n_sm, cudaStream_t s) {
+    dim3 grid((unsigned)(n_sm * 4));
+    if (k == 21) k_bloom<21><<<grid, BLOOM_NT, 0, s>>>(p);
+    else if (k == 31) k_bloom<31><<<grid, BLOOM_NT, 0, s>>>(p);
+    else k_bloom<0><<<grid, BLOOM_NT, 0, s>>>(p);
+}
+
+// returns XS_OK with *handled = false when the batch should go through k_bloom instead (same contract as
+// cobs_launch_bucketed: sizes from an upper bound of the window count, no host read, tail launch of the direct kernel)
+static int bloom_launch_bucketed(xs_bloom* bf, const BloomParams& p, cudaStream_t s, bool* handled) {
+    *handled = false;
+    if (!bf->bucketed || p.literal) return XS_OK;
+    if (p.sb.n_bases / p.sb.step < bf->bucket_min_windows) return XS_OK;
+    BloomBucketGeom g;
+    if (!bloom_bucket_geometry(bf->info.n_bits, (uint32_t)bf->info.k_hashes, bf->bucket_shift, g)) return XS_OK;
+    const uint64_t total = p.sb.n_bases / p.sb.step + p.sb.n_seq;
+    uint64_t budget = bf->bucket_budget.load(std::memory_order_relaxed);
+    if (budget == 0) {
+        size_t free_b = 0, total_b = 0;
+        XS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        budget = std::max<uint64_t>(1, std::min<uint64_t>(bf->bucket_scratch_bytes, free_b / 2));
+        bf->bucket_budget.store(budget, std::memory_order_relaxed);
+    }
+    const uint64_t nc_total = (total + BK_CH - 1) / BK_CH;
+    uint64_t nc_sub = std::min<uint64_t>(nc_total, budget / g.per_chunk);
+    if (nc_sub == 0 || nc_sub * BK_CH < bf->bucket_min_windows / 2) return XS_OK;
+    const uint64_t n_sub = (nc_total + nc_sub - 1) / nc_sub;
+    nc_sub = (nc_total + n_sub - 1) / n_sub;
+    nc_sub = std::min<uint64_t>(nc_sub, 0xFFFFFFFFu / BK_MAX_BUCKETS);
+
+    const size_t o_pos = 0;
+    const size_t o_wid = o_pos + align256(nc_sub * g.nb * g.cap * 4);
+    const size_t o_res = o_wid + align256(nc_sub * g.nb * g.cap * 2);
+    const size_t o_bc = o_res + align256(nc_sub * g.nb * g.cap);
+    const size_t o_ovf = o_bc + align256(nc_sub * g.nb * 2);
+    const size_t o_ctr = o_ovf + align256(nc_sub * (BK_CH / 32) * 4);
+    const size_t o_seq = o_ctr + align256(n_sub * 3 * 8);
+    const size_t bytes = o_seq + align256(nc_total * 8);
+    uint8_t* d = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&d, bytes, s);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        bf->bucket_budget.store(0, std::memory_order_relaxed);
+        return XS_OK;
+    }
+    int rc = XS_OK;
+    std::lock_guard<std::mutex> serial(bf->bucket_mu);
+    if (!bf->bucket_done && cudaEventCreateWithFlags(&bf->bucket_done, cudaEventDisableTiming) != cudaSuccess) bf->bucket_done = nullptr;
+    if (bf->bucket_done && bf->bucket_prev) cudaStreamWaitEvent(s, bf->bucket_done, 0);
+    e = cudaMemsetAsync(d + o_ctr, 0, n_sub * 3 * 8, s);
+    k_bucket_chunk_seq<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nc_total + 255) / 256, (uint64_t)bf->n_sm * 8)), 256, 0, s>>>(
+        p.sb, nc_total, reinterpret_cast<uint64_t*>(d + o_seq));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const bool prefetch = getenv("XS_BK_PREFETCH") ? atoi(getenv("XS_BK_PREFETCH")) != 0 : true;
+    const uint32_t k = bf->info.term_size;
+    for (uint64_t i = 0; i < n_sub && e == cudaSuccess; ++i) {
+        BloomBucketParams bp{};
+        bp.bl = p;
+        bp.pos = reinterpret_cast<uint32_t*>(d + o_pos); bp.wid = reinterpret_cast<uint16_t*>(d + o_wid); bp.res = d + o_res;
+        bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
+        bp.chunk_seq = reinterpret_cast<const uint64_t*>(d + o_seq);
+        bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
+        bp.chunk0 = i * nc_sub;
+        bp.nc = (uint32_t)std::min<uint64_t>(nc_sub, nc_total - bp.chunk0);
+        bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap; bp.prefetch = prefetch ? 1u : 0u;
+        if (k == 21) e = launch_bbucket_t<21>(bp, g, bf->n_sm, s);
+        else if (k == 31) e = launch_bbucket_t<31>(bp, g, bf->n_sm, s);
+        else e = launch_bbucket_t<0>(bp, g, bf->n_sm, s);
+    }
+    if (e == cudaSuccess) {
+        BloomParams tail = p;
+        tail.win_begin = nc_total * BK_CH;
+        KernelTimer kt(s, PROF_DIRECT);
+        launch_bloom_kernel(tail, k, bf->n_sm, s);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("bucketed Bloom query: ") + cudaGetErrorString(e));
+    if (bf->bucket_done && cudaEventRecord(bf->bucket_done, s) == cudaSuccess) bf->bucket_prev = true;
+    cudaFreeAsync(d, s);
+    if (rc == XS_OK) { *handled = true; bf->bucketed_queries.fetch_add(1, std::memory_order_relaxed); }
+    return rc;
+}
+
 static int bloom_launch(xs_bloom* bf, const SeqBatch& sb, uint32_t* d_out, cudaStream_t s, bool literal = false) {
     BloomParams p{};
     p.sb = sb;
     p.literal = literal ? 1u : 0u;
     p.bits = bf->d_bits; p.n_bits = bf->info.n_bits; p.magic = magic_of(bf->info.n_bits);
     p.k_hashes = (uint32_t)bf->info.k_hashes; p.out = d_out; p.seq0 = 0;
-    dim3 grid((unsigned)(bf->n_sm * 4));
+    bool handled = false;
+    XS_TRY(bloom_launch_bucketed(bf, p, s, &handled));
+    if (handled) return XS_OK;
     KernelTimer kt(s);
-    if (bf->info.term_size == 21) k_bloom<21><<<grid, BLOOM_NT, 0, s>>>(p);
-    else if (bf->info.term_size == 31) k_bloom<31><<<grid, BLOOM_NT, 0, s>>>(p);
-    else k_bloom<0><<<grid, BLOOM_NT, 0, s>>>(p);
+    launch_bloom_kernel(p, bf->info.term_size, bf->n_sm, s);
     XS_TRY(launch_ok("k_bloom"));
     return XS_OK;
 }
@@ -1127,6 +1273,7 @@ int xs_bloom_open(const char* path, uint32_t term_size, int device, xs_bloom** o
     if (rc != XS_OK) { fclose(f); return rc; }
     xs_bloom* bf = new xs_bloom();
     bf->n_sm = n_sm;
+    if (const char* v = getenv("XS_BUCKETED")) bf->bucketed = v[0] != '0';
     cudaError_t e = cudaMalloc((void**)&bf->d_bits, nbytes + 256);
     if (e != cudaSuccess) { fclose(f); delete bf; return fail(XS_ERR_NOMEM, std::string("bloom bit array: ") + cudaGetErrorString(e)); }
     // upload in slices through the row uploader (1 "row" = 1 MiB, remainder separately)
@@ -1148,9 +1295,27 @@ int xs_bloom_info(const xs_bloom* bf, xs_bloom_info_t* info) {
     return XS_OK;
 }
 
+int xs_bloom_set_bucketed(xs_bloom* bf, int enabled, uint64_t min_windows, uint64_t scratch_bytes, uint32_t bucket_shift) {
+    if (!bf) return fail(XS_ERR_ARG, "NULL filter");
+    if (bucket_shift > 31 || (bucket_shift && bucket_shift < 3)) return fail(XS_ERR_ARG, "bucket_shift must be 0 or in 3..31");
+    bf->bucketed = enabled ? 1 : 0;
+    if (min_windows) bf->bucket_min_windows = min_windows;
+    if (scratch_bytes) bf->bucket_scratch_bytes = scratch_bytes;
+    bf->bucket_budget.store(0);
+    bf->bucket_shift = bucket_shift;
+    return XS_OK;
+}
+
+int xs_bloom_bucketed_queries(const xs_bloom* bf, uint64_t* n) {
+    if (!bf || !n) return fail(XS_ERR_ARG, "NULL argument");
+    *n = bf->bucketed_queries.load();
+    return XS_OK;
+}
+
 int xs_bloom_close(xs_bloom* bf) {
     if (!bf) return XS_OK;
     DeviceGuard guard(bf->info.device);
+    if (bf->bucket_done) cudaEventDestroy(bf->bucket_done);
     if (bf->d_bits) cudaFree(bf->d_bits);
     delete bf;
     return XS_OK;

@@ -281,6 +281,16 @@ class BloomFilter:
         except Exception:
             pass
 
+    def set_bucketed(self, enabled: bool = True, min_windows: int = 0, scratch_bytes: int = 0, bucket_shift: int = 0) -> None:
+        """Tune the bucketed path large batches take (see ``xs_bloom_set_bucketed``)."""
+        check(lib().xs_bloom_set_bucketed(self._h, 1 if enabled else 0, int(min_windows), int(scratch_bytes), int(bucket_shift)))
+
+    @property
+    def bucketed_queries(self) -> int:
+        n = C.c_uint64()
+        check(lib().xs_bloom_bucketed_queries(self._h, C.byref(n)))
+        return int(n.value)
+
     def query(self, bases, seq_begin, seq_end, step: int = 1, out: np.ndarray | None = None) -> np.ndarray:
         """Hits per sequence ``[n_seq]`` uint32."""
         bases = _as_bases(bases)
