@@ -57,20 +57,31 @@ def bloom(td: Path):
     d_e = torch.from_numpy(he.view(np.int64)).to(dev)
     out = torch.empty(n_reads, dtype=torch.int32, device=dev)
     s = torch.cuda.current_stream().cuda_stream
-    engine.profile_enable(True)
-    engine.profile_read()
-    ms = timed(lambda: bf.query_device(reads.data_ptr(), n_reads * L, d_b.data_ptr(), d_e.data_ptr(), n_reads, 1, out.data_ptr(), s))
-    kms, kn = engine.profile_read()
-    engine.profile_enable(False)
-    # parity on a sample + probe statistics
+    run = lambda: bf.query_device(reads.data_ptr(), n_reads * L, d_b.data_ptr(), d_e.data_ptr(), n_reads, 1, out.data_ptr(), s)
     sample = 20000
     exp = oracle.BloomOracle(p, k).hits_batch(reads[: sample * L].cpu().numpy(), hb[:sample], he[:sample], 1, threads=8)
-    assert np.array_equal(out[:sample].cpu().numpy().astype(np.uint32), exp)
     lookups = n_reads * (L - k + 1)
-    frac_member = float(out.sum().item()) / lookups
-    print(json.dumps({"config": "cfg3 stage 1: genus Bloom, 13.8e9 bits, k_bloom=6, 10M x 150bp reads", "ms_per_step": ms,
-                      "kernel_ms": kms / max(kn, 1), "lookups_per_sec": lookups / ms * 1e3, "reads_per_sec": n_reads / ms * 1e3,
-                      "member_fraction": frac_member, "parity_sample_reads": sample}), flush=True)
+    ref_out = None
+    # the direct kernel (k_bloom), then the bucketed kernels (k_bbucket_*: the default for batches >= 32 Mi windows)
+    for path in ("direct", "bucketed"):
+        bf.set_bucketed(path == "bucketed")
+        out.zero_()
+        engine.profile_enable(True)
+        engine.profile_read()
+        ms = timed(run)
+        phases, launches = engine.profile_read_phases()
+        engine.profile_enable(False)
+        assert np.array_equal(out[:sample].cpu().numpy().astype(np.uint32), exp)
+        if ref_out is None:
+            ref_out = out.clone()
+        else:
+            assert torch.equal(ref_out, out)
+        frac_member = float(out.sum().item()) / lookups
+        steps = max(launches[0], 1) if path == "direct" else max(launches[1], 1)
+        print(json.dumps({"config": "cfg3 stage 1: genus Bloom, 13.8e9 bits, k_bloom=6, 10M x 150bp reads", "path": path, "ms_per_step": ms,
+                          "kernel_ms[direct,emit,fetch,reduce] per pass": [x / 7 for x in phases], "launches": launches,
+                          "lookups_per_sec": lookups / ms * 1e3, "reads_per_sec": n_reads / ms * 1e3,
+                          "member_fraction": frac_member, "parity_sample_reads": sample, "identical_outputs": True}), flush=True)
 
 
 def mlst(td: Path):

@@ -1078,7 +1078,7 @@ __device__ __forceinline__ uint32_t bbucket_live_chunks(const BloomBucketParams&
     return n < bp.nc ? (uint32_t)n : bp.nc;
 }
 
-template <int K>
+template <int K, int KH>   // KH: number of hash functions when known at compile time (6 for fpr 0.01), else 0
 __global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bbucket_emit(const BloomBucketParams bp) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const BloomParams& p = bp.bl;
@@ -1118,12 +1118,18 @@ __global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bbucket_emit(const BloomBucke
             bloom_term<K>(sb, pos, t);
             uint64_t hi = 0, lo = xxh3_64(t, k);
             bool over = false;
-            for (uint32_t j = 0; j < p.k_hashes; ++j) {
+            auto probe = [&]() {
                 const uint64_t ix = mod_barrett(lcg_next(hi, lo), p.n_bits, p.magic);
                 const uint32_t b = (uint32_t)(ix >> bp.bshift);
                 const uint32_t slot = atomicAdd(&s_cnt[b], 1u);
                 if (slot < cap) { s_pos[b * cap + slot] = (uint32_t)(ix & bmask); s_wid[b * cap + slot] = (uint16_t)lid; }
                 else over = true;
+            };
+            if (KH) {
+#pragma unroll
+                for (int j = 0; j < (KH ? KH : 1); ++j) probe();
+            } else {
+                for (uint32_t j = 0; j < p.k_hashes; ++j) probe();
             }
             if (over) atomicOr(&s_ovf[lid >> 5], 1u << (lid & 31));
         }
@@ -1226,14 +1232,29 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bbucket_reduce(const BloomBucketPa
         if (tid < BK_CH / 32) s_ovf[tid] = __ldg(bp.ovf + c * (BK_CH / 32) + tid);
         const uint64_t s_lo = chunk_seq_table<BK_NT>(sb, __ldg(bp.chunk_seq + bp.chunk0 + c), g0, g1, s_wseq, s_scan);
 
-        // ---- windows with a failed probe (warp w takes buckets w, w + 8, ...)
+        // ---- windows with a failed probe (warp w takes buckets w, w + 8, ...; a lane scans 16 result bytes at a time)
         for (uint32_t b = warp; b < nb; b += BK_NT / 32) {
             const uint32_t n = __ldg(bp.cnt_bc + (uint64_t)b * bp.nc + c);
-            const uint64_t blk = ((uint64_t)b * bp.nc + c) * cap;
-            for (uint32_t i = lane; i < n; i += 32) {
-                if (bp.res[blk + i] == 0) {
-                    const uint32_t w = bp.wid[blk + i] & (BK_CH - 1);
-                    atomicOr(&s_fail[w >> 5], 1u << (w & 31));
+            const uint64_t blk = ((uint64_t)b * bp.nc + c) * cap;           // cap is a multiple of 16
+            const uint4* r4 = reinterpret_cast<const uint4*>(bp.res + blk);
+            const uint4* w4 = reinterpret_cast<const uint4*>(bp.wid + blk);
+            for (uint32_t i16 = lane; i16 * 16 < n; i16 += 32) {
+                const uint4 r = ld_stream128(r4 + i16);
+                const uint4 wa = ld_stream128(w4 + 2 * i16), wb = ld_stream128(w4 + 2 * i16 + 1);
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+                const uint32_t ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                const uint32_t valid = n - i16 * 16;                        // records of this group that exist (>= 1)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t z = ~rw[q] & 0x01010101u;                      // result bytes are 0 or 1
+                    while (z) {
+                        const uint32_t t = (uint32_t)q * 4 + ((__ffs(z) - 1) >> 3);
+                        z &= z - 1;
+                        if (t < valid) {
+                            const uint32_t w = ((ww[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu) & (BK_CH - 1);
+                            atomicOr(&s_fail[w >> 5], 1u << (w & 31));
+                        }
+                    }
                 }
             }
         }

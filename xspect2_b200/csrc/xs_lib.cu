@@ -610,17 +610,17 @@ static bool bloom_bucket_geometry(uint64_t n_bits, uint32_t k_hashes, uint32_t s
     return true;
 }
 
-template <int K>
+template <int K, int KH>
 static cudaError_t launch_bbucket_t(const BloomBucketParams& bp, const BloomBucketGeom& g, int n_sm, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(k_bbucket_emit<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    cudaError_t e = cudaFuncSetAttribute(k_bbucket_emit<K, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bbucket_emit<K>, BK_EMIT_NT, g.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bbucket_emit<K, KH>, BK_EMIT_NT, g.smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorInvalidConfiguration;
     {
         KernelTimer kt(s, PROF_EMIT);
-        k_bbucket_emit<K><<<n_sm * occ, BK_EMIT_NT, g.smem, s>>>(bp);
+        k_bbucket_emit<K, KH><<<n_sm * occ, BK_EMIT_NT, g.smem, s>>>(bp);
     }
     {
         KernelTimer kt(s, PROF_FETCH);
@@ -699,9 +699,8 @@ static int bloom_launch_bucketed(xs_bloom* bf, const BloomParams& p, cudaStream_
         bp.chunk0 = i * nc_sub;
         bp.nc = (uint32_t)std::min<uint64_t>(nc_sub, nc_total - bp.chunk0);
         bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap; bp.prefetch = prefetch ? 1u : 0u;
-        if (k == 21) e = launch_bbucket_t<21>(bp, g, bf->n_sm, s);
-        else if (k == 31) e = launch_bbucket_t<31>(bp, g, bf->n_sm, s);
-        else e = launch_bbucket_t<0>(bp, g, bf->n_sm, s);
+        if (k == 21 && bf->info.k_hashes == 6) e = launch_bbucket_t<21, 6>(bp, g, bf->n_sm, s);
+        else e = launch_bbucket_t<0, 0>(bp, g, bf->n_sm, s);
     }
     if (e == cudaSuccess) {
         BloomParams tail = p;
