@@ -1232,14 +1232,9 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bbucket_reduce(const BloomBucketPa
         if (tid < BK_CH / 32) s_ovf[tid] = __ldg(bp.ovf + c * (BK_CH / 32) + tid);
         const uint64_t s_lo = chunk_seq_table<BK_NT>(sb, __ldg(bp.chunk_seq + bp.chunk0 + c), g0, g1, s_wseq, s_scan);
 
-        // ---- windows with a failed probe (warp w takes buckets w, w + 8, ...; a lane scans 16 result bytes at a time).
-        // The block counts are fetched up front and two blocks are in flight per warp: one dependent load chain per
-        // block made this loop latency-bound.
-        uint32_t myn = 0;
-        {
-            const uint32_t b = lane * (BK_NT / 32) + warp;
-            if (b < nb) myn = __ldg(bp.cnt_bc + (uint64_t)b * bp.nc + c);
-        }
+        // ---- windows with a failed probe.  Warp w takes buckets w, w + 8, ...; the (block, group of 16 records) pairs of
+        // all its blocks form one flat item space over the lanes, two items in flight per lane: one dependent load
+        // chain per block made this loop latency-bound.
         auto scan16 = [&](const uint4& r, const uint4& wa, const uint4& wb, uint32_t valid) {
             const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
             const uint32_t ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
@@ -1256,27 +1251,31 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bbucket_reduce(const BloomBucketPa
                 }
             }
         };
-        for (uint32_t t0 = 0; t0 * (BK_NT / 32) + warp < nb; t0 += 2) {
-            uint32_t n[2];
-            const uint4 *r4[2], *w4[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const uint32_t b = (t0 + u) * (BK_NT / 32) + warp;
-                n[u] = __shfl_sync(0xFFFFFFFFu, myn, (t0 + u) & 31);
-                if (b >= nb) n[u] = 0;
-                const uint64_t blk = ((uint64_t)(b < nb ? b : 0) * bp.nc + c) * cap;   // cap is a multiple of 16
-                r4[u] = reinterpret_cast<const uint4*>(bp.res + blk);
-                w4[u] = reinterpret_cast<const uint4*>(bp.wid + blk);
-            }
-            const uint32_t nmax = n[0] > n[1] ? n[0] : n[1];
-            for (uint32_t i16 = lane; i16 * 16 < nmax; i16 += 32) {
+        {
+            const uint32_t G = cap / 16;                                       // groups per block (cap is a multiple of 16)
+            const uint32_t n_items = nb > warp ? ((nb - warp + BK_NT / 32 - 1) / (BK_NT / 32)) * G : 0;
+            for (uint32_t it0 = lane; it0 < n_items; it0 += 64) {
                 uint4 r[2], wa[2], wb[2];
+                uint32_t valid[2] = {0, 0};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t it = it0 + u * 32;
+                    if (it < n_items) {
+                        const uint32_t t = it / G, i16 = it - t * G;
+                        const uint32_t b = t * (BK_NT / 32) + warp;
+                        const uint32_t n = __ldg(bp.cnt_bc + (uint64_t)b * bp.nc + c);
+                        if (i16 * 16 < n) {
+                            const uint64_t blk = ((uint64_t)b * bp.nc + c) * cap;
+                            const uint4* r4 = reinterpret_cast<const uint4*>(bp.res + blk);
+                            const uint4* w4 = reinterpret_cast<const uint4*>(bp.wid + blk);
+                            r[u] = ld_stream128(r4 + i16); wa[u] = ld_stream128(w4 + 2 * i16); wb[u] = ld_stream128(w4 + 2 * i16 + 1);
+                            valid[u] = n - i16 * 16;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int u = 0; u < 2; ++u)
-                    if (i16 * 16 < n[u]) { r[u] = ld_stream128(r4[u] + i16); wa[u] = ld_stream128(w4[u] + 2 * i16); wb[u] = ld_stream128(w4[u] + 2 * i16 + 1); }
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-                    if (i16 * 16 < n[u]) scan16(r[u], wa[u], wb[u], n[u] - i16 * 16);
+                    if (valid[u]) scan16(r[u], wa[u], wb[u], valid[u]);
             }
         }
         __syncthreads();
