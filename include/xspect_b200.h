@@ -173,9 +173,13 @@ int xs_scores_reduce_device(const void* d_counts, uint64_t n_seq, uint32_t n_doc
  * term_size is the model's k (the .bloom file does not store it). */
 int xs_bloom_open(const char* path, uint32_t term_size, int device, xs_bloom** out);
 int xs_bloom_info(const xs_bloom* bf, xs_bloom_info_t* info);
-/* The same bucketed path for the Bloom filter (probes grouped by 16 MB ranges of the bit array; all k probes of a
- * window are made, results identical).  Arguments as xs_cobs_set_bucketed; bucket_shift = log2 bits per bucket. */
-int xs_bloom_set_bucketed(xs_bloom* bf, int enabled, uint64_t min_windows, uint64_t scratch_bytes, uint32_t bucket_shift);
+/* The same bucketed path for the Bloom filter (probes grouped by 16 MB ranges of the bit array; results identical).
+ * The bucketed kernels make all k probes of a window while the direct kernel stops at the first zero bit, so they win
+ * only when enough windows are members: a sampling kernel estimates the member fraction on the device and the batch
+ * goes through the bucketed kernels when it is >= member_pct per cent (default 35, the measured crossover; 0 = always;
+ * -1 = keep).  Other arguments as xs_cobs_set_bucketed; bucket_shift = log2 bits per bucket. */
+int xs_bloom_set_bucketed(xs_bloom* bf, int enabled, uint64_t min_windows, uint64_t scratch_bytes, uint32_t bucket_shift,
+                          int member_pct);
 int xs_bloom_bucketed_queries(const xs_bloom* bf, uint64_t* n);
 int xs_bloom_close(xs_bloom* bf);
 

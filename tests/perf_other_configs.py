@@ -4,6 +4,7 @@ Test infrastructure: fixtures are built with the oracle's writers.  Run on a GPU
     python tests/perf_other_configs.py [bloom] [mlst] [wide]
 Prints one JSON line per config; numbers are recorded in profiles/."""
 import json
+import os
 import struct
 import sys
 import tempfile
@@ -51,7 +52,8 @@ def bloom(td: Path):
         f.write(bits.tobytes())
     del bits
     bf = engine.BloomFilter(p, k)
-    reads = synth.synth_reads(genome, n_reads, L, seed=4, device=dev)
+    frac = float(os.environ.get("XS_BLOOM_FRAC", 0.6))          # share of reads drawn from the genome in the filter
+    reads = synth.synth_reads(genome, n_reads, L, seed=4, frac_genome=frac, device=dev)
     hb, he = synth.fixed_offsets(n_reads, L)
     d_b = torch.from_numpy(hb.view(np.int64)).to(dev)
     d_e = torch.from_numpy(he.view(np.int64)).to(dev)
@@ -63,8 +65,9 @@ def bloom(td: Path):
     lookups = n_reads * (L - k + 1)
     ref_out = None
     # the direct kernel (k_bloom), then the bucketed kernels (k_bbucket_*: the default for batches >= 32 Mi windows)
-    for path in ("direct", "bucketed"):
-        bf.set_bucketed(path == "bucketed")
+    # ... "adaptive" = the default: a sampling kernel estimates the member fraction and the device picks the path
+    for path in ("direct", "bucketed", "adaptive"):
+        bf.set_bucketed(path != "direct", member_pct=0 if path == "bucketed" else 35)
         out.zero_()
         engine.profile_enable(True)
         engine.profile_read()

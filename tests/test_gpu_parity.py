@@ -423,12 +423,15 @@ def _check_bloom_bucketed(gpu, oracle, path, k, bases, b, e, step=1, scratch=0):
     shift = 3
     while ((int(bf.info.n_bits) - 1) >> shift) + 1 > 250:
         shift += 1
-    bf.set_bucketed(True, min_windows=1, scratch_bytes=scratch, bucket_shift=shift)
-    got = np.asarray(bf.query(bases, b, e, step)).copy()
-    assert bf.bucketed_queries >= 1, "the bucketed Bloom kernels did not run"
     exp = oracle.BloomOracle(path, k).hits_batch(bases, b, e, step, threads=4)
-    bad = np.flatnonzero(got != exp)
-    assert bad.size == 0, f"{bad.size} mismatches, first {bad[:5].tolist()}: got {got[bad[:5]]} exp {exp[bad[:5]]}"
+    # member_pct 0: always the bucketed kernels; 100 / 35: the device-side choice sends the batch (or not) through k_bloom
+    for pct in (0, 100, 35):
+        bf.set_bucketed(True, min_windows=1, scratch_bytes=scratch, bucket_shift=shift, member_pct=pct)
+        n0 = bf.bucketed_queries
+        got = np.asarray(bf.query(bases, b, e, step)).copy()
+        assert bf.bucketed_queries > n0, "the bucketed Bloom path was not taken"
+        bad = np.flatnonzero(got != exp)
+        assert bad.size == 0, f"member_pct {pct}: {bad.size} mismatches, first {bad[:5].tolist()}: got {got[bad[:5]]} exp {exp[bad[:5]]}"
     bf.set_bucketed(False)
     n0 = bf.bucketed_queries
     assert np.array_equal(bf.query(bases, b, e, step), got) and bf.bucketed_queries == n0

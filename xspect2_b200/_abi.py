@@ -54,7 +54,7 @@ SYMBOLS = {
     "xs_cobs_set_policy": (C.c_int, [_P, C.c_int]),
     "xs_cobs_set_bucketed": (C.c_int, [_P, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32]),
     "xs_cobs_bucketed_queries": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
-    "xs_bloom_set_bucketed": (C.c_int, [_P, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32]),
+    "xs_bloom_set_bucketed": (C.c_int, [_P, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int]),
     "xs_bloom_bucketed_queries": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "xs_cobs_close": (C.c_int, [_P]),
     "xs_cobs_query": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, C.c_int, _P]),

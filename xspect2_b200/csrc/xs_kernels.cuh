@@ -984,7 +984,17 @@ struct BloomParams {
     uint32_t* out;       // [n_seq]
     uint64_t seq0;
     uint64_t win_begin;  // k_bloom: first flat window to score (the bucketed path's tail launch), normally 0
+    // device-side choice between k_bloom and the bucketed kernels (both are enqueued, the one not chosen returns at
+    // once): adapt = {windows sampled, members among them} from k_bloom_sample, nullptr = no choice to make
+    const unsigned long long* adapt;
+    uint32_t adapt_pct;  // bucketed when members * 100 >= adapt_pct * sampled
 };
+
+__device__ __forceinline__ bool bloom_bucketed_chosen(const BloomParams& p) {
+    if (!p.adapt) return true;
+    const unsigned long long n = p.adapt[0], m = p.adapt[1];
+    return m * 100ULL >= (unsigned long long)p.adapt_pct * n;
+}
 
 constexpr int BLOOM_NT = 256;
 
@@ -1019,7 +1029,10 @@ __global__ void __launch_bounds__(BLOOM_NT, 4) k_bloom(const BloomParams p) {
     const uint64_t n_warps = ((uint64_t)gridDim.x * BLOOM_NT) >> 5;
 
     const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
-    const uint64_t first = p.win_begin < total ? p.win_begin : total;
+    // the tail launch of the bucketed path scores the windows from win_begin on, or all of them when the sampled
+    // member fraction said the bucketed kernels should not run
+    const uint64_t begin = (p.adapt && !bloom_bucketed_chosen(p)) ? 0 : p.win_begin;
+    const uint64_t first = begin < total ? begin : total;
     const uint64_t W = walk_tile_windows(total - first, n_warps);
     const uint64_t n_tiles = (total - first + W - 1) / W;
     for (;;) {
@@ -1071,7 +1084,29 @@ struct BloomBucketParams {
     uint32_t nc, n_buckets, bshift, cap, prefetch;   // bshift = log2 bits per bucket
 };
 
+// member fraction of every `stride`-th window of the batch (full membership test with early exit, like k_bloom)
+template <int K>
+__global__ void __launch_bounds__(256) k_bloom_sample(const BloomParams p, uint64_t stride, unsigned long long* __restrict__ counts) {
+    const SeqBatch& sb = p.sb;
+    const uint32_t k = K ? K : sb.k;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    uint32_t n = 0, m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i * stride < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = i * stride;
+        const uint64_t q = seq_of_window(sb.win_prefix, sb.n_seq, g);
+        const uint64_t pos = __ldg(sb.seq_begin + q) - sb.base_shift + (g - __ldg(sb.win_prefix + q)) * sb.step;
+        Term t;
+        bloom_term<K>(sb, pos, t);
+        ++n;
+        m += bloom_member(p, xxh3_64(t, k)) ? 1u : 0u;
+    }
+    n = __reduce_add_sync(0xFFFFFFFFu, n);
+    m = __reduce_add_sync(0xFFFFFFFFu, m);
+    if ((threadIdx.x & 31) == 0 && n) { atomicAdd(counts, (unsigned long long)n); atomicAdd(counts + 1, (unsigned long long)m); }
+}
+
 __device__ __forceinline__ uint32_t bbucket_live_chunks(const BloomBucketParams& bp, uint64_t total) {
+    if (!bloom_bucketed_chosen(bp.bl)) return 0;          // the batch goes through k_bloom
     const uint64_t first = bp.chunk0 * BK_CH;
     if (total <= first) return 0;
     const uint64_t n = (total - first + BK_CH - 1) / BK_CH;

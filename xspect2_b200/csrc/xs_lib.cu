@@ -117,6 +117,9 @@ struct xs_bloom {
     uint64_t bucket_min_windows = 32ULL << 20;
     uint64_t bucket_scratch_bytes = 24ULL << 30;
     uint32_t bucket_shift = 0;        // log2 bits per bucket, 0 = automatic
+    // the bucketed kernels make all k probes of a window, k_bloom stops at the first zero bit: bucketed wins when at
+    // least about a third of the windows are members (measured crossover); decided on the device from a sample
+    uint32_t bucket_member_pct = 35;  // 0 = always bucketed
     std::atomic<uint64_t> bucketed_queries{0};
     std::atomic<uint64_t> bucket_budget{0};
     std::mutex bucket_mu;
@@ -670,7 +673,8 @@ static int bloom_launch_bucketed(xs_bloom* bf, const BloomParams& p, cudaStream_
     const size_t o_bc = o_res + align256(nc_sub * g.nb * g.cap);
     const size_t o_ovf = o_bc + align256(nc_sub * g.nb * 2);
     const size_t o_ctr = o_ovf + align256(nc_sub * (BK_CH / 32) * 4);
-    const size_t o_seq = o_ctr + align256(n_sub * 3 * 8);
+    const size_t ctr_bytes = n_sub * 3 * 8 + 16;                  // work counters + {sampled, members}
+    const size_t o_seq = o_ctr + align256(ctr_bytes);
     const size_t bytes = o_seq + align256(nc_total * 8);
     uint8_t* d = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&d, bytes, s);
@@ -679,19 +683,29 @@ static int bloom_launch_bucketed(xs_bloom* bf, const BloomParams& p, cudaStream_
         bf->bucket_budget.store(0, std::memory_order_relaxed);
         return XS_OK;
     }
+    BloomParams pa = p;                                           // the query with the device-side choice attached
+    unsigned long long* d_adapt = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * n_sub;
+    if (bf->bucket_member_pct) { pa.adapt = d_adapt; pa.adapt_pct = bf->bucket_member_pct; }
     int rc = XS_OK;
     std::lock_guard<std::mutex> serial(bf->bucket_mu);
     if (!bf->bucket_done && cudaEventCreateWithFlags(&bf->bucket_done, cudaEventDisableTiming) != cudaSuccess) bf->bucket_done = nullptr;
     if (bf->bucket_done && bf->bucket_prev) cudaStreamWaitEvent(s, bf->bucket_done, 0);
-    e = cudaMemsetAsync(d + o_ctr, 0, n_sub * 3 * 8, s);
+    e = cudaMemsetAsync(d + o_ctr, 0, ctr_bytes, s);
     k_bucket_chunk_seq<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nc_total + 255) / 256, (uint64_t)bf->n_sm * 8)), 256, 0, s>>>(
         p.sb, nc_total, reinterpret_cast<uint64_t*>(d + o_seq));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const bool prefetch = getenv("XS_BK_PREFETCH") ? atoi(getenv("XS_BK_PREFETCH")) != 0 : true;
     const uint32_t k = bf->info.term_size;
+    if (pa.adapt) {                                               // ~256 k windows spread over the batch
+        const uint64_t stride = std::max<uint64_t>(1, total >> 18);
+        if (k == 21) k_bloom_sample<21><<<bf->n_sm * 2, 256, 0, s>>>(p, stride, d_adapt);
+        else if (k == 31) k_bloom_sample<31><<<bf->n_sm * 2, 256, 0, s>>>(p, stride, d_adapt);
+        else k_bloom_sample<0><<<bf->n_sm * 2, 256, 0, s>>>(p, stride, d_adapt);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     for (uint64_t i = 0; i < n_sub && e == cudaSuccess; ++i) {
         BloomBucketParams bp{};
-        bp.bl = p;
+        bp.bl = pa;
         bp.pos = reinterpret_cast<uint32_t*>(d + o_pos); bp.wid = reinterpret_cast<uint16_t*>(d + o_wid); bp.res = d + o_res;
         bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
         bp.chunk_seq = reinterpret_cast<const uint64_t*>(d + o_seq);
@@ -703,7 +717,7 @@ static int bloom_launch_bucketed(xs_bloom* bf, const BloomParams& p, cudaStream_
         else e = launch_bbucket_t<0, 0>(bp, g, bf->n_sm, s);
     }
     if (e == cudaSuccess) {
-        BloomParams tail = p;
+        BloomParams tail = pa;
         tail.win_begin = nc_total * BK_CH;
         KernelTimer kt(s, PROF_DIRECT);
         launch_bloom_kernel(tail, k, bf->n_sm, s);
@@ -1294,9 +1308,12 @@ int xs_bloom_info(const xs_bloom* bf, xs_bloom_info_t* info) {
     return XS_OK;
 }
 
-int xs_bloom_set_bucketed(xs_bloom* bf, int enabled, uint64_t min_windows, uint64_t scratch_bytes, uint32_t bucket_shift) {
+int xs_bloom_set_bucketed(xs_bloom* bf, int enabled, uint64_t min_windows, uint64_t scratch_bytes, uint32_t bucket_shift,
+                          int member_pct) {
     if (!bf) return fail(XS_ERR_ARG, "NULL filter");
     if (bucket_shift > 31 || (bucket_shift && bucket_shift < 3)) return fail(XS_ERR_ARG, "bucket_shift must be 0 or in 3..31");
+    if (member_pct > 100) return fail(XS_ERR_ARG, "member_pct must be <= 100");
+    if (member_pct >= 0) bf->bucket_member_pct = (uint32_t)member_pct;
     bf->bucketed = enabled ? 1 : 0;
     if (min_windows) bf->bucket_min_windows = min_windows;
     if (scratch_bytes) bf->bucket_scratch_bytes = scratch_bytes;

@@ -281,9 +281,12 @@ class BloomFilter:
         except Exception:
             pass
 
-    def set_bucketed(self, enabled: bool = True, min_windows: int = 0, scratch_bytes: int = 0, bucket_shift: int = 0) -> None:
-        """Tune the bucketed path large batches take (see ``xs_bloom_set_bucketed``)."""
-        check(lib().xs_bloom_set_bucketed(self._h, 1 if enabled else 0, int(min_windows), int(scratch_bytes), int(bucket_shift)))
+    def set_bucketed(self, enabled: bool = True, min_windows: int = 0, scratch_bytes: int = 0, bucket_shift: int = 0,
+                     member_pct: int = -1) -> None:
+        """Tune the bucketed path large batches take (see ``xs_bloom_set_bucketed``); ``member_pct=0`` forces it
+        whatever the sampled member fraction."""
+        check(lib().xs_bloom_set_bucketed(self._h, 1 if enabled else 0, int(min_windows), int(scratch_bytes), int(bucket_shift),
+                                          int(member_pct)))
 
     @property
     def bucketed_queries(self) -> int:
