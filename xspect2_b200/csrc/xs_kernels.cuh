@@ -5,10 +5,17 @@
 //                     canonical -> XXH64 x h -> Barrett mod -> h x 128-bit gathers -> AND ->
 //                     per-sequence document counts by warp ballot/popcount
 //                     (cobs Search.search behind probabilistic_filter_model.py:227)
+//   k_bucket_emit,    the same scoring for large batches against an index much larger than L2: probe records grouped
+//   k_bucket_fetch,     by L2-sized row ranges, rows gathered from L2, ANDed per window in shared memory (a random
+//   k_bucket_reduce     16-byte row gather from DRAM costs a 128-byte fetch; every row is probed many times per batch)
 //   k_cobs_wide       rows > 16 B: lanes own 16-byte column chunks, warp-coalesced row gathers (2h loads in
 //                     flight per lane), bit-plane counters, shared-memory count staging
 //   k_bloom           XXH3-64 -> 128-bit LCG -> bit probes with early exit
 //                     (probabilistic_single_filter_model.py:122-124,161-180)
+//   k_bloom_sample,   the bucketed scheme for the Bloom filter, chosen on the device per batch from a sampled member
+//   k_bbucket_emit,     fraction (all k probes are made there; k_bloom stops at the first zero bit)
+//   k_bbucket_fetch,
+//   k_bbucket_reduce
 //   k_scores_reduce   per-record best document / tie multiplicity and per-document totals over a count matrix
 //   k_cobs_build,     construction: the query hashing with an atomic OR instead of a gather
 //   k_bloom_build       (probabilistic_filter_model.py:169-194, probabilistic_single_filter_model.py:63-96)
@@ -19,7 +26,8 @@
 // that space (warp_walk), so lanes stay dense whatever the read lengths are; all bookkeeping
 // is warp-uniform (no shared memory, no CTA barrier on the narrow and Bloom paths).  Tiles and work
 // items are handed out through an atomic counter: a static equal split runs at the pace of the
-// slowest SM (profiles/microbench/gather_concurrent.cu).
+// slowest SM (profiles/microbench/gather_concurrent.cu).  The bucketed kernels cut the same flat space into
+// chunks of 2048 windows and resolve window -> sequence per chunk in shared memory (chunk_seq_table).
 #pragma once
 #include "xs_device.cuh"
 
