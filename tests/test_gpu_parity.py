@@ -165,6 +165,27 @@ def test_cobs_bucketed_runs_of_empty_records(gpu, oracle, tmp_path):
     _check_bucketed(gpu, oracle, p, bases, e - lens, e, dtype=1, scratch=2 << 20)
 
 
+def test_cobs_bucketed_not_canonical_index_and_column_shard(gpu, oracle, tmp_path):
+    """A non-canonical index (literal k-mers, windows with N are hashed as they are) and a document-column shard of a
+    wider index (rows of the shard <= 16 bytes) through the bucketed kernels."""
+    rng = np.random.default_rng(37)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 6, 21, 3, canonicalize=0)
+    genomes = [s for v in docs.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes, 500, (21, 260), sub=0.01, n_rate=0.004)
+    _check_bucketed(gpu, oracle, p, bases, b, e)
+    p2, docs2 = _mk_classic(oracle, tmp_path, rng, 200, 21, 7, length=1500, name="wide.cobs_classic")
+    genomes2 = [s for v in docs2.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes2, 400, (21, 200), sub=0.01, n_rate=0.002)
+    exp = oracle.CobsOracle(p2).counts_batch(bases, b, e, 1, threads=4)
+    for lo, hi in ((0, 96), (96, 200)):
+        ix = gpu.CobsIndex(p2, doc_begin=lo, doc_end=hi)
+        ix.set_bucketed(True, min_windows=1, bucket_shift=_bucket_shift(p2, gpu))
+        got = ix.query(bases, b, e)
+        assert ix.bucketed_queries >= 1
+        assert np.array_equal(np.asarray(got).astype(np.uint32), exp[:, lo:hi])
+        ix.close()
+
+
 def test_cobs_bucketed_shift_21_and_few_buckets(gpu, oracle, tmp_path):
     """Other geometries of the record word: 2^21 rows per bucket (one bucket here) and 2 rows per bucket."""
     rng = np.random.default_rng(23)
