@@ -500,7 +500,7 @@ __device__ __forceinline__ uint32_t bucket_live_chunks(const BucketParams& bp, u
 
 // Sequence of every window of the chunk [g0, g1): s_wseq[l] = (sequence of window g0 + l) - s_lo + 1, where s_lo (from
 // k_bucket_chunk_seq, also the return value) is the sequence of window g0.  Sequences that start inside the chunk mark their first window, an
-// inclusive max-scan carries the marks forward.  CTA-wide (NT threads); ends with a barrier.  This replaces warp_walk
+// inclusive max-scan carries the marks forward.  CTA-wide (NT threads); s_wseq must be zero on entry; ends with a barrier.  This replaces warp_walk
 // in the bucketed kernels: its 64-bit shuffle bookkeeping is hidden by DRAM latency in k_cobs_narrow but was a third
 // of k_bucket_emit's and half of k_bucket_reduce's instructions (profiles/r1_bucketed_notes.md).
 // sequence of the first window of every chunk: one binary search per chunk, all chunks in parallel (inside the
@@ -518,8 +518,7 @@ __device__ __forceinline__ uint64_t chunk_seq_table(const SeqBatch& sb, uint64_t
                                                     uint32_t* s_scan) {
     constexpr int PER = BK_CH / NT;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (uint32_t i = tid; i < BK_CH; i += NT) s_wseq[i] = 0;
-    __syncthreads();
+    // s_wseq arrives zeroed and the CTA synchronised (the callers clear it with their other per-chunk state)
     for (uint64_t q = s_lo + tid; q < sb.n_seq; q += NT) {
         const uint64_t p = __ldg(sb.win_prefix + q);
         if (p >= g1) break;
@@ -578,7 +577,7 @@ __global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bucket_emit(const BucketParam
     unsigned long long ticket = tid == 0 ? atomicAdd(bp.counter + 0, 1ULL) : 0ULL;
     for (;;) {
         if (tid == 0) s_chunk = ticket;
-        for (uint32_t i = tid; i < nb + 2 * (BK_CH / 32); i += BK_EMIT_NT) s_cnt[i] = 0;   // s_cnt, s_ovf, s_skp are contiguous
+        for (uint32_t i = tid; i < nb + 2 * (BK_CH / 32) + BK_CH; i += BK_EMIT_NT) s_cnt[i] = 0;   // s_cnt, s_ovf, s_skp, s_wseq are contiguous
         __syncthreads();
         const uint64_t c = s_chunk;
         if (c >= nc_live) break;
@@ -720,6 +719,7 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bucket_reduce(const __grid_constan
             uint4* z = reinterpret_cast<uint4*>(&s_m[0][0]);
             const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
             for (uint32_t i = tid; i < 4 * BK_CH / 4; i += BK_NT) z[i] = ones;
+            for (uint32_t i = tid; i < BK_CH; i += BK_NT) s_wseq[i] = 0;
         }
         __syncthreads();
         const uint64_t c = s_chunk;
@@ -1144,7 +1144,7 @@ __global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bbucket_emit(const BloomBucke
     unsigned long long ticket = tid == 0 ? atomicAdd(bp.counter + 0, 1ULL) : 0ULL;
     for (;;) {
         if (tid == 0) s_chunk = ticket;
-        for (uint32_t i = tid; i < nb4 + BK_CH / 32; i += BK_EMIT_NT) s_cnt[i] = 0;   // s_cnt and s_ovf are contiguous
+        for (uint32_t i = tid; i < nb4 + BK_CH / 32 + BK_CH; i += BK_EMIT_NT) s_cnt[i] = 0;   // s_cnt, s_ovf, s_wseq are contiguous
         __syncthreads();
         const uint64_t c = s_chunk;
         if (c >= nc_live) break;
@@ -1265,6 +1265,7 @@ __global__ void __launch_bounds__(BK_NT, 4) k_bbucket_reduce(const BloomBucketPa
     for (;;) {
         if (tid == 0) s_chunk = ticket;
         if (tid < BK_CH / 32) s_fail[tid] = 0;
+        for (uint32_t i = tid; i < BK_CH; i += BK_NT) s_wseq[i] = 0;
         __syncthreads();
         const uint64_t c = s_chunk;
         if (c >= nc_live) break;
