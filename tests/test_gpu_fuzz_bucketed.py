@@ -1,7 +1,9 @@
 """Randomised cross-check of the two kernel paths: for random geometries (documents, k, hashes, step, bucket size,
 scratch budget) and ragged inputs (reads, contigs, empty / short records, N, lower case, overlapping segments) the
 bucketed kernels must return exactly what the direct-gather kernels return; a subset is also checked against the
-oracle.  Both sides run on the GPU, so many cases fit in seconds."""
+oracle.  Both sides run on the GPU, so many cases fit in seconds (XS_FUZZ_CASES raises the number of cases)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -44,7 +46,7 @@ def _random_batch(rng, genomes, k):
     return bases, b.astype(np.uint64), e.astype(np.uint64)
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("XS_FUZZ_CASES", 24))))
 def test_cobs_bucketed_equals_direct(gpu, oracle, tmp_path, seed):
     rng = np.random.default_rng(9000 + seed)
     n_docs = int(rng.choice([1, 8, 33, 90, 96, 97, 128]))
@@ -79,7 +81,7 @@ def test_cobs_bucketed_equals_direct(gpu, oracle, tmp_path, seed):
         assert np.array_equal(got.astype(np.uint32), exp)
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("XS_FUZZ_CASES", 24)) // 2))
 def test_bloom_bucketed_equals_direct(gpu, oracle, tmp_path, seed):
     rng = np.random.default_rng(9500 + seed)
     k = int(rng.choice([13, 21, 31]))
