@@ -84,6 +84,29 @@ static uint64_t magic_of(uint64_t m) {
 // ----------------------------------------------------------------------------------------
 // handles
 // ----------------------------------------------------------------------------------------
+// Per-handle state of the bucketed path (shared by the COBS and the Bloom handle).
+struct BucketState {
+    int enabled = 1;                       // large batches go through the bucketed kernels
+    uint64_t min_windows = 32ULL << 20;    // measured crossover: ~25 M windows
+    uint64_t scratch_bytes = 24ULL << 30;  // upper bound of the scratch of one query
+    uint32_t shift = 0;                    // log2 rows / bits per bucket, 0 = automatic
+    std::atomic<uint64_t> queries{0};
+    std::atomic<uint64_t> budget{0};       // scratch bytes per query actually used; 0 = not asked yet
+    // bucketed queries of one handle run one after the other even when they are enqueued on different streams (the
+    // host pipeline uses three): their kernels compete for the same L2 slice and LSU path when they overlap
+    std::mutex mu;
+    cudaEvent_t done = nullptr;
+    bool prev = false;
+    void configure(int on, uint64_t min_w, uint64_t scratch, uint32_t sh) {
+        enabled = on ? 1 : 0;
+        if (min_w) min_windows = min_w;
+        if (scratch) scratch_bytes = scratch;
+        budget.store(0);
+        shift = sh;
+    }
+    void destroy() { if (done) cudaEventDestroy(done); done = nullptr; }
+};
+
 struct xs_cobs {
     xs_cobs_info_t info{};
     std::vector<PageDesc> pages;
@@ -95,36 +118,17 @@ struct xs_cobs {
     bool narrow = true;
     int n_sm = 148;
     int force_wide = 0;
-    int bucketed = 1;                 // large batches against a large narrow index go through the bucketed kernels
-    uint64_t bucket_min_windows = 32ULL << 20;
-    uint64_t bucket_scratch_bytes = 24ULL << 30;
-    uint32_t bucket_shift = 0;        // 0 = automatic
-    std::atomic<uint64_t> bucketed_queries{0};
-    std::atomic<uint64_t> bucket_budget{0};   // scratch bytes per query; 0 = not asked yet
-    // bucketed queries of one handle run one after the other even when they are enqueued on different streams (the
-    // host pipeline uses three): their kernels compete for the same L2 slice and LSU path when they overlap
-    std::mutex bucket_mu;
-    cudaEvent_t bucket_done = nullptr;
-    bool bucket_prev = false;
+    BucketState bk;
 };
 
 struct xs_bloom {
     xs_bloom_info_t info{};
     uint8_t* d_bits = nullptr;
     int n_sm = 148;
-    // bucketed probing of large batches (k_bbucket_emit / fetch / reduce), see xs_cobs
-    int bucketed = 1;
-    uint64_t bucket_min_windows = 32ULL << 20;
-    uint64_t bucket_scratch_bytes = 24ULL << 30;
-    uint32_t bucket_shift = 0;        // log2 bits per bucket, 0 = automatic
+    BucketState bk;                   // bucketed probing of large batches (k_bbucket_emit / fetch / reduce)
     // the bucketed kernels make all k probes of a window, k_bloom stops at the first zero bit: bucketed wins when at
     // least about a third of the windows are members (measured crossover); decided on the device from a sample
     uint32_t bucket_member_pct = 35;  // 0 = always bucketed
-    std::atomic<uint64_t> bucketed_queries{0};
-    std::atomic<uint64_t> bucket_budget{0};
-    std::mutex bucket_mu;
-    cudaEvent_t bucket_done = nullptr;
-    bool bucket_prev = false;
 };
 
 struct DeviceGuard {
@@ -395,7 +399,63 @@ static cudaError_t launch_wide(const WideParams& p, dim3 grid, size_t smem, int 
     return launch_wide_t<0, 0>(p, grid, smem, dt, s);
 }
 
-// ---- bucketed probing (k_bucket_emit / k_bucket_fetch / k_bucket_reduce) -------------------------------------
+// ---- bucketed probing: what the COBS and the Bloom path share on the host ------------------------------------
+struct SubBatches {
+    uint64_t nc_total = 0;   // chunks covering the upper bound of the window count
+    uint64_t nc_sub = 0;     // chunks per sub-batch (= per scratch buffer)
+    uint64_t n_sub = 0;
+};
+
+// No host read of the window count: chunking and scratch are sized from an upper bound that holds whenever the
+// sequences do not overlap (sum of ((len - k) / step + 1) <= n_bases / step + n_seq); the kernels read the true count
+// on the device and skip chunks beyond it, and windows beyond the bound (overlapping segments) are scored by a tail
+// launch of the direct kernel that normally finds nothing to do.  Sub-batches of nc_sub chunks go through emit ->
+// fetch -> reduce back to back on the caller's stream.  (Running the kernels of neighbouring sub-batches concurrently
+// on several streams was measured and lost: they compete for issue slots, the LSU path and L2,
+// profiles/r1_bucketed_notes.md.)  *ok = false: the batch is too small or there is too little memory.
+static int plan_sub_batches(BucketState& bk, const SeqBatch& sb, size_t per_chunk, SubBatches& sub, bool* ok) {
+    *ok = false;
+    uint64_t budget = bk.budget.load(std::memory_order_relaxed);
+    if (budget == 0) {     // asked once per handle (and again after a failed allocation): at most half of what is free
+        size_t free_b = 0, total_b = 0;
+        XS_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        budget = std::max<uint64_t>(1, std::min<uint64_t>(bk.scratch_bytes, free_b / 2));
+        bk.budget.store(budget, std::memory_order_relaxed);
+    }
+    const uint64_t bound = sb.n_bases / sb.step + sb.n_seq;
+    sub.nc_total = (bound + BK_CH - 1) / BK_CH;
+    sub.nc_sub = std::min<uint64_t>(sub.nc_total, budget / per_chunk);
+    if (sub.nc_sub == 0 || sub.nc_sub * BK_CH < bk.min_windows / 2) return XS_OK;    // too little memory for L2 re-use
+    sub.n_sub = (sub.nc_total + sub.nc_sub - 1) / sub.nc_sub;
+    sub.nc_sub = (sub.nc_total + sub.n_sub - 1) / sub.n_sub;
+    sub.nc_sub = std::min<uint64_t>(sub.nc_sub, 0xFFFFFFFFu / BK_MAX_BUCKETS);
+    sub.n_sub = (sub.nc_total + sub.nc_sub - 1) / sub.nc_sub;
+    *ok = true;
+    return XS_OK;
+}
+
+// holds the handle's lock while a bucketed query is enqueued and chains it behind the previous one
+struct BucketSerial {
+    BucketState& bk;
+    cudaStream_t s;
+    std::lock_guard<std::mutex> lock;
+    BucketSerial(BucketState& b, cudaStream_t st) : bk(b), s(st), lock(b.mu) {
+        if (!bk.done && cudaEventCreateWithFlags(&bk.done, cudaEventDisableTiming) != cudaSuccess) bk.done = nullptr;
+        if (bk.done && bk.prev) cudaStreamWaitEvent(s, bk.done, 0);
+    }
+    ~BucketSerial() { if (bk.done && cudaEventRecord(bk.done, s) == cudaSuccess) bk.prev = true; }
+};
+
+static unsigned chunk_seq_grid(uint64_t nc_total, int n_sm) {
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nc_total + 255) / 256, (uint64_t)n_sm * 8));
+}
+
+static bool bucket_prefetch_enabled() {
+    const char* v = getenv("XS_BK_PREFETCH");      // measurement switch (profiles/experiments/bucketed_phases.py)
+    return !(v && *v) || atoi(v) != 0;
+}
+
+// ---- bucketed probing, COBS (k_bucket_emit / k_bucket_fetch / k_bucket_reduce) ------------------------------
 struct BucketGeom {
     uint32_t nb = 0, bshift = 0, cap = 0;
     size_t smem = 0;        // dynamic shared memory of k_bucket_emit
@@ -456,85 +516,67 @@ static cudaError_t launch_bucket_t(const BucketParams& bp, const BucketGeom& g, 
 // returns XS_OK with *handled = false when the batch should go through k_cobs_narrow instead
 static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaStream_t s, bool* handled) {
     *handled = false;
-    if (!ix->bucketed || !ix->narrow || ix->force_wide || ix->pages.size() != 1) return XS_OK;
-    if (p.sb.n_bases / p.sb.step < ix->bucket_min_windows) return XS_OK;
+    BucketState& bk = ix->bk;
+    if (!bk.enabled || !ix->narrow || ix->force_wide || ix->pages.size() != 1) return XS_OK;
+    if (p.sb.n_bases / p.sb.step < bk.min_windows) return XS_OK;
     BucketGeom g;
-    if (!bucket_geometry(ix->pages[0].sig_size, ix->info.num_hashes, ix->bucket_shift, g)) return XS_OK;
-    // No host read of the window count: chunking and scratch are sized from an upper bound that holds whenever the
-    // sequences do not overlap (sum of ((len - k) / step + 1) <= n_bases / step + n_seq); the kernels read the true
-    // count on the device and skip chunks beyond it, and windows beyond the bound (overlapping segments) are scored by
-    // a tail launch of k_cobs_narrow that normally finds nothing to do.
-    const uint64_t total = p.sb.n_bases / p.sb.step + p.sb.n_seq;
-    // Sub-batches of nc_sub chunks go through emit -> fetch -> reduce back to back on the caller's stream.  (Running the
-    // three kernels of neighbouring sub-batches concurrently on three streams was measured and lost: they compete for
-    // issue slots and L2, profiles/r1_bucketed_notes.md.)
-    uint64_t budget = ix->bucket_budget.load(std::memory_order_relaxed);
-    if (budget == 0) {     // asked once per handle (and again after a failed allocation): at most half of what is free
-        size_t free_b = 0, total_b = 0;
-        XS_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        budget = std::max<uint64_t>(1, std::min<uint64_t>(ix->bucket_scratch_bytes, free_b / 2));
-        ix->bucket_budget.store(budget, std::memory_order_relaxed);
-    }
-    const uint64_t nc_total = (total + BK_CH - 1) / BK_CH;
-    uint64_t nc_sub = std::min<uint64_t>(nc_total, budget / g.per_chunk);
-    if (nc_sub == 0 || nc_sub * BK_CH < ix->bucket_min_windows / 2) return XS_OK;    // too little memory for L2 re-use
-    const uint64_t n_sub = (nc_total + nc_sub - 1) / nc_sub;
-    nc_sub = (nc_total + n_sub - 1) / n_sub;
-    nc_sub = std::min<uint64_t>(nc_sub, 0xFFFFFFFFu / BK_MAX_BUCKETS);
+    if (!bucket_geometry(ix->pages[0].sig_size, ix->info.num_hashes, bk.shift, g)) return XS_OK;
+    SubBatches sub;
+    bool ok = false;
+    XS_TRY(plan_sub_batches(bk, p.sb, g.per_chunk, sub, &ok));
+    if (!ok) return XS_OK;
 
     const size_t o_rows = 0;
-    const size_t o_rec = o_rows + align256(nc_sub * g.nb * g.cap * 16);
-    const size_t o_bc = o_rec + align256(nc_sub * g.nb * g.cap * 4);
-    const size_t o_cb = o_bc + align256(nc_sub * g.nb * 2);
-    const size_t o_ovf = o_cb + align256(nc_sub * g.nb * 2);
-    const size_t o_ctr = o_ovf + align256(nc_sub * 2 * (BK_CH / 32) * 4);
-    const size_t o_seq = o_ctr + align256(n_sub * 3 * 8);
-    const size_t bytes = o_seq + align256(nc_total * 8);
+    const size_t o_rec = o_rows + align256(sub.nc_sub * g.nb * g.cap * 16);
+    const size_t o_bc = o_rec + align256(sub.nc_sub * g.nb * g.cap * 4);
+    const size_t o_cb = o_bc + align256(sub.nc_sub * g.nb * 2);
+    const size_t o_ovf = o_cb + align256(sub.nc_sub * g.nb * 2);
+    const size_t o_ctr = o_ovf + align256(sub.nc_sub * 2 * (BK_CH / 32) * 4);
+    const size_t o_seq = o_ctr + align256(sub.n_sub * 3 * 8);
+    const size_t bytes = o_seq + align256(sub.nc_total * 8);
     uint8_t* d = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&d, bytes, s);
     if (e != cudaSuccess) {                                       // no room for the scratch: direct gathers
         cudaGetLastError();
-        ix->bucket_budget.store(0, std::memory_order_relaxed);
+        bk.budget.store(0, std::memory_order_relaxed);
         return XS_OK;
     }
-    int rc = XS_OK;
-    std::lock_guard<std::mutex> serial(ix->bucket_mu);
-    if (!ix->bucket_done && cudaEventCreateWithFlags(&ix->bucket_done, cudaEventDisableTiming) != cudaSuccess) ix->bucket_done = nullptr;
-    if (ix->bucket_done && ix->bucket_prev) cudaStreamWaitEvent(s, ix->bucket_done, 0);
-    e = cudaMemsetAsync(d + o_ctr, 0, n_sub * 3 * 8, s);
-    k_bucket_chunk_seq<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nc_total + 255) / 256, (uint64_t)ix->n_sm * 8)), 256, 0, s>>>(
-        p.sb, nc_total, reinterpret_cast<uint64_t*>(d + o_seq));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    const bool prefetch = getenv("XS_BK_PREFETCH") ? atoi(getenv("XS_BK_PREFETCH")) != 0 : true;
-    for (uint64_t i = 0; i < n_sub && e == cudaSuccess; ++i) {
-        BucketParams bp{};
-        bp.cp = p;
-        bp.rows = reinterpret_cast<uint4*>(d + o_rows); bp.rec = reinterpret_cast<uint32_t*>(d + o_rec);
-        bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.cnt_cb = reinterpret_cast<uint16_t*>(d + o_cb);
-        bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
-        bp.chunk_seq = reinterpret_cast<const uint64_t*>(d + o_seq);
-        bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
-        bp.chunk0 = i * nc_sub;
-        bp.nc = (uint32_t)std::min<uint64_t>(nc_sub, nc_total - bp.chunk0);
-        bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap;
-        bp.pack_id = ix->pages[0].n_docs <= 96 ? 1u : 0u;
-        bp.prefetch = prefetch ? 1u : 0u;
-        if (p.sb.k == 21 && p.num_hashes == 7) e = launch_bucket_t<21, 7>(bp, g, ix->n_sm, dt, s);
-        else e = launch_bucket_t<0, 0>(bp, g, ix->n_sm, dt, s);
-    }
-    if (e == cudaSuccess) {
-        CobsParams tail = p;
-        tail.win_begin = nc_total * BK_CH;
-        KernelTimer kt(s, PROF_DIRECT);
-        launch_narrow(tail, dim3((unsigned)(ix->n_sm * 4), 1), dt, s);
+    {
+        BucketSerial serial(bk, s);
+        e = cudaMemsetAsync(d + o_ctr, 0, sub.n_sub * 3 * 8, s);
+        k_bucket_chunk_seq<<<chunk_seq_grid(sub.nc_total, ix->n_sm), 256, 0, s>>>(p.sb, sub.nc_total, reinterpret_cast<uint64_t*>(d + o_seq));
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        e = cudaGetLastError();
+        const bool prefetch = bucket_prefetch_enabled();
+        for (uint64_t i = 0; i < sub.n_sub && e == cudaSuccess; ++i) {
+            BucketParams bp{};
+            bp.cp = p;
+            bp.rows = reinterpret_cast<uint4*>(d + o_rows); bp.rec = reinterpret_cast<uint32_t*>(d + o_rec);
+            bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.cnt_cb = reinterpret_cast<uint16_t*>(d + o_cb);
+            bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
+            bp.chunk_seq = reinterpret_cast<const uint64_t*>(d + o_seq);
+            bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
+            bp.chunk0 = i * sub.nc_sub;
+            bp.nc = (uint32_t)std::min<uint64_t>(sub.nc_sub, sub.nc_total - bp.chunk0);
+            bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap;
+            bp.pack_id = ix->pages[0].n_docs <= 96 ? 1u : 0u;
+            bp.prefetch = prefetch ? 1u : 0u;
+            if (p.sb.k == 21 && p.num_hashes == 7) e = launch_bucket_t<21, 7>(bp, g, ix->n_sm, dt, s);
+            else e = launch_bucket_t<0, 0>(bp, g, ix->n_sm, dt, s);
+        }
+        if (e == cudaSuccess) {
+            CobsParams tail = p;
+            tail.win_begin = sub.nc_total * BK_CH;
+            KernelTimer kt(s, PROF_DIRECT);
+            launch_narrow(tail, dim3((unsigned)(ix->n_sm * 4), 1), dt, s);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            e = cudaGetLastError();
+        }
     }
-    if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("bucketed query: ") + cudaGetErrorString(e));
-    if (ix->bucket_done && cudaEventRecord(ix->bucket_done, s) == cudaSuccess) ix->bucket_prev = true;
     cudaFreeAsync(d, s);
-    if (rc == XS_OK) { *handled = true; ix->bucketed_queries.fetch_add(1, std::memory_order_relaxed); }
-    return rc;
+    if (e != cudaSuccess) return fail(XS_ERR_CUDA, std::string("bucketed query: ") + cudaGetErrorString(e));
+    *handled = true;
+    bk.queries.fetch_add(1, std::memory_order_relaxed);
+    return XS_OK;
 }
 
 static int dtype_size(int dt) { return (dt == XS_U8 || dt == XS_U16 || dt == XS_U32) ? dt : 0; }
@@ -645,90 +687,79 @@ static void launch_bloom_kernel(const BloomParams& p, uint32_t k, int n_sm, cuda
 }
 
 // returns XS_OK with *handled = false when the batch should go through k_bloom instead (same contract as
-// cobs_launch_bucketed: sizes from an upper bound of the window count, no host read, tail launch of the direct kernel)
+// cobs_launch_bucketed)
 static int bloom_launch_bucketed(xs_bloom* bf, const BloomParams& p, cudaStream_t s, bool* handled) {
     *handled = false;
-    if (!bf->bucketed || p.literal) return XS_OK;
-    if (p.sb.n_bases / p.sb.step < bf->bucket_min_windows) return XS_OK;
+    BucketState& bk = bf->bk;
+    if (!bk.enabled || p.literal) return XS_OK;
+    if (p.sb.n_bases / p.sb.step < bk.min_windows) return XS_OK;
     BloomBucketGeom g;
-    if (!bloom_bucket_geometry(bf->info.n_bits, (uint32_t)bf->info.k_hashes, bf->bucket_shift, g)) return XS_OK;
-    const uint64_t total = p.sb.n_bases / p.sb.step + p.sb.n_seq;
-    uint64_t budget = bf->bucket_budget.load(std::memory_order_relaxed);
-    if (budget == 0) {
-        size_t free_b = 0, total_b = 0;
-        XS_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        budget = std::max<uint64_t>(1, std::min<uint64_t>(bf->bucket_scratch_bytes, free_b / 2));
-        bf->bucket_budget.store(budget, std::memory_order_relaxed);
-    }
-    const uint64_t nc_total = (total + BK_CH - 1) / BK_CH;
-    uint64_t nc_sub = std::min<uint64_t>(nc_total, budget / g.per_chunk);
-    if (nc_sub == 0 || nc_sub * BK_CH < bf->bucket_min_windows / 2) return XS_OK;
-    const uint64_t n_sub = (nc_total + nc_sub - 1) / nc_sub;
-    nc_sub = (nc_total + n_sub - 1) / n_sub;
-    nc_sub = std::min<uint64_t>(nc_sub, 0xFFFFFFFFu / BK_MAX_BUCKETS);
+    if (!bloom_bucket_geometry(bf->info.n_bits, (uint32_t)bf->info.k_hashes, bk.shift, g)) return XS_OK;
+    SubBatches sub;
+    bool ok = false;
+    XS_TRY(plan_sub_batches(bk, p.sb, g.per_chunk, sub, &ok));
+    if (!ok) return XS_OK;
 
     const size_t o_pos = 0;
-    const size_t o_wid = o_pos + align256(nc_sub * g.nb * g.cap * 4);
-    const size_t o_res = o_wid + align256(nc_sub * g.nb * g.cap * 2);
-    const size_t o_bc = o_res + align256(nc_sub * g.nb * g.cap);
-    const size_t o_ovf = o_bc + align256(nc_sub * g.nb * 2);
-    const size_t o_ctr = o_ovf + align256(nc_sub * (BK_CH / 32) * 4);
-    const size_t ctr_bytes = n_sub * 3 * 8 + 16;                  // work counters + {sampled, members}
+    const size_t o_wid = o_pos + align256(sub.nc_sub * g.nb * g.cap * 4);
+    const size_t o_res = o_wid + align256(sub.nc_sub * g.nb * g.cap * 2);
+    const size_t o_bc = o_res + align256(sub.nc_sub * g.nb * g.cap);
+    const size_t o_ovf = o_bc + align256(sub.nc_sub * g.nb * 2);
+    const size_t o_ctr = o_ovf + align256(sub.nc_sub * (BK_CH / 32) * 4);
+    const size_t ctr_bytes = sub.n_sub * 3 * 8 + 16;             // work counters + {sampled, members}
     const size_t o_seq = o_ctr + align256(ctr_bytes);
-    const size_t bytes = o_seq + align256(nc_total * 8);
+    const size_t bytes = o_seq + align256(sub.nc_total * 8);
     uint8_t* d = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&d, bytes, s);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        bf->bucket_budget.store(0, std::memory_order_relaxed);
+        bk.budget.store(0, std::memory_order_relaxed);
         return XS_OK;
     }
     BloomParams pa = p;                                           // the query with the device-side choice attached
-    unsigned long long* d_adapt = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * n_sub;
+    unsigned long long* d_adapt = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * sub.n_sub;
     if (bf->bucket_member_pct) { pa.adapt = d_adapt; pa.adapt_pct = bf->bucket_member_pct; }
-    int rc = XS_OK;
-    std::lock_guard<std::mutex> serial(bf->bucket_mu);
-    if (!bf->bucket_done && cudaEventCreateWithFlags(&bf->bucket_done, cudaEventDisableTiming) != cudaSuccess) bf->bucket_done = nullptr;
-    if (bf->bucket_done && bf->bucket_prev) cudaStreamWaitEvent(s, bf->bucket_done, 0);
-    e = cudaMemsetAsync(d + o_ctr, 0, ctr_bytes, s);
-    k_bucket_chunk_seq<<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nc_total + 255) / 256, (uint64_t)bf->n_sm * 8)), 256, 0, s>>>(
-        p.sb, nc_total, reinterpret_cast<uint64_t*>(d + o_seq));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    const bool prefetch = getenv("XS_BK_PREFETCH") ? atoi(getenv("XS_BK_PREFETCH")) != 0 : true;
     const uint32_t k = bf->info.term_size;
-    if (pa.adapt) {                                               // ~256 k windows spread over the batch
-        const uint64_t stride = std::max<uint64_t>(1, total >> 18);
-        if (k == 21) k_bloom_sample<21><<<bf->n_sm * 2, 256, 0, s>>>(p, stride, d_adapt);
-        else if (k == 31) k_bloom_sample<31><<<bf->n_sm * 2, 256, 0, s>>>(p, stride, d_adapt);
-        else k_bloom_sample<0><<<bf->n_sm * 2, 256, 0, s>>>(p, stride, d_adapt);
+    {
+        BucketSerial serial(bk, s);
+        e = cudaMemsetAsync(d + o_ctr, 0, ctr_bytes, s);
+        k_bucket_chunk_seq<<<chunk_seq_grid(sub.nc_total, bf->n_sm), 256, 0, s>>>(p.sb, sub.nc_total, reinterpret_cast<uint64_t*>(d + o_seq));
         g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (pa.adapt) {                                           // ~256 k windows spread over the batch
+            const uint64_t stride = std::max<uint64_t>(1, (sub.nc_total * BK_CH) >> 18);
+            if (k == 21) k_bloom_sample<21><<<bf->n_sm * 2, 256, 0, s>>>(p, stride, d_adapt);
+            else if (k == 31) k_bloom_sample<31><<<bf->n_sm * 2, 256, 0, s>>>(p, stride, d_adapt);
+            else k_bloom_sample<0><<<bf->n_sm * 2, 256, 0, s>>>(p, stride, d_adapt);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        const bool prefetch = bucket_prefetch_enabled();
+        for (uint64_t i = 0; i < sub.n_sub && e == cudaSuccess; ++i) {
+            BloomBucketParams bp{};
+            bp.bl = pa;
+            bp.pos = reinterpret_cast<uint32_t*>(d + o_pos); bp.wid = reinterpret_cast<uint16_t*>(d + o_wid); bp.res = d + o_res;
+            bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
+            bp.chunk_seq = reinterpret_cast<const uint64_t*>(d + o_seq);
+            bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
+            bp.chunk0 = i * sub.nc_sub;
+            bp.nc = (uint32_t)std::min<uint64_t>(sub.nc_sub, sub.nc_total - bp.chunk0);
+            bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap; bp.prefetch = prefetch ? 1u : 0u;
+            if (k == 21 && bf->info.k_hashes == 6) e = launch_bbucket_t<21, 6>(bp, g, bf->n_sm, s);
+            else e = launch_bbucket_t<0, 0>(bp, g, bf->n_sm, s);
+        }
+        if (e == cudaSuccess) {
+            BloomParams tail = pa;
+            tail.win_begin = sub.nc_total * BK_CH;
+            KernelTimer kt(s, PROF_DIRECT);
+            launch_bloom_kernel(tail, k, bf->n_sm, s);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            e = cudaGetLastError();
+        }
     }
-    for (uint64_t i = 0; i < n_sub && e == cudaSuccess; ++i) {
-        BloomBucketParams bp{};
-        bp.bl = pa;
-        bp.pos = reinterpret_cast<uint32_t*>(d + o_pos); bp.wid = reinterpret_cast<uint16_t*>(d + o_wid); bp.res = d + o_res;
-        bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
-        bp.chunk_seq = reinterpret_cast<const uint64_t*>(d + o_seq);
-        bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
-        bp.chunk0 = i * nc_sub;
-        bp.nc = (uint32_t)std::min<uint64_t>(nc_sub, nc_total - bp.chunk0);
-        bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap; bp.prefetch = prefetch ? 1u : 0u;
-        if (k == 21 && bf->info.k_hashes == 6) e = launch_bbucket_t<21, 6>(bp, g, bf->n_sm, s);
-        else e = launch_bbucket_t<0, 0>(bp, g, bf->n_sm, s);
-    }
-    if (e == cudaSuccess) {
-        BloomParams tail = pa;
-        tail.win_begin = nc_total * BK_CH;
-        KernelTimer kt(s, PROF_DIRECT);
-        launch_bloom_kernel(tail, k, bf->n_sm, s);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        e = cudaGetLastError();
-    }
-    if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("bucketed Bloom query: ") + cudaGetErrorString(e));
-    if (bf->bucket_done && cudaEventRecord(bf->bucket_done, s) == cudaSuccess) bf->bucket_prev = true;
     cudaFreeAsync(d, s);
-    if (rc == XS_OK) { *handled = true; bf->bucketed_queries.fetch_add(1, std::memory_order_relaxed); }
-    return rc;
+    if (e != cudaSuccess) return fail(XS_ERR_CUDA, std::string("bucketed Bloom query: ") + cudaGetErrorString(e));
+    *handled = true;
+    bk.queries.fetch_add(1, std::memory_order_relaxed);
+    return XS_OK;
 }
 
 static int bloom_launch(xs_bloom* bf, const SeqBatch& sb, uint32_t* d_out, cudaStream_t s, bool literal = false) {
@@ -1020,9 +1051,9 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
     ix->names = cf.names;
     const char* fw = getenv("XS_FORCE_WIDE");
     ix->force_wide = (fw && fw[0] == '1') ? 1 : 0;
-    if (const char* v = getenv("XS_BUCKETED")) ix->bucketed = v[0] != '0';
-    if (const char* v = getenv("XS_BUCKET_MIN_WINDOWS")) ix->bucket_min_windows = std::max<uint64_t>(1, strtoull(v, nullptr, 10));
-    if (const char* v = getenv("XS_BUCKET_SCRATCH_MB")) ix->bucket_scratch_bytes = strtoull(v, nullptr, 10) << 20;
+    if (const char* v = getenv("XS_BUCKETED")) ix->bk.enabled = v[0] != '0';
+    if (const char* v = getenv("XS_BUCKET_MIN_WINDOWS")) ix->bk.min_windows = std::max<uint64_t>(1, strtoull(v, nullptr, 10));
+    if (const char* v = getenv("XS_BUCKET_SCRATCH_MB")) ix->bk.scratch_bytes = strtoull(v, nullptr, 10) << 20;
     uint32_t col0 = doc_begin / 8;
     uint32_t n_col = cf.kind == XS_COBS_CLASSIC ? (doc_end - doc_begin + 7) / 8 : (uint32_t)cf.page_bytes;
     // HBM row stride: a row never straddles a 128-byte DRAM fetch (power of two up to 128 B, then multiples of 128 B)
@@ -1121,17 +1152,13 @@ int xs_cobs_set_policy(xs_cobs* ix, int policy) {
 int xs_cobs_set_bucketed(xs_cobs* ix, int enabled, uint64_t min_windows, uint64_t scratch_bytes, uint32_t bucket_shift) {
     if (!ix) return fail(XS_ERR_ARG, "NULL index");
     if (bucket_shift > BK_MAX_SHIFT) return fail(XS_ERR_ARG, "bucket_shift must be <= 21");
-    ix->bucketed = enabled ? 1 : 0;
-    if (min_windows) ix->bucket_min_windows = min_windows;
-    if (scratch_bytes) ix->bucket_scratch_bytes = scratch_bytes;
-    ix->bucket_budget.store(0);
-    ix->bucket_shift = bucket_shift;
+    ix->bk.configure(enabled, min_windows, scratch_bytes, bucket_shift);
     return XS_OK;
 }
 
 int xs_cobs_bucketed_queries(const xs_cobs* ix, uint64_t* n) {
     if (!ix || !n) return fail(XS_ERR_ARG, "NULL argument");
-    *n = ix->bucketed_queries.load();
+    *n = ix->bk.queries.load();
     return XS_OK;
 }
 
@@ -1141,7 +1168,7 @@ int xs_cobs_close(xs_cobs* ix) {
     if (ix->d_data) cudaFree(ix->d_data);
     if (ix->d_pages) cudaFree(ix->d_pages);
     if (ix->d_blocks) cudaFree(ix->d_blocks);
-    if (ix->bucket_done) cudaEventDestroy(ix->bucket_done);
+    ix->bk.destroy();
     delete ix;
     return XS_OK;
 }
@@ -1286,7 +1313,7 @@ int xs_bloom_open(const char* path, uint32_t term_size, int device, xs_bloom** o
     if (rc != XS_OK) { fclose(f); return rc; }
     xs_bloom* bf = new xs_bloom();
     bf->n_sm = n_sm;
-    if (const char* v = getenv("XS_BUCKETED")) bf->bucketed = v[0] != '0';
+    if (const char* v = getenv("XS_BUCKETED")) bf->bk.enabled = v[0] != '0';
     cudaError_t e = cudaMalloc((void**)&bf->d_bits, nbytes + 256);
     if (e != cudaSuccess) { fclose(f); delete bf; return fail(XS_ERR_NOMEM, std::string("bloom bit array: ") + cudaGetErrorString(e)); }
     // upload in slices through the row uploader (1 "row" = 1 MiB, remainder separately)
@@ -1314,24 +1341,20 @@ int xs_bloom_set_bucketed(xs_bloom* bf, int enabled, uint64_t min_windows, uint6
     if (bucket_shift > 31 || (bucket_shift && bucket_shift < 3)) return fail(XS_ERR_ARG, "bucket_shift must be 0 or in 3..31");
     if (member_pct > 100) return fail(XS_ERR_ARG, "member_pct must be <= 100");
     if (member_pct >= 0) bf->bucket_member_pct = (uint32_t)member_pct;
-    bf->bucketed = enabled ? 1 : 0;
-    if (min_windows) bf->bucket_min_windows = min_windows;
-    if (scratch_bytes) bf->bucket_scratch_bytes = scratch_bytes;
-    bf->bucket_budget.store(0);
-    bf->bucket_shift = bucket_shift;
+    bf->bk.configure(enabled, min_windows, scratch_bytes, bucket_shift);
     return XS_OK;
 }
 
 int xs_bloom_bucketed_queries(const xs_bloom* bf, uint64_t* n) {
     if (!bf || !n) return fail(XS_ERR_ARG, "NULL argument");
-    *n = bf->bucketed_queries.load();
+    *n = bf->bk.queries.load();
     return XS_OK;
 }
 
 int xs_bloom_close(xs_bloom* bf) {
     if (!bf) return XS_OK;
     DeviceGuard guard(bf->info.device);
-    if (bf->bucket_done) cudaEventDestroy(bf->bucket_done);
+    bf->bk.destroy();
     if (bf->d_bits) cudaFree(bf->d_bits);
     delete bf;
     return XS_OK;
