@@ -402,3 +402,31 @@ def test_native_filtered_fasta_equals_python_writer(tmp_path):
         seqio.write_fasta((r for r in get_record_iterator(src) if r.id in set(wanted)), buf)
         assert out.read_text() == buf.getvalue()
         assert [r.id for r in get_record_iterator(out)] == wanted
+
+
+def test_columnar_result_json_multi_threaded_writer(tmp_path, monkeypatch):
+    """More records than one formatting block: the writer formats blocks on several host threads and must still
+    produce the reference's bytes (and the same bytes as with one thread)."""
+    import json
+    import numpy as np
+    from xspect2_b200.engine import CobsIndex
+    from xspect2_b200.models.result import ColumnarModelResult, ModelResult
+    rng = np.random.default_rng(77)
+    n, d = 9001, 7
+    nk = rng.integers(1, 300, size=n).astype(np.int64)
+    counts = np.minimum(rng.integers(0, 400, size=(n, d)) * (rng.random((n, d)) < 0.5), nk[:, None]).astype(np.uint32)
+    ids = [f"r{i}" for i in range(n)]
+    names = [str(100 + j) for j in range(d)]
+    include = np.ones(d, bool)
+    include[2] = False
+    col = ColumnarModelResult("slug", ids, names, list(names), include, counts, nk, sparse_sampling_step=1, prediction="101", input_source="x.fq")
+    outs = []
+    for threads in ("1", "5", "32"):
+        monkeypatch.setenv("XS_RESULT_THREADS", threads)
+        out = tmp_path / f"t{threads}.json"
+        col.save(out)
+        outs.append(out.read_bytes())
+    assert outs[0] == outs[1] == outs[2]
+    hits = {rid: {names[j]: int(counts[i, j]) for j in CobsIndex.result_order(counts[i]).tolist() if include[j]} for i, rid in enumerate(ids)}
+    ref = ModelResult("slug", hits, {rid: int(v) for rid, v in zip(ids, nk)}, 1, "101", "x.fq")
+    assert outs[0].decode() == json.dumps(ref.to_dict(), indent=4)

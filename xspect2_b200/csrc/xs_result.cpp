@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -61,6 +63,76 @@ struct ScoreCache {   // per num_kmers value: the strings of all possible scores
     }
 };
 
+// one record's entry of the "hits" (mode 0) or "scores" (mode 1) section
+struct RecordFormatter {
+    const uint32_t* counts; uint32_t n_docs; const uint64_t* rec_index; uint64_t n_emit; const char* rec_keys;
+    const uint64_t* rec_key_end; const uint64_t* num_kmers; const std::vector<std::string>* dkey; const uint8_t* doc_include;
+    uint16_t* order_cache;   // [n_emit][n_docs] document order of every record, filled by mode 0 and reused by mode 1 (or null)
+
+    void rec_key(uint64_t i, const char** p, size_t* len) const {
+        uint64_t b = i ? rec_key_end[i - 1] : 0;
+        *p = rec_keys + b; *len = (size_t)(rec_key_end[i] - b);
+    }
+    static void row_order(const uint32_t* row, std::vector<uint32_t>& order) {
+        std::iota(order.begin(), order.end(), 0u);
+        std::partial_sort(order.begin(), order.end(), order.end(), [row](uint32_t a, uint32_t b) { return row[a] > row[b]; });
+    }
+    // records [i0, i1) appended to `out`; mode 0 also adds their hits / k-mers to the running totals.  The text is
+    // assembled with memcpy into a buffer grown per record to its worst case (no per-field allocation or printf).
+    void format(int mode, uint64_t i0, uint64_t i1, std::string& out, std::vector<uint64_t>& totals, uint64_t& kmers,
+                ScoreCache& cache) const {
+        std::vector<uint32_t> order(n_docs);
+        std::string scratch;
+        size_t key_bytes = 0;
+        for (uint32_t d = 0; d < n_docs; ++d) key_bytes += (*dkey)[d].size();
+        const size_t per_record = 64 + key_bytes + (size_t)n_docs * (14 + 2 + 24);   // + the record key
+        size_t used = out.size();
+        auto put = [](char*& c, const char* p, size_t len) { memcpy(c, p, len); c += len; };
+        auto put_u32 = [](char*& c, uint32_t v) {
+            char t[10];
+            int l = 0;
+            do { t[l++] = (char)('0' + v % 10); v /= 10; } while (v);
+            while (l) *c++ = t[--l];
+        };
+        for (uint64_t i = i0; i < i1; ++i) {
+            const uint32_t* row = counts + rec_index[i] * (uint64_t)n_docs;
+            if (mode == 1 && order_cache) {
+                const uint16_t* oc = order_cache + i * (uint64_t)n_docs;
+                for (uint32_t d = 0; d < n_docs; ++d) order[d] = oc[d];
+            } else {
+                row_order(row, order);
+                if (order_cache) {
+                    uint16_t* oc = order_cache + i * (uint64_t)n_docs;
+                    for (uint32_t d = 0; d < n_docs; ++d) oc[d] = (uint16_t)order[d];
+                }
+            }
+            if (mode == 0) {
+                for (uint32_t d = 0; d < n_docs; ++d) totals[d] += row[d];
+                kmers += num_kmers[i];
+            }
+            const char* kp; size_t kl;
+            rec_key(i, &kp, &kl);
+            if (out.size() < used + per_record + kl) out.resize(std::max(out.size() * 2, used + per_record + kl));
+            char* c = &out[used];
+            put(c, "        ", 8); put(c, kp, kl); put(c, ": {", 3);
+            bool any = false;
+            for (uint32_t d : order) {
+                if (!doc_include[d]) continue;
+                if (any) put(c, ",\n            ", 14); else put(c, "\n            ", 13);
+                any = true;
+                const std::string& key = (*dkey)[d];
+                put(c, key.data(), key.size()); put(c, ": ", 2);
+                if (mode == 0) put_u32(c, row[d]);
+                else { const std::string& sc = cache.get(row[d], num_kmers[i], scratch); put(c, sc.data(), sc.size()); }
+            }
+            if (any) put(c, "\n        }", 10); else put(c, "}", 1);
+            if (mode == 1 || i + 1 < n_emit) put(c, ",\n", 2);
+            used = (size_t)(c - out.data());
+        }
+        out.resize(used);
+    }
+};
+
 }  // namespace
 
 extern "C" int xs_result_write_json(const char* path, const char* prefix, const char* suffix, const uint32_t* counts,
@@ -76,48 +148,66 @@ extern "C" int xs_result_write_json(const char* path, const char* prefix, const 
     Out o(f);
     std::vector<std::string> dkey(n_docs);
     for (uint32_t d = 0; d < n_docs; ++d) dkey[d].assign(doc_keys + (d ? doc_key_end[d - 1] : 0), doc_keys + doc_key_end[d]);
-    std::vector<uint32_t> order(n_docs), first_order;
+    // the cobs result order of a record (std::partial_sort) is needed in both sections: kept between them when it fits
+    std::vector<uint16_t> order_cache;
+    if (n_docs <= 65535 && n_emit * (uint64_t)n_docs <= (512ULL << 20)) {
+        try { order_cache.resize(n_emit * (uint64_t)n_docs); } catch (...) { order_cache.clear(); }
+    }
+    const RecordFormatter fmt{counts, n_docs, rec_index, n_emit, rec_keys, rec_key_end, num_kmers, &dkey, doc_include,
+                              order_cache.empty() ? nullptr : order_cache.data()};
+    // label order of the "total" row = the first record's (result.py:86)
+    std::vector<uint32_t> first_order;
+    {
+        std::vector<uint32_t> order(n_docs);
+        RecordFormatter::row_order(counts + rec_index[0] * (uint64_t)n_docs, order);
+        for (uint32_t d : order) if (doc_include[d]) first_order.push_back(d);
+    }
     std::vector<uint64_t> totals(n_docs, 0);
     uint64_t total_kmers = 0;
-    ScoreCache cache;
-    std::string scratch;
-    auto row_order = [&](const uint32_t* row) {
-        std::iota(order.begin(), order.end(), 0u);
-        std::partial_sort(order.begin(), order.end(), order.end(), [row](uint32_t a, uint32_t b) { return row[a] > row[b]; });
-    };
-    auto rec_key = [&](uint64_t i, const char** p, size_t* len) {
-        uint64_t b = i ? rec_key_end[i - 1] : 0;
-        *p = rec_keys + b; *len = (size_t)(rec_key_end[i] - b);
-    };
-    // one pass per section; mode 0 = hits, 1 = scores
+
+    // Records are formatted in blocks by a wave of host threads (every record's text is independent of its
+    // neighbours); the blocks of a wave are written in order by a writer thread while the next wave is formatted
+    // into the second buffer set.  A read set's JSON is gigabytes: ~4 KB per record.
+    const uint64_t BLK = 2048;
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char* v = getenv("XS_RESULT_THREADS")) hw = (unsigned)std::max(1, atoi(v));
+    const unsigned T = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min<unsigned>(hw ? hw : 1, 32), (n_emit + BLK - 1) / BLK));
+    std::vector<std::string> bufs[2] = {std::vector<std::string>(T), std::vector<std::string>(T)};
+    std::vector<std::vector<uint64_t>> part_tot(T, std::vector<uint64_t>(n_docs, 0));
+    std::vector<uint64_t> part_km(T, 0);
+    std::vector<ScoreCache> caches(T);
     auto section = [&](int mode) {
-        for (uint64_t i = 0; i < n_emit; ++i) {
-            const uint32_t* row = counts + rec_index[i] * (uint64_t)n_docs;
-            row_order(row);
-            if (mode == 0) {
-                if (i == 0) { for (uint32_t d : order) if (doc_include[d]) first_order.push_back(d); }
-                for (uint32_t d = 0; d < n_docs; ++d) totals[d] += row[d];
-                total_kmers += num_kmers[i];
+        std::thread writer;
+        int set = 0;
+        for (uint64_t w0 = 0; w0 < n_emit; w0 += (uint64_t)T * BLK, set ^= 1) {
+            std::vector<std::string>& cur = bufs[set];
+            auto work = [&](unsigned t) {
+                const uint64_t i0 = std::min<uint64_t>(n_emit, w0 + (uint64_t)t * BLK), i1 = std::min<uint64_t>(n_emit, i0 + BLK);
+                cur[t].clear();
+                if (i0 < i1) fmt.format(mode, i0, i1, cur[t], part_tot[t], part_km[t], caches[t]);
+            };
+            if (T == 1) {
+                work(0);
+            } else {
+                std::vector<std::thread> th;
+                th.reserve(T - 1);
+                for (unsigned t = 1; t < T; ++t) th.emplace_back(work, t);
+                work(0);
+                for (auto& x : th) x.join();
             }
-            const char* kp; size_t kl;
-            rec_key(i, &kp, &kl);
-            o.put("        "); o.put(kp, kl); o.put(": {");
-            bool any = false;
-            for (uint32_t d : order) {
-                if (!doc_include[d]) continue;
-                o.put(any ? ",\n            " : "\n            ");
-                any = true;
-                o.put(dkey[d]); o.put(": ");
-                if (mode == 0) o.put_u64(row[d]); else o.put(cache.get(row[d], num_kmers[i], scratch));
-            }
-            o.put(any ? "\n        }" : "}");
-            if (mode == 0 && i + 1 < n_emit) o.put(",\n");
-            if (mode == 1) o.put(",\n");
+            if (writer.joinable()) writer.join();          // the previous wave is on disk; its buffer set is free again
+            if (T == 1) { o.put(cur[0]); }
+            else writer = std::thread([&o, &cur]() { for (const std::string& b : cur) o.put(b); });
         }
+        if (writer.joinable()) writer.join();
     };
     o.put(prefix);
     o.put("    \"hits\": {\n");
     section(0);
+    for (unsigned t = 0; t < T; ++t) {
+        for (uint32_t d = 0; d < n_docs; ++d) totals[d] += part_tot[t][d];
+        total_kmers += part_km[t];
+    }
     o.put("\n    },\n    \"scores\": {\n");
     section(1);
     o.put("        \"total\": {");
@@ -131,7 +221,7 @@ extern "C" int xs_result_write_json(const char* path, const char* prefix, const 
     o.put("\n    },\n    \"num_kmers\": {\n");
     for (uint64_t i = 0; i < n_emit; ++i) {
         const char* kp; size_t kl;
-        rec_key(i, &kp, &kl);
+        fmt.rec_key(i, &kp, &kl);
         o.put("        "); o.put(kp, kl); o.put(": "); o.put_u64(num_kmers[i]);
         if (i + 1 < n_emit) o.put(",\n");
     }
