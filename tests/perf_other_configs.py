@@ -123,8 +123,9 @@ def mlst(td: Path):
 
 
 def wide(td: Path):
-    D, h, k, S = 10_000, 7, 21, 4_000_000
-    row = D // 8
+    # XS_WIDE_D / XS_WIDE_S: other geometries of the wide-row kernel (e.g. D=300 -> 38-byte rows at a 64-byte stride)
+    D, h, k, S = int(os.environ.get("XS_WIDE_D", 10_000)), 7, 21, int(os.environ.get("XS_WIDE_S", 4_000_000))
+    row = (D + 7) // 8
     names = [f"d{i}" for i in range(D)]
     gen = torch.Generator(device=dev).manual_seed(6)
     p = td / "index.cobs_classic"
@@ -136,7 +137,6 @@ def wide(td: Path):
             b = torch.randint(0, 256, (n, row), generator=gen, device=dev, dtype=torch.uint8)
             f.write((a & b).cpu().numpy().tobytes())          # fill 0.25
     ix = engine.CobsIndex(p)
-    import os
     n_reads, L = int(os.environ.get('XS_PERF_READS', 1_000_000)), 150
     genome = synth.synth_genome(1_000_000, seed=7)
     reads = synth.synth_reads(genome, n_reads, L, seed=8, device=dev)
@@ -156,7 +156,7 @@ def wide(td: Path):
     lookups = n_reads * (L - k + 1)
     kernel_ms = kms / max(kn, 1)
     algo = lookups * h * row + n_reads * L * 3 // 8 + n_reads * D
-    print(json.dumps({"config": f"cfg5 geometry on one GPU: D={D} h={h} S={S} (row {row} B, stride {ix.info.row_stride} B), 1M x 150bp reads",
+    print(json.dumps({"config": f"wide rows on one GPU: D={D} h={h} S={S} (row {row} B, stride {ix.info.row_stride} B), {n_reads} x 150bp reads",
                       "ms_per_step": ms, "kernel_ms": kernel_ms, "lookups_per_sec": lookups / ms * 1e3,
                       "achieved_GBps": algo / kernel_ms / 1e6, "frac_of_hbm_peak": algo / kernel_ms / 1e6 / PEAK,
                       "parity_sample_reads": sample}), flush=True)
