@@ -57,7 +57,10 @@ def ncu_traffic(kernel: str = "k_cobs_narrow<21,7,u8>") -> tuple[float | None, f
     p = ROOT / "profiles" / "traffic.json"
     if not p.exists():
         return None, None
-    t = json.loads(p.read_text()).get(kernel)
+    doc = json.loads(p.read_text())
+    if doc.get("_source_sha256") != kernel_source_hash(doc.get("_sources", [])):
+        return None, None      # the capture is of other kernel sources than the ones running: no stale traffic
+    t = doc.get(kernel)
     if not t or (t["read_len"], t["sig_size"]) != (READ_LEN, SIG_SIZE):
         return None, None
     scale = N_READS / t["n_reads"]
@@ -65,6 +68,17 @@ def ncu_traffic(kernel: str = "k_cobs_narrow<21,7,u8>") -> tuple[float | None, f
         return None, None
     sectors = float(t.get("global_load_sectors") or 0) * scale
     return float(t["dram_bytes_read"] + t["dram_bytes_write"]) * scale, sectors or None
+
+
+def kernel_source_hash(files) -> str | None:
+    import hashlib
+    h = hashlib.sha256()
+    try:
+        for rel in files:
+            h.update((ROOT / rel).read_bytes())
+    except OSError:
+        return None
+    return h.hexdigest() if files else None
 
 
 def peaks() -> tuple[float, str]:
@@ -126,8 +140,9 @@ def build_workload(workdir: Path, device, rows_fn, seed_shift: int = 0):
     return path, reads
 
 
-def cpu_baseline(index_path: Path, h_bases: np.ndarray, n_sample: int, threads: int | None = None) -> dict:
-    """The oracle (CPU restatement of cobs Search.search behind probabilistic_filter_model.py:227) on host threads."""
+def cpu_baseline(index_path: Path, h_bases: np.ndarray, n_sample: int, threads: int | None = None) -> tuple[dict, np.ndarray]:
+    """The oracle (CPU restatement of cobs Search.search behind probabilistic_filter_model.py:227) on host threads.
+    Returns the baseline record and the oracle's [n_sample x D] counts (the parity gate compares them with the GPU's)."""
     from oracle import oracle
     orc = oracle.CobsOracle(index_path, load_complete=True)
     threads = threads or oracle.max_threads()
@@ -137,13 +152,27 @@ def cpu_baseline(index_path: Path, h_bases: np.ndarray, n_sample: int, threads: 
     sub = h_bases[: n_sample * READ_LEN]
     orc.counts_batch(sub[: 1000 * READ_LEN], b[:1000], e[:1000], 1, threads)   # warm the thread pool / pages
     t0 = time.perf_counter()
-    orc.counts_batch(sub, b, e, 1, threads)
+    counts = orc.counts_batch(sub, b, e, 1, threads)
     dt = time.perf_counter() - t0
     lookups = n_sample * (READ_LEN - K + 1)
     return {"value": lookups / dt, "unit": "lookups/s", "cores": threads, "kind": "port",
             "sample": f"first {n_sample} reads ({lookups} lookups) of the workload, {dt:.2f} s, oracle/xs_oracle.cpp "
                       f"on {threads} host threads (the reference itself is a single-threaded Python loop)",
-            "reads_per_sec": n_sample / dt, "host_cpus": os.cpu_count()}
+            "reads_per_sec": n_sample / dt, "host_cpus": os.cpu_count()}, counts
+
+
+def parity_gate(counts: np.ndarray, d_out, h_out: np.ndarray) -> dict:
+    """per-(read, document) hit counts of the timed program equal the oracle's before any
+    timing counts.  Compares the device-resident run (d_out) and the host-buffer run (h_out) with the oracle's
+    counts of the same reads; uint8 outputs saturate at 255 (a 150-bp read has 130 windows, so nothing saturates)."""
+    n = counts.shape[0]
+    exp = np.minimum(counts, 255).astype(np.uint8)
+    got_d = d_out[:n].cpu().numpy()
+    bad_d = int(np.count_nonzero((got_d != exp).any(axis=1)))
+    bad_h = int(np.count_nonzero((h_out[:n] != exp).any(axis=1)))
+    return {"reads": int(n), "documents": int(counts.shape[1]), "mismatches": bad_d + bad_h,
+            "mismatching_reads_device_run": bad_d, "mismatching_reads_host_run": bad_h,
+            "oracle_hits": int(counts.sum()), "against": "oracle/xs_oracle.cpp (CPU restatement of cobs Search.search)"}
 
 
 def run_reference(args, rank: int, world: int) -> None:
@@ -365,13 +394,16 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             "roofline": roof,
             "checksum_first_100k_reads": checksum,
         }
+        # parity gate (and, at N=1, the CPU baseline): rank 0's GPU counts against the oracle on the same reads
+        n_cpu = int(os.environ.get("XS_BENCH_CPU_SAMPLE", 1_000_000)) if world == 1 else \
+            int(os.environ.get("XS_BENCH_PARITY_SAMPLE", 100_000))
+        base, counts = cpu_baseline(path, h_bases, n_cpu)
         if world == 1:
-            try:
-                line["cpu_baseline"] = cpu_baseline(path, h_bases, int(os.environ.get("XS_BENCH_CPU_SAMPLE", 1_000_000)))
-            except Exception as exc:  # the baseline must not lose the GPU numbers
-                line["cpu_baseline"] = {"value": None, "unit": "lookups/s", "cores": 0, "kind": "port",
-                                        "sample": f"failed: {exc}"}
+            line["cpu_baseline"] = base
+        line["parity"] = parity_gate(counts, d_out, h_out)
         print(json.dumps(line), flush=True)
+        if line["parity"]["mismatches"]:
+            raise SystemExit(f"parity gate failed: {line['parity']}")
     finally:
         shutil.rmtree(workdir, ignore_errors=True)
 

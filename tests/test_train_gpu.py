@@ -166,9 +166,10 @@ def test_mlst_fit_builds_compact_indices(gpu, oracle, tmp_path):
     assert res.hits["a4"][1]["All results"]["Oxf_cpn60"]["Allele_ID_4"] == a4.size - 21 + 1
 
 
-def test_train_from_directory_and_cli(gpu, oracle, tmp_path, monkeypatch):
-    """train.train_from_directory (train.py:28-184 of the reference) on local data, then the trained models through
-    the CLI: `models train directory`, `models list`, `classify species`, `classify genus`."""
+def test_fit_models_then_cli(gpu, oracle, tmp_path, monkeypatch):
+    """The model classes' `fit` (GPU index / filter construction) on local data, saved where the CLI looks for
+    models, then the trained models through the CLI: `models list`, `classify species`, `classify genus`.  (The
+    training workflows of train.py are out of scope; `fit` is the 8(f)-4 row.)"""
     import importlib
     import json
     from click.testing import CliRunner
@@ -191,8 +192,22 @@ def test_train_from_directory_and_cli(gpu, oracle, tmp_path, monkeypatch):
     import xspect2_b200.main as main
     main = importlib.reload(main)
     runner = CliRunner()
-    r = runner.invoke(main.cli, ["models", "train", "directory", "-g", "Trained", "-i", str(data), "--svm-steps", "2"])
-    assert r.exit_code == 0, r.output
+    from xspect2_b200.definitions import get_xspect_model_path
+    from xspect2_b200.file_io import concatenate_metagenome, concatenate_species_fasta_files
+    from xspect2_b200.models.probabilistic_filter_svm_model import ProbabilisticFilterSVMModel
+    from xspect2_b200.models.probabilistic_single_filter_model import ProbabilisticSingleFilterModel
+    species_dir = tmp_path / "species"
+    species_dir.mkdir()
+    concatenate_species_fasta_files(sorted((data / "cobs").iterdir()), species_dir)
+    sp_model = ProbabilisticFilterSVMModel(k=21, model_display_name="Trained", author=None, author_email=None,
+                                           model_type="Species", base_path=get_xspect_model_path(), kernel="rbf", c=1.0)
+    sp_model.fit(species_dir, data / "svm", svm_step=2)
+    sp_model.save()
+    concatenate_metagenome(species_dir, tmp_path / "Trained.fasta")
+    ge_model = ProbabilisticSingleFilterModel(k=21, model_display_name="Trained", author=None, author_email=None,
+                                              model_type="Genus", base_path=get_xspect_model_path())
+    ge_model.fit(tmp_path / "Trained.fasta", "Trained")
+    ge_model.save()
     models = tmp_path / "home" / "xspect-data" / "models"
     assert (models / "trained-species.json").is_file() and (models / "trained-species" / "index.cobs_classic").is_file()
     assert (models / "trained-species" / "scores.csv").is_file() and (models / "trained-genus" / "filter.bloom").is_file()

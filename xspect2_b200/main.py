@@ -1,7 +1,7 @@
 """Command line interface: the reference's command tree for the prediction path
 (main.py:17-795): ``all``, ``models list``, ``classify {genus,species,mlst}``, ``filter {genus,species}`` with the
-same options, plus ``models train directory`` (local data, no network).  NCBI / PubMLST driven training, model download
-and the web UI are not offered."""
+same options.  The training workflows, model download and the web UI are not offered (the model classes' ``fit``
+methods build indices on the GPU)."""
 
 from pathlib import Path
 from uuid import uuid4
@@ -110,25 +110,6 @@ def list_models():
         click.echo(f"  {model_type}:")
         for name in names:
             click.echo(f"    - {name}")
-
-
-@models.group()
-def train():
-    """Train models."""
-
-
-@train.command(name="directory", help="Train a species (and possibly a genus) model based on local data.")
-@click.option("-g", "--genus", "model_genus", prompt=True)
-@click.option("-i", "--input-path", type=click.Path(exists=True, dir_okay=True, file_okay=True), prompt=True)
-@click.option("--meta", is_flag=True, help="Train a metagenome model for the genus.", default=True)
-@click.option("--svm-steps", type=int, default=1, help="SVM Sparse sampling step size (e. g. only every 500th kmer for step=500).")
-@click.option("--author", help="Author of the model.", default=None)
-@click.option("--author-email", help="Email of the author.", default=None)
-def train_directory(model_genus, input_path, svm_steps, meta, author, author_email):
-    click.echo(f"Training {model_genus} model with {svm_steps} SVM steps.")
-    from .train import train_from_directory
-
-    train_from_directory(model_genus, Path(input_path), svm_step=svm_steps, meta=meta, author=author, author_email=author_email)
 
 
 @cli.group(name="classify", help="Classify sequences using XspecT models.")
