@@ -111,6 +111,25 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
 int xs_cobs_info(const xs_cobs* ix, xs_cobs_info_t* info);
 /* document names of the whole file, '\n'-separated, no trailing NUL counted in *needed */
 int xs_cobs_doc_names(const xs_cobs* ix, char* buf, uint64_t cap, uint64_t* needed);
+/* Which reading of the file header matched.  The header layout of cobs-reloaded is restated from its published
+ * source (not checkable offline); xs_cobs_open tries the documented field order first and a few neighbouring orders /
+ * widths after it, and accepts one only when the end magic and the size identity
+ * (file_size - data_offset == sum signature_size x row bytes) hold.  Compact files: the zero padding before the
+ * end magic may be 0 or one whole page when the data is already aligned.  Never NULL. */
+const char* xs_cobs_header_layout(const xs_cobs* ix);
+/* The same header parse without a device (no CUDA call): what a file would load as. */
+typedef struct {
+    uint32_t kind, term_size, canonicalize, num_hashes, n_docs, n_pages;
+    uint64_t page_bytes, sig_size_max, data_offset, file_size;
+    char layout[64];
+} xs_cobs_header_t;
+int xs_cobs_probe_header(const char* path, xs_cobs_header_t* out);
+/* Structural self-check of a loaded index: per local document, the fraction of set bits over `sample_rows` evenly
+ * spaced rows of its page (0 = 65536).  An index built at its design load has max fill ~ fpr^(1/h) (0.518 for
+ * h = 7, fpr = 0.01; cobs calc_signature_size), and a k-mer absent from a document scores fill^h there: a known
+ * member sequence that scores near fill^h instead of near 1 means the hash / bit layout does not match the file
+ * (engine.CobsIndex.selfcheck).  fill: [doc_end - doc_begin] doubles, host memory. */
+int xs_cobs_doc_fill(const xs_cobs* ix, uint64_t sample_rows, double* fill);
 int xs_cobs_set_policy(xs_cobs* ix, int policy);
 /* Large batches against a large narrow-row classic index (16-byte rows, 256 MB .. 8.6 GB in HBM) are scored by the
  * bucketed kernels: probe records grouped by L2-sized row ranges, rows fetched from L2, ANDed per window in shared

@@ -188,8 +188,12 @@ def parse_cobs(path: str | os.PathLike) -> dict:
             raise ValueError("compact pages with differing num_hashes are not supported")
         names, pos = _read_names(buf, pos, n_docs)
         pad = (page_size - ((pos + 13) % page_size)) % page_size
-        pos += pad
-        if bytes(buf[pos:pos + 13]) != b"COMPACT_INDEX":
+        # remainder 0: cobs may write no padding or one whole page (not checkable offline); accept either
+        for cand in ([pad] if pad else [0, page_size]):
+            if bytes(buf[pos + cand:pos + cand + 13]) == b"COMPACT_INDEX":
+                pos += cand
+                break
+        else:
             raise ValueError("compact header end magic missing")
         pos += 13
         offs, o = [], 0
@@ -229,7 +233,7 @@ def classic_header(k: int, canonicalize: int, names: list[str], sig: int, num_ha
 
 
 def compact_header(k: int, canonicalize: int, names: list[str], page_size: int,
-                   sigs: list[int], num_hashes: int) -> bytes:
+                   sigs: list[int], num_hashes: int, pad_full_page: bool = False) -> bytes:
     h = b"COBS:" + b"COMPACT_INDEX" + struct.pack("<II", 1, k) + struct.pack("<B", canonicalize)
     h += struct.pack("<II", len(sigs), len(names)) + struct.pack("<Q", page_size)
     for s in sigs:
@@ -237,6 +241,8 @@ def compact_header(k: int, canonicalize: int, names: list[str], page_size: int,
     for n in names:
         h += n.encode("utf-8") + b"\n"
     pad = (page_size - ((len(h) + 13) % page_size)) % page_size
+    if pad == 0 and pad_full_page:      # the other reading of cobs' padding rule (range 1..page_size)
+        pad = page_size
     return h + b"\0" * pad + b"COMPACT_INDEX"
 
 

@@ -90,8 +90,11 @@ def test_species_predict_display_names_and_errors(world, oracle, tmp_path):
         model.calculate_hits("ACGT" * 30)
     with pytest.raises(ValueError):
         model.predict(tmp_path / "missing.fna")
-    with pytest.warns(UserWarning):
+    with pytest.raises(NotImplementedError):                                  # never a silently unfiltered result
         model.predict(rec, validation=True)
+    # 'misclassified' is a reserved record id of ModelResult (result.py:29)
+    res_m = model.predict([SeqRecord(rec.seq, "misclassified"), rec])
+    assert "misclassified" not in res_m.hits and res_m.misclassified == res_m.hits[rec.id]
     # whole training genome scores 1.0 on its own species (G3 shape)
     tid = next(iter(world["genomes"]))
     total = model.predict(SeqRecord(Seq(g.tobytes().decode()), "g")).get_scores()["total"]

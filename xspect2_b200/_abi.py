@@ -36,6 +36,15 @@ class BloomInfo(C.Structure):
     ]
 
 
+class CobsHeader(C.Structure):
+    _fields_ = [
+        ("kind", C.c_uint32), ("term_size", C.c_uint32), ("canonicalize", C.c_uint32), ("num_hashes", C.c_uint32),
+        ("n_docs", C.c_uint32), ("n_pages", C.c_uint32),
+        ("page_bytes", C.c_uint64), ("sig_size_max", C.c_uint64), ("data_offset", C.c_uint64), ("file_size", C.c_uint64),
+        ("layout", C.c_char * 64),
+    ]
+
+
 # every symbol include/xspect_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -51,6 +60,9 @@ SYMBOLS = {
     "xs_cobs_open": (C.c_int, [C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "xs_cobs_info": (C.c_int, [_P, C.POINTER(CobsInfo)]),
     "xs_cobs_doc_names": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "xs_cobs_header_layout": (C.c_char_p, [_P]),
+    "xs_cobs_probe_header": (C.c_int, [C.c_char_p, C.POINTER(CobsHeader)]),
+    "xs_cobs_doc_fill": (C.c_int, [_P, C.c_uint64, _P]),
     "xs_cobs_set_policy": (C.c_int, [_P, C.c_int]),
     "xs_cobs_set_bucketed": (C.c_int, [_P, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32]),
     "xs_cobs_bucketed_queries": (C.c_int, [_P, C.POINTER(C.c_uint64)]),

@@ -1534,4 +1534,23 @@ __global__ void k_restride(const uint8_t* __restrict__ src, uint64_t n_rows, uin
     }
 }
 
+// per-document fill of a page estimated from `n_sample` evenly spaced rows (xs_cobs_doc_fill): thread per
+// (sampled row, 32-document word), one atomic per set bit
+__global__ void __launch_bounds__(256) k_doc_fill(const PageDesc pg, uint64_t n_sample, uint32_t* __restrict__ counts) {
+    const uint32_t words = (pg.n_docs + 31) / 32;
+    const uint64_t total = n_sample * words;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / words;
+        const uint32_t w = (uint32_t)(i - r * words);
+        const uint64_t row = (unsigned __int128)r * pg.sig_size / n_sample;
+        uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(pg.data + row * pg.row_stride) + w);
+        while (v) {
+            const uint32_t b = __ffs(v) - 1;
+            v &= v - 1;
+            const uint32_t d = w * 32 + b;
+            if (d < pg.n_docs) atomicAdd(counts + pg.doc_off + d, 1u);
+        }
+    }
+}
+
 }  // namespace xs

@@ -112,6 +112,7 @@ struct xs_cobs {
     std::vector<PageDesc> pages;
     std::vector<ColBlock> blocks;
     std::string names;  // '\n' separated
+    std::string layout; // which candidate reading of the header matched (parse_cobs_header)
     uint8_t* d_data = nullptr;
     PageDesc* d_pages = nullptr;
     ColBlock* d_blocks = nullptr;
@@ -141,6 +142,8 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+static std::atomic<int> g_home_device{-1};
+
 static int device_setup(int device, int* n_sm) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -149,6 +152,7 @@ static int device_setup(int device, int* n_sm) {
                                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
     if (device < 0 || device >= n) return fail(XS_ERR_ARG, "device index out of range");
     XS_CUDA(cudaSetDevice(device));
+    { int none = -1; g_home_device.compare_exchange_strong(none, device); }
     XS_CUDA(cudaDeviceGetAttribute(n_sm, cudaDevAttrMultiProcessorCount, device));
     // random 16-byte row gathers: fetch single 32-byte sectors from HBM, not 64/128-byte groups
     cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
@@ -176,64 +180,125 @@ struct CobsFile {
 template <typename T>
 static bool rd(FILE* f, T* v) { return fread(v, sizeof(T), 1, f) == 1; }
 
-static int parse_cobs_header(FILE* f, const char* path, CobsFile& cf) {
-    char magic[18];
-    if (fread(magic, 1, 18, f) != 18 || memcmp(magic, "COBS:", 5) != 0)
-        return fail(XS_ERR_FORMAT, std::string(path) + ": not a COBS index (missing 'COBS:')");
-    bool classic = memcmp(magic + 5, "CLASSIC_INDEX", 13) == 0;
-    bool compact = memcmp(magic + 5, "COMPACT_INDEX", 13) == 0;
-    if (!classic && !compact) return fail(XS_ERR_FORMAT, std::string(path) + ": unknown COBS magic word");
-    uint32_t version = 0; uint8_t canon = 0;
-    if (!rd(f, &version) || !rd(f, &cf.k) || !rd(f, &canon)) return fail(XS_ERR_FORMAT, "truncated COBS header");
-    cf.canonicalize = canon;
+// One candidate reading of the header fields that follow "COBS:<MAGIC>".  The layout of cobs-reloaded's headers is
+// restated from its published source ([UNVERIFIED-3P]); the documented field order is
+// tried first and a few neighbouring orders / widths after it (Appendix A.1.3).  A candidate is accepted only when
+// every structural check holds: version 1, plausible field values, the end magic right after the document list (and
+// the compact padding), and the size identity  file_size - data_offset == sum(signature_size x row bytes).
+struct HeaderLayout {
+    const char* name;
+    bool canon_u32;      // canonicalize stored as uint32 instead of uint8
+    bool hashes_first;   // classic: num_hashes before signature_size; compact: per page {num_hashes, signature_size}
+    bool hashes_u32;     // classic: num_hashes stored as uint32
+    bool docs_first;     // compact: num_documents before num_pages
+};
+static const HeaderLayout kHeaderLayouts[] = {
+    {"cobs v1 (documented)", false, false, false, false},
+    {"num_hashes before signature_size", false, true, false, false},
+    {"32-bit num_hashes", false, false, true, false},
+    {"32-bit canonicalize", true, false, false, false},
+    {"documents before pages", false, false, false, true},
+};
+
+static int parse_cobs_header_as(FILE* f, const char* path, const HeaderLayout& L, bool classic, CobsFile& cf) {
+    cf = CobsFile();
+    if (fseek(f, 18, SEEK_SET) != 0) return fail(XS_ERR_IO, "seek failed");
+    uint32_t version = 0;
+    if (!rd(f, &version) || !rd(f, &cf.k)) return fail(XS_ERR_FORMAT, "truncated COBS header");
+    if (L.canon_u32) { uint32_t c = 0; if (!rd(f, &c)) return fail(XS_ERR_FORMAT, "truncated COBS header"); cf.canonicalize = c; }
+    else { uint8_t c = 0; if (!rd(f, &c)) return fail(XS_ERR_FORMAT, "truncated COBS header"); cf.canonicalize = c; }
     if (version != 1) return fail(XS_ERR_FORMAT, "unsupported COBS index version " + std::to_string(version));
+    if (cf.canonicalize > 1) return fail(XS_ERR_FORMAT, "canonicalize flag is not 0/1");
     uint64_t nh = 0;
     if (classic) {
         uint64_t sig = 0;
-        if (!rd(f, &cf.n_docs) || !rd(f, &sig) || !rd(f, &nh)) return fail(XS_ERR_FORMAT, "truncated COBS header");
+        uint32_t nh32 = 0;
+        if (!rd(f, &cf.n_docs)) return fail(XS_ERR_FORMAT, "truncated COBS header");
+        bool ok = L.hashes_first ? (rd(f, &nh) && rd(f, &sig))
+                                 : (rd(f, &sig) && (L.hashes_u32 ? rd(f, &nh32) : rd(f, &nh)));
+        if (!ok) return fail(XS_ERR_FORMAT, "truncated COBS header");
+        if (L.hashes_u32) nh = nh32;
         cf.kind = XS_COBS_CLASSIC; cf.n_pages = 1; cf.sig.push_back(sig);
         cf.page_bytes = ((uint64_t)cf.n_docs + 7) / 8;
     } else {
-        if (!rd(f, &cf.n_pages) || !rd(f, &cf.n_docs) || !rd(f, &cf.page_bytes))
-            return fail(XS_ERR_FORMAT, "truncated COBS header");
+        bool ok = L.docs_first ? (rd(f, &cf.n_docs) && rd(f, &cf.n_pages)) : (rd(f, &cf.n_pages) && rd(f, &cf.n_docs));
+        if (!ok || !rd(f, &cf.page_bytes)) return fail(XS_ERR_FORMAT, "truncated COBS header");
         cf.kind = XS_COBS_COMPACT;
         if (cf.n_pages == 0 || cf.n_pages > (1u << 24)) return fail(XS_ERR_FORMAT, "implausible compact page count");
+        if (cf.page_bytes == 0 || cf.page_bytes > (1u << 20)) return fail(XS_ERR_FORMAT, "implausible compact page size");
         for (uint32_t i = 0; i < cf.n_pages; ++i) {
             uint64_t s = 0, h = 0;
-            if (!rd(f, &s) || !rd(f, &h)) return fail(XS_ERR_FORMAT, "truncated COBS header");
+            if (!(L.hashes_first ? (rd(f, &h) && rd(f, &s)) : (rd(f, &s) && rd(f, &h)))) return fail(XS_ERR_FORMAT, "truncated COBS header");
             if (i == 0) nh = h;
             else if (h != nh) return fail(XS_ERR_UNSUPPORTED, "compact pages with differing num_hashes");
             cf.sig.push_back(s);
         }
     }
     cf.num_hashes = nh;
-    for (uint32_t i = 0; i < cf.n_docs; ++i) {
-        int c;
-        while ((c = fgetc(f)) != EOF && c != '\n') cf.names.push_back((char)c);
-        if (c == EOF) return fail(XS_ERR_FORMAT, "truncated COBS document list");
-        cf.names.push_back('\n');
-    }
-    long pos = ftell(f);
-    if (compact && cf.page_bytes) {
-        uint64_t pad = (cf.page_bytes - (((uint64_t)pos + 13) % cf.page_bytes)) % cf.page_bytes;
-        if (fseek(f, (long)pad, SEEK_CUR) != 0) return fail(XS_ERR_FORMAT, "truncated COBS header");
-    }
-    char endm[13];
-    if (fread(endm, 1, 13, f) != 13 || memcmp(endm, classic ? "CLASSIC_INDEX" : "COMPACT_INDEX", 13) != 0)
-        return fail(XS_ERR_FORMAT, std::string(path) + ": header end magic missing");
-    cf.data_off = (uint64_t)ftell(f);
-    if (fseek(f, 0, SEEK_END) != 0) return fail(XS_ERR_IO, "seek failed");
-    cf.file_size = (uint64_t)ftell(f);
-    unsigned __int128 need = 0;
-    for (uint64_t s : cf.sig) need += (unsigned __int128)s * cf.page_bytes;
-    if (need != (unsigned __int128)(cf.file_size - cf.data_off))
-        return fail(XS_ERR_FORMAT, std::string(path) + ": size identity violated (data bytes != sum signature_size x row bytes)");
     if (cf.k == 0) return fail(XS_ERR_FORMAT, "term_size 0");
     if (cf.k > 32) return fail(XS_ERR_UNSUPPORTED, "term_size > 32 is not supported");
     if (cf.num_hashes == 0 || cf.num_hashes > 64) return fail(XS_ERR_UNSUPPORTED, "num_hashes must be in 1..64");
-    for (uint64_t s : cf.sig)
-        if (s == 0 || s > (1ULL << 62)) return fail(XS_ERR_FORMAT, "implausible signature_size");
-    return XS_OK;
+    if (cf.n_docs == 0 || cf.n_docs > (1u << 28)) return fail(XS_ERR_FORMAT, "implausible document count");
+    for (uint64_t sg : cf.sig)
+        if (sg == 0 || sg > (1ULL << 62)) return fail(XS_ERR_FORMAT, "implausible signature_size");
+    for (uint32_t i = 0; i < cf.n_docs; ++i) {
+        int c;
+        size_t len = 0;
+        while ((c = fgetc(f)) != EOF && c != '\n') { cf.names.push_back((char)c); if (++len > 4096) return fail(XS_ERR_FORMAT, "document name too long"); }
+        if (c == EOF) return fail(XS_ERR_FORMAT, "truncated COBS document list");
+        cf.names.push_back('\n');
+    }
+    const long pos = ftell(f);
+    if (fseek(f, 0, SEEK_END) != 0) return fail(XS_ERR_IO, "seek failed");
+    cf.file_size = (uint64_t)ftell(f);
+    unsigned __int128 need = 0;
+    for (uint64_t sg : cf.sig) need += (unsigned __int128)sg * cf.page_bytes;
+    // compact: zero padding so that the data starts on a multiple of page_size.  cobs computes it as
+    // page_size - ((pos + 13) % page_size); whether a remainder of 0 pads nothing or a whole page is not checkable
+    // offline, so both are accepted — the end magic and the size identity decide.
+    uint64_t pads[2] = {0, 0};
+    int n_pads = 1;
+    if (!classic) {
+        const uint64_t r = (cf.page_bytes - (((uint64_t)pos + 13) % cf.page_bytes)) % cf.page_bytes;
+        pads[0] = r;
+        if (r == 0) { pads[1] = cf.page_bytes; n_pads = 2; }
+    }
+    for (int i = 0; i < n_pads; ++i) {
+        char endm[13];
+        if (fseek(f, pos + (long)pads[i], SEEK_SET) != 0 || fread(endm, 1, 13, f) != 13) continue;
+        if (memcmp(endm, classic ? "CLASSIC_INDEX" : "COMPACT_INDEX", 13) != 0) continue;
+        const uint64_t off = (uint64_t)pos + pads[i] + 13;
+        if (need != (unsigned __int128)(cf.file_size - off)) {
+            fail(XS_ERR_FORMAT, std::string(path) + ": size identity violated (data bytes != sum signature_size x row bytes)");
+            continue;
+        }
+        cf.data_off = off;
+        return XS_OK;
+    }
+    if (g_err.find("size identity") != std::string::npos) return XS_ERR_FORMAT;
+    return fail(XS_ERR_FORMAT, std::string(path) + ": header end magic missing");
+}
+
+static int parse_cobs_header(FILE* f, const char* path, CobsFile& cf, const char** layout_name = nullptr) {
+    char magic[18];
+    if (fseek(f, 0, SEEK_SET) != 0 || fread(magic, 1, 18, f) != 18 || memcmp(magic, "COBS:", 5) != 0)
+        return fail(XS_ERR_FORMAT, std::string(path) + ": not a COBS index (missing 'COBS:')");
+    const bool classic = memcmp(magic + 5, "CLASSIC_INDEX", 13) == 0;
+    const bool compact = memcmp(magic + 5, "COMPACT_INDEX", 13) == 0;
+    if (!classic && !compact) return fail(XS_ERR_FORMAT, std::string(path) + ": unknown COBS magic word");
+    int first_rc = XS_OK;
+    std::string first_err;
+    for (const HeaderLayout& L : kHeaderLayouts) {
+        if (classic && L.docs_first) continue;
+        if (compact && L.hashes_u32) continue;
+        const int rc = parse_cobs_header_as(f, path, L, classic, cf);
+        if (rc == XS_OK) {
+            if (layout_name) *layout_name = L.name;
+            return XS_OK;
+        }
+        if (first_rc == XS_OK) { first_rc = rc; first_err = g_err; }   // report what the documented layout said
+    }
+    return fail(first_rc, first_err);
 }
 
 // stream rows [n_rows x src_row] of the file into dst rows [dst_stride], keeping bytes [col0, col0+n_col)
@@ -1012,9 +1077,21 @@ int xs_device_count(int* n) {
     return XS_OK;
 }
 
+// device whose context page-locked host memory is allocated under: the first device a handle was opened on, else
+// XSPECT_B200_DEVICE / LOCAL_RANK, else 0 — so that a rank of a multi-GPU job never creates a context on GPU 0 just
+// to pin memory.  The allocation is portable (usable from every context).
+static int home_device() {
+    int d = g_home_device.load(std::memory_order_relaxed);
+    if (d >= 0) return d;
+    const char* v = getenv("XSPECT_B200_DEVICE");
+    if (!v || !*v) v = getenv("LOCAL_RANK");
+    return (v && *v) ? atoi(v) : 0;
+}
+
 int xs_host_alloc(uint64_t bytes, void** out) {
     if (!out) return fail(XS_ERR_ARG, "out is NULL");
-    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    DeviceGuard guard(home_device());
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA, cudaGetErrorString(e));
     return XS_OK;
 }
@@ -1029,7 +1106,8 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
     FILE* f = fopen(path, "rb");
     if (!f) return fail(XS_ERR_IO, std::string(path) + ": " + strerror(errno));
     CobsFile cf;
-    int rc = parse_cobs_header(f, path, cf);
+    const char* layout = "";
+    int rc = parse_cobs_header(f, path, cf, &layout);
     if (rc != XS_OK) { fclose(f); return rc; }
     if (doc_begin == 0 && doc_end == 0) doc_end = cf.n_docs;
     if (doc_end > cf.n_docs || doc_begin >= doc_end || (doc_begin % 8) != 0 || (doc_end % 8 != 0 && doc_end != cf.n_docs)) {
@@ -1049,6 +1127,7 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
     ix->info.device = device;
     ix->n_sm = n_sm;
     ix->names = cf.names;
+    ix->layout = layout;
     const char* fw = getenv("XS_FORCE_WIDE");
     ix->force_wide = (fw && fw[0] == '1') ? 1 : 0;
     if (const char* v = getenv("XS_BUCKETED")) ix->bk.enabled = v[0] != '0';
@@ -1132,6 +1211,51 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
 int xs_cobs_info(const xs_cobs* ix, xs_cobs_info_t* info) {
     if (!ix || !info) return fail(XS_ERR_ARG, "NULL argument");
     *info = ix->info;
+    return XS_OK;
+}
+
+const char* xs_cobs_header_layout(const xs_cobs* ix) { return ix ? ix->layout.c_str() : ""; }
+
+int xs_cobs_probe_header(const char* path, xs_cobs_header_t* out) {
+    if (!path || !out) return fail(XS_ERR_ARG, "path/out is NULL");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(XS_ERR_IO, std::string(path) + ": " + strerror(errno));
+    CobsFile cf;
+    const char* layout = "";
+    const int rc = parse_cobs_header(f, path, cf, &layout);
+    fclose(f);
+    if (rc != XS_OK) return rc;
+    memset(out, 0, sizeof(*out));
+    out->kind = (uint32_t)cf.kind; out->term_size = cf.k; out->canonicalize = cf.canonicalize;
+    out->num_hashes = (uint32_t)cf.num_hashes; out->n_docs = cf.n_docs; out->n_pages = cf.n_pages;
+    out->page_bytes = cf.page_bytes; out->sig_size_max = *std::max_element(cf.sig.begin(), cf.sig.end());
+    out->data_offset = cf.data_off; out->file_size = cf.file_size;
+    strncpy(out->layout, layout, sizeof(out->layout) - 1);
+    return XS_OK;
+}
+
+int xs_cobs_doc_fill(const xs_cobs* ix, uint64_t sample_rows, double* fill) {
+    if (!ix || !fill) return fail(XS_ERR_ARG, "NULL argument");
+    if (sample_rows == 0) sample_rows = 1 << 16;
+    DeviceGuard guard(ix->info.device);
+    const uint32_t n_local = ix->info.doc_end - ix->info.doc_begin;
+    uint32_t* d_cnt = nullptr;
+    XS_CUDA(cudaMalloc((void**)&d_cnt, (size_t)n_local * 4));
+    cudaError_t e = cudaMemset(d_cnt, 0, (size_t)n_local * 4);
+    std::vector<uint64_t> n_of(n_local, 1);
+    for (const PageDesc& pg : ix->pages) {
+        if (e != cudaSuccess || pg.n_docs == 0) continue;
+        const uint64_t n = std::min<uint64_t>(sample_rows, pg.sig_size);
+        k_doc_fill<<<ix->n_sm * 4, 256>>>(pg, n, d_cnt);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+        for (uint32_t d = 0; d < pg.n_docs; ++d) n_of[pg.doc_off + d] = n;
+    }
+    std::vector<uint32_t> h(n_local);
+    if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_cnt, (size_t)n_local * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_cnt);
+    if (e != cudaSuccess) return fail(XS_ERR_CUDA, std::string("xs_cobs_doc_fill: ") + cudaGetErrorString(e));
+    for (uint32_t d = 0; d < n_local; ++d) fill[d] = (double)h[d] / (double)n_of[d];
     return XS_OK;
 }
 
@@ -1228,7 +1352,15 @@ int xs_cobs_classify(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const 
     // and the per-document totals come back
     uint64_t* d_tot = nullptr;
     XS_CUDA(cudaMalloc((void**)&d_tot, ld * 8));
-    XS_CUDA(cudaMemset(d_tot, 0, ld * 8));
+    {   // the pipeline's streams are non-blocking (they do not order against the legacy stream): make the zeroing
+        // visible to all of them before any is created
+        cudaError_t e = cudaMemset(d_tot, 0, ld * 8);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            cudaFree(d_tot);
+            return fail(XS_ERR_CUDA, std::string("totals clear: ") + cudaGetErrorString(e));
+        }
+    }
     const uint64_t row = ld * 4 + 12;
     int rc = host_pipeline(bases, n_bases, seq_begin, seq_end, n_seq, row,
                            [&](const uint8_t* db, uint64_t span, const uint64_t* d_b, const uint64_t* d_e, uint64_t ns,
@@ -1492,7 +1624,14 @@ int xs_cobs_build(const char* out_path, int device, int kind, uint32_t k, uint32
         for (uint64_t pg = 0; pg < n_pages; ++pg) { uint64_t nh = num_hashes; pod(&sig[pg], 8); pod(&nh, 8); }
     }
     for (uint32_t r = 0; r < n_docs; ++r) { head += name[order[r]]; head += '\n'; }
-    if (kind == XS_COBS_COMPACT) head.append((row_bytes - ((head.size() + 13) % row_bytes)) % row_bytes, '\0');
+    if (kind == XS_COBS_COMPACT) {
+        // cobs pads so that the data starts on a multiple of page_size; when it already does, the two readings of its
+        // rule differ (0 bytes, or one whole page with XS_COMPACT_PAD_FULL=1).  Both readers here accept both.
+        uint64_t pad = (row_bytes - ((head.size() + 13) % row_bytes)) % row_bytes;
+        const char* full = getenv("XS_COMPACT_PAD_FULL");
+        if (pad == 0 && full && full[0] == '1') pad = row_bytes;
+        head.append(pad, '\0');
+    }
     head += kind == XS_COBS_CLASSIC ? "CLASSIC_INDEX" : "COMPACT_INDEX";
 
     DeviceGuard guard(device);

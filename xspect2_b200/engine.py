@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from pathlib import Path
 
 import numpy as np
@@ -25,7 +26,21 @@ _DT = {XS_U8: np.uint8, XS_U16: np.uint16, XS_U32: np.uint32}
 # --------------------------------------------------------------------------------------
 _POOL: dict[int, list[int]] = {}      # capacity -> free page-locked pointers (cudaMallocHost costs ~0.5 ms per MB)
 _POOL_BYTES = [0]
-_POOL_LIMIT = 8 << 30
+_POOL_LIMIT = int(os.environ.get("XSPECT_B200_PINNED_POOL_MB", 4096)) << 20
+_POOL_LOCK = threading.Lock()
+
+
+def trim_pinned_pool(keep_bytes: int = 0) -> int:
+    """Release cached page-locked blocks until at most ``keep_bytes`` stay in the pool; returns the bytes freed."""
+    freed = 0
+    with _POOL_LOCK:
+        for cap in sorted(_POOL, reverse=True):
+            free = _POOL[cap]
+            while free and _POOL_BYTES[0] > keep_bytes:
+                lib().xs_host_free(free.pop())
+                _POOL_BYTES[0] -= cap
+                freed += cap
+    return freed
 
 
 def _capacity(nbytes: int) -> int:
@@ -42,11 +57,13 @@ class _PinnedBlock:
 
     def __init__(self, nbytes: int):
         self.cap = _capacity(nbytes)
-        free = _POOL.get(self.cap)
-        if free:
-            self.ptr = free.pop()
-            _POOL_BYTES[0] -= self.cap
-        else:
+        self.ptr = None
+        with _POOL_LOCK:
+            free = _POOL.get(self.cap)
+            if free:
+                self.ptr = free.pop()
+                _POOL_BYTES[0] -= self.cap
+        if self.ptr is None:
             p = C.c_void_p()
             check(lib().xs_host_alloc(self.cap, C.byref(p)))
             self.ptr = p.value
@@ -57,10 +74,12 @@ class _PinnedBlock:
         ptr, self.ptr = getattr(self, "ptr", None), None
         if ptr:
             try:
-                if _POOL_BYTES[0] + self.cap <= _POOL_LIMIT:
-                    _POOL.setdefault(self.cap, []).append(ptr)
-                    _POOL_BYTES[0] += self.cap
-                else:
+                with _POOL_LOCK:
+                    keep = _POOL_BYTES[0] + self.cap <= _POOL_LIMIT
+                    if keep:
+                        _POOL.setdefault(self.cap, []).append(ptr)
+                        _POOL_BYTES[0] += self.cap
+                if not keep:
                     lib().xs_host_free(ptr)
             except Exception:  # interpreter shutdown
                 pass
@@ -131,6 +150,40 @@ class CobsIndex:
     num_hashes = property(lambda self: self.info.num_hashes)
     n_docs = property(lambda self: self.info.doc_end - self.info.doc_begin)
     device = property(lambda self: self.info.device)
+
+    @property
+    def header_layout(self) -> str:
+        """Which candidate reading of the file header matched (``xs_cobs_header_layout``)."""
+        return lib().xs_cobs_header_layout(self._h).decode()
+
+    def doc_fill(self, sample_rows: int = 0) -> np.ndarray:
+        """Fraction of set bits per local document over evenly spaced sample rows (``xs_cobs_doc_fill``)."""
+        fill = np.zeros(self.n_docs, np.float64)
+        check(lib().xs_cobs_doc_fill(self._h, int(sample_rows), _ptr(fill)))
+        return fill
+
+    def selfcheck(self, member_sequence=None, member_doc: str | int | None = None, step: int = 1) -> dict:
+        """Structural self-check of a real model file (everything inside cobs-reloaded is restated
+        from its published source and cannot be verified offline).  Reports the header reading that matched, the
+        per-document fill, and — given a sequence known to be part of one document's training data (G1/G3: a training
+        genome scores 1.0 on its own document) — its score there next to ``fill ** h``, the score a k-mer that is NOT in
+        the document gets.  ``consistent`` is False when the member scores like a stranger: wrong hash seeds, modulus,
+        bit order or row stride for this file."""
+        fill = self.doc_fill()
+        rep = {"header_layout": self.header_layout, "kind": "classic" if self.info.kind == _abi.XS_COBS_CLASSIC else "compact",
+               "n_docs": self.n_docs, "num_hashes": self.num_hashes, "term_size": self.k,
+               "fill_min": float(fill.min()), "fill_max": float(fill.max()),
+               "design_fill_fpr_0.01": 0.01 ** (1.0 / self.num_hashes),
+               "implausible_fill": bool(fill.max() > 0.75 or fill.max() < 0.02)}
+        if member_sequence is not None:
+            a = _as_bases(member_sequence)
+            d = self.names.index(member_doc) if isinstance(member_doc, str) else int(member_doc or 0)
+            n_win = max(0, (a.size - self.k) // step + 1)
+            score = float(self.counts(a, step)[d]) / max(n_win, 1)
+            stranger = float(fill[d]) ** self.num_hashes
+            rep.update({"member_doc": self.names[d], "member_score": score, "stranger_score": stranger,
+                        "consistent": bool(score > 0.5 and score > 4 * stranger) or bool(score > 0.9)})
+        return rep
 
     def set_policy(self, policy: int) -> None:
         check(lib().xs_cobs_set_policy(self._h, int(policy)))

@@ -278,6 +278,14 @@ class ProbabilisticFilterModel:
         """ModelResult for a record, a list of records, a record iterator or a fasta/fastq path
         (reference :237-331).  Later records with an id seen before overwrite earlier ones, one record not
         longer than k aborts the call — as in the reference's loop."""
+        if validation:
+            # the reference moves reads its alignment-based filter rejects into result.misclassified, which changes
+            # hits, totals and the SVM prediction; returning unfiltered hits under the same flag would be a silently
+            # different result
+            raise NotImplementedError(
+                "validation=True: the alignment-based misclassification filter (minimap2 mapping + Ripley's K, "
+                "reference probabilistic_filter_model.py:508-601) is outside the GPU scoring path"
+            )
         batch = self._to_batch(sequence_input)
         self._check_lengths(batch)
         cols = self.predict_arrays(batch, step)
@@ -287,12 +295,6 @@ class ProbabilisticFilterModel:
             doc_keys = list(cols.names)
         drop = exclude_ids if (exclude_ids and self._exclude_ids_apply) else ()
         include = np.array([name not in drop for name in cols.names], dtype=bool)
-        if validation:
-            warnings.warn(
-                "validation=True: the alignment-based misclassification filter (minimap2 mapping + Ripley's K, "
-                "reference :508-601) is outside the GPU scoring path and is not applied",
-                stacklevel=2,
-            )
         return ColumnarModelResult(self.slug(), batch.ids, cols.names, doc_keys, include, cols.counts, cols.num_kmers,
                                    sparse_sampling_step=step)
 

@@ -106,6 +106,11 @@ class ColumnarModelResult(ModelResult):
         self._hits = None
         self._num_kmers = None
         self._emit = None
+        if "misclassified" in ids:
+            # reserved key of the reference's ModelResult (result.py:29): a record with this id has its hits moved
+            # into the `misclassified` field.  Rare: take the dictionary path for such a batch.
+            self._materialize()
+            self.misclassified = self._hits.pop("misclassified", None)
 
     # ---- dictionary views, built on demand
     def _emit_index(self):
