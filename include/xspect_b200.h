@@ -169,6 +169,25 @@ int xs_cobs_classify(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const 
                      const uint64_t* seq_end, uint64_t n_seq, uint32_t step, uint32_t* best, uint32_t* best_count,
                      uint32_t* n_best, uint64_t* totals);
 
+/* Replaces, for ALL loci of an MLST scheme and all records of an input in one call, the chunk loop of
+ * ProbabilisticFilterMlstSchemeModel.calculate_hits:
+ *   probabilistic_filter_mlst_model.py:236-256  records of >= chunk_from_len (10000) bases: sequence_splitter
+ *       (:382-426) chunks of allele_len[l] bases (x10 from 1 Mbp, x100 from 10 Mbp, k-1 overlap, short remainder glued
+ *       to the last chunk), one search per chunk, scores > min_chunk_score (50) kept (:362-380), summed per allele,
+ *       dict in first-appearance order then stably sorted by descending sum
+ *   probabilistic_filter_mlst_model.py:272-286  shorter records: one search, every allele in cobs result order
+ * loci[l]: the locus' <locus>.cobs_compact handle (same device and k for all).  The bases are uploaded and packed
+ * once; every locus' chunk count matrix stays on the device, where the chunks with a score above the threshold are
+ * found and compacted; only those rows (normally one or two per record and locus) come back, and the library orders
+ * them with the same std::partial_sort cobs uses for its result list.
+ * Output, for locus l and record i (D_l = documents of locus l, off_l = n_seq * sum_{l' < l} D_l'):
+ *   out_n[l * n_seq + i]                     number of (allele, score) pairs
+ *   out_doc / out_score[off_l + i * D_l + j] document index / summed score of the j-th pair, j < out_n[...]
+ * All pointers are host memory. */
+int xs_mlst_query(xs_cobs* const* loci, uint32_t n_loci, const uint32_t* allele_len, const uint8_t* bases, uint64_t n_bases,
+                  const uint64_t* seq_begin, const uint64_t* seq_end, uint64_t n_seq, uint32_t step, uint32_t min_chunk_score,
+                  uint64_t chunk_from_len, uint32_t* out_n, uint32_t* out_doc, uint32_t* out_score);
+
 /* Result order of cobs Search.search (what _convert_cobs_result_to_dict iterates,
  * probabilistic_filter_model.py:393-409; MLST tie-breaks, probabilistic_filter_mlst_model.py:254-256,284):
  * all documents, std::partial_sort by score descending.  Host-only helper. */

@@ -357,6 +357,39 @@ def test_mlst_predict_file_batches_records(world, oracle, tmp_path):
         model.calculate_hits(Seq(lonely))
 
 
+def test_mlst_query_many_hot_chunks_and_steps(world, oracle):
+    """xs_mlst_query keeps 16 hot chunk rows per record and locus on the device path; a record with more (a locus
+    repeated many times) takes the fallback that reads the flagged rows back.  Both must equal the oracle's chunk loop,
+    order included, also with sparse sampling."""
+    from xspect2_b200 import engine
+    from xspect2_b200.models.probabilistic_filter_mlst_model import ProbabilisticFilterMlstSchemeModel
+    model = ProbabilisticFilterMlstSchemeModel.load(world["ml_json"])
+    rng = np.random.default_rng(91)
+    loci = list(model.loci)
+    al = world["alleles"]
+    parts = []
+    for rep in range(23):                                        # 23 copies of locus 0 alleles (> 16 hot chunks), 2 of locus 1
+        parts += [synth.random_dna(rng, 1500 + 37 * rep), al[loci[0]][f"Allele_ID_{1 + rep % 5}"]]
+    parts += [synth.random_dna(rng, 4000), al[loci[1]]["Allele_ID_7"], synth.random_dna(rng, 2600), al[loci[1]]["Allele_ID_8"]]
+    many = np.concatenate(parts)
+    short = al[loci[2]]["Allele_ID_3"]
+    plain = np.concatenate([synth.random_dna(rng, 8000), al[loci[2]]["Allele_ID_11"], synth.random_dna(rng, 4000)])
+    seqs = [many, short, plain, many[:-5]]
+    sizes = np.array([x.size for x in seqs], np.uint64)
+    end = np.cumsum(sizes, dtype=np.uint64)
+    indices = [srch.index for srch in model.indices]
+    for step in (1, 3):
+        res = engine.mlst_query(indices, model.avg_locus_bp_size, np.concatenate(seqs), end - sizes, end, step)
+        for li, locus in enumerate(loci):
+            orc = oracle.CobsOracle(model.get_cobs_index_path(locus), load_complete=False)
+            for ri, sq in enumerate(seqs):
+                exp = oracle.mlst_locus_scores(orc, sq.tobytes().decode(), model.avg_locus_bp_size[li], step)
+                docs, scores = res[li][ri]
+                got = [(indices[li].names[d], v) for d, v in zip(docs.tolist(), scores.tolist())]
+                assert got == list(exp.items()), (step, locus, ri)
+    assert len(res[0][0][0]) >= 5                                # the repeated locus really produced several alleles
+
+
 # ------------------------------------------------------------------------------ workflows + CLI
 def test_workflows_and_cli(world, oracle, tmp_path, monkeypatch):
     monkeypatch.setenv("HOME", str(world["root"].parent))

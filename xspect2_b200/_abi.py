@@ -72,6 +72,7 @@ SYMBOLS = {
     "xs_cobs_query": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, C.c_int, _P]),
     "xs_cobs_query_device": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, C.c_int, _P, _P]),
     "xs_cobs_classify": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, _P, _P, _P, _P]),
+    "xs_mlst_query": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, _P, _P, _P]),
     "xs_cobs_result_order": (C.c_int, [_P, C.c_uint32, _P]),
     "xs_cobs_result_order_batch": (C.c_int, [_P, C.c_uint64, C.c_uint32, _P]),
     "xs_scores_reduce_device": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _P, _P, _P, _P, _P]),

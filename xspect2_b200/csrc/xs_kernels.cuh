@@ -1534,6 +1534,61 @@ __global__ void k_restride(const uint8_t* __restrict__ src, uint64_t n_rows, uin
     }
 }
 
+// ----------------------------------------------------------------------------------------
+// MLST epilogue (probabilistic_filter_mlst_model.py:236-256): the count matrix [n_seg x n_docs] of one locus stays on
+// the device; a chunk matters only when some allele scores above the threshold in it ("hot").  k_mlst_hot flags the
+// hot segments (one warp per row); k_mlst_compact keeps, per record and in chunk order, the indices and rows of its
+// first `cap` hot segments.  Records below the chunking length have one segment, which is always kept.
+// ----------------------------------------------------------------------------------------
+template <typename CntT>
+__global__ void __launch_bounds__(256) k_mlst_hot(const CntT* __restrict__ counts, uint64_t n_seg, uint32_t n_docs, uint32_t thr,
+                                                  const uint8_t* __restrict__ seg_always, uint8_t* __restrict__ hot) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t sg = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; sg < n_seg; sg += n_warps) {
+        const CntT* row = counts + sg * n_docs;
+        bool any = seg_always[sg] != 0;
+        for (uint32_t d = lane; d < n_docs && !any; d += 32) any = (uint32_t)row[d] > thr;
+        any = __any_sync(0xFFFFFFFFu, any);
+        if (lane == 0) hot[sg] = any ? 1 : 0;
+    }
+}
+
+template <typename CntT>
+__global__ void __launch_bounds__(256) k_mlst_compact(const CntT* __restrict__ counts, const uint64_t* __restrict__ rec_seg0,
+                                                      uint32_t n_docs, const uint8_t* __restrict__ hot, uint32_t cap,
+                                                      uint32_t* __restrict__ n_hot, uint32_t* __restrict__ hot_seg,
+                                                      uint32_t* __restrict__ hot_rows) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    extern __shared__ uint32_t s_list[];   // [cap] local segment indices
+    const uint32_t rec = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t g0 = rec_seg0[rec], g1 = rec_seg0[rec + 1];
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (uint64_t t0 = g0; t0 < g1; t0 += 256) {
+        const uint64_t sg = t0 + tid;
+        const bool h = sg < g1 && hot[sg];
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, h);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t pre = s_base;
+        for (uint32_t w = 0; w < warp; ++w) pre += s_warp[w];
+        const uint32_t pos = pre + __popc(bal & ((1u << lane) - 1u));
+        if (h && pos < cap) s_list[pos] = (uint32_t)(sg - g0);
+        __syncthreads();
+        if (tid == 0) { uint32_t t = 0; for (uint32_t w = 0; w < 8; ++w) t += s_warp[w]; s_base += t; }
+        __syncthreads();
+    }
+    const uint32_t total = s_base, kept = total < cap ? total : cap;
+    if (tid == 0) n_hot[rec] = total;
+    for (uint32_t i = tid; i < kept; i += 256) hot_seg[(uint64_t)rec * cap + i] = s_list[i];
+    for (uint64_t i = tid; i < (uint64_t)kept * n_docs; i += 256) {
+        const uint32_t r = (uint32_t)(i / n_docs), d = (uint32_t)(i - (uint64_t)r * n_docs);
+        hot_rows[((uint64_t)rec * cap + r) * n_docs + d] = (uint32_t)counts[(g0 + s_list[r]) * n_docs + d];
+    }
+}
+
 // per-document fill of a page estimated from `n_sample` evenly spaced rows (xs_cobs_doc_fill): thread per
 // (sampled row, 32-document word), one atomic per set bit
 __global__ void __launch_bounds__(256) k_doc_fill(const PageDesc pg, uint64_t n_sample, uint32_t* __restrict__ counts) {

@@ -1386,6 +1386,222 @@ int xs_cobs_classify(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const 
     return rc;
 }
 
+// ----------------------------------------------------------------------------------------
+// MLST: chunked scoring of every locus of a scheme (probabilistic_filter_mlst_model.py:236-286)
+// ----------------------------------------------------------------------------------------
+struct MlstSegs {                 // the sequence_splitter chunks of all records for one locus, as byte segments
+    std::vector<uint64_t> begin, end, rec_seg0;
+    std::vector<uint8_t> always;  // segment of an unchunked record: kept whatever it scores
+    uint64_t max_windows = 0;
+};
+
+// sequence_splitter (:382-426) as segments of the record [b, e).  The one non-contiguous chunk (a remainder shorter
+// than k glued to the last chunk, repeating the k-1 overlap bases) is materialised in `extra`, which is appended
+// to the device copy of the bases at offset extra_base.
+static int mlst_segments(const uint8_t* bases, const uint64_t* sb, const uint64_t* se, uint64_t n_seq, uint32_t k, uint32_t step,
+                         uint32_t allele_len, uint64_t chunk_from, uint64_t extra_base, std::vector<uint8_t>& extra, MlstSegs& out) {
+    out.rec_seg0.assign(1, 0);
+    for (uint64_t i = 0; i < n_seq; ++i) {
+        const uint64_t b = sb[i], e = se[i], n = e - b;
+        auto push = [&](uint64_t x, uint64_t y, uint8_t always) {
+            out.begin.push_back(x); out.end.push_back(y); out.always.push_back(always);
+            const uint64_t len = y - x;
+            if (len >= k) out.max_windows = std::max(out.max_windows, (len - k) / step + 1);
+        };
+        if (n < chunk_from) {
+            push(b, e, 1);
+        } else {
+            const uint64_t sub = n < 1000000 ? (uint64_t)allele_len : n < 10000000 ? (uint64_t)allele_len * 10 : (uint64_t)allele_len * 100;
+            if (sub < k) return fail(XS_ERR_ARG, "MLST chunk length (average allele length) must be at least k");
+            const uint64_t stride = sub - k + 1;
+            uint64_t start = 0;
+            const size_t first = out.begin.size();
+            while (start + sub <= n) { push(b + start, b + start + sub, 0); start += stride; }
+            if (start < n) {
+                if (n - start < k) {
+                    if (out.begin.size() == first) return fail(XS_ERR_ARG, "MLST record shorter than k");
+                    // last chunk += remainder: bytes [last, last + sub) followed by [start, n)
+                    const uint64_t last = out.begin.back();
+                    const uint64_t x = extra_base + extra.size();
+                    extra.insert(extra.end(), bases + last, bases + last + sub);
+                    extra.insert(extra.end(), bases + b + start, bases + e);
+                    out.begin.back() = x; out.end.back() = x + sub + (n - start);
+                    out.max_windows = std::max(out.max_windows, (sub + (n - start) - k) / step + 1);
+                } else {
+                    push(b + start, e, 0);
+                }
+            }
+        }
+        out.rec_seg0.push_back(out.begin.size());
+    }
+    return XS_OK;
+}
+
+// result-dict order of one record and locus from its kept rows (chunk order): first appearance while walking each
+// row in cobs result order, then a stable sort by descending sum (:244-256); an unchunked record returns its single
+// row in cobs result order, zeros included (:272-286)
+static void mlst_order(const uint32_t* rows, uint32_t n_rows, uint32_t n_docs, bool chunked, uint32_t thr,
+                       std::vector<uint32_t>& scratch, uint32_t* out_doc, uint32_t* out_score, uint32_t* out_n) {
+    std::vector<uint32_t>& idx = scratch;
+    idx.resize(n_docs);
+    if (!chunked) {
+        std::iota(idx.begin(), idx.end(), 0u);
+        const uint32_t* sc = rows;
+        std::partial_sort(idx.begin(), idx.end(), idx.end(), [sc](uint32_t a, uint32_t b) { return sc[a] > sc[b]; });
+        for (uint32_t j = 0; j < n_docs; ++j) { out_doc[j] = idx[j]; out_score[j] = sc[idx[j]]; }
+        *out_n = n_docs;
+        return;
+    }
+    std::vector<uint64_t> sum(n_docs, 0);
+    std::vector<uint32_t> seen;
+    for (uint32_t r = 0; r < n_rows; ++r) {
+        const uint32_t* sc = rows + (uint64_t)r * n_docs;
+        std::iota(idx.begin(), idx.end(), 0u);
+        std::partial_sort(idx.begin(), idx.end(), idx.end(), [sc](uint32_t a, uint32_t b) { return sc[a] > sc[b]; });
+        for (uint32_t j = 0; j < n_docs; ++j) {
+            const uint32_t d = idx[j], v = sc[d];
+            if (v <= thr) break;             // descending: nothing above the threshold follows
+            if (sum[d] == 0) seen.push_back(d);
+            sum[d] += v;
+        }
+    }
+    std::stable_sort(seen.begin(), seen.end(), [&](uint32_t a, uint32_t b) { return sum[a] > sum[b]; });
+    for (size_t j = 0; j < seen.size(); ++j) { out_doc[j] = seen[j]; out_score[j] = (uint32_t)std::min<uint64_t>(sum[seen[j]], 0xFFFFFFFFu); }
+    *out_n = (uint32_t)seen.size();
+}
+
+int xs_mlst_query(xs_cobs* const* loci, uint32_t n_loci, const uint32_t* allele_len, const uint8_t* bases, uint64_t n_bases,
+                  const uint64_t* seq_begin, const uint64_t* seq_end, uint64_t n_seq, uint32_t step, uint32_t min_chunk_score,
+                  uint64_t chunk_from_len, uint32_t* out_n, uint32_t* out_doc, uint32_t* out_score) {
+    if (!loci || !n_loci || !allele_len || (n_seq && (!seq_begin || !seq_end || !out_n || !out_doc || !out_score)) || (n_bases && !bases))
+        return fail(XS_ERR_ARG, "NULL argument");
+    if (step == 0) return fail(XS_ERR_ARG, "step must be >= 1");
+    const int device = loci[0]->info.device;
+    const uint32_t k = loci[0]->info.term_size;
+    for (uint32_t l = 0; l < n_loci; ++l) {
+        if (!loci[l]) return fail(XS_ERR_ARG, "NULL locus index");
+        if (loci[l]->info.device != device || loci[l]->info.term_size != k)
+            return fail(XS_ERR_ARG, "all loci of a scheme must share the device and the k-mer length");
+    }
+    for (uint64_t i = 0; i < n_seq; ++i)
+        if (seq_end[i] < seq_begin[i] || seq_end[i] > n_bases) return fail(XS_ERR_ARG, "sequence offsets out of range");
+    if (n_seq == 0) return XS_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the index's device");
+
+    // chunk segments of every locus; glued last chunks are appended behind the bases
+    std::vector<MlstSegs> segs(n_loci);
+    std::vector<uint8_t> extra;
+    for (uint32_t l = 0; l < n_loci; ++l)
+        XS_TRY(mlst_segments(bases, seq_begin, seq_end, n_seq, k, step, allele_len[l], chunk_from_len, n_bases, extra, segs[l]));
+    const uint64_t total_bases = n_bases + extra.size();
+
+    const uint32_t CAP = 16;        // hot chunks kept per record; more (repeats of a locus) take the fallback below
+    struct LocusBuf {
+        uint64_t* d_seg = nullptr; uint8_t* d_always = nullptr; void* d_counts = nullptr; uint8_t* d_hot = nullptr;
+        uint32_t *d_nhot = nullptr, *d_hseg = nullptr, *d_hrows = nullptr;
+        std::vector<uint32_t> nhot, hseg, hrows;
+        int dt = XS_U16; uint32_t n_docs = 0; uint64_t n_seg = 0;
+    };
+    std::vector<LocusBuf> lb(n_loci);
+    cudaStream_t s = nullptr;
+    uint8_t* d_bases = nullptr;
+    int rc = XS_OK;
+    auto cuda_ok = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == XS_OK) rc = fail(e == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    cuda_ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "stream");
+    if (rc == XS_OK && cuda_ok(cudaMallocAsync((void**)&d_bases, total_bases + 64, s), "bases allocation")) {
+        cuda_ok(cudaMemcpyAsync(d_bases, bases, n_bases, cudaMemcpyHostToDevice, s), "bases upload");
+        if (!extra.empty()) cuda_ok(cudaMemcpyAsync(d_bases + n_bases, extra.data(), extra.size(), cudaMemcpyHostToDevice, s), "bases upload");
+    }
+    for (uint32_t l = 0; l < n_loci && rc == XS_OK; ++l) {
+        xs_cobs* ix = loci[l];
+        LocusBuf& b = lb[l];
+        const MlstSegs& sg = segs[l];
+        b.n_docs = ix->info.doc_end - ix->info.doc_begin;
+        b.n_seg = sg.begin.size();
+        b.dt = sg.max_windows <= 65535 ? XS_U16 : XS_U32;
+        const uint64_t nsg = b.n_seg;
+        if (!cuda_ok(cudaMallocAsync((void**)&b.d_seg, (2 * nsg + n_seq + 1) * 8, s), "segment allocation")) break;
+        if (!cuda_ok(cudaMallocAsync((void**)&b.d_always, 2 * nsg + 16, s), "segment allocation")) break;
+        b.d_hot = b.d_always + nsg;
+        if (!cuda_ok(cudaMallocAsync(&b.d_counts, std::max<uint64_t>(1, nsg * b.n_docs * (uint64_t)b.dt), s), "count matrix allocation")) break;
+        if (!cuda_ok(cudaMallocAsync((void**)&b.d_nhot, (n_seq + n_seq * CAP + n_seq * CAP * (uint64_t)b.n_docs) * 4, s), "hot row allocation")) break;
+        b.d_hseg = b.d_nhot + n_seq;
+        b.d_hrows = b.d_hseg + n_seq * CAP;
+        cuda_ok(cudaMemcpyAsync(b.d_seg, sg.begin.data(), nsg * 8, cudaMemcpyHostToDevice, s), "segment upload");
+        cuda_ok(cudaMemcpyAsync(b.d_seg + nsg, sg.end.data(), nsg * 8, cudaMemcpyHostToDevice, s), "segment upload");
+        cuda_ok(cudaMemcpyAsync(b.d_seg + 2 * nsg, sg.rec_seg0.data(), (n_seq + 1) * 8, cudaMemcpyHostToDevice, s), "segment upload");
+        cuda_ok(cudaMemcpyAsync(b.d_always, sg.always.data(), nsg, cudaMemcpyHostToDevice, s), "segment upload");
+        if (rc != XS_OK) break;
+        rc = cobs_query_dev(ix, d_bases, total_bases, b.d_seg, b.d_seg + nsg, nsg, 0, step, b.dt, b.d_counts, s);
+        if (rc != XS_OK) break;
+        const unsigned hgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nsg + 7) / 8, (uint64_t)ix->n_sm * 8));
+        if (b.dt == XS_U16) {
+            k_mlst_hot<uint16_t><<<hgrid, 256, 0, s>>>((const uint16_t*)b.d_counts, nsg, b.n_docs, min_chunk_score, b.d_always, b.d_hot);
+            k_mlst_compact<uint16_t><<<(unsigned)n_seq, 256, CAP * 4, s>>>((const uint16_t*)b.d_counts, b.d_seg + 2 * nsg, b.n_docs, b.d_hot, CAP, b.d_nhot, b.d_hseg, b.d_hrows);
+        } else {
+            k_mlst_hot<uint32_t><<<hgrid, 256, 0, s>>>((const uint32_t*)b.d_counts, nsg, b.n_docs, min_chunk_score, b.d_always, b.d_hot);
+            k_mlst_compact<uint32_t><<<(unsigned)n_seq, 256, CAP * 4, s>>>((const uint32_t*)b.d_counts, b.d_seg + 2 * nsg, b.n_docs, b.d_hot, CAP, b.d_nhot, b.d_hseg, b.d_hrows);
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        rc = launch_ok("k_mlst_hot / k_mlst_compact");
+        if (rc != XS_OK) break;
+        b.nhot.resize(n_seq); b.hseg.resize(n_seq * CAP); b.hrows.resize(n_seq * CAP * (uint64_t)b.n_docs);
+        cuda_ok(cudaMemcpyAsync(b.nhot.data(), b.d_nhot, n_seq * 4, cudaMemcpyDeviceToHost, s), "result copy");
+        cuda_ok(cudaMemcpyAsync(b.hseg.data(), b.d_hseg, n_seq * CAP * 4, cudaMemcpyDeviceToHost, s), "result copy");
+        cuda_ok(cudaMemcpyAsync(b.hrows.data(), b.d_hrows, n_seq * CAP * (uint64_t)b.n_docs * 4, cudaMemcpyDeviceToHost, s), "result copy");
+    }
+    if (s) cuda_ok(cudaStreamSynchronize(s), "MLST query");
+
+    // ordering on the host from the few kept rows (libstdc++ partial_sort = cobs' own result order)
+    if (rc == XS_OK) {
+        std::vector<uint32_t> scratch, full;
+        uint64_t col0 = 0;
+        for (uint32_t l = 0; l < n_loci && rc == XS_OK; ++l) {
+            LocusBuf& b = lb[l];
+            const MlstSegs& sg = segs[l];
+            for (uint64_t i = 0; i < n_seq && rc == XS_OK; ++i) {
+                const bool chunked = (seq_end[i] - seq_begin[i]) >= chunk_from_len;
+                uint32_t* od = out_doc + col0 + i * b.n_docs;
+                uint32_t* os = out_score + col0 + i * b.n_docs;
+                const uint32_t nh = b.nhot[i];
+                const uint32_t* rows = b.hrows.data() + i * CAP * (uint64_t)b.n_docs;
+                uint32_t n_rows = nh;
+                if (nh > CAP) {
+                    // more hot chunks than kept: fetch this record's hot rows from the count matrix still on the device
+                    const uint64_t g0 = sg.rec_seg0[i], g1 = sg.rec_seg0[i + 1];
+                    std::vector<uint8_t> hot(g1 - g0);
+                    if (!cuda_ok(cudaMemcpy(hot.data(), b.d_hot + g0, g1 - g0, cudaMemcpyDeviceToHost), "hot flags copy")) break;
+                    full.clear();
+                    std::vector<uint8_t> raw((size_t)b.n_docs * b.dt);
+                    for (uint64_t g = g0; g < g1; ++g) {
+                        if (!hot[g - g0]) continue;
+                        if (!cuda_ok(cudaMemcpy(raw.data(), (const uint8_t*)b.d_counts + g * b.n_docs * (uint64_t)b.dt, raw.size(), cudaMemcpyDeviceToHost), "row copy")) break;
+                        for (uint32_t d = 0; d < b.n_docs; ++d)
+                            full.push_back(b.dt == XS_U16 ? (uint32_t)reinterpret_cast<const uint16_t*>(raw.data())[d] : reinterpret_cast<const uint32_t*>(raw.data())[d]);
+                    }
+                    rows = full.data();
+                    n_rows = (uint32_t)(full.size() / b.n_docs);
+                }
+                mlst_order(rows, n_rows, b.n_docs, chunked, min_chunk_score, scratch, od, os, out_n + (uint64_t)l * n_seq + i);
+            }
+            col0 += n_seq * b.n_docs;
+        }
+    }
+    for (LocusBuf& b : lb) {
+        if (b.d_seg) cudaFreeAsync(b.d_seg, s);
+        if (b.d_always) cudaFreeAsync(b.d_always, s);
+        if (b.d_counts) cudaFreeAsync(b.d_counts, s);
+        if (b.d_nhot) cudaFreeAsync(b.d_nhot, s);
+    }
+    if (d_bases) cudaFreeAsync(d_bases, s);
+    if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    return rc;
+}
+
 int xs_cobs_result_order(const uint32_t* scores, uint32_t n_docs, uint32_t* order) {
     if ((!scores || !order) && n_docs) return fail(XS_ERR_ARG, "NULL argument");
     std::vector<uint32_t> idx(n_docs);

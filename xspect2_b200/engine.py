@@ -304,6 +304,35 @@ class Search:
         return [SearchResult(self.index.names[i], int(c[i])) for i in CobsIndex.result_order(c)]
 
 
+def mlst_query(indices: list[CobsIndex], allele_len, bases, seq_begin, seq_end, step: int = 1,
+               min_chunk_score: int = 50, chunk_from_len: int = 10000):
+    """All loci of an MLST scheme over all records in one call (``xs_mlst_query``): chunking, per-chunk threshold and
+    per-allele sums on the device.  Returns ``out[locus][record] = (doc_indices, scores)`` in the reference's
+    result-dict order (probabilistic_filter_mlst_model.py:236-286)."""
+    bases = _as_bases(bases)
+    b, e = _as_u64(seq_begin), _as_u64(seq_end)
+    n, nl = b.size, len(indices)
+    handles = (C.c_void_p * nl)(*[ix._h for ix in indices])
+    alen = np.ascontiguousarray(allele_len, dtype=np.uint32)
+    docs = [ix.n_docs for ix in indices]
+    total = n * int(sum(docs))
+    out_n = np.zeros(nl * n, np.uint32)
+    out_doc = np.empty(max(total, 1), np.uint32)
+    out_score = np.empty(max(total, 1), np.uint32)
+    check(lib().xs_mlst_query(handles, nl, _ptr(alen), _ptr(bases), bases.size, _ptr(b), _ptr(e), n, int(step),
+                              int(min_chunk_score), int(chunk_from_len), _ptr(out_n), _ptr(out_doc), _ptr(out_score)))
+    res, off = [], 0
+    for li, d in enumerate(docs):
+        per = []
+        for i in range(n):
+            m = int(out_n[li * n + i])
+            o = off + i * d
+            per.append((out_doc[o:o + m], out_score[o:o + m]))
+        res.append(per)
+        off += n * d
+    return res
+
+
 # --------------------------------------------------------------------------------------
 # Bloom
 # --------------------------------------------------------------------------------------

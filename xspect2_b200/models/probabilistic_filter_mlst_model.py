@@ -175,49 +175,22 @@ class ProbabilisticFilterMlstSchemeModel(ProbabilisticFilterModel):
         return {r.doc_name: r.score for r in cobs_result if not kmer_threshold or r.score > 50}
 
     def _score_records(self, seqs: list[np.ndarray], step: int) -> list[list[dict]]:
-        """``out[record][locus]`` = allele -> score in the reference's dict order, for all records at once: one
-        batched query per locus over every chunk of every record (records >= 10000 bp are chunked, :236-256;
-        shorter ones are searched whole, :272-286)."""
-        out = [[None] * len(self.indices) for _ in seqs]
-        for li, search in enumerate(self.indices):
-            ix = search.index
+        """``out[record][locus]`` = allele -> score in the reference's dict order, for all records and all loci in
+        one ``xs_mlst_query`` call: records >= 10000 bp are chunked (:236-256; chunk scores > 50 summed per allele,
+        first-appearance order, stable sort by -score), shorter ones are searched whole (:272-286).  Chunking,
+        threshold and sums run on the device; only the few chunk rows that pass the threshold come back."""
+        sizes = np.fromiter((sb.size for sb in seqs), dtype=np.uint64, count=len(seqs))
+        end = np.cumsum(sizes, dtype=np.uint64)
+        begin = end - sizes
+        bases = np.concatenate(seqs) if len(seqs) > 1 else seqs[0]
+        indices = [search.index for search in self.indices]
+        res = engine.mlst_query(indices, self.avg_locus_bp_size, bases, begin, end, step)
+        out = [[None] * len(indices) for _ in seqs]
+        for li, ix in enumerate(indices):
             names = ix.names
-            parts, begins, ends, owner = [], [], [], []
-            off = 0
-            for ri, sb in enumerate(seqs):
-                if sb.size >= 10000:
-                    bases, b, e = self._chunk_segments(sb, self.avg_locus_bp_size[li])
-                else:
-                    bases, b, e = sb, np.zeros(1, np.uint64), np.array([sb.size], np.uint64)
-                parts.append(bases)
-                begins.append(b + np.uint64(off))
-                ends.append(e + np.uint64(off))
-                owner.append(np.full(b.size, ri, dtype=np.int64))
-                off += bases.size
-            counts = ix.query(np.concatenate(parts), np.concatenate(begins), np.concatenate(ends), step=step)
-            owner = np.concatenate(owner)
-            first = np.searchsorted(owner, np.arange(len(seqs)), side="left")
-            last = np.searchsorted(owner, np.arange(len(seqs)), side="right")
-            for ri, sb in enumerate(seqs):
-                rows = np.asarray(counts[first[ri]:last[ri]])
-                if sb.size >= 10000:
-                    # per-allele sum over chunks of the chunk scores > 50; dict order = first appearance (chunk order,
-                    # cobs result order inside a chunk), then a stable sort by -score
-                    all_counts: dict[str, int] = {}
-                    hot = np.flatnonzero((rows > 50).any(axis=1))
-                    if hot.size:
-                        sub = np.ascontiguousarray(rows[hot]).astype(np.uint32)
-                        order = engine.result_order_batch(sub)
-                        for r in range(hot.size):
-                            row = sub[r]
-                            for j in order[r].tolist():
-                                v = int(row[j])
-                                if v > 50:
-                                    all_counts[names[j]] = all_counts.get(names[j], 0) + v
-                    out[ri][li] = dict(sorted(all_counts.items(), key=lambda item: -item[1]))
-                else:
-                    row = rows[0].astype(np.uint32)
-                    out[ri][li] = {names[j]: int(row[j]) for j in engine.CobsIndex.result_order(row).tolist()}
+            for ri in range(len(seqs)):
+                docs, scores = res[li][ri]
+                out[ri][li] = {names[d]: v for d, v in zip(docs.tolist(), scores.tolist())}
         return out
 
     def _assemble(self, seq_len: int, per_locus: list[dict], limit: bool, limit_number: int) -> list[dict]:
