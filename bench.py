@@ -216,6 +216,175 @@ def run_reference(args, rank: int, world: int) -> None:
         shutil.rmtree(workdir, ignore_errors=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 5: the document-column sharded index with the NCCL score all-gather
+# ---------------------------------------------------------------------------------------------------------------------
+CFG5_D, CFG5_H, CFG5_K, CFG5_SEED = 10_000, 7, 21, 6
+CFG5_S = int(os.environ.get("XS_CFG5_ROWS", 96_000_000))
+CFG5_READS = int(os.environ.get("XS_CFG5_READS", 2_000_000))
+CFG5_TILE = int(os.environ.get("XS_CFG5_TILE", 100_000))
+
+
+def run_cfg5(args, rank: int, world: int, local_rank: int) -> dict:
+    """D = 10 000 documents, h = 7, k = 21, S = 96 000 000 rows (1250-byte rows, 120 GB) — rows from the counter-based
+    generator of xs_cobs_create_synthetic, each rank generating its 128-document-aligned column range straight into
+    HBM.  One fixed read set for every N (strong scaling): a step = CFG5_READS x 150 bp in tiles of CFG5_TILE reads;
+    every rank scores every tile against its columns, xs_allgather_scores (ncclAllGather) combines the score rows on
+    a side stream while the next tile is scored, xs_sharded_reduce_device takes per-read argmax / tie in place.
+    Parity on rank 0 against the oracle regenerating the same rows: full score rows of a sample, calls of a larger one."""
+    import torch
+    import torch.distributed as dist
+    from xspect2_b200 import distributed as xd, engine, synth
+    from xspect2_b200._abi import XS_U8
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.empty_cache()
+    engine.device_trim(local_rank)
+    shards = xd.column_shards(CFG5_D, world)
+    lo, hi = shards[rank]
+    t0 = time.perf_counter()
+    try:
+        ix = engine.CobsIndex.synthetic(CFG5_D, CFG5_S, CFG5_K, CFG5_H, CFG5_SEED, device=local_rank, doc_begin=lo, doc_end=hi)
+        failed = 0
+    except MemoryError as exc:
+        ix, failed, why = None, 1, str(exc)
+    if world > 1:
+        f = torch.tensor([failed], device=dev)
+        dist.all_reduce(f, op=dist.ReduceOp.MAX)
+        failed = int(f.item())
+    if failed:
+        return {"skipped": f"column shard does not fit in HBM on some rank ({why if ix is None else 'another rank'})"}
+    gen_s = time.perf_counter() - t0
+    comm = xd.make_comm(rank, world, local_rank) if world > 1 else None
+    n_reads = CFG5_READS - CFG5_READS % CFG5_TILE
+    genome = synth.synth_genome(1_000_000, seed=7)
+    reads = synth.synth_reads(genome, n_reads, READ_LEN, seed=7, device=dev)          # identical on every rank
+    hb, he = synth.fixed_offsets(CFG5_TILE, READ_LEN)
+    d_b = torch.from_numpy(hb.view(np.int64)).to(dev)
+    d_e = torch.from_numpy(he.view(np.int64)).to(dev)
+    tiles = [(reads.data_ptr() + t * CFG5_TILE * READ_LEN, CFG5_TILE * READ_LEN, d_b.data_ptr(), d_e.data_ptr(), CFG5_TILE)
+             for t in range(n_reads // CFG5_TILE)]
+    widths = [b - a for a, b in shards]
+    stream = torch.cuda.current_stream(dev)
+    best_all = torch.empty(n_reads, dtype=torch.int32, device=dev)
+    cnt_all = torch.empty(n_reads, dtype=torch.int32, device=dev)
+    nb_all = torch.empty(n_reads, dtype=torch.int32, device=dev)
+
+    def keep(t, best, cnt, nb):
+        sl = slice(t * CFG5_TILE, (t + 1) * CFG5_TILE)
+        best_all[sl], cnt_all[sl], nb_all[sl] = best, cnt, nb
+
+    if world > 1:
+        scorer = xd.ShardedScorer(ix, shards, comm, XS_U8, CFG5_TILE)
+
+        def step(timed=False):
+            scorer.run(iter(tiles), 1, keep, time_exchange=timed)
+    else:
+        w1 = -(-CFG5_D // 16) * 16
+        local = torch.empty((CFG5_TILE, w1), dtype=torch.uint8, device=dev)
+
+        def step(timed=False):
+            for t, (b0, nb_, pb, pe, n) in enumerate(tiles):
+                ix.query_device(b0, nb_, pb, pe, n, 1, XS_U8, local.data_ptr(), stream.cuda_stream, ld=w1)
+                sl = slice(t * CFG5_TILE, (t + 1) * CFG5_TILE)
+                engine.sharded_reduce_device(local.data_ptr(), n, XS_U8, local_rank, w1, [CFG5_D], best_all[sl].data_ptr(),
+                                             cnt_all[sl].data_ptr(), nb_all[sl].data_ptr(), 0, stream.cuda_stream)
+
+    steps = max(1, min(args.steps, int(os.environ.get("XS_CFG5_STEPS", 3))))
+    step()
+    step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    engine.profile_enable(True)
+    engine.profile_read()
+    launches0 = engine.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        step(timed=True)                     # every step ends with the comm stream drained (consume() waits for it)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    k_ms, k_n = engine.profile_read()
+    engine.profile_enable(False)
+    launches = engine.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    lookups = n_reads * (READ_LEN - CFG5_K + 1)
+    out = {
+        "workload": f"cfg5: D={CFG5_D} h={CFG5_H} k={CFG5_K} S={CFG5_S} synthetic classic index (counter-based rows, fill 0.25), "
+                    f"{n_reads} x {READ_LEN}bp reads per step in tiles of {CFG5_TILE} (the same read set at every N: strong scaling)",
+        "parallelism": f"document columns sharded x{world}, every rank scores every read" + (", NCCL all-gather of score rows" if world > 1 else ""),
+        "exchange": "allgather" if world > 1 else "none (one GPU holds all columns)",
+        "n_gpus": world, "steps": steps, "scaling": "strong",
+        "lookups_per_s": lookups * steps / (ms / 1e3), "reads_per_s": n_reads * steps / (ms / 1e3),
+        "ms_per_step": ms / steps, "ms_per_tile": ms / steps / len(tiles),
+        "scoring_kernel_ms_per_step": k_ms / steps, "gpu_launches": int(launches),
+        "row_bytes_per_gpu": int(ix.info.row_stride), "docs_per_gpu": widths, "index_bytes_per_gpu": int(ix.info.hbm_bytes),
+        "index_generate_s": round(gen_s, 2),
+        "allgather_bytes_per_tile_per_gpu": int(world * CFG5_TILE * (scorer.w if world > 1 else 0)),
+    }
+    if world > 1:
+        out["allgather_ms_per_step"] = scorer.exchange_ms / steps
+        out["allgather_ms_per_tile"] = scorer.exchange_ms / steps / len(tiles)
+        out["nccl_version"] = comm.nccl_version
+        bytes_in = (world - 1) * CFG5_TILE * scorer.w
+        out["allgather_GBps_in_per_gpu"] = bytes_in / (out["allgather_ms_per_tile"] / 1e3) / 1e9 if out["allgather_ms_per_tile"] else None
+    # algorithmic bytes of the scoring kernel on this rank: h x local row bytes per lookup + packed reads + local score tile
+    peak, _ = peaks()
+    row_local = (widths[rank] + 7) // 8
+    algo = lookups * CFG5_H * row_local + n_reads * READ_LEN * 3 // 8 + n_reads * widths[rank]
+    if k_ms > 0:
+        out["roofline"] = {"bound": "hbm", "kernel": "k_cobs_wide<21,7,u8> (rank 0's column shard)", "achieved": algo / (k_ms / steps / 1e3) / 1e9,
+                           "peak": peak, "unit": "GB/s", "frac": algo / (k_ms / steps / 1e3) / 1e9 / peak,
+                           "row_bytes_useful": row_local, "row_stride": int(ix.info.row_stride)}
+    if rank == 0:
+        from oracle import oracle
+        orc = oracle.SynthCobsOracle(CFG5_D, CFG5_S, CFG5_K, CFG5_H, CFG5_SEED)
+        n_calls = min(n_reads, int(os.environ.get("XS_CFG5_PARITY", 10_000)))
+        n_rows = min(n_calls, 500)
+        h_reads = reads[: n_calls * READ_LEN].cpu().numpy()
+        b = np.arange(n_calls, dtype=np.uint64) * np.uint64(READ_LEN)
+        exp = np.minimum(orc.counts_batch(h_reads, b, b + np.uint64(READ_LEN), 1, oracle.max_threads()), 255)
+        e_best = exp.argmax(axis=1)
+        e_cnt = exp.max(axis=1)
+        e_nb = (exp == e_cnt[:, None]).sum(axis=1)
+        bad = int(np.count_nonzero((best_all[:n_calls].cpu().numpy() != e_best) | (cnt_all[:n_calls].cpu().numpy() != e_cnt)
+                                   | (nb_all[:n_calls].cpu().numpy() != e_nb)))
+        out["parity"] = {"reads": int(n_calls), "mismatches": bad, "checked": "per-read first best document, its count and tie multiplicity",
+                         "against": "oracle/xs_oracle.cpp regenerating the synthetic rows on the CPU"}
+    # full score rows of a small sample through the same exchange (every rank takes part; rank 0 compares)
+    n_rows = min(500, CFG5_TILE)
+    if world > 1:
+        loc = torch.zeros((n_rows, scorer.w), dtype=torch.uint8, device=dev)
+        al = torch.empty((world, n_rows, scorer.w), dtype=torch.uint8, device=dev)
+        ix.query_device(reads.data_ptr(), n_rows * READ_LEN, d_b.data_ptr(), d_e.data_ptr(), n_rows, 1, XS_U8, loc.data_ptr(),
+                        stream.cuda_stream, ld=scorer.w)
+        comm.allgather_scores(loc.data_ptr(), n_rows, scorer.w, al.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        got = torch.cat([al[g, :, : widths[g]] for g in range(world)], dim=1).cpu().numpy()
+    else:
+        loc = torch.zeros((n_rows, CFG5_D), dtype=torch.uint8, device=dev)
+        ix.query_device(reads.data_ptr(), n_rows * READ_LEN, d_b.data_ptr(), d_e.data_ptr(), n_rows, 1, XS_U8, loc.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        got = loc.cpu().numpy()
+    if rank == 0:
+        bad_rows = int(np.count_nonzero((got != exp[:n_rows]).any(axis=1)))
+        out["parity"]["score_rows_checked"] = int(n_rows)
+        out["parity"]["score_row_mismatches"] = bad_rows
+        out["parity"]["mismatches"] += bad_rows
+    if comm is not None:
+        comm.close()
+    ix.close()
+    del reads
+    torch.cuda.empty_cache()
+    return out
+
+
+
 def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     import torch
     import torch.distributed as dist
@@ -328,6 +497,16 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             e2e_s = float(t.item())
         same = bool(np.array_equal(h_out[:100000], d_out[:100000].cpu().numpy()))
 
+        # ---- second leg, every rank: BASELINE config 5 (document-column sharded index + NCCL score all-gather)
+        cfg5 = None
+        if os.environ.get("XS_BENCH_CFG5", "1") != "0":
+            try:
+                cfg5 = run_cfg5(args, rank, world, local_rank)
+            except Exception as exc:      # the second leg must not lose the headline numbers
+                cfg5 = {"failed": f"{type(exc).__name__}: {exc}"}
+                if world > 1:
+                    raise
+
         if rank != 0:
             return
         peak, peak_src = peaks()
@@ -394,6 +573,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             "roofline": roof,
             "checksum_first_100k_reads": checksum,
         }
+        if cfg5 is not None:
+            line["cfg5"] = cfg5
         # parity gate (and, at N=1, the CPU baseline): rank 0's GPU counts against the oracle on the same reads
         n_cpu = int(os.environ.get("XS_BENCH_CPU_SAMPLE", 1_000_000)) if world == 1 else \
             int(os.environ.get("XS_BENCH_PARITY_SAMPLE", 100_000))
@@ -402,8 +583,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             line["cpu_baseline"] = base
         line["parity"] = parity_gate(counts, d_out, h_out)
         print(json.dumps(line), flush=True)
-        if line["parity"]["mismatches"]:
-            raise SystemExit(f"parity gate failed: {line['parity']}")
+        if line["parity"]["mismatches"] or (cfg5 or {}).get("parity", {}).get("mismatches"):
+            raise SystemExit(f"parity gate failed: {line['parity']} / cfg5 {(cfg5 or {}).get('parity')}")
     finally:
         shutil.rmtree(workdir, ignore_errors=True)
 

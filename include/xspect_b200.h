@@ -32,6 +32,7 @@ extern "C" {
 
 typedef struct xs_cobs xs_cobs;   /* a COBS classic/compact index resident in HBM */
 typedef struct xs_bloom xs_bloom; /* an rbloom bit array resident in HBM */
+typedef struct xs_comm xs_comm;   /* one rank's NCCL communicator of a document-column sharded index */
 
 enum xs_status {
     XS_OK = 0,
@@ -40,7 +41,8 @@ enum xs_status {
     XS_ERR_FORMAT = -3,      /* not a COBS / rbloom file, size identity violated */
     XS_ERR_CUDA = -4,        /* CUDA runtime error, or no device */
     XS_ERR_NOMEM = -5,       /* host or device allocation failed */
-    XS_ERR_UNSUPPORTED = -6  /* valid input this build does not handle (k > 32, ...) */
+    XS_ERR_UNSUPPORTED = -6, /* valid input this build does not handle (k > 32, ...) */
+    XS_ERR_NCCL = -7         /* libnccl missing or an NCCL call failed (document-column sharded exchange) */
 };
 
 /* element type of the per-document count matrix written by xs_cobs_query* */
@@ -90,6 +92,10 @@ uint64_t xs_launch_count(void);
  * (k_cobs_narrow / k_cobs_wide / k_bloom) with CUDA events on the stream it is launched on;
  * xs_profile_read synchronises those events, returns the summed kernel time and launch count since
  * the last read, and clears them. */
+/* Query workspaces and the bucketed path's scratch come from the device's stream-ordered memory pool and stay cached
+ * there between queries (up to 24 GiB after a large batch).  xs_device_trim synchronises the device and returns the
+ * cached memory to the driver — call it before loading another large index. */
+int xs_device_trim(int device);
 int xs_profile_enable(int on);
 int xs_profile_read(double* kernel_ms, uint64_t* launches);
 /* the same, split by kernel: [0] k_cobs_narrow / k_cobs_wide / k_bloom, [1] k_bucket_emit, [2] k_bucket_fetch,
@@ -282,6 +288,47 @@ int xs_result_write_json(const char* path, const char* prefix, const char* suffi
                          uint32_t n_docs, const uint64_t* rec_index, uint64_t n_emit, const char* rec_keys,
                          const uint64_t* rec_key_end, const uint64_t* num_kmers, const char* doc_keys,
                          const uint64_t* doc_key_end, const uint8_t* doc_include);
+
+/* ---- document-column sharded index: the exchange step (BASELINE config 5) ----------------
+ * An index too large for one GPU is split by document columns: rank g opens its range with
+ * xs_cobs_open(path, dev, doc_begin_g, doc_end_g), every rank scores every record against its columns, and the
+ * per-record score rows are combined with an NCCL all-gather over NVLink.  The reference has no counterpart (one
+ * process, one cobs Search over the whole file, probabilistic_filter_model.py:389); the consumer of the combined
+ * rows is what the reference's benchmark does with them — per-read argmax with ties = ambiguous
+ * (scripts/benchmark/main.nf:417-436).
+ *
+ * libnccl.so.2 is bound at run time (the one already loaded in the process — torch's — else the system's, else
+ * $XSPECT_B200_NCCL); no NCCL, no sharded exchange (XS_ERR_NCCL) — everything else works without it.
+ * Rank 0 creates an id (xs_comm_unique_id, 128 bytes), hands it to the other ranks by any means (a file, MPI,
+ * torch.distributed), and every rank calls xs_comm_init(id, rank, world, device). */
+int xs_comm_unique_id(uint8_t* id128);
+int xs_comm_init(const uint8_t* id128, int rank, int world, int device, xs_comm** out);
+int xs_comm_info(const xs_comm* c, int* rank, int* world, int* nccl_version);
+int xs_comm_destroy(xs_comm* c);
+/* like xs_cobs_query_device with an explicit output row length ld >= local documents (the padding columns are
+ * zero): every rank writes score tiles of one common width, so the all-gather needs no pad or concat pass */
+int xs_cobs_query_device_ld(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_seq_begin,
+                            const uint64_t* d_seq_end, uint64_t n_seq, uint32_t step, int out_dtype, uint64_t ld, void* d_out,
+                            void* stream);
+/* ncclAllGather of one score tile: d_local = this rank's [n_seq x row_bytes] block, d_all = [world][n_seq][row_bytes]
+ * (rank-major), asynchronous on `stream` */
+int xs_allgather_scores(xs_comm* c, const void* d_local, uint64_t n_seq, uint64_t row_bytes, void* d_all, void* stream);
+/* ncclAllReduce(sum) of per-document uint64 totals, in place (file-level scores of a read-sharded or column-sharded job) */
+int xs_allreduce_totals(xs_comm* c, uint64_t* d_totals, uint64_t n, void* stream);
+/* the consumer, in place on what the all-gather delivered: d_all = [world][n_seq][w] counts of `dtype`, rank g's
+ * block holding widths[g] <= w documents per record.  Per record: first document (global index) with the maximum
+ * count, that count, the number of documents sharing it (> 1 = ambiguous, main.nf:417-436); d_totals (optional,
+ * uint64 [sum widths], caller-zeroed) accumulates per-document totals.  Any output pointer may be NULL. */
+int xs_sharded_reduce_device(const void* d_all, uint64_t n_seq, int dtype, int device, uint32_t world, uint32_t w,
+                             const uint32_t* widths, uint32_t* d_best, uint32_t* d_best_count, uint32_t* d_n_best,
+                             uint64_t* d_totals, void* stream);
+/* A classic index whose rows come from a counter-based generator instead of a file (measurement support for
+ * BASELINE config 5: D = 10 000 x S = 96 000 000 is 120 GB; each rank generates its column shard straight into HBM,
+ * the oracle regenerates the rows its parity sample touches).  32 documents of row r, word v:
+ * m = mix64(seed ^ r * 0x9E3779B97F4A7C15 ^ v * 0xD1B54A32D192ED03), bits = hi32(m) & lo32(m) (splitmix64 finaliser;
+ * fill 0.25).  doc_begin must be a multiple of 32.  Queries go through the same kernels as a loaded file. */
+int xs_cobs_create_synthetic(int device, uint32_t n_docs, uint32_t doc_begin, uint32_t doc_end, uint64_t sig_size,
+                             uint32_t term_size, uint32_t num_hashes, uint64_t seed, xs_cobs** out);
 
 /* ---- single stages (host buffers; used by the parity tests to pin each kernel alone) ----- */
 /* 2-bit packing: packed[w] holds bases [32w, 32w+32), base j in bits [2j, 2j+1], A=0 C=1 G=2 T=3;

@@ -97,6 +97,9 @@ def lib() -> C.CDLL:
                                            C.c_uint64, C.c_uint32, C.c_void_p, C.c_int]
         L.xso_bloom_insert.argtypes = [C.POINTER(_BloomT), C.c_void_p, C.c_void_p, C.c_uint64]
         L.xso_max_threads.restype = C.c_int
+        L.xso_synth_row.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
+        L.xso_cobs_query_batch_synth.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -402,6 +405,29 @@ class CobsOracle:
         order = np.zeros(s.size, dtype=np.uint32)
         lib().xso_cobs_result_order(s.ctypes.data, s.size, order.ctypes.data)
         return order
+
+
+class SynthCobsOracle:
+    """The query of ``CobsOracle`` against the synthetic classic index of BASELINE config 5 (rows from the
+    counter-based generator documented at ``xs_cobs_create_synthetic``; the index exists nowhere as a file)."""
+
+    def __init__(self, n_docs: int, sig_size: int, k: int, num_hashes: int, seed: int, policy: int = POLICY_SKIP):
+        self.n_docs, self.sig_size, self.k, self.num_hashes, self.seed, self.policy = n_docs, sig_size, k, num_hashes, seed, policy
+
+    def row(self, r: int) -> np.ndarray:
+        """Row ``r`` as bytes, little-endian 32-document words (the file layout of a classic index row)."""
+        w = np.zeros((self.n_docs + 31) // 32, dtype=np.uint32)
+        lib().xso_synth_row(self.seed, r, self.n_docs, w.ctypes.data)
+        return w.view(np.uint8)[: (self.n_docs + 7) // 8].copy()
+
+    def counts_batch(self, bases, seq_begin, seq_end, step: int = 1, threads: int = 1) -> np.ndarray:
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        b = np.ascontiguousarray(seq_begin, dtype=np.uint64)
+        e = np.ascontiguousarray(seq_end, dtype=np.uint64)
+        out = np.zeros((b.size, self.n_docs), dtype=np.uint32)
+        lib().xso_cobs_query_batch_synth(self.seed, self.n_docs, self.sig_size, self.num_hashes, self.k, 1, self.policy,
+                                         bases.ctypes.data, b.ctypes.data, e.ctypes.data, b.size, step, out.ctypes.data, threads)
+        return out
 
     def search(self, query: str, step: int = 1) -> list[SearchResult]:
         """All documents, ordered like ClassicSearch::search (A.2.5c/d)."""

@@ -327,6 +327,51 @@ void xso_cobs_query_batch(const xso_cobs_t* ix, const uint8_t* bases, const uint
     });
 }
 
+// The same query against the synthetic index of BASELINE config 5 (bench.py's column-sharded leg): a classic index
+// of n_docs documents x sig_size rows that exists nowhere as a file; 32 documents of row r, word v, are
+//   m = splitmix64_finalise(seed ^ r * 0x9E3779B97F4A7C15 ^ v * 0xD1B54A32D192ED03);  bits = hi32(m) & lo32(m)
+// (include/xspect_b200.h, xs_cobs_create_synthetic).  Rows are regenerated on the fly for every probe.
+static inline uint64_t synth_mix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 27; x *= 0x94D049BB133111EBULL; x ^= x >> 31; return x;
+}
+static inline uint32_t synth_row_word(uint64_t seed, uint64_t row, uint32_t word) {
+    const uint64_t w = synth_mix64(seed ^ (row * 0x9E3779B97F4A7C15ULL) ^ ((uint64_t)word * 0xD1B54A32D192ED03ULL));
+    return (uint32_t)(w >> 32) & (uint32_t)w;
+}
+void xso_synth_row(uint64_t seed, uint64_t row, uint32_t n_docs, uint32_t* words_out) {
+    const uint32_t nw = (n_docs + 31) / 32;
+    for (uint32_t v = 0; v < nw; ++v) {
+        uint32_t x = synth_row_word(seed, row, v);
+        if (v * 32 + 32 > n_docs) x &= (1u << (n_docs - v * 32)) - 1u;
+        words_out[v] = x;
+    }
+}
+void xso_cobs_query_batch_synth(uint64_t seed, uint32_t n_docs, uint64_t sig_size, uint32_t num_hashes, uint32_t k,
+                                int canonicalize, int policy, const uint8_t* bases, const uint64_t* seq_begin,
+                                const uint64_t* seq_end, uint64_t n_seq, uint32_t step, uint32_t* counts, int n_threads) {
+    const uint32_t nw = (n_docs + 31) / 32;
+    parallel_for(n_seq, n_threads, [&](uint64_t i) {
+        uint32_t* out = counts + i * n_docs;
+        for (uint32_t d = 0; d < n_docs; ++d) out[d] = 0;
+        const uint8_t* seq = bases + seq_begin[i];
+        const uint64_t len = seq_end[i] - seq_begin[i];
+        if (len < k || step == 0) return;
+        uint8_t term[256];
+        std::vector<uint32_t> acc(nw), row(nw);
+        for (uint64_t p = 0; p + k <= len; p += step) {
+            if (!xso_cobs_term(seq + p, k, canonicalize, policy, term)) continue;
+            for (uint32_t j = 0; j < num_hashes; ++j) {
+                xso_synth_row(seed, xso_xxh64(term, k, j) % sig_size, n_docs, j == 0 ? acc.data() : row.data());
+                if (j) for (uint32_t v = 0; v < nw; ++v) acc[v] &= row[v];
+            }
+            for (uint32_t v = 0; v < nw; ++v) {
+                uint32_t x = acc[v];
+                while (x) { const int b = __builtin_ctz(x); x &= x - 1; out[v * 32 + b]++; }
+            }
+        }
+    });
+}
+
 // row ids for every sampled window of one sequence: rows[(w*num_hashes + j)*n_pages + pg];
 // valid[w] = 0 for skipped windows.  Used to pin the hash stage of the CUDA path on its own.
 void xso_cobs_rows(const xso_cobs_t* ix, const uint8_t* seq, uint64_t len, uint32_t step,

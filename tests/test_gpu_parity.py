@@ -542,3 +542,57 @@ def test_concurrent_queries_on_one_handle(gpu, oracle, tmp_path):
     assert not errors, errors
     for (gc, gb), (ec, eb) in zip(got, expected):
         assert np.array_equal(gc, ec) and np.array_equal(gb, eb)
+
+
+# ------------------------------------------------------------------------------------------ config 5 building blocks
+def test_synthetic_index_ld_rows_and_sharded_epilogue(gpu, oracle):
+    """BASELINE config 5 on one GPU: the synthetic index (rows from the counter-based generator, regenerated by the
+    oracle), column shards opened side by side, score tiles written at a common padded row length
+    (xs_cobs_query_device_ld), laid out [shard][record][w] as ncclAllGather delivers them, and the in-place epilogue
+    (xs_sharded_reduce_device): first best document, its count, tie multiplicity, totals."""
+    import torch
+    from xspect2_b200 import distributed as xd
+    from xspect2_b200._abi import XS_U8, XS_U16
+    D, S, K, H, seed = 1000, 20011, 21, 3, 6
+    orc = oracle.SynthCobsOracle(D, S, K, H, seed)
+    rng = np.random.default_rng(12)
+    genome = synth.random_dna(rng, 5000)
+    bases, b, e = synth.sample_reads(rng, [genome], 700, (21, 400), n_rate=0.003)
+    exp = orc.counts_batch(bases, b, e, 1, threads=4)
+    assert exp.max() > 3                       # fill 0.25 ** 3 over 1000 documents: real ties and real maxima
+    whole = gpu.CobsIndex.synthetic(D, S, K, H, seed)
+    assert whole.n_docs == D and whole.header_layout.startswith("synthetic")
+    assert np.array_equal(whole.query(bases, b, e, 1, dtype=4), exp)
+    assert abs(whole.doc_fill().mean() - 0.25) < 0.01
+    dev = torch.device("cuda", 0)
+    d_bases = torch.from_numpy(bases).to(dev)
+    d_b = torch.from_numpy(b.view(np.int64)).to(dev)
+    d_e = torch.from_numpy(e.view(np.int64)).to(dev)
+    n = b.size
+    for world in (1, 3, 8):
+        shards = xd.column_shards(D, world)
+        widths = [hi - lo for lo, hi in shards]
+        for dt, tdt, mx in ((XS_U8, torch.uint8, 255), (XS_U16, torch.uint16, 65535)):
+            unit = 16 // dt
+            w = -(-max(widths) // unit) * unit
+            al = torch.full((world, n, w), 7, dtype=tdt, device=dev)          # stale values must be overwritten
+            for g, (lo, hi) in enumerate(shards):
+                sh = gpu.CobsIndex.synthetic(D, S, K, H, seed, doc_begin=lo, doc_end=hi)
+                sh.query_device(d_bases.data_ptr(), bases.size, d_b.data_ptr(), d_e.data_ptr(), n, 1, dt, al[g].data_ptr(), 0, ld=w)
+                torch.cuda.synchronize()
+                sh.close()
+            got = torch.cat([al[g, :, : widths[g]] for g in range(world)], dim=1).cpu().numpy()
+            ref = np.minimum(exp, mx)
+            assert np.array_equal(got, ref), (world, dt)
+            assert int(al[0, :, widths[0]:].to(torch.int64).sum()) == 0       # padding columns are zero
+            best = torch.empty(n, dtype=torch.int32, device=dev)
+            cnt = torch.empty(n, dtype=torch.int32, device=dev)
+            nb = torch.empty(n, dtype=torch.int32, device=dev)
+            tot = torch.zeros(D, dtype=torch.int64, device=dev)
+            gpu.sharded_reduce_device(al.data_ptr(), n, dt, 0, w, widths, best.data_ptr(), cnt.data_ptr(), nb.data_ptr(), tot.data_ptr(), 0)
+            torch.cuda.synchronize()
+            assert np.array_equal(best.cpu().numpy(), ref.argmax(axis=1)), (world, dt)
+            assert np.array_equal(cnt.cpu().numpy(), ref.max(axis=1))
+            assert np.array_equal(nb.cpu().numpy(), (ref == ref.max(axis=1)[:, None]).sum(axis=1))
+            assert np.array_equal(tot.cpu().numpy(), ref.sum(axis=0, dtype=np.int64))
+    whole.close()

@@ -58,6 +58,26 @@ def _worker(rank: int, world: int, port: int, tmp: str):
         lo_d, hi_d = sh.shards[rank]
         assert np.array_equal(totals.cpu().numpy(), f8[:, lo_d:hi_d].sum(axis=0))
 
+        # ---- the exchange behind the C ABI: xs_comm_init + xs_cobs_query_device_ld + xs_allgather_scores (ncclAllGather)
+        # + xs_sharded_reduce_device consuming [world][n][w] in place, double-buffered over the tiles
+        comm = xd.make_comm(rank, world, rank)
+        assert comm.nccl_version > 20000
+        scorer = xd.ShardedScorer(sh.index, sh.shards, comm, XS_U8, 1000)
+        res = {}
+        scorer.run(iter(tiles), 1, lambda t, bst, c, nb_: res.__setitem__(t, (bst.cpu().numpy(), c.cpu().numpy(), nb_.cpu().numpy())),
+                   time_exchange=True)
+        assert sorted(res) == [0, 1, 2, 3] and scorer.exchange_ms > 0
+        assert np.array_equal(np.concatenate([res[t][0] for t in range(4)]), f8.argmax(axis=1))
+        assert np.array_equal(np.concatenate([res[t][1] for t in range(4)]), f8.max(axis=1))
+        assert np.array_equal(np.concatenate([res[t][2] for t in range(4)]), (f8 == f8.max(axis=1)[:, None]).sum(axis=1))
+        tot = torch.from_numpy(f8[:, lo_d:hi_d].sum(axis=0)).to(dev)
+        full_tot = torch.zeros(f8.shape[1], dtype=torch.int64, device=dev)
+        full_tot[lo_d:hi_d] = tot
+        comm.allreduce_totals(full_tot.data_ptr(), full_tot.numel(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(full_tot.cpu().numpy(), f8.sum(axis=0))
+        comm.close()
+
         # ---- read sharding: whole index per GPU, a slice of the records per rank, totals all-reduced
         ix = engine.CobsIndex(path, device=rank)
         lo, hi = xd.read_shard(b.size, rank, world)

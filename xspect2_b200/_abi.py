@@ -14,7 +14,7 @@ _PKG = Path(__file__).resolve().parent
 _LIB_PATH = _PKG / "libxspect_b200.so"
 
 XS_OK = 0
-XS_ERR_ARG, XS_ERR_IO, XS_ERR_FORMAT, XS_ERR_CUDA, XS_ERR_NOMEM, XS_ERR_UNSUPPORTED = -1, -2, -3, -4, -5, -6
+XS_ERR_ARG, XS_ERR_IO, XS_ERR_FORMAT, XS_ERR_CUDA, XS_ERR_NOMEM, XS_ERR_UNSUPPORTED, XS_ERR_NCCL = -1, -2, -3, -4, -5, -6, -7
 XS_U8, XS_U16, XS_U32 = 1, 2, 4
 XS_NONACGT_SKIP, XS_NONACGT_LITERAL = 0, 1
 XS_COBS_CLASSIC, XS_COBS_COMPACT = 1, 2
@@ -52,6 +52,7 @@ SYMBOLS = {
     "xs_last_error": (C.c_char_p, []),
     "xs_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "xs_launch_count": (C.c_uint64, []),
+    "xs_device_trim": (C.c_int, [C.c_int]),
     "xs_profile_enable": (C.c_int, [C.c_int]),
     "xs_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "xs_profile_read_phases": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -71,6 +72,15 @@ SYMBOLS = {
     "xs_cobs_close": (C.c_int, [_P]),
     "xs_cobs_query": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, C.c_int, _P]),
     "xs_cobs_query_device": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, C.c_int, _P, _P]),
+    "xs_cobs_query_device_ld": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, C.c_int, C.c_uint64, _P, _P]),
+    "xs_comm_unique_id": (C.c_int, [_P]),
+    "xs_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "xs_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "xs_comm_destroy": (C.c_int, [_P]),
+    "xs_allgather_scores": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _P, _P]),
+    "xs_allreduce_totals": (C.c_int, [_P, _P, C.c_uint64, _P]),
+    "xs_sharded_reduce_device": (C.c_int, [_P, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P, _P]),
+    "xs_cobs_create_synthetic": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(_P)]),
     "xs_cobs_classify": (C.c_int, [_P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, _P, _P, _P, _P]),
     "xs_mlst_query": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_uint64, _P, _P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, _P, _P, _P]),
     "xs_cobs_result_order": (C.c_int, [_P, C.c_uint32, _P]),

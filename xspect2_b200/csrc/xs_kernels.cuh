@@ -1589,6 +1589,104 @@ __global__ void __launch_bounds__(256) k_mlst_compact(const CntT* __restrict__ c
     }
 }
 
+// ----------------------------------------------------------------------------------------
+// Synthetic index rows (BASELINE config 5: a 120 GB index that no file holds).  Counter-based: 32 documents of row r
+// are   w = mix64(seed ^ r * C1 ^ word * C2);  bits = hi32(w) & lo32(w)   (fill 0.25), so any row can be regenerated
+// anywhere (the oracle does, for the parity sample) without materialising the index.
+// ----------------------------------------------------------------------------------------
+XS_HD uint64_t synth_mix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 27; x *= 0x94D049BB133111EBULL; x ^= x >> 31; return x;
+}
+XS_HD uint32_t synth_row_word(uint64_t seed, uint64_t row, uint32_t word) {
+    const uint64_t w = synth_mix64(seed ^ (row * 0x9E3779B97F4A7C15ULL) ^ ((uint64_t)word * 0xD1B54A32D192ED03ULL));
+    return (uint32_t)(w >> 32) & (uint32_t)w;
+}
+// fills rows [0, n_rows) of a column shard: bytes [col0, col0 + n_col) of every row at dst_stride, zero padded;
+// documents >= n_docs_total are zero like in a real file's last byte
+__global__ void __launch_bounds__(256) k_synth_rows(uint8_t* __restrict__ dst, uint64_t n_rows, uint32_t dst_stride, uint32_t col0,
+                                                    uint32_t n_col, uint32_t n_docs_total, uint64_t seed) {
+    const uint32_t words = dst_stride / 4;
+    const uint64_t total = n_rows * words;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / words;
+        const uint32_t w = (uint32_t)(i - r * words);
+        uint32_t v = 0;
+        if (w * 4 < n_col) {
+            const uint32_t gw = (col0 + w * 4) / 4;             // col0 is a multiple of 4 (document shards are 128-aligned)
+            v = synth_row_word(seed, r, gw);
+            const uint32_t d0 = gw * 32;
+            if (d0 + 32 > n_docs_total) v &= d0 >= n_docs_total ? 0u : ((1u << (n_docs_total - d0)) - 1u);
+            const uint32_t keep = n_col - w * 4;                  // bytes of this word inside the shard
+            if (keep < 4) v &= (1u << (8 * keep)) - 1u;
+        }
+        reinterpret_cast<uint32_t*>(dst + r * dst_stride)[w] = v;
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// Epilogue of the document-column sharded exchange (config 5): `all` = what ncclAllGather delivered,
+// [world][n_seq][w] counts, rank g's block holding its widths[g] local documents per record (zero padded to w).
+// Per record: first document with the maximum count over all shards, that count, how many documents share it, and
+// (optionally) per-document totals.  Consumed in place: no concatenation pass.  One warp per record.
+// ----------------------------------------------------------------------------------------
+struct ShardLayout {
+    uint32_t world;
+    uint32_t w;                  // padded documents per rank block
+    uint32_t width[16];          // documents of rank g
+    uint32_t doc0[16];           // first global document of rank g
+};
+
+template <typename CntT>
+__global__ void __launch_bounds__(256) k_sharded_reduce(const CntT* __restrict__ all, uint64_t n_seq, const ShardLayout lay,
+                                                        uint32_t* __restrict__ best, uint32_t* __restrict__ best_count,
+                                                        uint32_t* __restrict__ n_best, unsigned long long* __restrict__ totals) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    constexpr uint32_t VEC = 16 / sizeof(CntT);
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_seq; r += n_warps) {
+        uint32_t mx = 0, idx = 0xFFFFFFFFu, cnt = 0;
+        for (uint32_t g = 0; g < lay.world; ++g) {
+            const CntT* row = all + ((uint64_t)g * n_seq + r) * lay.w;
+            const uint32_t wd = lay.width[g];
+            if ((lay.w % VEC) == 0) {           // 16-byte aligned rows: vector loads
+                for (uint32_t d0 = lane * VEC; d0 < wd; d0 += 32 * VEC) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(row + d0);
+                    const CntT* e = reinterpret_cast<const CntT*>(&q);
+#pragma unroll
+                    for (uint32_t j = 0; j < VEC; ++j) {
+                        if (d0 + j >= wd) break;
+                        const uint32_t v = e[j], d = lay.doc0[g] + d0 + j;
+                        if (idx == 0xFFFFFFFFu || v > mx) { mx = v; idx = d; cnt = 1; }
+                        else if (v == mx) ++cnt;
+                        if (totals && v) atomicAdd(totals + d, (unsigned long long)v);
+                    }
+                }
+            } else {
+                for (uint32_t d0 = lane; d0 < wd; d0 += 32) {
+                    const uint32_t v = row[d0], d = lay.doc0[g] + d0;
+                    if (idx == 0xFFFFFFFFu || v > mx) { mx = v; idx = d; cnt = 1; }
+                    else if (v == mx) ++cnt;
+                    if (totals && v) atomicAdd(totals + d, (unsigned long long)v);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t omx = __shfl_xor_sync(0xFFFFFFFFu, mx, o), oidx = __shfl_xor_sync(0xFFFFFFFFu, idx, o),
+                           ocnt = __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+            if (oidx != 0xFFFFFFFFu) {
+                if (idx == 0xFFFFFFFFu || omx > mx) { mx = omx; idx = oidx; cnt = ocnt; }
+                else if (omx == mx) { cnt += ocnt; idx = oidx < idx ? oidx : idx; }
+            }
+        }
+        if (lane == 0) {
+            if (best) best[r] = idx;
+            if (best_count) best_count[r] = mx;
+            if (n_best) n_best[r] = cnt;
+        }
+    }
+}
+
 // per-document fill of a page estimated from `n_sample` evenly spaced rows (xs_cobs_doc_fill): thread per
 // (sampled row, 32-document word), one atomic per set bit
 __global__ void __launch_bounds__(256) k_doc_fill(const PageDesc pg, uint64_t n_sample, uint32_t* __restrict__ counts) {

@@ -648,8 +648,9 @@ static int dtype_size(int dt) { return (dt == XS_U8 || dt == XS_U16 || dt == XS_
 
 // all pointers device; asynchronous on s
 // the scoring kernel of a prepared batch (narrow or wide rows)
-static int cobs_launch(xs_cobs* ix, const SeqBatch& sb, const uint64_t* chunk_prefix, int dt, void* d_out, cudaStream_t s) {
-    const uint64_t ld = ix->info.doc_end - ix->info.doc_begin;
+static int cobs_launch(xs_cobs* ix, const SeqBatch& sb, const uint64_t* chunk_prefix, int dt, void* d_out, cudaStream_t s,
+                       uint64_t ld_override = 0) {
+    const uint64_t ld = ld_override ? ld_override : ix->info.doc_end - ix->info.doc_begin;
     const bool wide = !ix->narrow || ix->force_wide;
     CobsParams p{};
     p.sb = sb; p.pages = ix->d_pages; p.n_pages = (uint32_t)ix->pages.size();
@@ -680,8 +681,8 @@ static int cobs_launch(xs_cobs* ix, const SeqBatch& sb, const uint64_t* chunk_pr
 
 static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_begin,
                           const uint64_t* d_end, uint64_t n_seq, uint64_t base_shift, uint32_t step, int dt,
-                          void* d_out, cudaStream_t s) {
-    const uint64_t ld = ix->info.doc_end - ix->info.doc_begin;
+                          void* d_out, cudaStream_t s, uint64_t ld_override = 0) {
+    const uint64_t ld = ld_override ? ld_override : ix->info.doc_end - ix->info.doc_begin;
     XS_CUDA(cudaMemsetAsync(d_out, 0, n_seq * ld * (uint64_t)dt, s));
     if (n_seq == 0) return XS_OK;
     Workspace ws;
@@ -689,7 +690,7 @@ static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
     const bool wide = !ix->narrow || ix->force_wide;
     XS_TRY(prepare_batch(ws, sb, d_bases, n_bases, d_begin, d_end, n_seq, base_shift, ix->info.term_size, step,
                          wide ? WIDE_CHUNK : 0, ix->n_sm, s));
-    return cobs_launch(ix, sb, ws.prefix2, dt, d_out, s);   // ws goes back to the stream-ordered pool on scope exit
+    return cobs_launch(ix, sb, ws.prefix2, dt, d_out, s, ld_override);   // ws goes back to the stream-ordered pool on scope exit
 }
 
 // ---- Bloom, bucketed probing (k_bbucket_emit / k_bbucket_fetch / k_bbucket_reduce) ---------------------------
@@ -1095,6 +1096,15 @@ int xs_host_alloc(uint64_t bytes, void** out) {
     if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA, cudaGetErrorString(e));
     return XS_OK;
 }
+int xs_device_trim(int device) {
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the device");
+    XS_CUDA(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    XS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    XS_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return XS_OK;
+}
 int xs_host_free(void* p) {
     if (p) XS_CUDA(cudaFreeHost(p));
     return XS_OK;
@@ -1208,6 +1218,211 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
     return XS_OK;
 }
 
+// A classic index whose rows come from the counter-based generator of k_synth_rows instead of a file (BASELINE
+// config 5: D = 10 000, S = 96 000 000 is a 120 GB index; the bench generates each rank's column shard straight into
+// HBM and the oracle regenerates the rows its parity sample touches).  Same handle, same kernels as xs_cobs_open.
+int xs_cobs_create_synthetic(int device, uint32_t n_docs, uint32_t doc_begin, uint32_t doc_end, uint64_t sig_size,
+                             uint32_t term_size, uint32_t num_hashes, uint64_t seed, xs_cobs** out) {
+    if (!out) return fail(XS_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (doc_begin == 0 && doc_end == 0) doc_end = n_docs;
+    if (n_docs == 0 || doc_end > n_docs || doc_begin >= doc_end || (doc_begin % 32) != 0 || (doc_end % 8 != 0 && doc_end != n_docs))
+        return fail(XS_ERR_ARG, "document shard must be [multiple of 32, multiple of 8 or n_docs) within the index");
+    if (sig_size == 0 || term_size == 0 || term_size > 32 || num_hashes == 0 || num_hashes > 64)
+        return fail(XS_ERR_ARG, "bad synthetic index geometry");
+    DeviceGuard guard(device);
+    int n_sm = 0;
+    XS_TRY(device_setup(device, &n_sm));
+    xs_cobs* ix = new xs_cobs();
+    ix->info.device = device;
+    ix->n_sm = n_sm;
+    ix->layout = "synthetic rows (k_synth_rows)";
+    for (uint32_t d = 0; d < n_docs; ++d) { ix->names += "d" + std::to_string(d); ix->names.push_back('\n'); }
+    const uint32_t col0 = doc_begin / 8, n_col = (doc_end - doc_begin + 7) / 8;
+    uint32_t stride = 16;
+    while (stride < n_col && stride < 128) stride <<= 1;
+    if (n_col > 128) stride = (n_col + 127) & ~127u;
+    ix->narrow = stride == 16;
+    const uint64_t total = sig_size * stride;
+    cudaError_t e = cudaMalloc((void**)&ix->d_data, total + 256);
+    if (e != cudaSuccess) { delete ix; return fail(XS_ERR_NOMEM, "synthetic index of " + std::to_string(total) + " bytes does not fit in HBM: " + cudaGetErrorString(e)); }
+    k_synth_rows<<<n_sm * 16, 256>>>(ix->d_data, sig_size, stride, col0, n_col, n_docs, seed);
+    int rc = launch_ok("k_synth_rows");
+    PageDesc pd{};
+    pd.data = ix->d_data; pd.sig_size = sig_size; pd.magic = magic_of(sig_size); pd.row_stride = stride;
+    pd.n_docs = doc_end - doc_begin; pd.doc_off = 0;
+    ix->pages.push_back(pd);
+    const uint32_t C = (n_col + 15) / 16, nb = (C + WIDE_MAX_COLS - 1) / WIDE_MAX_COLS, per = (C + nb - 1) / nb;
+    for (uint32_t c0 = 0; c0 < C; c0 += per) {
+        ColBlock cb{0, c0, std::min(per, C - c0), 0};
+        const uint64_t dlo = (uint64_t)c0 * 128, dhi = std::min<uint64_t>((uint64_t)(c0 + cb.n_cols) * 128, pd.n_docs);
+        cb.n_docs = dhi > dlo ? (uint32_t)(dhi - dlo) : 0;
+        if (cb.n_docs) ix->blocks.push_back(cb);
+    }
+    if (rc == XS_OK && (cudaMalloc((void**)&ix->d_pages, sizeof(PageDesc)) != cudaSuccess ||
+                        cudaMalloc((void**)&ix->d_blocks, std::max<size_t>(1, ix->blocks.size()) * sizeof(ColBlock)) != cudaSuccess))
+        rc = fail(XS_ERR_NOMEM, "descriptor allocation failed");
+    if (rc == XS_OK) {
+        cudaMemcpy(ix->d_pages, ix->pages.data(), sizeof(PageDesc), cudaMemcpyHostToDevice);
+        if (!ix->blocks.empty()) cudaMemcpy(ix->d_blocks, ix->blocks.data(), ix->blocks.size() * sizeof(ColBlock), cudaMemcpyHostToDevice);
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = fail(XS_ERR_CUDA, std::string("synthetic index: ") + cudaGetErrorString(e));
+    }
+    if (rc != XS_OK) { std::string keep = g_err; xs_cobs_close(ix); g_err = keep; return rc; }
+    xs_cobs_info_t& in = ix->info;
+    in.kind = XS_COBS_CLASSIC; in.term_size = term_size; in.canonicalize = 1; in.num_hashes = num_hashes; in.n_docs_total = n_docs;
+    in.doc_begin = doc_begin; in.doc_end = doc_end; in.n_pages = 1; in.page_bytes = ((uint64_t)n_docs + 7) / 8; in.row_stride = stride;
+    in.sig_size_max = sig_size; in.hbm_bytes = total; in.device = device; in.policy = XS_NONACGT_SKIP;
+    *out = ix;
+    return XS_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+// NCCL exchange of the document-column sharded path.  libnccl is bound at run time (dlopen): the
+// library has no link-time dependency on it, single-GPU users never load it, and inside a torch process the NCCL
+// torch already loaded is the one used.
+// ----------------------------------------------------------------------------------------
+#include <dlfcn.h>
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm;
+struct NcclApi {
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm*, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(nccl_comm) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int*) = nullptr;
+    void* handle = nullptr;
+    std::string err;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* env = getenv("XSPECT_B200_NCCL");
+        void* h = nullptr;
+        if (env && *env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);    // already in the process (torch)
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { const char* m = dlerror(); api.err = std::string("libnccl.so.2 cannot be loaded: ") + (m ? m : "?"); return; }
+        api.handle = h;
+        auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p && api.err.empty()) api.err = std::string("NCCL symbol missing: ") + n; return p; };
+        api.GetUniqueId = (int (*)(nccl_uid*))sym("ncclGetUniqueId");
+        api.CommInitRank = (int (*)(nccl_comm*, int, nccl_uid, int))sym("ncclCommInitRank");
+        api.CommDestroy = (int (*)(nccl_comm))sym("ncclCommDestroy");
+        api.AllGather = (int (*)(const void*, void*, size_t, int, nccl_comm, cudaStream_t))sym("ncclAllGather");
+        api.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t))sym("ncclAllReduce");
+        api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+        api.GetVersion = (int (*)(int*))sym("ncclGetVersion");
+    });
+    return &api;
+}
+}  // namespace
+
+struct xs_comm {
+    nccl_comm comm = nullptr;
+    int rank = 0, world = 1, device = 0;
+};
+
+static int nccl_fail(NcclApi* a, int r, const char* what) {
+    return fail(XS_ERR_NCCL, std::string(what) + ": " + (a->GetErrorString ? a->GetErrorString(r) : "NCCL error"));
+}
+
+int xs_comm_unique_id(uint8_t* id128) {
+    if (!id128) return fail(XS_ERR_ARG, "NULL argument");
+    NcclApi* a = nccl_api();
+    if (!a->err.empty()) return fail(XS_ERR_NCCL, a->err);
+    nccl_uid id;
+    int r = a->GetUniqueId(&id);
+    if (r != 0) return nccl_fail(a, r, "ncclGetUniqueId");
+    memcpy(id128, id.internal, 128);
+    return XS_OK;
+}
+
+int xs_comm_init(const uint8_t* id128, int rank, int world, int device, xs_comm** out) {
+    if (!id128 || !out) return fail(XS_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) return fail(XS_ERR_ARG, "rank/world out of range (world <= 16)");
+    NcclApi* a = nccl_api();
+    if (!a->err.empty()) return fail(XS_ERR_NCCL, a->err);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the device");
+    nccl_uid id;
+    memcpy(id.internal, id128, 128);
+    xs_comm* c = new xs_comm();
+    c->rank = rank; c->world = world; c->device = device;
+    int r = a->CommInitRank(&c->comm, world, id, rank);
+    if (r != 0) { delete c; return nccl_fail(a, r, "ncclCommInitRank"); }
+    *out = c;
+    return XS_OK;
+}
+
+int xs_comm_destroy(xs_comm* c) {
+    if (!c) return XS_OK;
+    NcclApi* a = nccl_api();
+    if (c->comm && a->CommDestroy) { DeviceGuard guard(c->device); a->CommDestroy(c->comm); }
+    delete c;
+    return XS_OK;
+}
+
+int xs_comm_info(const xs_comm* c, int* rank, int* world, int* nccl_version) {
+    if (!c) return fail(XS_ERR_ARG, "NULL communicator");
+    if (rank) *rank = c->rank;
+    if (world) *world = c->world;
+    if (nccl_version) { *nccl_version = 0; NcclApi* a = nccl_api(); if (a->GetVersion) a->GetVersion(nccl_version); }
+    return XS_OK;
+}
+
+int xs_allgather_scores(xs_comm* c, const void* d_local, uint64_t n_seq, uint64_t row_bytes, void* d_all, void* stream) {
+    if (!c || (n_seq && row_bytes && (!d_local || !d_all))) return fail(XS_ERR_ARG, "NULL argument");
+    if (n_seq == 0 || row_bytes == 0) return XS_OK;
+    NcclApi* a = nccl_api();
+    DeviceGuard guard(c->device);
+    int r = a->AllGather(d_local, d_all, (size_t)(n_seq * row_bytes), /*ncclUint8*/ 1, c->comm, (cudaStream_t)stream);
+    if (r != 0) return nccl_fail(a, r, "ncclAllGather");
+    return XS_OK;
+}
+
+int xs_allreduce_totals(xs_comm* c, uint64_t* d_totals, uint64_t n, void* stream) {
+    if (!c || (n && !d_totals)) return fail(XS_ERR_ARG, "NULL argument");
+    if (n == 0) return XS_OK;
+    NcclApi* a = nccl_api();
+    DeviceGuard guard(c->device);
+    int r = a->AllReduce(d_totals, d_totals, (size_t)n, /*ncclUint64*/ 5, /*ncclSum*/ 0, c->comm, (cudaStream_t)stream);
+    if (r != 0) return nccl_fail(a, r, "ncclAllReduce");
+    return XS_OK;
+}
+
+int xs_sharded_reduce_device(const void* d_all, uint64_t n_seq, int dtype, int device, uint32_t world, uint32_t w,
+                             const uint32_t* widths, uint32_t* d_best, uint32_t* d_best_count, uint32_t* d_n_best,
+                             uint64_t* d_totals, void* stream) {
+    if (!dtype_size(dtype)) return fail(XS_ERR_ARG, "dtype must be XS_U8, XS_U16 or XS_U32");
+    if (world == 0 || world > 16 || !widths) return fail(XS_ERR_ARG, "world must be 1..16");
+    if (n_seq == 0) return XS_OK;
+    if (!d_all) return fail(XS_ERR_ARG, "NULL count buffer");
+    ShardLayout lay{};
+    lay.world = world; lay.w = w;
+    uint32_t d0 = 0;
+    for (uint32_t g = 0; g < world; ++g) {
+        if (widths[g] > w) return fail(XS_ERR_ARG, "a shard is wider than the padded block");
+        lay.width[g] = widths[g]; lay.doc0[g] = d0; d0 += widths[g];
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the device");
+    int n_sm = 0;
+    XS_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_seq + 7) / 8, (uint64_t)n_sm * 8));
+    unsigned long long* tot = reinterpret_cast<unsigned long long*>(d_totals);
+    if (dtype == XS_U8) k_sharded_reduce<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)d_all, n_seq, lay, d_best, d_best_count, d_n_best, tot);
+    else if (dtype == XS_U16) k_sharded_reduce<uint16_t><<<grid, 256, 0, s>>>((const uint16_t*)d_all, n_seq, lay, d_best, d_best_count, d_n_best, tot);
+    else k_sharded_reduce<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*)d_all, n_seq, lay, d_best, d_best_count, d_n_best, tot);
+    return launch_ok("k_sharded_reduce");
+}
+
 int xs_cobs_info(const xs_cobs* ix, xs_cobs_info_t* info) {
     if (!ix || !info) return fail(XS_ERR_ARG, "NULL argument");
     *info = ix->info;
@@ -1307,6 +1522,18 @@ int xs_cobs_query_device(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases, 
     if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the index's device");
     return cobs_query_dev(ix, d_bases, n_bases, d_seq_begin, d_seq_end, n_seq, 0, step, out_dtype, d_out,
                           (cudaStream_t)stream);
+}
+
+int xs_cobs_query_device_ld(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases, const uint64_t* d_seq_begin,
+                            const uint64_t* d_seq_end, uint64_t n_seq, uint32_t step, int out_dtype, uint64_t ld, void* d_out,
+                            void* stream) {
+    if (!ix || (!d_out && n_seq) || (n_seq && (!d_seq_begin || !d_seq_end))) return fail(XS_ERR_ARG, "NULL argument");
+    if (step == 0) return fail(XS_ERR_ARG, "step must be >= 1");
+    if (!dtype_size(out_dtype)) return fail(XS_ERR_ARG, "out_dtype must be XS_U8, XS_U16 or XS_U32");
+    if (ld < ix->info.doc_end - ix->info.doc_begin) return fail(XS_ERR_ARG, "ld is smaller than the number of local documents");
+    DeviceGuard guard(ix->info.device);
+    if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the index's device");
+    return cobs_query_dev(ix, d_bases, n_bases, d_seq_begin, d_seq_end, n_seq, 0, step, out_dtype, d_out, (cudaStream_t)stream, ld);
 }
 
 int xs_cobs_query(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const uint64_t* seq_begin,

@@ -167,6 +167,92 @@ class ColumnShardedIndex:
         return totals
 
 
+def make_comm(rank: int, world: int, device: int, group=None):
+    """This rank's ``engine.Comm`` (the library's own NCCL communicator, ``xs_comm_init``): rank 0 creates the id and
+    ``torch.distributed`` — already up for the launch plumbing — carries the 128 bytes to the others."""
+    from . import engine
+
+    box = [engine.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return engine.Comm(box[0], rank, world, device)
+
+
+class ShardedScorer:
+    """Document-column sharded scoring with the exchange behind the C ABI (BASELINE config 5):
+    every rank scores every record tile against its columns into ``[n, w]`` rows of one common padded width
+    (``xs_cobs_query_device_ld``), ``xs_allgather_scores`` (ncclAllGather over NVLink) delivers ``[world][n][w]`` on a
+    side stream while the next tile is being scored, and ``xs_sharded_reduce_device`` consumes that buffer in place:
+    per-record first best document, its count and the tie multiplicity (the reference benchmark's per-read call,
+    scripts/benchmark/main.nf:417-436).  No pad, concat or eager pass over the tile."""
+
+    def __init__(self, index, shards: list[tuple[int, int]], comm, dtype: int, max_tile: int):
+        from ._abi import XS_U8, XS_U16
+
+        self.index, self.shards, self.comm, self.dtype = index, shards, comm, dtype
+        self.world = len(shards)
+        self.widths = [hi - lo for lo, hi in shards]
+        item = int(dtype)
+        unit = 16 // item
+        self.w = -(-max(self.widths) // unit) * unit                 # rows stay 16-byte multiples for the vector loads
+        self.tdt = {XS_U8: torch.uint8, XS_U16: torch.uint16}.get(dtype, torch.uint32)
+        self.dev = torch.device("cuda", index.device)
+        self.max_tile = max_tile
+        self.local = [torch.empty((max_tile, self.w), dtype=self.tdt, device=self.dev) for _ in range(2)]
+        self.all = [torch.empty((self.world, max_tile, self.w), dtype=self.tdt, device=self.dev) for _ in range(2)]
+        self.comm_stream = torch.cuda.Stream(device=self.dev)
+        self.exchange_ms = 0.0
+
+    def run(self, tiles: Iterator[tuple[int, int, int, int, int]], step: int,
+            consume: Callable[[int, torch.Tensor, torch.Tensor, torch.Tensor], None], time_exchange: bool = False) -> None:
+        """``tiles`` = ``(d_bases, n_bases, d_begin, d_end, n_seq)`` device pointers; ``consume(tile, best, count,
+        n_best)`` is called in tile order once a tile's epilogue has finished."""
+        from . import engine
+
+        compute = torch.cuda.current_stream(self.dev)
+        free = [None, None]          # event: the exchange that read local[slot] has finished
+        pending = []
+        timers = []
+        for t, (d_bases, n_bases, d_begin, d_end, n_seq) in enumerate(tiles):
+            if n_seq > self.max_tile:
+                raise ValueError("tile larger than max_tile")
+            slot = t & 1
+            if free[slot] is not None:
+                compute.wait_event(free[slot])
+            loc, al = self.local[slot], self.all[slot]
+            self.index.query_device(d_bases, n_bases, d_begin, d_end, n_seq, step, self.dtype, loc.data_ptr(),
+                                    compute.cuda_stream, ld=self.w)
+            scored = torch.cuda.Event()
+            scored.record(compute)
+            best = torch.empty(n_seq, dtype=torch.int32, device=self.dev)
+            cnt = torch.empty(n_seq, dtype=torch.int32, device=self.dev)
+            nb = torch.empty(n_seq, dtype=torch.int32, device=self.dev)
+            cs = self.comm_stream
+            cs.wait_event(scored)
+            if time_exchange:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(cs)
+            # blocks of [world][n_seq][w] inside the slot's buffer (contiguous for this n_seq)
+            self.comm.allgather_scores(loc.data_ptr(), n_seq, self.w * int(self.dtype), al.data_ptr(), cs.cuda_stream)
+            if time_exchange:
+                e1.record(cs)
+                timers.append((e0, e1))
+            engine.sharded_reduce_device(al.data_ptr(), n_seq, self.dtype, self.index.device, self.w, self.widths,
+                                         best.data_ptr(), cnt.data_ptr(), nb.data_ptr(), 0, cs.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(cs)
+            free[slot] = done
+            pending.append((t, best, cnt, nb, done))
+            while len(pending) > 1:
+                pt, b_, c_, n_, ev = pending.pop(0)
+                ev.synchronize()
+                consume(pt, b_, c_, n_)
+        for pt, b_, c_, n_, ev in pending:
+            ev.synchronize()
+            consume(pt, b_, c_, n_)
+        if time_exchange:
+            self.exchange_ms += sum(a.elapsed_time(b) for a, b in timers)
+
+
 def _doc_count(path) -> int:
     """num_documents from a COBS classic header (A.1) without loading the index."""
     import struct

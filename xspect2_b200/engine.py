@@ -117,6 +117,11 @@ def _as_u64(a) -> np.ndarray:
     return a
 
 
+def device_trim(device: int = 0) -> None:
+    """Return the library's cached device workspaces / bucketed scratch to the driver (``xs_device_trim``)."""
+    check(lib().xs_device_trim(int(device)))
+
+
 def pick_dtype(max_windows: int) -> int:
     """Smallest count type that cannot saturate for sequences of at most ``max_windows`` windows."""
     return XS_U8 if max_windows <= 255 else XS_U16 if max_windows <= 65535 else XS_U32
@@ -128,12 +133,15 @@ def pick_dtype(max_windows: int) -> int:
 class CobsIndex:
     """A COBS classic / compact index file resident in one GPU's HBM (optionally a column shard)."""
 
-    def __init__(self, path, device: int = 0, doc_begin: int = 0, doc_end: int = 0):
+    def __init__(self, path, device: int = 0, doc_begin: int = 0, doc_end: int = 0, _handle=None):
         self._h = C.c_void_p()
         self.path = str(path)
-        if not os.path.isfile(self.path):
-            raise FileNotFoundError(f"Index file not found at {self.path}")
-        check(lib().xs_cobs_open(self.path.encode(), int(device), int(doc_begin), int(doc_end), C.byref(self._h)))
+        if _handle is not None:
+            self._h = _handle
+        else:
+            if not os.path.isfile(self.path):
+                raise FileNotFoundError(f"Index file not found at {self.path}")
+            check(lib().xs_cobs_open(self.path.encode(), int(device), int(doc_begin), int(doc_end), C.byref(self._h)))
         info = _abi.CobsInfo()
         check(lib().xs_cobs_info(self._h, C.byref(info)))
         self.info = info
@@ -144,6 +152,16 @@ class CobsIndex:
         names = buf.raw[: need.value].decode("utf-8").split("\n")
         self.all_names = names[:-1] if names and names[-1] == "" else names
         self.names = self.all_names[info.doc_begin : info.doc_end]
+
+    @classmethod
+    def synthetic(cls, n_docs: int, sig_size: int, k: int, num_hashes: int, seed: int, device: int = 0, doc_begin: int = 0,
+                  doc_end: int = 0) -> "CobsIndex":
+        """A classic index (or a document-column shard of it) whose rows come from the counter-based generator of
+        ``xs_cobs_create_synthetic`` — BASELINE config 5's 120 GB index, generated straight into HBM."""
+        h = C.c_void_p()
+        check(lib().xs_cobs_create_synthetic(int(device), int(n_docs), int(doc_begin), int(doc_end), int(sig_size), int(k),
+                                             int(num_hashes), int(seed), C.byref(h)))
+        return cls(f"<synthetic D={n_docs} S={sig_size} seed={seed}>", _handle=h)
 
     # geometry
     k = property(lambda self: self.info.term_size)
@@ -242,9 +260,14 @@ class CobsIndex:
         return best, cnt, nb, totals
 
     def query_device(self, d_bases: int, n_bases: int, d_begin: int, d_end: int, n_seq: int, step: int, dtype: int,
-                     d_out: int, stream: int = 0) -> None:
-        """Same with raw device pointers on this index's GPU; asynchronous on ``stream``."""
-        check(lib().xs_cobs_query_device(self._h, d_bases, n_bases, d_begin, d_end, n_seq, int(step), int(dtype), d_out, stream))
+                     d_out: int, stream: int = 0, ld: int = 0) -> None:
+        """Same with raw device pointers on this index's GPU; asynchronous on ``stream``.  ``ld`` > 0: output rows of
+        that many elements (zero padded) instead of ``n_docs``."""
+        if ld:
+            check(lib().xs_cobs_query_device_ld(self._h, d_bases, n_bases, d_begin, d_end, n_seq, int(step), int(dtype), int(ld),
+                                                d_out, stream))
+        else:
+            check(lib().xs_cobs_query_device(self._h, d_bases, n_bases, d_begin, d_end, n_seq, int(step), int(dtype), d_out, stream))
 
     def counts(self, sequence, step: int = 1) -> np.ndarray:
         """uint32 hit counts of one sequence."""
@@ -302,6 +325,55 @@ class Search:
             raise RuntimeError("query too short for the index term size")
         c = self.index.counts(query, step)
         return [SearchResult(self.index.names[i], int(c[i])) for i in CobsIndex.result_order(c)]
+
+
+class Comm:
+    """One rank's NCCL communicator for the document-column sharded exchange (``xs_comm_*``).  ``unique_id()`` on
+    rank 0, ship the 128 bytes to the other ranks, ``Comm(id, rank, world, device)`` everywhere."""
+
+    def __init__(self, uid: bytes, rank: int, world: int, device: int):
+        self._h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        check(lib().xs_comm_init(buf, int(rank), int(world), int(device), C.byref(self._h)))
+        self.rank, self.world, self.device = rank, world, device
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        check(lib().xs_comm_unique_id(buf))
+        return bytes(buf)
+
+    @property
+    def nccl_version(self) -> int:
+        v = C.c_int()
+        check(lib().xs_comm_info(self._h, None, None, C.byref(v)))
+        return int(v.value)
+
+    def allgather_scores(self, d_local: int, n_seq: int, row_bytes: int, d_all: int, stream: int = 0) -> None:
+        check(lib().xs_allgather_scores(self._h, d_local, int(n_seq), int(row_bytes), d_all, stream))
+
+    def allreduce_totals(self, d_totals: int, n: int, stream: int = 0) -> None:
+        check(lib().xs_allreduce_totals(self._h, d_totals, int(n), stream))
+
+    def close(self) -> None:
+        h, self._h = self._h, C.c_void_p()
+        if h:
+            lib().xs_comm_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sharded_reduce_device(d_all: int, n_seq: int, dtype: int, device: int, w: int, widths, d_best: int, d_best_count: int,
+                          d_n_best: int, d_totals: int = 0, stream: int = 0) -> None:
+    """Per-record first best document / count / tie multiplicity over ``[world][n_seq][w]`` all-gathered score blocks,
+    in place (``xs_sharded_reduce_device``)."""
+    wd = np.ascontiguousarray(widths, dtype=np.uint32)
+    check(lib().xs_sharded_reduce_device(d_all, int(n_seq), int(dtype), int(device), wd.size, int(w), _ptr(wd), d_best or None,
+                                         d_best_count or None, d_n_best or None, d_totals or None, stream))
 
 
 def mlst_query(indices: list[CobsIndex], allele_len, bases, seq_begin, seq_end, step: int = 1,
