@@ -385,6 +385,143 @@ def run_cfg5(args, rank: int, world: int, local_rank: int) -> dict:
 
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE config 3: genus Bloom filter -> threshold 0.7 -> species COBS + SVM, 50 M reads read-sharded over the GPUs
+# ---------------------------------------------------------------------------------------------------------------------
+CFG3_READS = int(os.environ.get("XS_CFG3_READS", 50_000_000))
+CFG3_BLOOM_BITS = int(os.environ.get("XS_CFG3_BLOOM_BITS", 13_800_000_008))
+
+
+def build_cfg3_models(workdir: Path, index_path: Path, genome: np.ndarray, device: int):
+    """Model directories in the reference's layout (definitions.py:10-46): the genus filter.bloom (built by the
+    library's own GPU builder at the stated size, then brought to the design fill of 0.5 with random bits) and the
+    species model = the config-2 index plus a synthetic scores.csv (4 rows per species) for the SVM."""
+    import torch
+    from xspect2_b200 import engine
+    models = workdir / "models"
+    (models / "synth-species").mkdir(parents=True)
+    (models / "synth-genus").mkdir(parents=True)
+    os.symlink(index_path, models / "synth-species" / "index.cobs_classic")
+    names = [f"{1000 + d}" for d in range(D)]
+    rng = np.random.default_rng(3)
+    with open(models / "synth-species" / "scores.csv", "w") as f:
+        f.write("file," + ",".join(sorted(names)) + ",label_id\n")
+        for i, lab in enumerate(sorted(names)):
+            for rep in range(4):
+                x = np.round(rng.uniform(0, 0.2, size=len(names)), 2)
+                x[i] = round(1.0 - 0.05 * rep, 2)
+                f.write(f"acc{i}_{rep}," + ",".join(str(v) for v in x) + f",{lab}\n")
+    meta = {"model_slug": "synth-species", "k": K, "model_display_name": "Synth", "author": None, "author_email": None,
+            "model_type": "Species", "model_class": "ProbabilisticFilterSVMModel", "display_names": {n: f"Synth sp{n}" for n in names},
+            "fpr": 0.01, "num_hashes": H, "training_accessions": None, "kernel": "rbf", "C": 1.0, "svm_accessions": None}
+    (models / "synth-species.json").write_text(json.dumps(meta))
+    bloom = models / "synth-genus" / "filter.bloom"
+    n_items = int(CFG3_BLOOM_BITS * (np.log(2.0) ** 2) / -np.log(0.01))          # expected_items that gives this many bits at fpr 0.01
+    engine.build_bloom(bloom, K, n_items, 0.01, genome, np.array([0], np.uint64), np.array([genome.size], np.uint64), device=device)
+    raw = np.fromfile(bloom, dtype=np.uint8)
+    dev = torch.device("cuda", device)
+    gen = torch.Generator(device=dev).manual_seed(11)
+    bits = torch.from_numpy(raw[8:]).to(dev)
+    for o in range(0, bits.numel(), 1 << 28):
+        part = bits[o : o + (1 << 28)]
+        part |= torch.randint(0, 256, (part.numel(),), generator=gen, device=dev, dtype=torch.uint8)
+    raw[8:] = bits.cpu().numpy()
+    raw.tofile(bloom)
+    k_hashes = int(np.frombuffer(raw[:8].tobytes(), dtype="<u8")[0])
+    del bits, raw
+    gmeta = {"model_slug": "synth-genus", "k": K, "model_display_name": "Synth", "author": None, "author_email": None,
+             "model_type": "Genus", "model_class": "ProbabilisticSingleFilterModel", "display_names": {"Synth": "Synth"},
+             "fpr": 0.01, "num_hashes": 1, "training_accessions": None}
+    (models / "synth-genus.json").write_text(json.dumps(gmeta))
+    return models, k_hashes, (bloom.stat().st_size - 8) * 8
+
+
+def run_cfg3(args, rank: int, world: int, local_rank: int, workdir: Path, index_path: Path) -> dict:
+    """The stages of `xspect all` (main.py:105-145) fused on the device (pipeline.genus_then_species_sharded): every
+    rank loads both models into its HBM and takes the contiguous slice [i*N/G, (i+1)*N/G) of 50 M reads from pinned host
+    memory; genus Bloom -> keep round(hits/num_kmers, 2) >= 0.7 -> species index on the kept reads -> device
+    argmax/totals; the D species totals are all-reduced and the SVM predicts from the global scores."""
+    import torch
+    import torch.distributed as dist
+    from xspect2_b200 import distributed as xd, engine, synth
+    from xspect2_b200.models.probabilistic_filter_svm_model import ProbabilisticFilterSVMModel
+    from xspect2_b200.models.probabilistic_single_filter_model import ProbabilisticSingleFilterModel
+    from xspect2_b200.pipeline import genus_then_species_sharded
+    from xspect2_b200.seqio import SequenceBatch
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.empty_cache()
+    engine.device_trim(local_rank)
+    genome = synth.synth_genome(GENOME_LEN, seed=1, n_rate=0.0001)
+    t0 = time.perf_counter()
+    models, k_hashes, n_bits = build_cfg3_models(workdir / "cfg3", index_path, genome, local_rank)
+    genus = ProbabilisticSingleFilterModel.load(models / "synth-genus.json", device=local_rank)
+    species = ProbabilisticFilterSVMModel.load(models / "synth-species.json", device=local_rank)
+    setup_s = time.perf_counter() - t0
+    lo, hi = xd.read_shard(CFG3_READS, rank, world)
+    n_local = hi - lo
+    # rank r's slice of the job's read set: generated in blocks of 1 M reads whose seeds depend on the block index only,
+    # so the union over ranks is the same 50 M reads at every N (strong scaling)
+    h_bases = engine.pinned_empty(n_local * READ_LEN, np.uint8)
+    blk = 1_000_000
+    for b0 in range(lo - lo % blk, hi, blk):
+        part = synth.synth_reads(genome, blk, READ_LEN, seed=4_000 + b0 // blk, device=dev)
+        a, z = max(b0, lo), min(b0 + blk, hi)
+        torch.from_numpy(h_bases[(a - lo) * READ_LEN : (z - lo) * READ_LEN]).copy_(part[(a - b0) * READ_LEN : (z - b0) * READ_LEN])
+        del part
+    hb, he = synth.fixed_offsets(n_local, READ_LEN)
+    batch = SequenceBatch(None, h_bases, hb, he, None, np.zeros(0, np.uint8), np.zeros(n_local, np.uint64))
+    steps = max(1, min(args.steps, int(os.environ.get("XS_CFG3_STEPS", 2))))
+    out = genus_then_species_sharded(genus, species, batch, 0.7, 1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = engine.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = genus_then_species_sharded(genus, species, batch, 0.7, 1)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    launches = engine.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    kept = out["global_kept"]
+    res = {
+        "workload": f"cfg3: {CFG3_READS} x {READ_LEN}bp reads (the same read set at every N: strong scaling), genus Bloom "
+                    f"({n_bits} bits, k_bloom={k_hashes}, fill 0.5) -> keep rounded score >= 0.7 -> species COBS D={D} S={SIG_SIZE} "
+                    "-> device argmax/totals -> all-reduce of the species totals -> SVM on the global scores",
+        "parallelism": f"read-sharded x{world}, both models replicated per GPU, one {D}-element all-reduce",
+        "n_gpus": world, "steps": steps, "scaling": "strong",
+        "reads_per_s": CFG3_READS * steps / dt, "s_per_pass": dt / steps,
+        "lookups_per_s": (CFG3_READS + kept) * (READ_LEN - K + 1) * steps / dt,
+        "kept_reads": kept, "prediction": out["prediction"], "gpu_launches": int(launches),
+        "e2e": "reads start in pinned host memory: H2D of the rank's slice, both stages, D2H of hits / calls inside the timed region",
+        "h2d_bytes_per_pass_per_gpu": int(n_local * READ_LEN + 16 * n_local), "setup_s": round(setup_s, 1),
+    }
+    if rank == 0:
+        from oracle import oracle
+        sample = min(n_local, int(os.environ.get("XS_CFG3_PARITY", 20_000)))
+        eg = oracle.BloomOracle(models / "synth-genus" / "filter.bloom", K).hits_batch(h_bases, hb[:sample], he[:sample], 1, threads=oracle.max_threads())
+        bad_g = int(np.count_nonzero(out["genus_hits"][:sample] != eg))
+        ki = out["kept_index"][:2000]
+        es = oracle.CobsOracle(index_path).counts_batch(h_bases, hb[ki], he[ki], 1, threads=oracle.max_threads())
+        bad_s = int(np.count_nonzero((out["best_hits"][: ki.size] != es.max(axis=1)) | (out["best"][: ki.size] != es.argmax(axis=1))))
+        nk = (READ_LEN - K + 1)
+        keep_exp = np.array([round(int(h_) / nk, 2) >= 0.7 for h_ in eg])
+        bad_k = int(np.count_nonzero(out["kept"][:sample] != keep_exp))
+        res["parity"] = {"genus_reads": int(sample), "genus_hit_mismatches": bad_g, "threshold_mask_mismatches": bad_k,
+                         "species_reads": int(ki.size), "species_call_mismatches": bad_s, "mismatches": bad_g + bad_k + bad_s,
+                         "against": "oracle/xs_oracle.cpp (rbloom membership / cobs search restated) on rank 0's reads"}
+    genus.bf.filter.close()
+    species.index.index.close()
+    del batch, h_bases
+    torch.cuda.empty_cache()
+    return res
+
+
+
 def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     import torch
     import torch.distributed as dist
@@ -507,6 +644,16 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                 if world > 1:
                     raise
 
+        # ---- third leg, every rank: BASELINE config 3 (genus Bloom -> species COBS + SVM, read-sharded)
+        cfg3 = None
+        if os.environ.get("XS_BENCH_CFG3", "1") != "0":
+            try:
+                cfg3 = run_cfg3(args, rank, world, local_rank, workdir, path)
+            except Exception as exc:
+                cfg3 = {"failed": f"{type(exc).__name__}: {exc}"}
+                if world > 1:
+                    raise
+
         if rank != 0:
             return
         peak, peak_src = peaks()
@@ -575,6 +722,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         }
         if cfg5 is not None:
             line["cfg5"] = cfg5
+        if cfg3 is not None:
+            line["cfg3"] = cfg3
         # parity gate (and, at N=1, the CPU baseline): rank 0's GPU counts against the oracle on the same reads
         n_cpu = int(os.environ.get("XS_BENCH_CPU_SAMPLE", 1_000_000)) if world == 1 else \
             int(os.environ.get("XS_BENCH_PARITY_SAMPLE", 100_000))
@@ -583,8 +732,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             line["cpu_baseline"] = base
         line["parity"] = parity_gate(counts, d_out, h_out)
         print(json.dumps(line), flush=True)
-        if line["parity"]["mismatches"] or (cfg5 or {}).get("parity", {}).get("mismatches"):
-            raise SystemExit(f"parity gate failed: {line['parity']} / cfg5 {(cfg5 or {}).get('parity')}")
+        if line["parity"]["mismatches"] or (cfg5 or {}).get("parity", {}).get("mismatches") or (cfg3 or {}).get("parity", {}).get("mismatches"):
+            raise SystemExit(f"parity gate failed: {line['parity']} / cfg5 {(cfg5 or {}).get('parity')} / cfg3 {(cfg3 or {}).get('parity')}")
     finally:
         shutil.rmtree(workdir, ignore_errors=True)
 

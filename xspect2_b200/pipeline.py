@@ -39,7 +39,8 @@ def min_hits_table(max_kmers: int, threshold: float) -> np.ndarray:
     return t
 
 
-def genus_then_species(genus_model, species_model, sequence_input, threshold: float = 0.7, step: int = 1) -> dict:
+def genus_then_species(genus_model, species_model, sequence_input, threshold: float = 0.7, step: int = 1,
+                       predict: bool = True) -> dict:
     """Score every record against the genus filter, keep those reaching ``threshold`` and classify them with the
     species model; returns per-record genus hits, the kept mask, read-level species calls for the kept records,
     file-level species totals / scores and (for an SVM species model) the prediction."""
@@ -100,8 +101,35 @@ def genus_then_species(genus_model, species_model, sequence_input, threshold: fl
     total_kmers = int(num_kmers[keep].sum())
     out["total_hits"] = {name: int(v) for name, v in zip(ix.names, totals_h)}
     out["total_scores"] = {name: round(v / total_kmers, 2) for name, v in out["total_hits"].items()} if total_kmers else {}
+    out["total_kmers"] = total_kmers
+    out["prediction"] = None
+    if predict and hasattr(species_model, "_get_svm") and total_kmers:
+        x = [list(dict(sorted(out["total_scores"].items())).values())]
+        out["prediction"] = str(species_model._get_svm(None).predict(x)[0])
+    return out
+
+
+def genus_then_species_sharded(genus_model, species_model, sequence_input, threshold: float = 0.7, step: int = 1, group=None) -> dict:
+    """``genus_then_species`` over read-sharded ranks (BASELINE config 3: one process per GPU, both model files
+    replicated in every GPU's HBM, each rank holding a contiguous slice of the reads): per-record results stay on the
+    rank that scored them; the per-document species totals and the k-mer count of the kept reads are summed with one
+    small all-reduce (the only collective — hit counts are additive over reads), and the file-level scores and the SVM
+    prediction are computed from the global totals exactly as ``ProbabilisticFilterSVMModel.predict`` does from one
+    file's totals (probabilistic_filter_svm_model.py:209-223)."""
+    import torch.distributed as dist
+
+    from .distributed import allreduce_totals
+
+    out = genus_then_species(genus_model, species_model, sequence_input, threshold, step, predict=False)
+    names = out["labels"]
+    local = np.array([out["total_hits"][n] for n in names] + [out["total_kmers"], int(out["kept"].sum()), len(out["kept"])], dtype=np.int64)
+    glob = allreduce_totals(local, group).cpu().numpy() if dist.is_initialized() else local
+    total_kmers = int(glob[len(names)])
+    out["global_total_hits"] = {n: int(v) for n, v in zip(names, glob[: len(names)])}
+    out["global_total_scores"] = {n: round(v / total_kmers, 2) for n, v in out["global_total_hits"].items()} if total_kmers else {}
+    out["global_kept"], out["global_records"] = int(glob[len(names) + 1]), int(glob[len(names) + 2])
     out["prediction"] = None
     if hasattr(species_model, "_get_svm") and total_kmers:
-        x = [list(dict(sorted(out["total_scores"].items())).values())]
+        x = [list(dict(sorted(out["global_total_scores"].items())).values())]
         out["prediction"] = str(species_model._get_svm(None).predict(x)[0])
     return out
