@@ -421,6 +421,117 @@ __global__ void __launch_bounds__(NARROW_NT, 4) k_cobs_narrow(const CobsParams p
 }
 
 // ----------------------------------------------------------------------------------------
+// COBS, narrow rows, several pages (compact indices: one <locus>.cobs_compact of an MLST scheme has ~10 pages of 64
+// alleles).  k_cobs_narrow walks the batch once per page (grid.y) and hashes every window again for each of them;
+// here a window is extracted, canonicalised and hashed ONCE (XXH64 does not depend on the page, only `% signature_size`
+// does) and its rows are gathered from all pages, PAGES_PG pages in flight per lane.  Per-page document counts of the
+// current sequence live in shared memory (one private slice per warp, no atomics); rows may sit at an 8-byte stride
+// (page_size <= 8: two rows per 16 bytes, which halves the index's L2 footprint — an MLST locus then fits in L2).
+// ----------------------------------------------------------------------------------------
+constexpr int PAGES_NT = 256;
+constexpr int PAGES_PG = 8;
+
+__device__ __forceinline__ uint4 page_row(const PageDesc& pg, uint64_t hv) {
+    const uint64_t r = mod_barrett(hv, pg.sig_size, pg.magic);
+    if (pg.row_stride == 8) {
+        uint2 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(pg.data + r * 8));
+        return make_uint4(v.x, v.y, 0u, 0u);
+    }
+    return ldg128(pg.data + r * 16);
+}
+
+template <int K, int H, typename OutT>
+__global__ void __launch_bounds__(PAGES_NT) k_cobs_pages(const CobsParams p) {
+    extern __shared__ uint32_t s_pages_cnt[];                 // [warps][n_pages * 128]
+    const SeqBatch& sb = p.sb;
+    const uint32_t k = K ? K : sb.k;
+    const uint32_t h = H ? H : p.num_hashes;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_pages = p.n_pages;
+    uint32_t* my = s_pages_cnt + (size_t)warp * n_pages * 128;
+    for (uint32_t i = lane; i < n_pages * 128; i += 32) my[i] = 0;
+    __syncwarp();
+    const uint64_t n_warps = ((uint64_t)gridDim.x * PAGES_NT) >> 5;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    const uint64_t W = walk_tile_windows(total, n_warps);
+    const uint64_t n_tiles = (total + W - 1) / W;
+    OutT* out = reinterpret_cast<OutT*>(p.out);
+    for (;;) {
+        const uint64_t tile = next_tile(sb.tile_counter, lane);
+        if (tile >= n_tiles) break;
+        const uint64_t t0 = tile * W, t1 = t0 + W < total ? t0 + W : total;
+        bool valid = false;
+        Xxh64Pre pre;
+        uint64_t hv0 = 0;
+        warp_walk(
+            sb, t0, t1, lane,
+            [&](bool has, uint64_t pos, uint64_t) {
+                valid = false;
+                if (has) {
+                    Term t;
+                    valid = cobs_term<K>(sb, pos, p.canonicalize != 0, p.policy, t);
+                    if (valid) {
+                        xxh64_prepare(t, k, pre);
+                        hv0 = xxh64_finish(pre, k, 0);
+                    }
+                }
+            },
+            [&](uint32_t segmask) {
+                const bool mine = valid && ((segmask >> lane) & 1u);
+                for (uint32_t p0 = 0; p0 < n_pages; p0 += PAGES_PG) {
+                    uint4 m[PAGES_PG];
+#pragma unroll
+                    for (int q = 0; q < PAGES_PG; ++q) {
+                        m[q] = make_uint4(0, 0, 0, 0);
+                        if (p0 + q < n_pages && mine) {
+                            const PageDesc pg = p.pages[p0 + q];
+                            m[q] = page_row(pg, hv0);
+                            for (uint32_t j = 1; j < h; ++j) {
+                                const uint4 v = page_row(pg, xxh64_finish(pre, k, (uint64_t)j));
+                                m[q].x &= v.x; m[q].y &= v.y; m[q].z &= v.z; m[q].w &= v.w;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < PAGES_PG; ++q) {
+                        if (p0 + q >= n_pages) break;
+                        const uint32_t mw[4] = {m[q].x, m[q].y, m[q].z, m[q].w};
+                        uint32_t* c = my + (size_t)(p0 + q) * 128;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            uint32_t u = __reduce_or_sync(0xFFFFFFFFu, mw[w]);
+                            while (u) {
+                                const uint32_t b = __ffs(u) - 1;
+                                u &= u - 1;
+                                const uint32_t v = __popc(__ballot_sync(0xFFFFFFFFu, (mw[w] >> b) & 1u));
+                                if (lane == b) c[w * 32 + b] += v;
+                            }
+                        }
+                    }
+                }
+            },
+            [&](uint64_t seq, bool complete, uint64_t nwin) {
+                __syncwarp();
+                const bool nosat = nwin <= (uint64_t)out_max<OutT>();
+                OutT* row = out + (p.seq0 + seq) * p.ld;
+                for (uint32_t i = lane; i < n_pages * 128; i += 32) {
+                    const uint32_t v = my[i];
+                    if (v) {
+                        const PageDesc& pg = p.pages[i >> 7];
+                        const uint32_t d = i & 127;
+                        if (d < pg.n_docs) {
+                            if (complete) out_store<OutT>(row + pg.doc_off + d, v); else out_add<OutT>(row + pg.doc_off + d, v, nosat);
+                        }
+                        my[i] = 0;
+                    }
+                }
+                __syncwarp();
+            });
+    }
+}
+
+// ----------------------------------------------------------------------------------------
 // COBS, narrow rows, bucketed probing (large batches against an index much larger than L2).
 //
 // A random 16-byte row gather costs a 128-byte DRAM fetch, so k_cobs_narrow moves ~10x the bytes it uses.  For large

@@ -117,6 +117,7 @@ struct xs_cobs {
     PageDesc* d_pages = nullptr;
     ColBlock* d_blocks = nullptr;
     bool narrow = true;
+    bool pages_kernel = false;   // several narrow pages: k_cobs_pages (one pass, windows hashed once) instead of k_cobs_narrow per page
     int n_sm = 148;
     int force_wide = 0;
     BucketState bk;
@@ -440,6 +441,34 @@ static void launch_narrow(const CobsParams& p, dim3 grid, int dt, cudaStream_t s
     else launch_narrow_t<0, 0>(p, grid, dt, s);
 }
 
+// several pages of narrow rows (compact indices): one pass, every window hashed once (k_cobs_pages)
+static size_t pages_smem(size_t n_pages) { return (size_t)(PAGES_NT / 32) * n_pages * 128 * 4; }
+static const size_t PAGES_SMEM_MAX = 160 * 1024;
+
+template <int K, int H, typename T>
+static cudaError_t launch_pages_tt(const CobsParams& p, int n_sm, cudaStream_t s) {
+    const size_t smem = pages_smem(p.n_pages);
+    cudaError_t e = cudaFuncSetAttribute(k_cobs_pages<K, H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cobs_pages<K, H, T>, PAGES_NT, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+    k_cobs_pages<K, H, T><<<n_sm * std::min(occ, 6), PAGES_NT, smem, s>>>(p);
+    return cudaSuccess;
+}
+template <int K, int H>
+static cudaError_t launch_pages_t(const CobsParams& p, int n_sm, int dt, cudaStream_t s) {
+    if (dt == XS_U8) return launch_pages_tt<K, H, uint8_t>(p, n_sm, s);
+    if (dt == XS_U16) return launch_pages_tt<K, H, uint16_t>(p, n_sm, s);
+    return launch_pages_tt<K, H, uint32_t>(p, n_sm, s);
+}
+static cudaError_t launch_pages(const CobsParams& p, int n_sm, int dt, cudaStream_t s) {
+    if (p.sb.k == 31 && p.num_hashes == 1) return launch_pages_t<31, 1>(p, n_sm, dt, s);
+    if (p.sb.k == 21 && p.num_hashes == 1) return launch_pages_t<21, 1>(p, n_sm, dt, s);
+    return launch_pages_t<0, 0>(p, n_sm, dt, s);
+}
+
 template <int K, int H, typename T>
 static cudaError_t launch_wide_tt(const WideParams& p, dim3 grid, size_t smem, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(k_cobs_wide<K, H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -657,6 +686,12 @@ static int cobs_launch(xs_cobs* ix, const SeqBatch& sb, const uint64_t* chunk_pr
     p.num_hashes = ix->info.num_hashes; p.canonicalize = ix->info.canonicalize; p.policy = ix->info.policy;
     p.out = d_out; p.ld = ld; p.seq0 = 0;
     if (!wide) {
+        if (ix->pages_kernel) {
+            KernelTimer kt(s);
+            cudaError_t e = launch_pages(p, ix->n_sm, dt, s);
+            if (e != cudaSuccess) return fail(XS_ERR_CUDA, std::string("k_cobs_pages: ") + cudaGetErrorString(e));
+            return launch_ok("k_cobs_pages");
+        }
         bool handled = false;
         XS_TRY(cobs_launch_bucketed(ix, p, dt, s, &handled));
         if (handled) return XS_OK;
@@ -1150,6 +1185,12 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
     while (stride < n_col && stride < 128) stride <<= 1;
     if (n_col > 128) stride = (n_col + 127) & ~127u;
     ix->narrow = stride == 16;
+    // compact indices (several pages of narrow rows) are scored by k_cobs_pages; their rows of <= 8 bytes sit at an
+    // 8-byte stride (half the L2 footprint: one MLST locus of 600 alleles is 34 MB instead of 67 MB)
+    const char* no_pages = getenv("XS_NO_PAGES_KERNEL");
+    ix->pages_kernel = ix->narrow && !ix->force_wide && cf.kind == XS_COBS_COMPACT && cf.n_pages > 1 &&
+                       pages_smem(cf.n_pages) <= PAGES_SMEM_MAX && !(no_pages && no_pages[0] == '1');
+    if (ix->pages_kernel && n_col <= 8) stride = 8;
     const uint32_t n_chunks = (n_col + 15) / 16;     // 16-byte chunks that hold documents
 
     uint64_t total = 0;
