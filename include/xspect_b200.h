@@ -277,6 +277,23 @@ int xs_fastx_read(const xs_fastx* fx, uint8_t* bases, uint64_t* seq_begin, uint6
 int xs_fastx_filter_fasta(const xs_fastx* fx, const uint8_t* keep, const char* out_path);
 int xs_fastx_close(xs_fastx* fx);
 
+/* File -> read-level calls in one streamed call (the loop of probabilistic_filter_model.py:291-310 over
+ * file_io.get_record_iterator(path), followed by the per-read argmax / tie rule of scripts/benchmark/main.nf:417-436):
+ * blocks of ~block_bytes (0 = 96 MiB) of the FASTA / FASTQ file are cut at record starts, parsed by all host threads
+ * straight into page-locked staging buffers, and copied, scored (xs_cobs_query_device) and reduced
+ * (xs_scores_reduce_device) on three streams while the next block is being parsed; only 12 bytes per record come
+ * back.  Wrapped (multi-line) FASTQ is not accepted here (XS_ERR_FORMAT) — use xs_fastx_open + xs_cobs_classify.
+ * Results: per record the first best document, its count, the number of documents sharing it, the sequence length
+ * (num_kmers = ceil((len - k + 1) / step) is the caller's arithmetic; n_short counts records with len <= k, which
+ * make the reference raise ValueError), record ids, and per-document totals. */
+typedef struct xs_file_calls xs_file_calls;
+int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t step, uint64_t block_bytes, xs_file_calls** out);
+int xs_file_calls_info(const xs_file_calls* r, uint64_t* n_records, uint64_t* n_bases, uint64_t* n_id_bytes, uint64_t* n_short,
+                       uint64_t* n_docs, double* parse_s, double* total_s);
+int xs_file_calls_read(const xs_file_calls* r, uint32_t* best, uint32_t* best_count, uint32_t* n_best, uint64_t* seq_len,
+                       char* ids, uint64_t* id_end, uint64_t* totals);
+int xs_file_calls_free(xs_file_calls* r);
+
 /* ---- result writer (host only) -------------------------------------------------------------------
  * Replaces ModelResult.save = json.dumps(self.to_dict(), indent=4) (models/result.py:151-189) for results held as
  * a count matrix: writes byte-identical JSON without building the nested dictionaries.  counts is [* x n_docs]

@@ -407,6 +407,14 @@ class CobsOracle:
         return order
 
 
+    def search(self, query: str, step: int = 1) -> list[SearchResult]:
+        """All documents, ordered like ClassicSearch::search (A.2.5c/d)."""
+        if len(query) < self.k:
+            raise RuntimeError("query too short for index term size")
+        c = self.counts(query, step)
+        return [SearchResult(self.names[i], int(c[i])) for i in self.result_order(c)]
+
+
 class SynthCobsOracle:
     """The query of ``CobsOracle`` against the synthetic classic index of BASELINE config 5 (rows from the
     counter-based generator documented at ``xs_cobs_create_synthetic``; the index exists nowhere as a file)."""
@@ -428,13 +436,6 @@ class SynthCobsOracle:
         lib().xso_cobs_query_batch_synth(self.seed, self.n_docs, self.sig_size, self.num_hashes, self.k, 1, self.policy,
                                          bases.ctypes.data, b.ctypes.data, e.ctypes.data, b.size, step, out.ctypes.data, threads)
         return out
-
-    def search(self, query: str, step: int = 1) -> list[SearchResult]:
-        """All documents, ordered like ClassicSearch::search (A.2.5c/d)."""
-        if len(query) < self.k:
-            raise RuntimeError("query too short for index term size")
-        c = self.counts(query, step)
-        return [SearchResult(self.names[i], int(c[i])) for i in self.result_order(c)]
 
 
 class BloomOracle:

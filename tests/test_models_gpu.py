@@ -138,6 +138,52 @@ def test_species_predict_summary_matches_predict(world, oracle, tmp_path):
             assert int(summ["num_kmers"][i]) == res.num_kmers[rid]
 
 
+def test_streamed_file_calls_equal_two_pass_reader(world, oracle, tmp_path):
+    """xs_cobs_classify_file (blocks of the file parsed on all host threads while earlier blocks are scored) returns
+    what the two-pass reader + xs_cobs_classify return — FASTA with wrapped lines, 4-line FASTQ, many tiny blocks —
+    and hands wrapped FASTQ and short records over to the paths that own those cases."""
+    from xspect2_b200.models.probabilistic_filter_model import ProbabilisticFilterModel
+    from xspect2_b200.seqio import SequenceBatch
+    model = ProbabilisticFilterModel.load(world["sp_json"])
+    ix = model.index.index
+    recs = _records(world, 900)
+    fq, fa = tmp_path / "in.fastq", tmp_path / "in.fna"
+    mf.write_fastq(fq, recs)
+    mf.write_fasta(fa, recs, wrap=60)
+    for path, fmt in ((fq, 2), (fa, 1)):
+        batch = SequenceBatch.from_file(path)
+        best, cnt, nb, totals = ix.classify(batch.bases, batch.begin, batch.end, 1)
+        for block in (0, 3000, 40_000):
+            r = ix.classify_file(path, fmt, 1, block_bytes=block)
+            assert np.array_equal(r["best"], best) and np.array_equal(r["best_hits"], cnt) and np.array_equal(r["n_best"], nb), (path, block)
+            assert np.array_equal(r["totals"], totals) and np.array_equal(r["seq_len"], batch.end - batch.begin)
+            assert r["id_buf"].tobytes() == batch._id_buf.tobytes() and np.array_equal(r["id_end"], batch._id_end)
+            assert r["n_short"] == 0 and r["n_bases"] == batch.bases.size
+    summ = model.predict_summary(fq)
+    assert "streamed" in summ and summ["batch"].ids == [r[0] for r in recs]
+    # wrapped FASTQ: the streaming reader declines, predict_summary falls back to the two-pass reader
+    wrapped = tmp_path / "wrapped.fastq"
+    with open(wrapped, "w") as f:
+        for rid, sq in recs[:50]:
+            sq = sq if isinstance(sq, str) else sq.tobytes().decode()
+            h = len(sq) // 2
+            f.write(f"@{rid}\n{sq[:h]}\n{sq[h:]}\n+\n{'I' * h}\n{'I' * (len(sq) - h)}\n")
+    with pytest.raises(ValueError):
+        ix.classify_file(wrapped, 2, 1)
+    s2 = model.predict_summary(wrapped)
+    assert "streamed" not in s2 and np.array_equal(s2["best"], summ["best"][:50])
+    # one record not longer than k aborts, as in the reference's loop
+    short = tmp_path / "short.fastq"
+    mf.write_fastq(short, recs[:10] + [("tiny", "ACGTACGTAC")])
+    with pytest.raises(ValueError, match="longer than k"):
+        model.predict_summary(short)
+    # malformed FASTQ keeps Biopython's message through the fallback
+    bad = tmp_path / "bad.fastq"
+    bad.write_text("@r1\nACGTACGTACGTACGTACGTACGTACGT\n+\nIIII\n")
+    with pytest.raises(ValueError, match="Lengths of sequence and quality"):
+        model.predict_summary(bad)
+
+
 # ------------------------------------------------------------------------------ SVM model
 def test_svm_prediction_matches_reference_flow(world, oracle, tmp_path):
     from sklearn.svm import SVC

@@ -184,11 +184,117 @@ int run(const xs_fastx* fx, const uint8_t* p, const uint8_t* end, Sink& sk) {
     return fx->format == 2 ? parse_fastq(p, end, sk) : parse_fasta(p, end, sk);
 }
 
+// line [p, nl) starting at p; returns the start of the next line (end when there is none)
+inline const uint8_t* next_line(const uint8_t* p, const uint8_t* end) {
+    const uint8_t* nl = find_nl(p, end);
+    return nl < end ? nl + 1 : end;
+}
+
+// Is `p` (the first byte of a line) the start of a FASTQ record?  '@' alone is not enough — it is also a quality
+// character — so the 4-line shape is checked: '@' title, sequence, '+' line, quality of the sequence's length, and
+// then another '@' (or the end).  Wrapped FASTQ does not pass; the streaming reader then falls back to the two-pass
+// reader (xs_fastx_open), which parses serially from the start.
+bool fastq_record_at(const uint8_t* p, const uint8_t* end) {
+    if (p >= end || *p != '@') return false;
+    const uint8_t* l1 = next_line(p, end);
+    if (l1 >= end) return false;
+    const uint8_t* l2 = next_line(l1, end);
+    if (l2 >= end || *l2 != '+') return false;
+    const uint8_t* l3 = next_line(l2, end);
+    const uint8_t* l4 = next_line(l3, end);
+    const uint64_t seq_len = (uint64_t)(rstrip(l1, l2) - l1), qual_len = (uint64_t)(rstrip(l3, l4) - l3);
+    if (seq_len != qual_len) return false;
+    return l4 >= end || *l4 == '@';
+}
+
 }  // namespace
+
+// ---- streaming access for xs_cobs_classify_file (xs_lib.cu): blocks of the file parsed by all host threads ----
+// first record start at or after `off` (a line start): FASTA '>' / FASTQ 4-line shape; fx->size when there is none
+uint64_t xs_fastx_sync(const xs_fastx* fx, uint64_t off) {
+    const uint8_t* base = fx->data;
+    const uint8_t* end = base + fx->size;
+    const uint8_t* p = base + std::min(off, fx->size);
+    if (p > base && p[-1] != '\n') p = next_line(p, end);     // move to a line start
+    while (p < end) {
+        if (fx->format == 1 ? *p == '>' : fastq_record_at(p, end)) return (uint64_t)(p - base);
+        p = next_line(p, end);
+    }
+    return fx->size;
+}
+
+// Parses [a, b) — both record starts (or the file's end) — with n_thr threads: a counting pass over sub-ranges, a
+// prefix sum, then a fill pass that writes every sub-range at its place.  `sizes` receives {records, bases, id bytes};
+// with bases == nullptr only the counting pass runs (the caller sizes its staging buffers from it).
+// begin / end are offsets into `bases` of this block; max_len = longest record, n_short = records not longer than k.
+int xs_fastx_parse_block(const xs_fastx* fx, uint64_t a, uint64_t b, unsigned n_thr, std::vector<uint64_t>& cuts,
+                         std::vector<Checkpoint>& cps, uint8_t* bases, uint64_t* seq_begin, uint64_t* seq_end, char* ids,
+                         uint64_t* id_end, uint64_t sizes[3]) {
+    const bool count_only = bases == nullptr && seq_begin == nullptr;
+    if (count_only) {
+        cuts.clear();
+        cuts.push_back(a);
+        n_thr = std::max(1u, n_thr);
+        for (unsigned t = 1; t < n_thr; ++t) {
+            const uint64_t c = xs_fastx_sync(fx, a + (b - a) * t / n_thr);
+            if (c > cuts.back() && c < b) cuts.push_back(c);
+        }
+        cuts.push_back(b);
+        cps.assign(cuts.size(), Checkpoint{0, 0, 0, 0});
+    }
+    const size_t n_seg = cuts.size() - 1;
+    std::atomic<size_t> next(0);
+    std::atomic<int> status(XS_OK);
+    auto work = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n_seg) break;
+            Sink sk;
+            if (!count_only) {
+                sk.bases = bases; sk.seq_begin = seq_begin; sk.seq_end = seq_end; sk.ids = ids; sk.id_end = id_end; sk.write = true;
+                sk.n_rec = cps[i].rec; sk.n_bases = cps[i].base; sk.n_id = cps[i].id;
+            }
+            const int rc = run(fx, fx->data + cuts[i], fx->data + cuts[i + 1], sk);
+            if (rc != XS_OK) { status.store(rc); continue; }
+            if (count_only) cps[i + 1] = Checkpoint{cuts[i + 1], sk.n_rec, sk.n_bases, sk.n_id};   // this segment's own counts
+        }
+    };
+    if (n_seg <= 1 || n_thr <= 1) work();
+    else {
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < std::min<size_t>(n_thr, n_seg); ++t) th.emplace_back(work);
+        for (auto& t : th) t.join();
+    }
+    if (status.load() != XS_OK) return status.load();
+    if (count_only) {
+        cps[0] = Checkpoint{cuts[0], 0, 0, 0};
+        for (size_t i = 1; i <= n_seg; ++i) {               // per-segment counts -> running cursors
+            cps[i].rec += cps[i - 1].rec; cps[i].base += cps[i - 1].base; cps[i].id += cps[i - 1].id;
+        }
+        sizes[0] = cps[n_seg].rec; sizes[1] = cps[n_seg].base; sizes[2] = cps[n_seg].id;
+    }
+    return XS_OK;
+}
 
 extern "C" {
 
-int xs_fastx_open(const char* path, int format, xs_fastx** out) {
+static int fastx_open_impl(const char* path, int format, bool sizing_pass, xs_fastx** out);
+int xs_fastx_open(const char* path, int format, xs_fastx** out) { return fastx_open_impl(path, format, true, out); }
+}  // extern "C"
+// maps the file without the sizing pass (streaming reader)
+int xs_fastx_open_stream(const char* path, int format, xs_fastx** out) { return fastx_open_impl(path, format, false, out); }
+uint64_t xs_fastx_file_size(const xs_fastx* fx) { return fx->size; }
+// true when [a, b) holds only whitespace (FASTQ: nothing but blank lines may precede the first record the streaming
+// reader found; anything else means the 4-line shape check skipped real data, e.g. wrapped FASTQ)
+bool xs_fastx_blank(const xs_fastx* fx, uint64_t a, uint64_t b) {
+    for (uint64_t i = a; i < b && i < fx->size; ++i)
+        if (!is_space(fx->data[i])) return false;
+    return true;
+}
+int xs_fastx_format(const xs_fastx* fx) { return fx->format; }
+extern "C" {
+
+static int fastx_open_impl(const char* path, int format, bool sizing_pass, xs_fastx** out) {
     if (!path || !out) return xs_set_error(XS_ERR_ARG, "path/out is NULL");
     *out = nullptr;
     if (format != 1 && format != 2) return xs_set_error(XS_ERR_ARG, "format must be 1 (fasta) or 2 (fastq)");
@@ -204,6 +310,7 @@ int xs_fastx_open(const char* path, int format, xs_fastx** out) {
         madvise(m, fx->size, MADV_SEQUENTIAL);
         fx->data = (const uint8_t*)m;
     }
+    if (!sizing_pass) { *out = fx; return XS_OK; }
     Sink sk;
     sk.cps = &fx->cps; sk.file_base = fx->data;
     int rc = run(fx, fx->data, fx->data + fx->size, sk);

@@ -10,8 +10,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <numeric>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -21,6 +23,18 @@
 #include "xs_kernels.cuh"
 
 using namespace xs;
+
+// streaming access to the native FASTA / FASTQ reader (xs_fastx.cpp), C++ linkage
+struct Checkpoint { uint64_t off, rec, base, id; };
+struct xs_fastx;
+int xs_fastx_open_stream(const char* path, int format, xs_fastx** out);
+uint64_t xs_fastx_file_size(const xs_fastx* fx);
+uint64_t xs_fastx_sync(const xs_fastx* fx, uint64_t off);
+bool xs_fastx_blank(const xs_fastx* fx, uint64_t a, uint64_t b);
+int xs_fastx_format(const xs_fastx* fx);
+int xs_fastx_parse_block(const xs_fastx* fx, uint64_t a, uint64_t b, unsigned n_thr, std::vector<uint64_t>& cuts,
+                         std::vector<Checkpoint>& cps, uint8_t* bases, uint64_t* seq_begin, uint64_t* seq_end, char* ids,
+                         uint64_t* id_end, uint64_t sizes[3]);
 
 // ----------------------------------------------------------------------------------------
 // errors
@@ -1653,6 +1667,201 @@ int xs_cobs_classify(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const 
     cudaFree(d_tot);
     return rc;
 }
+
+// ----------------------------------------------------------------------------------------
+// File -> read-level calls, streamed: blocks of the FASTA / FASTQ file are parsed by all host threads straight into
+// page-locked staging buffers while the previous blocks are copied, scored and reduced on the device.
+// ----------------------------------------------------------------------------------------
+
+struct xs_file_calls {
+    std::vector<uint32_t> best, best_count, n_best;
+    std::vector<uint64_t> seq_len, id_end, totals;
+    std::vector<char> ids;
+    uint64_t n_bases = 0, n_short = 0, n_blocks = 0;
+    double parse_s = 0, total_s = 0;
+};
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t step, uint64_t block_bytes, xs_file_calls** out) {
+    if (!ix || !path || !out) return fail(XS_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (step == 0) return fail(XS_ERR_ARG, "step must be >= 1");
+    xs_fastx* fx = nullptr;
+    XS_TRY(xs_fastx_open_stream(path, format, &fx));
+    DeviceGuard guard(ix->info.device);
+    if (!guard.ok) { xs_fastx_close(fx); return fail(XS_ERR_CUDA, "cannot select the index's device"); }
+    const double t_start = now_s();
+    const uint64_t fsize = xs_fastx_file_size(fx);
+    if (block_bytes == 0) block_bytes = 96ULL << 20;            // ~300 k 150-bp FASTQ reads: enough windows for the bucketed kernels
+    const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    const uint64_t ld = ix->info.doc_end - ix->info.doc_begin;
+    const uint32_t k = ix->info.term_size;
+    xs_file_calls* res = new xs_file_calls();
+    res->totals.assign(ld, 0);
+    const int NS = 3;
+    struct Slot {
+        uint8_t* h = nullptr; size_t h_cap = 0;          // pinned staging: bases | begin | end
+        uint8_t* d = nullptr; size_t d_cap = 0;          // device: bases | begin | end | counts | best | cnt | nb
+        uint32_t* h_res = nullptr; size_t r_cap = 0;     // pinned results: best | cnt | nb
+        cudaStream_t s = nullptr; cudaEvent_t done = nullptr;
+        uint64_t rec0 = 0, n_rec = 0; bool busy = false;
+    } slot[NS];
+    uint64_t* d_tot = nullptr;
+    int rc = XS_OK;
+    auto cuda_ok = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == XS_OK) rc = fail(e == cudaErrorMemoryAllocation ? XS_ERR_NOMEM : XS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        return e == cudaSuccess;
+    };
+    cuda_ok(cudaMalloc((void**)&d_tot, std::max<uint64_t>(ld, 1) * 8), "totals");
+    if (rc == XS_OK) cuda_ok(cudaMemset(d_tot, 0, ld * 8), "totals");
+    if (rc == XS_OK) cuda_ok(cudaDeviceSynchronize(), "totals");
+    for (int i = 0; i < NS && rc == XS_OK; ++i) {
+        cuda_ok(cudaStreamCreateWithFlags(&slot[i].s, cudaStreamNonBlocking), "stream");
+        cuda_ok(cudaEventCreateWithFlags(&slot[i].done, cudaEventDisableTiming), "event");
+    }
+    auto retire = [&](Slot& sl) {       // results of the slot's block -> the result vectors
+        if (!sl.busy) return;
+        cuda_ok(cudaEventSynchronize(sl.done), "block");
+        if (rc == XS_OK) {
+            memcpy(res->best.data() + sl.rec0, sl.h_res, sl.n_rec * 4);
+            memcpy(res->best_count.data() + sl.rec0, sl.h_res + sl.n_rec, sl.n_rec * 4);
+            memcpy(res->n_best.data() + sl.rec0, sl.h_res + 2 * sl.n_rec, sl.n_rec * 4);
+        }
+        sl.busy = false;
+    };
+    std::vector<uint64_t> cuts;
+    std::vector<Checkpoint> cps;
+    uint64_t a = rc == XS_OK ? xs_fastx_sync(fx, 0) : fsize;
+    if (rc == XS_OK && format == 2 && !xs_fastx_blank(fx, 0, a))
+        rc = fail(XS_ERR_FORMAT, "the streaming reader accepts 4-line FASTQ only (wrapped or malformed records found)");
+    uint64_t rec_total = 0;
+    int bi = 0;
+    while (rc == XS_OK && a < fsize) {
+        uint64_t b = a + block_bytes >= fsize ? fsize : xs_fastx_sync(fx, a + block_bytes);
+        if (b <= a) b = fsize;
+        Slot& sl = slot[bi % NS];
+        retire(sl);
+        if (rc != XS_OK) break;
+        const double tp = now_s();
+        uint64_t sizes[3] = {0, 0, 0};
+        rc = xs_fastx_parse_block(fx, a, b, hw, cuts, cps, nullptr, nullptr, nullptr, nullptr, nullptr, sizes);
+        if (rc != XS_OK) break;
+        const uint64_t nr = sizes[0], nb = sizes[1], nid = sizes[2];
+        const size_t o_b = align256(nb + 64), need_h = o_b + 2 * align256(nr * 8);
+        if (need_h > sl.h_cap) {
+            if (sl.h) cudaFreeHost(sl.h);
+            sl.h = nullptr; sl.h_cap = 0;
+            if (!cuda_ok(cudaHostAlloc((void**)&sl.h, need_h + need_h / 8, cudaHostAllocPortable), "pinned staging")) break;
+            sl.h_cap = need_h + need_h / 8;
+        }
+        if (nr * 12 > sl.r_cap) {
+            if (sl.h_res) cudaFreeHost(sl.h_res);
+            sl.h_res = nullptr; sl.r_cap = 0;
+            if (!cuda_ok(cudaHostAlloc((void**)&sl.h_res, nr * 12 + nr, cudaHostAllocPortable), "pinned results")) break;
+            sl.r_cap = nr * 12 + nr;
+        }
+        uint64_t* h_b = reinterpret_cast<uint64_t*>(sl.h + o_b);
+        uint64_t* h_e = reinterpret_cast<uint64_t*>(sl.h + o_b + align256(nr * 8));
+        const size_t id0 = res->ids.size();
+        res->ids.resize(id0 + nid);
+        res->id_end.resize(rec_total + nr);
+        rc = xs_fastx_parse_block(fx, a, b, hw, cuts, cps, sl.h, h_b, h_e, res->ids.data() + id0, res->id_end.data() + rec_total, sizes);
+        if (rc != XS_OK) break;
+        res->seq_len.resize(rec_total + nr);
+        uint64_t max_len = 0, n_short = 0;
+        for (uint64_t i = 0; i < nr; ++i) {
+            const uint64_t len = h_e[i] - h_b[i];
+            res->seq_len[rec_total + i] = len;
+            res->id_end[rec_total + i] += id0;
+            max_len = std::max(max_len, len);
+            n_short += len <= k;
+        }
+        res->n_short += n_short;
+        res->n_bases += nb;
+        res->best.resize(rec_total + nr); res->best_count.resize(rec_total + nr); res->n_best.resize(rec_total + nr);
+        res->parse_s += now_s() - tp;
+        // device side of the block
+        const uint64_t max_win = max_len >= k ? (max_len - k) / step + 1 : 0;
+        const int dt = max_win <= 255 ? XS_U8 : max_win <= 65535 ? XS_U16 : XS_U32;
+        const size_t o_cnt = need_h, o_res = o_cnt + align256(nr * ld * (uint64_t)dt + 16), need_d = o_res + align256(nr * 12 + 16);
+        if (need_d > sl.d_cap) {
+            if (sl.d) cudaFree(sl.d);
+            sl.d = nullptr; sl.d_cap = 0;
+            if (!cuda_ok(cudaMalloc((void**)&sl.d, need_d + need_d / 8), "device block buffers")) break;
+            sl.d_cap = need_d + need_d / 8;
+        }
+        if (nr) {
+            cuda_ok(cudaMemcpyAsync(sl.d, sl.h, need_h, cudaMemcpyHostToDevice, sl.s), "H2D copy");
+            uint64_t* d_b = reinterpret_cast<uint64_t*>(sl.d + o_b);
+            uint64_t* d_e = reinterpret_cast<uint64_t*>(sl.d + o_b + align256(nr * 8));
+            uint32_t* d_best = reinterpret_cast<uint32_t*>(sl.d + o_res);
+            if (rc == XS_OK) rc = cobs_query_dev(ix, sl.d, nb, d_b, d_e, nr, 0, step, dt, sl.d + o_cnt, sl.s);
+            if (rc == XS_OK) {
+                const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nr + REDUCE_ROWS - 1) / REDUCE_ROWS, (uint64_t)ix->n_sm * 8));
+                unsigned long long* tot = reinterpret_cast<unsigned long long*>(d_tot);
+                if (dt == XS_U8) k_scores_reduce<uint8_t><<<grid, REDUCE_NT, 0, sl.s>>>((const uint8_t*)(sl.d + o_cnt), nr, (uint32_t)ld, d_best, d_best + nr, d_best + 2 * nr, tot);
+                else if (dt == XS_U16) k_scores_reduce<uint16_t><<<grid, REDUCE_NT, 0, sl.s>>>((const uint16_t*)(sl.d + o_cnt), nr, (uint32_t)ld, d_best, d_best + nr, d_best + 2 * nr, tot);
+                else k_scores_reduce<uint32_t><<<grid, REDUCE_NT, 0, sl.s>>>((const uint32_t*)(sl.d + o_cnt), nr, (uint32_t)ld, d_best, d_best + nr, d_best + 2 * nr, tot);
+                rc = launch_ok("k_scores_reduce");
+            }
+            if (rc == XS_OK) cuda_ok(cudaMemcpyAsync(sl.h_res, d_best, nr * 12, cudaMemcpyDeviceToHost, sl.s), "D2H copy");
+            if (rc == XS_OK) cuda_ok(cudaEventRecord(sl.done, sl.s), "event");
+            sl.rec0 = rec_total; sl.n_rec = nr; sl.busy = rc == XS_OK;
+        }
+        rec_total += nr;
+        a = b; ++bi; ++res->n_blocks;
+    }
+    for (int i = 0; i < NS; ++i) retire(slot[(bi + i) % NS]);
+    if (rc == XS_OK && d_tot) {
+        cuda_ok(cudaDeviceSynchronize(), "file query");
+        if (rc == XS_OK) cuda_ok(cudaMemcpy(res->totals.data(), d_tot, ld * 8, cudaMemcpyDeviceToHost), "totals copy");
+    } else {
+        cudaDeviceSynchronize();
+    }
+    for (int i = 0; i < NS; ++i) {
+        if (slot[i].h) cudaFreeHost(slot[i].h);
+        if (slot[i].h_res) cudaFreeHost(slot[i].h_res);
+        if (slot[i].d) cudaFree(slot[i].d);
+        if (slot[i].s) cudaStreamDestroy(slot[i].s);
+        if (slot[i].done) cudaEventDestroy(slot[i].done);
+    }
+    if (d_tot) cudaFree(d_tot);
+    xs_fastx_close(fx);
+    res->total_s = now_s() - t_start;
+    if (rc != XS_OK) { delete res; return rc; }
+    *out = res;
+    return XS_OK;
+}
+
+int xs_file_calls_info(const xs_file_calls* r, uint64_t* n_records, uint64_t* n_bases, uint64_t* n_id_bytes, uint64_t* n_short,
+                       uint64_t* n_docs, double* parse_s, double* total_s) {
+    if (!r) return fail(XS_ERR_ARG, "NULL result");
+    if (n_records) *n_records = r->best.size();
+    if (n_bases) *n_bases = r->n_bases;
+    if (n_id_bytes) *n_id_bytes = r->ids.size();
+    if (n_short) *n_short = r->n_short;
+    if (n_docs) *n_docs = r->totals.size();
+    if (parse_s) *parse_s = r->parse_s;
+    if (total_s) *total_s = r->total_s;
+    return XS_OK;
+}
+
+int xs_file_calls_read(const xs_file_calls* r, uint32_t* best, uint32_t* best_count, uint32_t* n_best, uint64_t* seq_len,
+                       char* ids, uint64_t* id_end, uint64_t* totals) {
+    if (!r) return fail(XS_ERR_ARG, "NULL result");
+    const size_t n = r->best.size();
+    if (best) memcpy(best, r->best.data(), n * 4);
+    if (best_count) memcpy(best_count, r->best_count.data(), n * 4);
+    if (n_best) memcpy(n_best, r->n_best.data(), n * 4);
+    if (seq_len) memcpy(seq_len, r->seq_len.data(), n * 8);
+    if (ids) memcpy(ids, r->ids.data(), r->ids.size());
+    if (id_end) memcpy(id_end, r->id_end.data(), n * 8);
+    if (totals) memcpy(totals, r->totals.data(), r->totals.size() * 8);
+    return XS_OK;
+}
+
+int xs_file_calls_free(xs_file_calls* r) { delete r; return XS_OK; }
 
 // ----------------------------------------------------------------------------------------
 // MLST: chunked scoring of every locus of a scheme (probabilistic_filter_mlst_model.py:236-286)

@@ -259,6 +259,26 @@ class CobsIndex:
                                      _ptr(nb), _ptr(totals)))
         return best, cnt, nb, totals
 
+    def classify_file(self, path, fmt: int, step: int = 1, block_bytes: int = 0) -> dict:
+        """Read-level calls of a FASTA (``fmt`` 1) / 4-line FASTQ (``fmt`` 2) file, streamed (``xs_cobs_classify_file``):
+        parsing on all host threads, host-to-device copies, scoring and the argmax epilogue overlap block by block.
+        Returns ``best, best_hits, n_best, seq_len, totals`` plus the raw record-id buffer (``id_buf``, ``id_end``)."""
+        h = C.c_void_p()
+        check(lib().xs_cobs_classify_file(self._h, str(path).encode(), int(fmt), int(step), int(block_bytes), C.byref(h)))
+        try:
+            n, nb, nid, nshort, nd = (C.c_uint64() for _ in range(5))
+            ps, ts = C.c_double(), C.c_double()
+            check(lib().xs_file_calls_info(h, C.byref(n), C.byref(nb), C.byref(nid), C.byref(nshort), C.byref(nd), C.byref(ps), C.byref(ts)))
+            best, cnt, nbst = (np.empty(n.value, np.uint32) for _ in range(3))
+            seq_len, id_end = np.empty(n.value, np.uint64), np.empty(n.value, np.uint64)
+            ids = np.empty(nid.value, np.uint8)
+            totals = np.zeros(nd.value, np.uint64)
+            check(lib().xs_file_calls_read(h, _ptr(best), _ptr(cnt), _ptr(nbst), _ptr(seq_len), _ptr(ids), _ptr(id_end), _ptr(totals)))
+        finally:
+            lib().xs_file_calls_free(h)
+        return {"best": best, "best_hits": cnt, "n_best": nbst, "seq_len": seq_len, "totals": totals, "id_buf": ids, "id_end": id_end,
+                "n_bases": int(nb.value), "n_short": int(nshort.value), "parse_s": ps.value, "total_s": ts.value}
+
     def query_device(self, d_bases: int, n_bases: int, d_begin: int, d_end: int, n_seq: int, step: int, dtype: int,
                      d_out: int, stream: int = 0, ld: int = 0) -> None:
         """Same with raw device pointers on this index's GPU; asynchronous on ``stream``.  ``ld`` > 0: output rows of

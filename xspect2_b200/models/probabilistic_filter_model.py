@@ -254,6 +254,10 @@ class ProbabilisticFilterModel:
         Returns ``{"batch", "labels", "best", "best_hits", "ambiguous", "num_kmers", "total_hits", "total_scores"}``
         (record ids are ``result["batch"].ids``, decoded on first use);
         ``total_scores`` equals ``ModelResult.get_scores()["total"]`` for input without duplicate ids."""
+        if isinstance(sequence_input, Path):
+            streamed = self._predict_summary_streamed(sequence_input, step)
+            if streamed is not None:
+                return streamed
         batch = sequence_input if isinstance(sequence_input, SequenceBatch) else self._to_batch(sequence_input)
         self._check_lengths(batch)
         ix = self.index.index
@@ -265,6 +269,35 @@ class ProbabilisticFilterModel:
             "batch": batch, "labels": ix.names, "best": best, "best_hits": cnt, "ambiguous": nb > 1, "num_kmers": num_kmers,
             "total_hits": total_hits,
             "total_scores": {n: round(v / total_kmers, 2) for n, v in total_hits.items()} if total_kmers else {},
+        }
+
+    def _predict_summary_streamed(self, path: Path, step: int):
+        """``predict_summary`` of a file with parsing, copies and kernels overlapped (``xs_cobs_classify_file``); None when
+        the streaming reader does not take the file (wrapped FASTQ, unknown extension: the two-pass reader decides)."""
+        from ..definitions import fasta_endings, fastq_endings
+        suffix = path.suffix[1:]
+        fmt = 2 if suffix in fastq_endings else 1 if suffix in fasta_endings else 0
+        if not fmt or not path.is_file():
+            return None
+        ix = self.index.index
+        try:
+            r = ix.classify_file(path, fmt, step)
+        except ValueError:
+            return None
+        if r["n_short"]:
+            raise ValueError("Invalid sequence, must be longer than k")
+        n = r["best"].size
+        begin = np.zeros(n, np.uint64)
+        lengths = r["seq_len"].astype(np.int64)
+        batch = SequenceBatch(None, np.zeros(0, np.uint8), begin, r["seq_len"], None, r["id_buf"], r["id_end"])
+        num_kmers = -((lengths - self.k + 1) // -step)
+        total_kmers = int(num_kmers.sum())
+        total_hits = {name: int(v) for name, v in zip(ix.names, r["totals"])}
+        return {
+            "batch": batch, "labels": ix.names, "best": r["best"], "best_hits": r["best_hits"], "ambiguous": r["n_best"] > 1,
+            "num_kmers": num_kmers, "total_hits": total_hits,
+            "total_scores": {name: round(v / total_kmers, 2) for name, v in total_hits.items()} if total_kmers else {},
+            "streamed": {"parse_s": r["parse_s"], "total_s": r["total_s"]},
         }
 
     def predict(
