@@ -569,6 +569,15 @@ struct BucketParams {
     uint32_t n_buckets, bshift, cap;
     uint32_t pack_id;     // rows hold <= 96 documents: the fourth word is free for the local window
     uint32_t prefetch;    // k_bucket_fetch prefetches the next bucket's rows into L2
+    // hash-ahead: k_bucket_fetch of sub-batch i also hashes the windows of sub-batch i + 1 (its warps wait on L2 gathers
+    // most of the time; the XXH64 work fills the idle issue slots), so k_bucket_emit only has to scatter row ids
+    uint32_t* pre_rows;        // [nc][H][BK_CH] row ids of this sub-batch's windows (written by the previous fetch), or null
+    uint32_t* pre_skp;         // [nc][BK_CH / 32] windows that are not scored
+    uint32_t* next_rows;       // the same two arrays of the NEXT sub-batch, filled by this launch of k_bucket_fetch
+    uint32_t* next_skp;
+    uint64_t next_chunk0;      // first chunk of the next sub-batch
+    uint32_t next_nc;          // its chunks (0 = nothing to hash)
+    uint32_t fetch_off;        // 1: this launch only hashes (the first sub-batch of a query)
 };
 
 __device__ __forceinline__ uint32_t ld_stream32(const uint32_t* p) {
@@ -662,7 +671,7 @@ __device__ __forceinline__ uint64_t chunk_seq_table(const SeqBatch& sb, uint64_t
 
 constexpr int BK_EMIT_NT = 512;
 
-template <int K, int H>
+template <int K, int H, bool PRE>
 __global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bucket_emit(const BucketParams bp) {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     const CobsParams& p = bp.cp;
@@ -696,6 +705,31 @@ __global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bucket_emit(const BucketParam
         const uint64_t g0 = (bp.chunk0 + c) * BK_CH;
         const uint64_t g1 = g0 + BK_CH < total ? g0 + BK_CH : total;
         const uint32_t nwin = (uint32_t)(g1 - g0);
+        if (PRE) {
+            // row ids and the skip bitmap of this chunk were computed by the previous sub-batch's k_bucket_fetch
+            if (tid < BK_CH / 32) s_skp[tid] = __ldg(bp.pre_skp + c * (BK_CH / 32) + tid);
+            __syncthreads();
+            const uint32_t* rows = bp.pre_rows + (size_t)c * h * BK_CH;
+#pragma unroll 1
+            for (uint32_t lid = tid; lid < nwin; lid += BK_EMIT_NT) {
+                if ((s_skp[lid >> 5] >> (lid & 31)) & 1u) continue;
+                bool over = false;
+                auto put = [&](uint32_t j) {
+                    const uint32_t row = ld_stream32(rows + j * BK_CH + lid);
+                    const uint32_t b = row >> bp.bshift;
+                    const uint32_t slot = atomicAdd(&s_cnt[b], 1u);
+                    if (slot < cap) s_rec[b * cap + slot] = (lid << bp.bshift) | (row & rmask);
+                    else over = true;
+                };
+                if (H) {
+#pragma unroll
+                    for (int j = 0; j < (H ? H : 1); ++j) put((uint32_t)j);
+                } else {
+                    for (uint32_t j = 0; j < h; ++j) put(j);
+                }
+                if (over) atomicOr(&s_ovf[lid >> 5], 1u << (lid & 31));
+            }
+        } else {
         const uint64_t s_lo = chunk_seq_table<BK_EMIT_NT>(sb, __ldg(bp.chunk_seq + bp.chunk0 + c), g0, g1, s_wseq, s_scan);
 #pragma unroll 1
         for (uint32_t lid = tid; lid < nwin; lid += BK_EMIT_NT) {
@@ -724,6 +758,7 @@ __global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bucket_emit(const BucketParam
             }
             if (over) atomicOr(&s_ovf[lid >> 5], 1u << (lid & 31));
         }
+        }
         __syncthreads();
         // blocks go out in whole 32-byte sectors (cap is a multiple of 8; the slack words are never read)
         for (uint32_t b = warp; b < nb; b += BK_EMIT_NT / 32) {
@@ -744,13 +779,86 @@ __global__ void __launch_bounds__(BK_EMIT_NT, 2) k_bucket_emit(const BucketParam
 }
 
 constexpr uint32_t BK_FETCH_SPAN = 8;   // consecutive (bucket, chunk) blocks per warp hand-out
+constexpr uint32_t BK_HASH_UNIT = 256;  // windows per hash-ahead unit (8 warp rounds)
 
+// first i >= lo with prefix[i + 1] > g, i.e. the sequence of flat window g, searching upwards from a known lower bound
+__device__ __forceinline__ uint64_t seq_of_window_from(const uint64_t* __restrict__ prefix, uint64_t n, uint64_t lo, uint64_t g) {
+    uint64_t step = 1, hi = lo + 1;
+    while (hi < n && __ldg(prefix + hi) <= g) { lo = hi; step <<= 1; hi = lo + step; }
+    if (hi > n) hi = n;
+    while (hi - lo > 1) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (__ldg(prefix + mid) <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// hash-ahead unit: row ids of BK_HASH_UNIT consecutive windows of the next sub-batch (one warp, 32 windows per round)
+template <int K, int H>
+__device__ __forceinline__ void bucket_hash_unit(const BucketParams& bp, uint64_t hu, uint64_t total, uint32_t lane) {
+    const CobsParams& p = bp.cp;
+    const SeqBatch& sb = p.sb;
+    const uint32_t k = K ? K : sb.k;
+    const uint32_t h = H ? H : p.num_hashes;
+    constexpr uint32_t PER = BK_CH / BK_HASH_UNIT;
+    const uint64_t cn = hu / PER;                                   // chunk of the next sub-batch
+    const uint32_t l0 = (uint32_t)(hu % PER) * BK_HASH_UNIT;        // first local window of the unit
+    const uint64_t c_glob = bp.next_chunk0 + cn;
+    const uint64_t g_chunk = c_glob * BK_CH;
+    if (g_chunk + l0 >= total) return;
+    const PageDesc pg = p.pages[0];
+    const uint32_t sig32 = (uint32_t)pg.sig_size;
+    uint32_t* rows = bp.next_rows + (size_t)cn * h * BK_CH;
+    uint64_t s_first = seq_of_window_from(sb.win_prefix, sb.n_seq, __ldg(bp.chunk_seq + c_glob), g_chunk + l0);
+    for (uint32_t r = 0; r < BK_HASH_UNIT / 32; ++r) {
+        const uint32_t lid = l0 + r * 32 + lane;
+        const uint64_t g = g_chunk + lid;
+        const bool has = g < total;
+        // sequence of window g: prefix of the 32 sequences after s_first in the lanes, 5-step search over shuffles
+        const uint64_t qi = s_first + 1 + lane;
+        const uint64_t P = __ldg(sb.win_prefix + (qi < sb.n_seq ? qi : sb.n_seq));
+        uint32_t lo = 0, hi = 32;                                   // smallest idx in [0, 32] with P[idx] > g (32 = none)
+#pragma unroll
+        for (int it = 0; it < 6; ++it) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint64_t pm = __shfl_sync(0xFFFFFFFFu, P, mid & 31);
+            if (lo < hi) { if (pm <= g) lo = mid + 1; else hi = mid; }
+        }
+        uint64_t seq = s_first + lo;
+        if (has && lo == 32) seq = seq_of_window_from(sb.win_prefix, sb.n_seq, s_first + 32, g);   // > 32 sequences in one round
+        bool ok = false;
+        if (has) {
+            const uint64_t pos = __ldg(sb.seq_begin + seq) - sb.base_shift + (g - __ldg(sb.win_prefix + seq)) * sb.step;
+            Term t;
+            ok = cobs_term<K>(sb, pos, p.canonicalize != 0, p.policy, t);
+            if (ok) {
+                Xxh64Pre pre;
+                xxh64_prepare(t, k, pre);
+                if (H) {
+#pragma unroll
+                    for (int j = 0; j < (H ? H : 1); ++j)
+                        rows[j * BK_CH + lid] = mod_barrett_small(xxh64_finish(pre, k, (uint64_t)j), sig32, pg.magic);
+                } else {
+                    for (uint32_t j = 0; j < h; ++j)
+                        rows[j * BK_CH + lid] = mod_barrett_small(xxh64_finish(pre, k, (uint64_t)j), sig32, pg.magic);
+                }
+            }
+        }
+        const uint32_t skip = __ballot_sync(0xFFFFFFFFu, has && !ok);
+        if (lane == 0) bp.next_skp[cn * (BK_CH / 32) + (lid >> 5)] = skip;
+        // the next round starts in (or after) the sequence of this round's last window
+        const uint32_t last = 31 - __clz(__ballot_sync(0xFFFFFFFFu, has) | 1u);
+        s_first = __shfl_sync(0xFFFFFFFFu, seq, last);
+    }
+}
+
+template <int K, int H, bool HASH>
 __global__ void __launch_bounds__(BK_NT) k_bucket_fetch(const BucketParams bp) {
     const SeqBatch& sb = bp.cp.sb;
     const PageDesc pg = bp.cp.pages[0];
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
-    const uint32_t nc_live = bucket_live_chunks(bp, total);
+    const uint32_t nc_live = bp.fetch_off ? 0u : bucket_live_chunks(bp, total);
     const uint64_t n_units = (uint64_t)bp.n_buckets * nc_live;    // unit = bucket * nc_live + chunk: bucket-major sweep
     const uint32_t rmask = (1u << bp.bshift) - 1u;
     const uint32_t cap = bp.cap;
@@ -759,9 +867,33 @@ __global__ void __launch_bounds__(BK_NT) k_bucket_fetch(const BucketParams bp) {
     const uint64_t slice_lines = ((16ULL << bp.bshift) + 127) / 128;
     const uint32_t pf_per_unit = nc_live ? (uint32_t)((slice_lines + nc_live - 1) / nc_live) : 0;
     const uint64_t index_lines = (pg.sig_size * 16 + 127) / 128;
+    // tickets interleave R fetch spans with one hash-ahead unit, so both queues drain together
+    const uint64_t n_spans = (n_units + BK_FETCH_SPAN - 1) / BK_FETCH_SPAN;
+    uint64_t n_hash = 0;
+    if (HASH && bp.next_nc) {
+        const uint64_t first = bp.next_chunk0 * BK_CH;
+        uint64_t live = total > first ? (total - first + BK_CH - 1) / BK_CH : 0;
+        if (live > bp.next_nc) live = bp.next_nc;
+        n_hash = live * (BK_CH / BK_HASH_UNIT);
+    }
+    uint64_t R = n_hash ? (n_spans + n_hash / 2) / n_hash : 1;
+    if (R == 0) R = 1;
+    const uint64_t groups_f = (n_spans + R - 1) / R;
+    const uint64_t n_tickets = HASH ? (groups_f > n_hash ? groups_f : n_hash) * (R + 1) : n_spans;
     for (;;) {
-        const uint64_t u0 = next_tile(bp.counter + 1, lane) * BK_FETCH_SPAN;
-        if (u0 >= n_units) break;
+        const uint64_t t = next_tile(bp.counter + 1, lane);
+        if (t >= n_tickets) break;
+        uint64_t span = t;
+        if (HASH) {
+            const uint64_t grp = t / (R + 1), pos = t % (R + 1);
+            if (pos == R) {
+                if (grp < n_hash) bucket_hash_unit<K, H>(bp, grp, total, lane);
+                continue;
+            }
+            span = grp * R + pos;
+            if (span >= n_spans) continue;
+        }
+        const uint64_t u0 = span * BK_FETCH_SPAN;
         const uint64_t u1 = u0 + BK_FETCH_SPAN < n_units ? u0 + BK_FETCH_SPAN : n_units;
         for (uint64_t u = u0; u < u1; ++u) {
             const uint32_t b = (uint32_t)(u / nc_live), c = (uint32_t)(u % nc_live);

@@ -594,22 +594,40 @@ static bool bucket_geometry(uint64_t sig, uint32_t h, uint32_t shift_override, B
     return true;
 }
 
-template <int K, int H>
-static cudaError_t launch_bucket_t(const BucketParams& bp, const BucketGeom& g, int n_sm, int dt, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(k_bucket_emit<K, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+template <int K, int H, bool PRE>
+static cudaError_t launch_bucket_emit(const BucketParams& bp, const BucketGeom& g, int n_sm, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(k_bucket_emit<K, H, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bucket_emit<K, H>, BK_EMIT_NT, g.smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bucket_emit<K, H, PRE>, BK_EMIT_NT, g.smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorInvalidConfiguration;
-    {
-        KernelTimer kt(s, PROF_EMIT);
-        k_bucket_emit<K, H><<<n_sm * occ, BK_EMIT_NT, g.smem, s>>>(bp);
+    KernelTimer kt(s, PROF_EMIT);
+    k_bucket_emit<K, H, PRE><<<n_sm * occ, BK_EMIT_NT, g.smem, s>>>(bp);
+    return cudaSuccess;
+}
+
+template <int K, int H>
+static cudaError_t launch_bucket_fetch(const BucketParams& bp, int n_sm, cudaStream_t s) {
+    KernelTimer kt(s, PROF_FETCH);
+    if (bp.next_nc) {
+        int occ = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bucket_fetch<K, H, true>, BK_NT, 0);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorInvalidConfiguration;
+        k_bucket_fetch<K, H, true><<<n_sm * std::min(occ, 8), BK_NT, 0, s>>>(bp);
+    } else {
+        k_bucket_fetch<K, H, false><<<n_sm * 8, BK_NT, 0, s>>>(bp);
     }
-    {
-        KernelTimer kt(s, PROF_FETCH);
-        k_bucket_fetch<<<n_sm * 8, BK_NT, 0, s>>>(bp);
-    }
+    return cudaSuccess;
+}
+
+template <int K, int H>
+static cudaError_t launch_bucket_t(const BucketParams& bp, const BucketGeom& g, int n_sm, int dt, cudaStream_t s) {
+    cudaError_t e = bp.pre_rows ? launch_bucket_emit<K, H, true>(bp, g, n_sm, s) : launch_bucket_emit<K, H, false>(bp, g, n_sm, s);
+    if (e != cudaSuccess) return e;
+    e = launch_bucket_fetch<K, H>(bp, n_sm, s);
+    if (e != cudaSuccess) return e;
     {
         KernelTimer kt(s, PROF_REDUCE);
         const bool pk = bp.pack_id != 0;
@@ -621,6 +639,11 @@ static cudaError_t launch_bucket_t(const BucketParams& bp, const BucketGeom& g, 
     return cudaGetLastError();
 }
 
+static bool bucket_hash_ahead_enabled() {
+    const char* v = getenv("XS_BK_HASH_AHEAD");      // measurement switch: 0 = k_bucket_emit hashes its own windows (round 1)
+    return !(v && *v) || atoi(v) != 0;
+}
+
 // returns XS_OK with *handled = false when the batch should go through k_cobs_narrow instead
 static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaStream_t s, bool* handled) {
     *handled = false;
@@ -629,9 +652,14 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
     if (p.sb.n_bases / p.sb.step < bk.min_windows) return XS_OK;
     BucketGeom g;
     if (!bucket_geometry(ix->pages[0].sig_size, ix->info.num_hashes, bk.shift, g)) return XS_OK;
+    // hash-ahead: k_bucket_fetch of sub-batch i also computes the row ids of sub-batch i + 1 (XXH64 in the issue slots its
+    // warps leave idle while they wait on L2 gathers); k_bucket_emit then only scatters them
+    const uint32_t nh = ix->info.num_hashes;
+    const bool ahead = bucket_hash_ahead_enabled();
+    const size_t pre_chunk = ahead ? (size_t)nh * BK_CH * 4 + (BK_CH / 32) * 4 : 0;
     SubBatches sub;
     bool ok = false;
-    XS_TRY(plan_sub_batches(bk, p.sb, g.per_chunk, sub, &ok));
+    XS_TRY(plan_sub_batches(bk, p.sb, g.per_chunk + pre_chunk, sub, &ok));
     if (!ok) return XS_OK;
 
     const size_t o_rows = 0;
@@ -640,8 +668,10 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
     const size_t o_cb = o_bc + align256(sub.nc_sub * g.nb * 2);
     const size_t o_ovf = o_cb + align256(sub.nc_sub * g.nb * 2);
     const size_t o_ctr = o_ovf + align256(sub.nc_sub * 2 * (BK_CH / 32) * 4);
-    const size_t o_seq = o_ctr + align256(sub.n_sub * 3 * 8);
-    const size_t bytes = o_seq + align256(sub.nc_total * 8);
+    const size_t o_seq = o_ctr + align256((sub.n_sub + 1) * 3 * 8);
+    const size_t o_pre = o_seq + align256(sub.nc_total * 8);
+    const size_t o_pskp = o_pre + (ahead ? align256(sub.nc_sub * nh * BK_CH * 4) : 0);
+    const size_t bytes = o_pskp + (ahead ? align256(sub.nc_sub * (BK_CH / 32) * 4) : 0);
     uint8_t* d = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&d, bytes, s);
     if (e != cudaSuccess) {                                       // no room for the scratch: direct gathers
@@ -651,25 +681,46 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
     }
     {
         BucketSerial serial(bk, s);
-        e = cudaMemsetAsync(d + o_ctr, 0, sub.n_sub * 3 * 8, s);
+        e = cudaMemsetAsync(d + o_ctr, 0, (sub.n_sub + 1) * 3 * 8, s);
         k_bucket_chunk_seq<<<chunk_seq_grid(sub.nc_total, ix->n_sm), 256, 0, s>>>(p.sb, sub.nc_total, reinterpret_cast<uint64_t*>(d + o_seq));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         const bool prefetch = bucket_prefetch_enabled();
-        for (uint64_t i = 0; i < sub.n_sub && e == cudaSuccess; ++i) {
-            BucketParams bp{};
+        const bool k21h7 = p.sb.k == 21 && p.num_hashes == 7;
+        auto fill = [&](BucketParams& bp, uint64_t i) {
             bp.cp = p;
             bp.rows = reinterpret_cast<uint4*>(d + o_rows); bp.rec = reinterpret_cast<uint32_t*>(d + o_rec);
             bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.cnt_cb = reinterpret_cast<uint16_t*>(d + o_cb);
             bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
             bp.chunk_seq = reinterpret_cast<const uint64_t*>(d + o_seq);
             bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
-            bp.chunk0 = i * sub.nc_sub;
-            bp.nc = (uint32_t)std::min<uint64_t>(sub.nc_sub, sub.nc_total - bp.chunk0);
+            bp.chunk0 = std::min<uint64_t>(i, sub.n_sub) * sub.nc_sub;
+            bp.nc = i < sub.n_sub ? (uint32_t)std::min<uint64_t>(sub.nc_sub, sub.nc_total - bp.chunk0) : 0u;
             bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap;
             bp.pack_id = ix->pages[0].n_docs <= 96 ? 1u : 0u;
             bp.prefetch = prefetch ? 1u : 0u;
-            if (p.sb.k == 21 && p.num_hashes == 7) e = launch_bucket_t<21, 7>(bp, g, ix->n_sm, dt, s);
-            else e = launch_bucket_t<0, 0>(bp, g, ix->n_sm, dt, s);
+        };
+        if (ahead) {      // prologue: the row ids of sub-batch 0 (the same kernel with nothing to fetch)
+            BucketParams bp{};
+            fill(bp, sub.n_sub);
+            bp.fetch_off = 1;
+            bp.next_rows = reinterpret_cast<uint32_t*>(d + o_pre); bp.next_skp = reinterpret_cast<uint32_t*>(d + o_pskp);
+            bp.next_chunk0 = 0;
+            bp.next_nc = (uint32_t)std::min<uint64_t>(sub.nc_sub, sub.nc_total);
+            e = k21h7 ? launch_bucket_fetch<21, 7>(bp, ix->n_sm, s) : launch_bucket_fetch<0, 0>(bp, ix->n_sm, s);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        for (uint64_t i = 0; i < sub.n_sub && e == cudaSuccess; ++i) {
+            BucketParams bp{};
+            fill(bp, i);
+            if (ahead) {
+                bp.pre_rows = reinterpret_cast<uint32_t*>(d + o_pre); bp.pre_skp = reinterpret_cast<uint32_t*>(d + o_pskp);
+                if (i + 1 < sub.n_sub) {
+                    bp.next_rows = bp.pre_rows; bp.next_skp = bp.pre_skp;
+                    bp.next_chunk0 = (i + 1) * sub.nc_sub;
+                    bp.next_nc = (uint32_t)std::min<uint64_t>(sub.nc_sub, sub.nc_total - bp.next_chunk0);
+                }
+            }
+            e = k21h7 ? launch_bucket_t<21, 7>(bp, g, ix->n_sm, dt, s) : launch_bucket_t<0, 0>(bp, g, ix->n_sm, dt, s);
         }
         if (e == cudaSuccess) {
             CobsParams tail = p;
