@@ -276,6 +276,71 @@ int xs_fastx_parse_block(const xs_fastx* fx, uint64_t a, uint64_t b, unsigned n_
     return XS_OK;
 }
 
+// Single-pass variant for the streaming classifier: sub-range i of [a, b) is parsed straight into the staging buffer
+// at the offset it has in the file block (a record's bases never outnumber its bytes, so the regions cannot
+// overlap); begin / end offsets, ids and id ends go to per-thread arrays that the caller compacts (16 bytes per
+// record against ~300 bytes of file).  seg_* describe what each sub-range produced.
+struct FastxSegOut {
+    uint64_t base0 = 0, n_bases = 0;      // region of the staging buffer this segment filled
+    uint64_t n_rec = 0, n_id = 0;
+    uint64_t* begin = nullptr; uint64_t* end = nullptr; uint64_t* id_end = nullptr; char* ids = nullptr;
+    uint64_t cap_rec = 0, cap_id = 0;
+};
+
+int xs_fastx_parse_block_1pass(const xs_fastx* fx, uint64_t a, uint64_t b, unsigned n_thr, uint8_t* staging,
+                               std::vector<FastxSegOut>& segs) {
+    std::vector<uint64_t> cuts;
+    cuts.push_back(a);
+    n_thr = std::max(1u, n_thr);
+    for (unsigned t = 1; t < n_thr; ++t) {
+        const uint64_t c = xs_fastx_sync(fx, a + (b - a) * t / n_thr);
+        if (c > cuts.back() && c < b) cuts.push_back(c);
+    }
+    cuts.push_back(b);
+    const size_t n_seg = cuts.size() - 1;
+    if (segs.size() < n_seg) segs.resize(n_seg);
+    const uint64_t min_rec = fx->format == 2 ? 6 : 2;      // "@\n\n+\n\n" / ">\n"
+    for (size_t i = 0; i < n_seg; ++i) {
+        FastxSegOut& so = segs[i];
+        const uint64_t bytes = cuts[i + 1] - cuts[i];
+        const uint64_t need_rec = bytes / min_rec + 2, need_id = bytes + 1;
+        if (so.cap_rec < need_rec) {
+            delete[] so.begin; delete[] so.end; delete[] so.id_end;
+            so.begin = new uint64_t[need_rec]; so.end = new uint64_t[need_rec]; so.id_end = new uint64_t[need_rec];   // untouched pages cost nothing
+            so.cap_rec = need_rec;
+        }
+        if (so.cap_id < need_id) { delete[] so.ids; so.ids = new char[need_id]; so.cap_id = need_id; }
+        so.base0 = cuts[i] - a; so.n_bases = so.n_rec = so.n_id = 0;
+    }
+    for (size_t i = n_seg; i < segs.size(); ++i) segs[i].n_rec = segs[i].n_bases = segs[i].n_id = 0;
+    std::atomic<size_t> next(0);
+    std::atomic<int> status(XS_OK);
+    auto work = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n_seg) break;
+            FastxSegOut& so = segs[i];
+            Sink sk;
+            sk.bases = staging; sk.seq_begin = so.begin; sk.seq_end = so.end; sk.ids = so.ids; sk.id_end = so.id_end; sk.write = true;
+            sk.n_rec = 0; sk.n_bases = so.base0; sk.n_id = 0;
+            const int rc = run(fx, fx->data + cuts[i], fx->data + cuts[i + 1], sk);
+            if (rc != XS_OK) { status.store(rc); continue; }
+            so.n_rec = sk.n_rec; so.n_bases = sk.n_bases - so.base0; so.n_id = sk.n_id;
+        }
+    };
+    if (n_seg <= 1 || n_thr <= 1) work();
+    else {
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < std::min<size_t>(n_thr, n_seg); ++t) th.emplace_back(work);
+        for (auto& t : th) t.join();
+    }
+    return status.load();
+}
+
+void xs_fastx_seg_free(std::vector<FastxSegOut>& segs) {
+    for (FastxSegOut& so : segs) { delete[] so.begin; delete[] so.end; delete[] so.id_end; delete[] so.ids; so = FastxSegOut(); }
+}
+
 extern "C" {
 
 static int fastx_open_impl(const char* path, int format, bool sizing_pass, xs_fastx** out);

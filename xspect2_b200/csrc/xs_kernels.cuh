@@ -563,7 +563,7 @@ struct BucketParams {
     uint16_t* cnt_cb;     // [nc][n_buckets]
     uint32_t* ovf;        // [nc][2][BK_CH / 32]   windows to score with direct gathers | windows that are not scored
     const uint64_t* chunk_seq;   // [all chunks of the batch] sequence of each chunk's first window (k_bucket_chunk_seq)
-    unsigned long long* counter;   // [3] work hand-out of the three kernels, zeroed
+    unsigned long long* counter;   // [4] work hand-out of emit / fetch / reduce / k_bucket_hash, zeroed
     uint64_t chunk0;      // first chunk of this sub-batch in the flat window space
     uint32_t nc;          // chunks of this sub-batch
     uint32_t n_buckets, bshift, cap;
@@ -852,8 +852,25 @@ __device__ __forceinline__ void bucket_hash_unit(const BucketParams& bp, uint64_
     }
 }
 
+// the hash-ahead work alone, for a side stream next to k_bucket_fetch / k_bucket_reduce of the previous sub-batch
+template <int K, int H>
+__global__ void __launch_bounds__(BK_NT) k_bucket_hash(const BucketParams bp) {
+    const SeqBatch& sb = bp.cp.sb;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    const uint64_t first = bp.next_chunk0 * BK_CH;
+    uint64_t live = total > first ? (total - first + BK_CH - 1) / BK_CH : 0;
+    if (live > bp.next_nc) live = bp.next_nc;
+    const uint64_t n_hash = live * (BK_CH / BK_HASH_UNIT);
+    for (;;) {
+        const uint64_t t = next_tile(bp.counter + 3, lane);
+        if (t >= n_hash) break;
+        bucket_hash_unit<K, H>(bp, t, total, lane);
+    }
+}
+
 template <int K, int H, bool HASH>
-__global__ void __launch_bounds__(BK_NT) k_bucket_fetch(const BucketParams bp) {
+__global__ void __launch_bounds__(BK_NT, HASH ? 4 : 1) k_bucket_fetch(const BucketParams bp) {
     const SeqBatch& sb = bp.cp.sb;
     const PageDesc pg = bp.cp.pages[0];
     const uint32_t lane = threadIdx.x & 31;

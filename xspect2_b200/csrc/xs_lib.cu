@@ -32,6 +32,14 @@ uint64_t xs_fastx_file_size(const xs_fastx* fx);
 uint64_t xs_fastx_sync(const xs_fastx* fx, uint64_t off);
 bool xs_fastx_blank(const xs_fastx* fx, uint64_t a, uint64_t b);
 int xs_fastx_format(const xs_fastx* fx);
+struct FastxSegOut {
+    uint64_t base0 = 0, n_bases = 0;
+    uint64_t n_rec = 0, n_id = 0;
+    uint64_t* begin = nullptr; uint64_t* end = nullptr; uint64_t* id_end = nullptr; char* ids = nullptr;
+    uint64_t cap_rec = 0, cap_id = 0;
+};
+int xs_fastx_parse_block_1pass(const xs_fastx* fx, uint64_t a, uint64_t b, unsigned n_thr, uint8_t* staging, std::vector<FastxSegOut>& segs);
+void xs_fastx_seg_free(std::vector<FastxSegOut>& segs);
 int xs_fastx_parse_block(const xs_fastx* fx, uint64_t a, uint64_t b, unsigned n_thr, std::vector<uint64_t>& cuts,
                          std::vector<Checkpoint>& cps, uint8_t* bases, uint64_t* seq_begin, uint64_t* seq_end, char* ids,
                          uint64_t* id_end, uint64_t sizes[3]);
@@ -91,6 +99,11 @@ struct KernelTimer {
     }
 };
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 static uint64_t magic_of(uint64_t m) {
     return m <= 1 ? ~0ULL : (uint64_t)((((unsigned __int128)1) << 64) / m);
 }
@@ -111,6 +124,8 @@ struct BucketState {
     std::mutex mu;
     cudaEvent_t done = nullptr;
     bool prev = false;
+    cudaStream_t side = nullptr;           // hash-ahead on a side stream (XS_BK_HASH_AHEAD=2)
+    cudaEvent_t ev_emit = nullptr, ev_hash = nullptr;
     void configure(int on, uint64_t min_w, uint64_t scratch, uint32_t sh) {
         enabled = on ? 1 : 0;
         if (min_w) min_windows = min_w;
@@ -118,7 +133,13 @@ struct BucketState {
         budget.store(0);
         shift = sh;
     }
-    void destroy() { if (done) cudaEventDestroy(done); done = nullptr; }
+    void destroy() {
+        if (done) cudaEventDestroy(done);
+        if (side) cudaStreamDestroy(side);
+        if (ev_emit) cudaEventDestroy(ev_emit);
+        if (ev_hash) cudaEventDestroy(ev_hash);
+        done = ev_emit = ev_hash = nullptr; side = nullptr;
+    }
 };
 
 struct xs_cobs {
@@ -610,6 +631,11 @@ static cudaError_t launch_bucket_emit(const BucketParams& bp, const BucketGeom& 
 template <int K, int H>
 static cudaError_t launch_bucket_fetch(const BucketParams& bp, int n_sm, cudaStream_t s) {
     KernelTimer kt(s, PROF_FETCH);
+    static const int fetch_ctas = env_int("XS_BK_FETCH_CTAS", 8);
+    if (bp.next_nc && !bp.next_rows) {   // side-stream mode: plain fetch, the grid leaves room for k_bucket_hash's CTAs
+        k_bucket_fetch<K, H, false><<<n_sm * fetch_ctas, BK_NT, 0, s>>>(bp);
+        return cudaSuccess;
+    }
     if (bp.next_nc) {
         int occ = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bucket_fetch<K, H, true>, BK_NT, 0);
@@ -620,6 +646,42 @@ static cudaError_t launch_bucket_fetch(const BucketParams& bp, int n_sm, cudaStr
         k_bucket_fetch<K, H, false><<<n_sm * 8, BK_NT, 0, s>>>(bp);
     }
     return cudaSuccess;
+}
+
+template <int K, int H>
+static void launch_bucket_reduce(const BucketParams& bp, int n_sm, int dt, cudaStream_t s) {
+        KernelTimer kt(s, PROF_REDUCE);
+        const bool pk = bp.pack_id != 0;
+        if (dt == XS_U8) { if (pk) k_bucket_reduce<K, H, uint8_t, true><<<n_sm * 4, BK_NT, 0, s>>>(bp); else k_bucket_reduce<K, H, uint8_t, false><<<n_sm * 4, BK_NT, 0, s>>>(bp); }
+        else if (dt == XS_U16) { if (pk) k_bucket_reduce<K, H, uint16_t, true><<<n_sm * 4, BK_NT, 0, s>>>(bp); else k_bucket_reduce<K, H, uint16_t, false><<<n_sm * 4, BK_NT, 0, s>>>(bp); }
+        else { if (pk) k_bucket_reduce<K, H, uint32_t, true><<<n_sm * 4, BK_NT, 0, s>>>(bp); else k_bucket_reduce<K, H, uint32_t, false><<<n_sm * 4, BK_NT, 0, s>>>(bp); }
+}
+
+// side-stream hash-ahead: emit(i) [scatter of precomputed row ids] -> { fetch(i) -> reduce(i) } next to k_bucket_hash(i + 1)
+template <int K, int H>
+static cudaError_t launch_bucket_side(const BucketParams& bp, const BucketGeom& g, int n_sm, int dt, cudaStream_t s, cudaStream_t side,
+                                      cudaEvent_t ev_emit, cudaEvent_t ev_hash) {
+    static const int hash_ctas = env_int("XS_BK_HASH_CTAS", 1);
+    cudaError_t e = launch_bucket_emit<K, H, true>(bp, g, n_sm, s);
+    if (e != cudaSuccess) return e;
+    if (bp.next_nc) {
+        cudaEventRecord(ev_emit, s);                 // the row-id buffer is free once emit has read it
+        cudaStreamWaitEvent(side, ev_emit, 0);
+        BucketParams hb = bp;
+        hb.next_rows = bp.pre_rows; hb.next_skp = bp.pre_skp;
+        hb.counter = bp.counter + 4;                 // the next sub-batch's counters
+        k_bucket_hash<K, H><<<n_sm * hash_ctas, BK_NT, 0, side>>>(hb);
+        cudaEventRecord(ev_hash, side);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    BucketParams fb = bp;
+    fb.next_rows = nullptr;                          // plain fetch
+    e = launch_bucket_fetch<K, H>(fb, n_sm, s);
+    if (e != cudaSuccess) return e;
+    launch_bucket_reduce<K, H>(bp, n_sm, dt, s);
+    if (bp.next_nc) cudaStreamWaitEvent(s, ev_hash, 0);
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    return cudaGetLastError();
 }
 
 template <int K, int H>
@@ -639,10 +701,13 @@ static cudaError_t launch_bucket_t(const BucketParams& bp, const BucketGeom& g, 
     return cudaGetLastError();
 }
 
-static bool bucket_hash_ahead_enabled() {
-    const char* v = getenv("XS_BK_HASH_AHEAD");      // measurement switch: 0 = k_bucket_emit hashes its own windows (round 1)
-    return !(v && *v) || atoi(v) != 0;
+// measurement switch: 0 = k_bucket_emit hashes its own windows (round 1); 1 = k_bucket_fetch of sub-batch i also hashes
+// the windows of sub-batch i + 1; 2 = k_bucket_hash of sub-batch i + 1 on a side stream next to fetch / reduce of sub-batch i
+static int bucket_hash_ahead_mode() {
+    const char* v = getenv("XS_BK_HASH_AHEAD");
+    return (v && *v) ? atoi(v) : 0;
 }
+
 
 // returns XS_OK with *handled = false when the batch should go through k_cobs_narrow instead
 static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaStream_t s, bool* handled) {
@@ -655,7 +720,8 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
     // hash-ahead: k_bucket_fetch of sub-batch i also computes the row ids of sub-batch i + 1 (XXH64 in the issue slots its
     // warps leave idle while they wait on L2 gathers); k_bucket_emit then only scatters them
     const uint32_t nh = ix->info.num_hashes;
-    const bool ahead = bucket_hash_ahead_enabled();
+    const int ahead_mode = bucket_hash_ahead_mode();
+    const bool ahead = ahead_mode != 0;
     const size_t pre_chunk = ahead ? (size_t)nh * BK_CH * 4 + (BK_CH / 32) * 4 : 0;
     SubBatches sub;
     bool ok = false;
@@ -668,7 +734,7 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
     const size_t o_cb = o_bc + align256(sub.nc_sub * g.nb * 2);
     const size_t o_ovf = o_cb + align256(sub.nc_sub * g.nb * 2);
     const size_t o_ctr = o_ovf + align256(sub.nc_sub * 2 * (BK_CH / 32) * 4);
-    const size_t o_seq = o_ctr + align256((sub.n_sub + 1) * 3 * 8);
+    const size_t o_seq = o_ctr + align256((sub.n_sub + 1) * 4 * 8);
     const size_t o_pre = o_seq + align256(sub.nc_total * 8);
     const size_t o_pskp = o_pre + (ahead ? align256(sub.nc_sub * nh * BK_CH * 4) : 0);
     const size_t bytes = o_pskp + (ahead ? align256(sub.nc_sub * (BK_CH / 32) * 4) : 0);
@@ -681,7 +747,7 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
     }
     {
         BucketSerial serial(bk, s);
-        e = cudaMemsetAsync(d + o_ctr, 0, (sub.n_sub + 1) * 3 * 8, s);
+        e = cudaMemsetAsync(d + o_ctr, 0, (sub.n_sub + 1) * 4 * 8, s);
         k_bucket_chunk_seq<<<chunk_seq_grid(sub.nc_total, ix->n_sm), 256, 0, s>>>(p.sb, sub.nc_total, reinterpret_cast<uint64_t*>(d + o_seq));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         const bool prefetch = bucket_prefetch_enabled();
@@ -692,21 +758,32 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
             bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.cnt_cb = reinterpret_cast<uint16_t*>(d + o_cb);
             bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
             bp.chunk_seq = reinterpret_cast<const uint64_t*>(d + o_seq);
-            bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
+            bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 4 * i;
             bp.chunk0 = std::min<uint64_t>(i, sub.n_sub) * sub.nc_sub;
             bp.nc = i < sub.n_sub ? (uint32_t)std::min<uint64_t>(sub.nc_sub, sub.nc_total - bp.chunk0) : 0u;
             bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap;
             bp.pack_id = ix->pages[0].n_docs <= 96 ? 1u : 0u;
             bp.prefetch = prefetch ? 1u : 0u;
         };
-        if (ahead) {      // prologue: the row ids of sub-batch 0 (the same kernel with nothing to fetch)
+        if (ahead_mode == 2 && !bk.side) {
+            if (cudaStreamCreateWithFlags(&bk.side, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&bk.ev_emit, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&bk.ev_hash, cudaEventDisableTiming) != cudaSuccess)
+                e = cudaErrorUnknown;
+        }
+        if (ahead && e == cudaSuccess) {      // prologue: the row ids of sub-batch 0
             BucketParams bp{};
             fill(bp, sub.n_sub);
             bp.fetch_off = 1;
             bp.next_rows = reinterpret_cast<uint32_t*>(d + o_pre); bp.next_skp = reinterpret_cast<uint32_t*>(d + o_pskp);
             bp.next_chunk0 = 0;
             bp.next_nc = (uint32_t)std::min<uint64_t>(sub.nc_sub, sub.nc_total);
-            e = k21h7 ? launch_bucket_fetch<21, 7>(bp, ix->n_sm, s) : launch_bucket_fetch<0, 0>(bp, ix->n_sm, s);
+            if (ahead_mode == 2) {
+                if (k21h7) k_bucket_hash<21, 7><<<ix->n_sm * 4, BK_NT, 0, s>>>(bp); else k_bucket_hash<0, 0><<<ix->n_sm * 4, BK_NT, 0, s>>>(bp);
+                e = cudaGetLastError();
+            } else {
+                e = k21h7 ? launch_bucket_fetch<21, 7>(bp, ix->n_sm, s) : launch_bucket_fetch<0, 0>(bp, ix->n_sm, s);
+            }
             g_launches.fetch_add(1, std::memory_order_relaxed);
         }
         for (uint64_t i = 0; i < sub.n_sub && e == cudaSuccess; ++i) {
@@ -720,7 +797,11 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
                     bp.next_nc = (uint32_t)std::min<uint64_t>(sub.nc_sub, sub.nc_total - bp.next_chunk0);
                 }
             }
-            e = k21h7 ? launch_bucket_t<21, 7>(bp, g, ix->n_sm, dt, s) : launch_bucket_t<0, 0>(bp, g, ix->n_sm, dt, s);
+            if (ahead_mode == 2)
+                e = k21h7 ? launch_bucket_side<21, 7>(bp, g, ix->n_sm, dt, s, bk.side, bk.ev_emit, bk.ev_hash)
+                          : launch_bucket_side<0, 0>(bp, g, ix->n_sm, dt, s, bk.side, bk.ev_emit, bk.ev_hash);
+            else
+                e = k21h7 ? launch_bucket_t<21, 7>(bp, g, ix->n_sm, dt, s) : launch_bucket_t<0, 0>(bp, g, ix->n_sm, dt, s);
         }
         if (e == cudaSuccess) {
             CobsParams tail = p;
@@ -905,7 +986,7 @@ static int bloom_launch_bucketed(xs_bloom* bf, const BloomParams& p, cudaStream_
             bp.pos = reinterpret_cast<uint32_t*>(d + o_pos); bp.wid = reinterpret_cast<uint16_t*>(d + o_wid); bp.res = d + o_res;
             bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
             bp.chunk_seq = reinterpret_cast<const uint64_t*>(d + o_seq);
-            bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
+            bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 4 * i;
             bp.chunk0 = i * sub.nc_sub;
             bp.nc = (uint32_t)std::min<uint64_t>(sub.nc_sub, sub.nc_total - bp.chunk0);
             bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap; bp.prefetch = prefetch ? 1u : 0u;
@@ -1781,8 +1862,7 @@ int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t st
         }
         sl.busy = false;
     };
-    std::vector<uint64_t> cuts;
-    std::vector<Checkpoint> cps;
+    std::vector<FastxSegOut> segs;
     uint64_t a = rc == XS_OK ? xs_fastx_sync(fx, 0) : fsize;
     if (rc == XS_OK && format == 2 && !xs_fastx_blank(fx, 0, a))
         rc = fail(XS_ERR_FORMAT, "the streaming reader accepts 4-line FASTQ only (wrapped or malformed records found)");
@@ -1795,16 +1875,31 @@ int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t st
         retire(sl);
         if (rc != XS_OK) break;
         const double tp = now_s();
-        uint64_t sizes[3] = {0, 0, 0};
-        rc = xs_fastx_parse_block(fx, a, b, hw, cuts, cps, nullptr, nullptr, nullptr, nullptr, nullptr, sizes);
-        if (rc != XS_OK) break;
-        const uint64_t nr = sizes[0], nb = sizes[1], nid = sizes[2];
-        const size_t o_b = align256(nb + 64), need_h = o_b + 2 * align256(nr * 8);
-        if (need_h > sl.h_cap) {
+        // staging: the block's bytes as an upper bound of its bases (every parser thread fills its own region), then
+        // begin | end, sized after the parse
+        const uint64_t span = b - a;
+        const size_t o_b = align256(span + 64);
+        const uint64_t rec_cap = span / (format == 2 ? 6 : 2) + 2;
+        size_t need_h = o_b + 2 * align256(std::min<uint64_t>(rec_cap, span / 16 + 4096) * 8);     // typical; regrown below if short
+        auto grow_h = [&](size_t need) {
+            if (need <= sl.h_cap) return true;
+            uint8_t* nh = nullptr;
+            if (!cuda_ok(cudaHostAlloc((void**)&nh, need + need / 8, cudaHostAllocPortable), "pinned staging")) return false;
             if (sl.h) cudaFreeHost(sl.h);
-            sl.h = nullptr; sl.h_cap = 0;
-            if (!cuda_ok(cudaHostAlloc((void**)&sl.h, need_h + need_h / 8, cudaHostAllocPortable), "pinned staging")) break;
-            sl.h_cap = need_h + need_h / 8;
+            sl.h = nh; sl.h_cap = need + need / 8;
+            return true;
+        };
+        if (!grow_h(need_h)) break;
+        rc = xs_fastx_parse_block_1pass(fx, a, b, hw, sl.h, segs);
+        if (rc != XS_OK) break;
+        uint64_t nr = 0, nb = 0, nid = 0;
+        for (const FastxSegOut& so : segs) { nr += so.n_rec; nb += so.n_bases; nid += so.n_id; }
+        need_h = o_b + 2 * align256(nr * 8);
+        if (need_h > sl.h_cap) {       // more records than the typical bound: keep the parsed bases, move to a larger buffer
+            uint8_t* old = sl.h; sl.h = nullptr; const size_t old_cap = sl.h_cap; sl.h_cap = 0;
+            if (!grow_h(need_h)) { cudaFreeHost(old); break; }
+            memcpy(sl.h, old, std::min<size_t>(old_cap, o_b));
+            cudaFreeHost(old);
         }
         if (nr * 12 > sl.r_cap) {
             if (sl.h_res) cudaFreeHost(sl.h_res);
@@ -1814,19 +1909,25 @@ int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t st
         }
         uint64_t* h_b = reinterpret_cast<uint64_t*>(sl.h + o_b);
         uint64_t* h_e = reinterpret_cast<uint64_t*>(sl.h + o_b + align256(nr * 8));
+        // compaction of the per-thread record arrays (16 bytes per record) + ids
         const size_t id0 = res->ids.size();
         res->ids.resize(id0 + nid);
         res->id_end.resize(rec_total + nr);
-        rc = xs_fastx_parse_block(fx, a, b, hw, cuts, cps, sl.h, h_b, h_e, res->ids.data() + id0, res->id_end.data() + rec_total, sizes);
-        if (rc != XS_OK) break;
         res->seq_len.resize(rec_total + nr);
-        uint64_t max_len = 0, n_short = 0;
-        for (uint64_t i = 0; i < nr; ++i) {
-            const uint64_t len = h_e[i] - h_b[i];
-            res->seq_len[rec_total + i] = len;
-            res->id_end[rec_total + i] += id0;
-            max_len = std::max(max_len, len);
-            n_short += len <= k;
+        uint64_t max_len = 0, n_short = 0, r0 = 0, i0 = 0;
+        for (const FastxSegOut& so : segs) {
+            if (!so.n_rec) continue;
+            memcpy(h_b + r0, so.begin, so.n_rec * 8);
+            memcpy(h_e + r0, so.end, so.n_rec * 8);
+            memcpy(res->ids.data() + id0 + i0, so.ids, so.n_id);
+            for (uint64_t i = 0; i < so.n_rec; ++i) {
+                const uint64_t len = so.end[i] - so.begin[i];
+                res->seq_len[rec_total + r0 + i] = len;
+                res->id_end[rec_total + r0 + i] = id0 + i0 + so.id_end[i];
+                max_len = std::max(max_len, len);
+                n_short += len <= k;
+            }
+            r0 += so.n_rec; i0 += so.n_id;
         }
         res->n_short += n_short;
         res->n_bases += nb;
@@ -1843,11 +1944,13 @@ int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t st
             sl.d_cap = need_d + need_d / 8;
         }
         if (nr) {
-            cuda_ok(cudaMemcpyAsync(sl.d, sl.h, need_h, cudaMemcpyHostToDevice, sl.s), "H2D copy");
+            for (const FastxSegOut& so : segs)      // only the filled part of every parser region travels
+                if (so.n_bases) cuda_ok(cudaMemcpyAsync(sl.d + so.base0, sl.h + so.base0, so.n_bases, cudaMemcpyHostToDevice, sl.s), "H2D copy");
+            cuda_ok(cudaMemcpyAsync(sl.d + o_b, sl.h + o_b, 2 * align256(nr * 8), cudaMemcpyHostToDevice, sl.s), "H2D copy");
             uint64_t* d_b = reinterpret_cast<uint64_t*>(sl.d + o_b);
             uint64_t* d_e = reinterpret_cast<uint64_t*>(sl.d + o_b + align256(nr * 8));
             uint32_t* d_best = reinterpret_cast<uint32_t*>(sl.d + o_res);
-            if (rc == XS_OK) rc = cobs_query_dev(ix, sl.d, nb, d_b, d_e, nr, 0, step, dt, sl.d + o_cnt, sl.s);
+            if (rc == XS_OK) rc = cobs_query_dev(ix, sl.d, span, d_b, d_e, nr, 0, step, dt, sl.d + o_cnt, sl.s);
             if (rc == XS_OK) {
                 const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nr + REDUCE_ROWS - 1) / REDUCE_ROWS, (uint64_t)ix->n_sm * 8));
                 unsigned long long* tot = reinterpret_cast<unsigned long long*>(d_tot);
@@ -1863,6 +1966,7 @@ int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t st
         rec_total += nr;
         a = b; ++bi; ++res->n_blocks;
     }
+    xs_fastx_seg_free(segs);
     for (int i = 0; i < NS; ++i) retire(slot[(bi + i) % NS]);
     if (rc == XS_OK && d_tot) {
         cuda_ok(cudaDeviceSynchronize(), "file query");
