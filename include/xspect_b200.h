@@ -13,8 +13,15 @@
  *   - every function returns an int: XS_OK (0) or a negative xs_status; the message for the
  *     calling thread is returned by xs_last_error()
  *   - handles own their device (HBM) memory until xs_*_close; callers own all input and
- *     output buffers; handles are immutable after open, so concurrent queries from several
- *     host threads are allowed
+ *     output buffers; the index data is immutable after open, so queries from several host
+ *     threads on one handle are safe.  How much they overlap depends on the path: small batches
+ *     (direct kernels) run concurrently on their own streams; large batches that take the bucketed
+ *     kernels (xs_cobs_set_bucketed / xs_bloom_set_bucketed) are serialised per handle — a mutex
+ *     while they are enqueued plus an event chain on the device — because two bucketed sweeps
+ *     would evict each other's L2-resident row range.  Two workers that need large batches in
+ *     parallel on one GPU open the model twice (2.4 GB per copy for the species model).
+ *   - the only library kernel on the path is cub::DeviceScan::ExclusiveSum over the windows-per-
+ *     record array (0.03 % of a step); everything else is this library's own kernels
  *   - there is NO CPU fallback: every query needs a CUDA device and fails with XS_ERR_CUDA
  *     otherwise
  *   - sequences are described by two arrays seq_begin[i], seq_end[i] (byte offsets into

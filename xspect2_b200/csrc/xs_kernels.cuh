@@ -555,7 +555,10 @@ constexpr int BK_WARP_WIN = BK_CH / (BK_NT / 32);
 constexpr uint32_t BK_MAX_BUCKETS = 256;
 constexpr uint32_t BK_MAX_SHIFT = 21;  // 11 + 21 = 32 bits per probe record
 
+struct alignas(64) TensorMap128 { uint64_t q[16]; };   // a CUtensorMap (driver API), opaque here
+
 struct BucketParams {
+    TensorMap128 tmap;     // 2-D view of the index rows [sig_size][4 x u32] for tile::gather4 (k_bucket_fetch_tma)
     CobsParams cp;
     uint32_t* rec;        // [n_buckets][nc][cap]  (local window << bshift) | (row & (2^bshift - 1))
     uint4* rows;          // [nc][n_buckets][cap]  fetched rows; .w = local window when pack_id
@@ -578,6 +581,7 @@ struct BucketParams {
     uint64_t next_chunk0;      // first chunk of the next sub-batch
     uint32_t next_nc;          // its chunks (0 = nothing to hash)
     uint32_t fetch_off;        // 1: this launch only hashes (the first sub-batch of a query)
+    uint32_t use_tma;          // k_bucket_fetch_tma: records per lane and pass fetched with tile::gather4 (0 = LSU only)
 };
 
 __device__ __forceinline__ uint32_t ld_stream32(const uint32_t* p) {
@@ -938,6 +942,109 @@ __global__ void __launch_bounds__(BK_NT, HASH ? 4 : 1) k_bucket_fetch(const Buck
                     const uint32_t i = i0 + q * 32 + lane;
                     if (i < n) v[q] = ldg128_keep(base + (uint64_t)(r[q] & rmask) * 16, keep);
                 }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t i = i0 + q * 32 + lane;
+                    if (i < n) {
+                        if (bp.pack_id) v[q].w = r[q] >> bp.bshift;
+                        st_stream128(dst + i, v[q]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// k_bucket_fetch with part of the gathers moved to the TMA unit.  The LSU path tops out at one L1TEX tag lookup per
+// gathered row (~168 G rows/s); Blackwell's tile::gather4 tensor copy fetches four rows of a 2-D tensor by row index
+// with one instruction and does not pass through L1TEX (profiles/microbench/gather_tma4.cu: 88 G rows/s alone,
+// additive next to LSU gathers).  Per pass over a block of <= 128 records a lane takes TMAQ of its four records
+// through gather4 (the quad leader issues one copy for the quad's four rows into a 64-byte shared-memory slot,
+// completion on a per-warp mbarrier) and the others through ld.global.nc as before.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int TMAQ>
+__global__ void __launch_bounds__(BK_NT) k_bucket_fetch_tma(const __grid_constant__ BucketParams bp) {
+    __shared__ __align__(128) uint8_t s_slot[BK_NT / 32][TMAQ][8][128];   // [warp][q][quad] 64 bytes used of each 128
+    __shared__ __align__(8) uint64_t s_bar[BK_NT / 32];
+    const SeqBatch& sb = bp.cp.sb;
+    const PageDesc pg = bp.cp.pages[0];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    const uint32_t nc_live = bucket_live_chunks(bp, total);
+    const uint64_t n_units = (uint64_t)bp.n_buckets * nc_live;
+    const uint32_t rmask = (1u << bp.bshift) - 1u;
+    const uint32_t cap = bp.cap;
+    const uint64_t keep = l2_policy_evict_last();
+    const uint64_t slice_lines = ((16ULL << bp.bshift) + 127) / 128;
+    const uint32_t pf_per_unit = nc_live ? (uint32_t)((slice_lines + nc_live - 1) / nc_live) : 0;
+    const uint64_t index_lines = (pg.sig_size * 16 + 127) / 128;
+    const uint32_t bar = smem_addr(&s_bar[warp]);
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t phase = 0;
+    constexpr int LSUQ = 4 - TMAQ;
+    for (;;) {
+        const uint64_t u0 = next_tile(bp.counter + 1, lane) * BK_FETCH_SPAN;
+        if (u0 >= n_units) break;
+        const uint64_t u1 = u0 + BK_FETCH_SPAN < n_units ? u0 + BK_FETCH_SPAN : n_units;
+        for (uint64_t u = u0; u < u1; ++u) {
+            const uint32_t b = (uint32_t)(u / nc_live), c = (uint32_t)(u % nc_live);
+            const uint32_t n = __ldg(bp.cnt_bc + (uint64_t)b * bp.nc + c);
+            const uint32_t* src = bp.rec + ((uint64_t)b * bp.nc + c) * cap;
+            uint4* dst = bp.rows + ((uint64_t)c * bp.n_buckets + b) * cap;
+            const uint32_t row0 = b << bp.bshift;
+            const uint8_t* base = pg.data + (uint64_t)row0 * 16;
+            if (bp.prefetch && b + 1 < bp.n_buckets) {
+                for (uint32_t l = lane; l < pf_per_unit; l += 32) {
+                    const uint64_t in_slice = (uint64_t)c * pf_per_unit + l;
+                    const uint64_t line = (uint64_t)(b + 1) * slice_lines + in_slice;
+                    if (in_slice < slice_lines && line < index_lines) prefetch_l2_keep(pg.data + line * 128, keep);
+                }
+            }
+            for (uint32_t i0 = 0; i0 < n; i0 += 128) {
+                uint32_t r[4];
+                uint4 v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t i = i0 + q * 32 + lane;
+                    r[q] = i < n ? ld_stream32(src + i) : 0u;
+                }
+                // ---- TMA part: records q >= LSUQ
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(TMAQ * 8 * 64) : "memory");
+                __syncwarp();
+#pragma unroll
+                for (int q = LSUQ; q < 4; ++q) {
+                    const int32_t my = (int32_t)(row0 + (r[q] & rmask));       // records past n read row0 (ignored below)
+                    const int32_t a0 = __shfl_sync(0xFFFFFFFFu, my, (lane & ~3u) + 0), a1 = __shfl_sync(0xFFFFFFFFu, my, (lane & ~3u) + 1),
+                                  a2 = __shfl_sync(0xFFFFFFFFu, my, (lane & ~3u) + 2), a3 = __shfl_sync(0xFFFFFFFFu, my, (lane & ~3u) + 3);
+                    if ((lane & 3u) == 0)
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
+                                     " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+                                     :: "r"(smem_addr(&s_slot[warp][q - LSUQ][lane >> 2][0])), "l"(&bp.tmap), "r"(bar), "r"(0), "r"(a0), "r"(a1),
+                                        "r"(a2), "r"(a3), "l"(keep) : "memory");
+                }
+                // ---- LSU part
+#pragma unroll
+                for (int q = 0; q < LSUQ; ++q) {
+                    const uint32_t i = i0 + q * 32 + lane;
+                    if (i < n) v[q] = ldg128_keep(base + (uint64_t)(r[q] & rmask) * 16, keep);
+                }
+                {
+                    uint32_t done = 0;
+                    while (!done)
+                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+                    phase ^= 1;
+                }
+#pragma unroll
+                for (int q = LSUQ; q < 4; ++q)
+                    v[q] = *reinterpret_cast<const uint4*>(&s_slot[warp][q - LSUQ][lane >> 2][(lane & 3u) * 16]);
+                __syncwarp();          // every lane has read its slot before the next pass overwrites it
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint32_t i = i0 + q * 32 + lane;

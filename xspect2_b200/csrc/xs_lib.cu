@@ -18,6 +18,7 @@
 #include <vector>
 
 #include <cub/device/device_scan.cuh>
+#include <cuda.h>      // CUtensorMap + cuTensorMapEncodeTiled's signature; the entry point is fetched at run time
 
 #include "../../include/xspect_b200.h"
 #include "xs_kernels.cuh"
@@ -152,6 +153,8 @@ struct xs_cobs {
     PageDesc* d_pages = nullptr;
     ColBlock* d_blocks = nullptr;
     bool narrow = true;
+    TensorMap128 tmap{};         // rows of a one-page narrow index as a [sig_size][4 x u32] tensor (tile::gather4 fetch variant)
+    bool has_tmap = false;
     bool pages_kernel = false;   // several narrow pages: k_cobs_pages (one pass, windows hashed once) instead of k_cobs_narrow per page
     int n_sm = 148;
     int force_wide = 0;
@@ -177,6 +180,32 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
+
+struct StreamSlot {
+    uint8_t* h = nullptr; size_t h_cap = 0;          // pinned staging: bases | begin | end
+    uint8_t* d = nullptr; size_t d_cap = 0;          // device: bases | begin | end | counts | best | cnt | nb
+    uint32_t* h_res = nullptr; size_t r_cap = 0;     // pinned results: best | cnt | nb
+    cudaStream_t s = nullptr; cudaEvent_t done = nullptr;
+    uint64_t rec0 = 0, n_rec = 0; bool busy = false;
+};
+static const int STREAM_NS = 3;
+static std::mutex g_stream_mu;
+static StreamSlot g_stream_slot[STREAM_NS];
+static int g_stream_dev = -1;
+static void stream_slots_release() {       // caller holds g_stream_mu (or is single-threaded)
+    if (g_stream_dev < 0) return;
+    DeviceGuard guard(g_stream_dev);
+    for (StreamSlot& sl : g_stream_slot) {
+        if (sl.s) cudaStreamSynchronize(sl.s);
+        if (sl.h) cudaFreeHost(sl.h);
+        if (sl.h_res) cudaFreeHost(sl.h_res);
+        if (sl.d) cudaFree(sl.d);
+        if (sl.s) cudaStreamDestroy(sl.s);
+        if (sl.done) cudaEventDestroy(sl.done);
+        sl = StreamSlot();
+    }
+    g_stream_dev = -1;
+}
 
 static std::atomic<int> g_home_device{-1};
 
@@ -632,6 +661,11 @@ template <int K, int H>
 static cudaError_t launch_bucket_fetch(const BucketParams& bp, int n_sm, cudaStream_t s) {
     KernelTimer kt(s, PROF_FETCH);
     static const int fetch_ctas = env_int("XS_BK_FETCH_CTAS", 8);
+    if (bp.use_tma && !(bp.next_nc && bp.next_rows) && !bp.fetch_off) {       // part of the gathers through the TMA unit
+        if (bp.use_tma >= 2) k_bucket_fetch_tma<2><<<n_sm * fetch_ctas, BK_NT, 0, s>>>(bp);
+        else k_bucket_fetch_tma<1><<<n_sm * fetch_ctas, BK_NT, 0, s>>>(bp);
+        return cudaSuccess;
+    }
     if (bp.next_nc && !bp.next_rows) {   // side-stream mode: plain fetch, the grid leaves room for k_bucket_hash's CTAs
         k_bucket_fetch<K, H, false><<<n_sm * fetch_ctas, BK_NT, 0, s>>>(bp);
         return cudaSuccess;
@@ -752,8 +786,10 @@ static int cobs_launch_bucketed(xs_cobs* ix, const CobsParams& p, int dt, cudaSt
         g_launches.fetch_add(1, std::memory_order_relaxed);
         const bool prefetch = bucket_prefetch_enabled();
         const bool k21h7 = p.sb.k == 21 && p.num_hashes == 7;
+        static const int tma_q = env_int("XS_BK_TMA", 0);      // records per lane and pass that go through tile::gather4 (0, 1, 2)
         auto fill = [&](BucketParams& bp, uint64_t i) {
             bp.cp = p;
+            if (ix->has_tmap && tma_q) { bp.tmap = ix->tmap; bp.use_tma = (uint32_t)tma_q; }
             bp.rows = reinterpret_cast<uint4*>(d + o_rows); bp.rec = reinterpret_cast<uint32_t*>(d + o_rec);
             bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.cnt_cb = reinterpret_cast<uint16_t*>(d + o_cb);
             bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
@@ -1281,6 +1317,10 @@ int xs_device_trim(int device) {
     DeviceGuard guard(device);
     if (!guard.ok) return fail(XS_ERR_CUDA, "cannot select the device");
     XS_CUDA(cudaDeviceSynchronize());
+    {   // the streaming file reader's cached staging buffers
+        std::lock_guard<std::mutex> lk(g_stream_mu);
+        if (g_stream_dev == device) stream_slots_release();
+    }
     cudaMemPool_t pool;
     XS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     XS_CUDA(cudaMemPoolTrimTo(pool, 0));
@@ -1289,6 +1329,29 @@ int xs_device_trim(int device) {
 int xs_host_free(void* p) {
     if (p) XS_CUDA(cudaFreeHost(p));
     return XS_OK;
+}
+
+// 2-D tensor map over 16-byte rows for cp.async.bulk.tensor tile::gather4 (k_bucket_fetch_tma); false when the driver
+// entry point is missing or the geometry does not fit (rows >= 2^31)
+static bool make_row_tensor_map(const uint8_t* d_rows, uint64_t n_rows, TensorMap128* out) {
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static_assert(sizeof(CUtensorMap) == sizeof(TensorMap128), "CUtensorMap is 128 bytes");
+    if (n_rows == 0 || n_rows >= (1ULL << 31)) return false;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) { cudaGetLastError(); return false; }
+    cuuint64_t gdim[2] = {4, n_rows};
+    cuuint64_t gstr[1] = {16};
+    cuuint32_t box[2] = {4, 1};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap tm;
+    CUresult r = ((EncodeTiled)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)d_rows, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    memcpy(out, &tm, sizeof(tm));
+    return true;
 }
 
 int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_end, xs_cobs** out) {
@@ -1401,6 +1464,8 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
     in.page_bytes = cf.page_bytes; in.row_stride = stride;
     in.sig_size_max = *std::max_element(cf.sig.begin(), cf.sig.end());
     in.hbm_bytes = total; in.device = device; in.policy = XS_NONACGT_SKIP;
+    if (ix->narrow && ix->pages.size() == 1 && ix->pages[0].row_stride == 16)
+        ix->has_tmap = make_row_tensor_map(ix->pages[0].data, ix->pages[0].sig_size, &ix->tmap);
     *out = ix;
     return XS_OK;
 }
@@ -1831,14 +1896,13 @@ int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t st
     const uint32_t k = ix->info.term_size;
     xs_file_calls* res = new xs_file_calls();
     res->totals.assign(ld, 0);
-    const int NS = 3;
-    struct Slot {
-        uint8_t* h = nullptr; size_t h_cap = 0;          // pinned staging: bases | begin | end
-        uint8_t* d = nullptr; size_t d_cap = 0;          // device: bases | begin | end | counts | best | cnt | nb
-        uint32_t* h_res = nullptr; size_t r_cap = 0;     // pinned results: best | cnt | nb
-        cudaStream_t s = nullptr; cudaEvent_t done = nullptr;
-        uint64_t rec0 = 0, n_rec = 0; bool busy = false;
-    } slot[NS];
+    // staging buffers, streams and events are kept between calls (page-locking ~100 MB per slot costs more than
+    // parsing a block); calls on one process take turns
+    std::lock_guard<std::mutex> stream_lock(g_stream_mu);
+    if (g_stream_dev != ix->info.device) { stream_slots_release(); g_stream_dev = ix->info.device; }
+    const int NS = STREAM_NS;
+    StreamSlot* slot = g_stream_slot;
+    for (int i = 0; i < NS; ++i) { slot[i].busy = false; slot[i].rec0 = slot[i].n_rec = 0; }
     uint64_t* d_tot = nullptr;
     int rc = XS_OK;
     auto cuda_ok = [&](cudaError_t e, const char* what) {
@@ -1849,10 +1913,10 @@ int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t st
     if (rc == XS_OK) cuda_ok(cudaMemset(d_tot, 0, ld * 8), "totals");
     if (rc == XS_OK) cuda_ok(cudaDeviceSynchronize(), "totals");
     for (int i = 0; i < NS && rc == XS_OK; ++i) {
-        cuda_ok(cudaStreamCreateWithFlags(&slot[i].s, cudaStreamNonBlocking), "stream");
-        cuda_ok(cudaEventCreateWithFlags(&slot[i].done, cudaEventDisableTiming), "event");
+        if (!slot[i].s) cuda_ok(cudaStreamCreateWithFlags(&slot[i].s, cudaStreamNonBlocking), "stream");
+        if (!slot[i].done) cuda_ok(cudaEventCreateWithFlags(&slot[i].done, cudaEventDisableTiming), "event");
     }
-    auto retire = [&](Slot& sl) {       // results of the slot's block -> the result vectors
+    auto retire = [&](StreamSlot& sl) {       // results of the slot's block -> the result vectors
         if (!sl.busy) return;
         cuda_ok(cudaEventSynchronize(sl.done), "block");
         if (rc == XS_OK) {
@@ -1871,7 +1935,7 @@ int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t st
     while (rc == XS_OK && a < fsize) {
         uint64_t b = a + block_bytes >= fsize ? fsize : xs_fastx_sync(fx, a + block_bytes);
         if (b <= a) b = fsize;
-        Slot& sl = slot[bi % NS];
+        StreamSlot& sl = slot[bi % NS];
         retire(sl);
         if (rc != XS_OK) break;
         const double tp = now_s();
@@ -1880,7 +1944,7 @@ int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t st
         const uint64_t span = b - a;
         const size_t o_b = align256(span + 64);
         const uint64_t rec_cap = span / (format == 2 ? 6 : 2) + 2;
-        size_t need_h = o_b + 2 * align256(std::min<uint64_t>(rec_cap, span / 16 + 4096) * 8);     // typical; regrown below if short
+        size_t need_h = o_b + 2 * align256(std::min<uint64_t>(rec_cap, span / 64 + 4096) * 8);     // typical; regrown below if short
         auto grow_h = [&](size_t need) {
             if (need <= sl.h_cap) return true;
             uint8_t* nh = nullptr;
@@ -1973,13 +2037,6 @@ int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t st
         if (rc == XS_OK) cuda_ok(cudaMemcpy(res->totals.data(), d_tot, ld * 8, cudaMemcpyDeviceToHost), "totals copy");
     } else {
         cudaDeviceSynchronize();
-    }
-    for (int i = 0; i < NS; ++i) {
-        if (slot[i].h) cudaFreeHost(slot[i].h);
-        if (slot[i].h_res) cudaFreeHost(slot[i].h_res);
-        if (slot[i].d) cudaFree(slot[i].d);
-        if (slot[i].s) cudaStreamDestroy(slot[i].s);
-        if (slot[i].done) cudaEventDestroy(slot[i].done);
     }
     if (d_tot) cudaFree(d_tot);
     xs_fastx_close(fx);
