@@ -965,7 +965,7 @@ __global__ void __launch_bounds__(BK_NT, HASH ? 4 : 1) k_bucket_fetch(const Buck
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int TMAQ>
+template <int TMAQ, int VAR>      // VAR bit 0: no L2 cache hint on the tensor copies; bit 1: one lane polls the mbarrier
 __global__ void __launch_bounds__(BK_NT) k_bucket_fetch_tma(const __grid_constant__ BucketParams bp) {
     __shared__ __align__(128) uint8_t s_slot[BK_NT / 32][TMAQ][8][128];   // [warp][q][quad] 64 bytes used of each 128
     __shared__ __align__(8) uint64_t s_bar[BK_NT / 32];
@@ -1022,11 +1022,18 @@ __global__ void __launch_bounds__(BK_NT) k_bucket_fetch_tma(const __grid_constan
                     const int32_t my = (int32_t)(row0 + (r[q] & rmask));       // records past n read row0 (ignored below)
                     const int32_t a0 = __shfl_sync(0xFFFFFFFFu, my, (lane & ~3u) + 0), a1 = __shfl_sync(0xFFFFFFFFu, my, (lane & ~3u) + 1),
                                   a2 = __shfl_sync(0xFFFFFFFFu, my, (lane & ~3u) + 2), a3 = __shfl_sync(0xFFFFFFFFu, my, (lane & ~3u) + 3);
-                    if ((lane & 3u) == 0)
-                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
-                                     " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
-                                     :: "r"(smem_addr(&s_slot[warp][q - LSUQ][lane >> 2][0])), "l"(&bp.tmap), "r"(bar), "r"(0), "r"(a0), "r"(a1),
-                                        "r"(a2), "r"(a3), "l"(keep) : "memory");
+                    if ((lane & 3u) == 0) {
+                        if (VAR & 1)
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+                                         " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                                         :: "r"(smem_addr(&s_slot[warp][q - LSUQ][lane >> 2][0])), "l"(&bp.tmap), "r"(bar), "r"(0), "r"(a0), "r"(a1),
+                                            "r"(a2), "r"(a3) : "memory");
+                        else
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint"
+                                         " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+                                         :: "r"(smem_addr(&s_slot[warp][q - LSUQ][lane >> 2][0])), "l"(&bp.tmap), "r"(bar), "r"(0), "r"(a0), "r"(a1),
+                                            "r"(a2), "r"(a3), "l"(keep) : "memory");
+                    }
                 }
                 // ---- LSU part
 #pragma unroll
@@ -1034,13 +1041,14 @@ __global__ void __launch_bounds__(BK_NT) k_bucket_fetch_tma(const __grid_constan
                     const uint32_t i = i0 + q * 32 + lane;
                     if (i < n) v[q] = ldg128_keep(base + (uint64_t)(r[q] & rmask) * 16, keep);
                 }
-                {
+                if (!(VAR & 2) || lane == 0) {
                     uint32_t done = 0;
                     while (!done)
                         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                                      : "=r"(done) : "r"(bar), "r"(phase) : "memory");
-                    phase ^= 1;
                 }
+                phase ^= 1;
+                __syncwarp();
 #pragma unroll
                 for (int q = LSUQ; q < 4; ++q)
                     v[q] = *reinterpret_cast<const uint4*>(&s_slot[warp][q - LSUQ][lane >> 2][(lane & 3u) * 16]);

@@ -662,8 +662,12 @@ static cudaError_t launch_bucket_fetch(const BucketParams& bp, int n_sm, cudaStr
     KernelTimer kt(s, PROF_FETCH);
     static const int fetch_ctas = env_int("XS_BK_FETCH_CTAS", 8);
     if (bp.use_tma && !(bp.next_nc && bp.next_rows) && !bp.fetch_off) {       // part of the gathers through the TMA unit
-        if (bp.use_tma >= 2) k_bucket_fetch_tma<2><<<n_sm * fetch_ctas, BK_NT, 0, s>>>(bp);
-        else k_bucket_fetch_tma<1><<<n_sm * fetch_ctas, BK_NT, 0, s>>>(bp);
+        static const int var = env_int("XS_BK_TMA_VAR", 0);
+        if (bp.use_tma >= 2) k_bucket_fetch_tma<2, 0><<<n_sm * fetch_ctas, BK_NT, 0, s>>>(bp);
+        else if (var == 1) k_bucket_fetch_tma<1, 1><<<n_sm * fetch_ctas, BK_NT, 0, s>>>(bp);
+        else if (var == 2) k_bucket_fetch_tma<1, 2><<<n_sm * fetch_ctas, BK_NT, 0, s>>>(bp);
+        else if (var == 3) k_bucket_fetch_tma<1, 3><<<n_sm * fetch_ctas, BK_NT, 0, s>>>(bp);
+        else k_bucket_fetch_tma<1, 0><<<n_sm * fetch_ctas, BK_NT, 0, s>>>(bp);
         return cudaSuccess;
     }
     if (bp.next_nc && !bp.next_rows) {   // side-stream mode: plain fetch, the grid leaves room for k_bucket_hash's CTAs
@@ -1022,7 +1026,7 @@ static int bloom_launch_bucketed(xs_bloom* bf, const BloomParams& p, cudaStream_
             bp.pos = reinterpret_cast<uint32_t*>(d + o_pos); bp.wid = reinterpret_cast<uint16_t*>(d + o_wid); bp.res = d + o_res;
             bp.cnt_bc = reinterpret_cast<uint16_t*>(d + o_bc); bp.ovf = reinterpret_cast<uint32_t*>(d + o_ovf);
             bp.chunk_seq = reinterpret_cast<const uint64_t*>(d + o_seq);
-            bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 4 * i;
+            bp.counter = reinterpret_cast<unsigned long long*>(d + o_ctr) + 3 * i;
             bp.chunk0 = i * sub.nc_sub;
             bp.nc = (uint32_t)std::min<uint64_t>(sub.nc_sub, sub.nc_total - bp.chunk0);
             bp.n_buckets = g.nb; bp.bshift = g.bshift; bp.cap = g.cap; bp.prefetch = prefetch ? 1u : 0u;
