@@ -1019,7 +1019,12 @@ __global__ void __launch_bounds__(BK_NT) k_bucket_fetch_tma(const __grid_constan
                 __syncwarp();
 #pragma unroll
                 for (int q = LSUQ; q < 4; ++q) {
-                    const int32_t my = (int32_t)(row0 + (r[q] & rmask));       // records past n read row0 (ignored below)
+                    // slots past the block's end must not all fetch one row: every warp of the GPU sweeps the same bucket, and
+                    // thousands of copies of one sector serialise in its L2 slice (measured: 8x slower fetch).  They
+                    // re-fetch the lane's first record instead (or a lane-specific row), and the result is ignored.
+                    const uint32_t iq = i0 + q * 32 + lane;
+                    const uint32_t rr = iq < n ? r[q] : (i0 + lane < n ? r[0] : (threadIdx.x * 2654435761u + blockIdx.x * 40503u));
+                    const int32_t my = (int32_t)(row0 + (rr & rmask));
                     const int32_t a0 = __shfl_sync(0xFFFFFFFFu, my, (lane & ~3u) + 0), a1 = __shfl_sync(0xFFFFFFFFu, my, (lane & ~3u) + 1),
                                   a2 = __shfl_sync(0xFFFFFFFFu, my, (lane & ~3u) + 2), a3 = __shfl_sync(0xFFFFFFFFu, my, (lane & ~3u) + 3);
                     if ((lane & 3u) == 0) {
