@@ -102,16 +102,29 @@ class ClockSampler:
                                           "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
         except OSError:
             return
-        self.thread = threading.Thread(target=lambda: self.rows.extend(self.proc.stdout), daemon=True)
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), line))
+        self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
-    def stop(self) -> dict:
+    def mark(self) -> float:
+        return time.perf_counter()
+
+    def stop(self, t0: float | None = None, t1: float | None = None) -> dict:
+        """Summary of the samples that arrived inside [t0, t1] (the timed region); nvidia-smi needs ~0.5 s to deliver its
+        first line, so the sampler is started before the warm-up steps and a region shorter than the sampling period falls
+        back to the samples of the whole warm-up + timed phase (the same kernels under the same load), which is noted."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.thread.join(timeout=2)
+        rows = [ln for ts, ln in self.rows if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.25)]
+        window = "timed region"
+        if not rows:
+            rows, window = [ln for _, ln in self.rows], "warm-up + timed region (timed region shorter than the sampling period)"
         sm, mx, reasons, pw = [], [], set(), []
-        for line in self.rows:
+        for line in rows:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
@@ -123,7 +136,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 def build_workload(workdir: Path, device, rows_fn, seed_shift: int = 0):
@@ -222,7 +235,7 @@ def run_reference(args, rank: int, world: int) -> None:
 CFG5_D, CFG5_H, CFG5_K, CFG5_SEED = 10_000, 7, 21, 6
 CFG5_S = int(os.environ.get("XS_CFG5_ROWS", 96_000_000))
 CFG5_READS = int(os.environ.get("XS_CFG5_READS", 2_000_000))
-CFG5_TILE = int(os.environ.get("XS_CFG5_TILE", 100_000))
+CFG5_TILE = int(os.environ.get("XS_CFG5_TILE", 250_000))
 
 
 def run_cfg5(args, rank: int, world: int, local_rank: int) -> dict:
@@ -324,6 +337,10 @@ def run_cfg5(args, rank: int, world: int, local_rank: int) -> dict:
         "ms_per_step": ms / steps, "ms_per_tile": ms / steps / len(tiles),
         "scoring_kernel_ms_per_step": k_ms / steps, "gpu_launches": int(launches),
         "row_bytes_per_gpu": int(ix.info.row_stride), "docs_per_gpu": widths, "index_bytes_per_gpu": int(ix.info.hbm_bytes),
+        # every row probe costs whole 128-byte DRAM fetches: 10 per probe on one GPU (1250-byte rows), ceil(10 / N) on the
+        # widest shard of N GPUs -> strong scaling is bounded by 10 / (N * ceil(10 / N)): 1.0, 0.83, 0.625 at N = 2, 4, 8
+        "dram_lines_per_row_probe": int(ix.info.row_stride) // 128,
+        "strong_scaling_bound_from_128B_fetches": round(10 / (world * -(-10 // world)), 3),
         "index_generate_s": round(gen_s, 2),
         "allgather_bytes_per_tile_per_gpu": int(world * CFG5_TILE * (scorer.w if world > 1 else 0)),
     }
@@ -599,6 +616,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
                             d_out.data_ptr(), stream.cuda_stream)
 
         # ---- device-resident timing
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         for _ in range(max(args.warmup, 3)):
             step_device()
         torch.cuda.synchronize()
@@ -631,17 +650,17 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         engine.profile_enable(True)
         engine.profile_read()
         launches0 = engine.launch_count()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        t_reg0 = sampler.mark()
         ev0.record(stream)
         for _ in range(args.steps):
             step_device()
         ev1.record(stream)
         torch.cuda.synchronize()
+        t_reg1 = sampler.mark()
         ms = ev0.elapsed_time(ev1)
-        clocks = sampler.stop()
+        clocks = sampler.stop(t_reg0, t_reg1)
         phase_ms, phase_n = engine.profile_read_phases()
         kernel_ms, kernel_launches = sum(phase_ms), sum(phase_n)
         engine.profile_enable(False)
