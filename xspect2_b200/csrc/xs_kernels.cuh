@@ -874,7 +874,7 @@ __global__ void __launch_bounds__(BK_NT) k_bucket_hash(const BucketParams bp) {
 }
 
 template <int K, int H, bool HASH>
-__global__ void __launch_bounds__(BK_NT, HASH ? 4 : 1) k_bucket_fetch(const BucketParams bp) {
+__global__ void __launch_bounds__(BK_NT, HASH ? 4 : 6) k_bucket_fetch(const BucketParams bp) {
     const SeqBatch& sb = bp.cp.sb;
     const PageDesc pg = bp.cp.pages[0];
     const uint32_t lane = threadIdx.x & 31;
@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(BK_NT, HASH ? 4 : 1) k_bucket_fetch(const Buck
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int TMAQ, int VAR>      // VAR bit 0: no L2 cache hint on the tensor copies; bit 1: one lane polls the mbarrier
-__global__ void __launch_bounds__(BK_NT) k_bucket_fetch_tma(const __grid_constant__ BucketParams bp) {
+__global__ void __launch_bounds__(BK_NT, 6) k_bucket_fetch_tma(const __grid_constant__ BucketParams bp) {
     __shared__ __align__(128) uint8_t s_slot[BK_NT / 32][TMAQ][8][128];   // [warp][q][quad] 64 bytes used of each 128
     __shared__ __align__(8) uint64_t s_bar[BK_NT / 32];
     const SeqBatch& sb = bp.cp.sb;
@@ -2023,12 +2023,42 @@ __global__ void __launch_bounds__(256) k_sharded_reduce(const CntT* __restrict__
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     constexpr uint32_t VEC = 16 / sizeof(CntT);
+    uint32_t n_docs_total = 0;
+    for (uint32_t g = 0; g < lay.world; ++g) n_docs_total += lay.width[g];
     for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_seq; r += n_warps) {
         uint32_t mx = 0, idx = 0xFFFFFFFFu, cnt = 0;
         for (uint32_t g = 0; g < lay.world; ++g) {
             const CntT* row = all + ((uint64_t)g * n_seq + r) * lay.w;
             const uint32_t wd = lay.width[g];
-            if ((lay.w % VEC) == 0) {           // 16-byte aligned rows: vector loads
+            if (sizeof(CntT) == 1 && (lay.w % VEC) == 0) {
+                // uint8 counts, four per word: all-zero words (most of a score row) cost three instructions; the padding
+                // columns behind wd are zero and never tie with a positive maximum.  A record whose maximum is 0 is
+                // resolved after the loop (every document ties).
+                for (uint32_t d0 = lane * 16; d0 < wd; d0 += 32 * 16) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(row + d0);
+                    const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t w = wv[j];
+                        if (w == 0) continue;
+                        uint32_t m = __vmaxu4(w, __byte_perm(w, 0, 0x1032));
+                        m = __vmaxu4(m, __byte_perm(m, 0, 0x2301)) & 0xFFu;
+                        if (m >= mx) {
+                            const uint32_t eq = __vcmpeq4(w, m * 0x01010101u);
+                            const uint32_t c = (uint32_t)__popc(eq) >> 3;
+                            if (m > mx || idx == 0xFFFFFFFFu) { mx = m; idx = lay.doc0[g] + d0 + j * 4 + ((__ffs(eq) - 1) >> 3); cnt = c; }
+                            else cnt += c;
+                        }
+                        if (totals) {
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                const uint32_t v = (w >> (8 * b)) & 0xFFu;
+                                if (v) atomicAdd(totals + lay.doc0[g] + d0 + j * 4 + b, (unsigned long long)v);
+                            }
+                        }
+                    }
+                }
+            } else if ((lay.w % VEC) == 0) {           // 16-byte aligned rows: vector loads
                 for (uint32_t d0 = lane * VEC; d0 < wd; d0 += 32 * VEC) {
                     const uint4 q = *reinterpret_cast<const uint4*>(row + d0);
                     const CntT* e = reinterpret_cast<const CntT*>(&q);
@@ -2059,6 +2089,7 @@ __global__ void __launch_bounds__(256) k_sharded_reduce(const CntT* __restrict__
                 else if (omx == mx) { cnt += ocnt; idx = oidx < idx ? oidx : idx; }
             }
         }
+        if (sizeof(CntT) == 1 && (lay.w % VEC) == 0 && (idx == 0xFFFFFFFFu || mx == 0)) { mx = 0; idx = 0; cnt = n_docs_total; }
         if (lane == 0) {
             if (best) best[r] = idx;
             if (best_count) best_count[r] = mx;
