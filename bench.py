@@ -733,7 +733,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         k_ms = kernel_ms / args.steps                      # scoring-kernel time per step (one launch, or the bucketed kernels)
         achieved = algo_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else None
         if uses_bucketed:
-            names = ["k_bucket_emit<21,7>", "k_bucket_fetch", "k_bucket_reduce<21,7,u8>"]
+            names = ["k_bucket_emit<21,7,0>", "k_bucket_fetch<21,7,0>", "k_bucket_reduce<21,7,u8,1>"]
             parts = [ncu_traffic(n) for n in names]
             traffic = sum(t for t, _ in parts) if all(t is not None for t, _ in parts) else None
             kernel_name = "bucketed probing: k_bucket_emit<21,7> + k_bucket_fetch + k_bucket_reduce<21,7,u8> (per step)"

@@ -46,6 +46,8 @@ def main() -> None:
     ap.add_argument("--read-len", type=int, default=150)
     ap.add_argument("--sig-size", type=int, default=150_000_001)
     ap.add_argument("--source-note", default="")
+    ap.add_argument("--first-launch-only", action="store_true", help="use only the first captured launch of every kernel")
+    ap.add_argument("--merge", action="store_true", help="keep the entries of kernels this report does not contain")
     args = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", args.report, "--page", "raw", "--csv"], check=True, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -57,13 +59,18 @@ def main() -> None:
     for r in rows[2:]:
         name = short_name(r[col["Kernel Name"]])
         e = acc.setdefault(name, {"n": 0, "rd": 0.0, "wr": 0.0, "sect": 0.0, "ms": 0.0})
+        if args.first_launch_only and e["n"]:
+            continue
         e["n"] += 1
         for key, metric in (("rd", "dram__bytes_read.sum"), ("wr", "dram__bytes_write.sum")):
             e[key] += float(r[col[metric]].replace(",", "")) * scale.get(units[col[metric]], 1)
         if "lts__t_sectors_srcunit_tex_op_read.sum" in col:
             e["sect"] += float(r[col["lts__t_sectors_srcunit_tex_op_read.sum"]].replace(",", "") or 0)
         e["ms"] += float(r[col["gpu__time_duration.sum"]].replace(",", ""))
-    out = {"_source_sha256": source_hash(), "_sources": KERNEL_SOURCES}
+    out = {}
+    if args.merge and (ROOT / "profiles" / "traffic.json").exists():
+        out = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+    out["_source_sha256"], out["_sources"] = source_hash(), KERNEL_SOURCES
     for name, e in acc.items():
         out[name] = {"n_reads": args.reads_per_launch, "read_len": args.read_len, "sig_size": args.sig_size,
                      "dram_bytes_read": e["rd"] / e["n"], "dram_bytes_write": e["wr"] / e["n"],
