@@ -285,10 +285,11 @@ struct FastxSegOut {
     uint64_t n_rec = 0, n_id = 0;
     uint64_t* begin = nullptr; uint64_t* end = nullptr; uint64_t* id_end = nullptr; char* ids = nullptr;
     uint64_t cap_rec = 0, cap_id = 0;
+    uint64_t max_len = 0, n_short = 0;    // longest record; records not longer than k_short
 };
 
 int xs_fastx_parse_block_1pass(const xs_fastx* fx, uint64_t a, uint64_t b, unsigned n_thr, uint8_t* staging,
-                               std::vector<FastxSegOut>& segs) {
+                               std::vector<FastxSegOut>& segs, uint64_t k_short) {
     std::vector<uint64_t> cuts;
     cuts.push_back(a);
     n_thr = std::max(1u, n_thr);
@@ -310,9 +311,9 @@ int xs_fastx_parse_block_1pass(const xs_fastx* fx, uint64_t a, uint64_t b, unsig
             so.cap_rec = need_rec;
         }
         if (so.cap_id < need_id) { delete[] so.ids; so.ids = new char[need_id]; so.cap_id = need_id; }
-        so.base0 = cuts[i] - a; so.n_bases = so.n_rec = so.n_id = 0;
+        so.base0 = cuts[i] - a; so.n_bases = so.n_rec = so.n_id = 0; so.max_len = so.n_short = 0;
     }
-    for (size_t i = n_seg; i < segs.size(); ++i) segs[i].n_rec = segs[i].n_bases = segs[i].n_id = 0;
+    for (size_t i = n_seg; i < segs.size(); ++i) segs[i].n_rec = segs[i].n_bases = segs[i].n_id = segs[i].max_len = segs[i].n_short = 0;
     std::atomic<size_t> next(0);
     std::atomic<int> status(XS_OK);
     auto work = [&]() {
@@ -335,6 +336,13 @@ int xs_fastx_parse_block_1pass(const xs_fastx* fx, uint64_t a, uint64_t b, unsig
             const int rc = run(fx, fx->data + cuts[i], fx->data + cuts[i + 1], sk);
             if (rc != XS_OK) { status.store(rc); continue; }
             so.n_rec = sk.n_rec; so.n_bases = sk.n_bases - so.base0; so.n_id = sk.n_id;
+            uint64_t mx = 0, ns = 0;
+            for (uint64_t r = 0; r < so.n_rec; ++r) {
+                const uint64_t len = so.end[r] - so.begin[r];
+                mx = len > mx ? len : mx;
+                ns += len <= k_short;
+            }
+            so.max_len = mx; so.n_short = ns;
         }
     };
     if (n_seg <= 1 || n_thr <= 1) work();

@@ -38,8 +38,10 @@ struct FastxSegOut {
     uint64_t n_rec = 0, n_id = 0;
     uint64_t* begin = nullptr; uint64_t* end = nullptr; uint64_t* id_end = nullptr; char* ids = nullptr;
     uint64_t cap_rec = 0, cap_id = 0;
+    uint64_t max_len = 0, n_short = 0;
 };
-int xs_fastx_parse_block_1pass(const xs_fastx* fx, uint64_t a, uint64_t b, unsigned n_thr, uint8_t* staging, std::vector<FastxSegOut>& segs);
+int xs_fastx_parse_block_1pass(const xs_fastx* fx, uint64_t a, uint64_t b, unsigned n_thr, uint8_t* staging, std::vector<FastxSegOut>& segs,
+                               uint64_t k_short);
 void xs_fastx_seg_free(std::vector<FastxSegOut>& segs);
 int xs_fastx_parse_block(const xs_fastx* fx, uint64_t a, uint64_t b, unsigned n_thr, std::vector<uint64_t>& cuts,
                          std::vector<Checkpoint>& cps, uint8_t* bases, uint64_t* seq_begin, uint64_t* seq_end, char* ids,
@@ -206,6 +208,31 @@ static void stream_slots_release() {       // caller holds g_stream_mu (or is si
     }
     g_stream_dev = -1;
 }
+
+// growable buffer without value-initialisation (std::vector::resize would touch every new page once more)
+template <typename T>
+struct RawBuf {
+    T* p = nullptr; size_t n = 0, cap = 0;
+    ~RawBuf() { free(p); }
+    bool grow(size_t want) {
+        if (want <= cap) { n = want; return true; }
+        size_t c = std::max<size_t>(want, cap + cap / 2 + 1024);
+        T* q = (T*)realloc(p, c * sizeof(T));
+        if (!q) return false;
+        p = q; cap = c; n = want;
+        return true;
+    }
+    bool reserve(size_t c) {
+        if (c <= cap) return true;
+        T* q = (T*)realloc(p, c * sizeof(T));
+        if (!q) return false;
+        p = q; cap = c;
+        return true;
+    }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    size_t size() const { return n; }
+};
 
 static std::atomic<int> g_home_device{-1};
 
@@ -1875,9 +1902,10 @@ int xs_cobs_classify(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const 
 // ----------------------------------------------------------------------------------------
 
 struct xs_file_calls {
-    std::vector<uint32_t> best, best_count, n_best;
-    std::vector<uint64_t> seq_len, id_end, totals;
-    std::vector<char> ids;
+    RawBuf<uint32_t> best, best_count, n_best;
+    RawBuf<uint64_t> seq_len, id_end;
+    RawBuf<char> ids;
+    std::vector<uint64_t> totals;
     uint64_t n_bases = 0, n_short = 0, n_blocks = 0;
     double parse_s = 0, total_s = 0;
 };
@@ -1958,10 +1986,16 @@ int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t st
             return true;
         };
         if (!grow_h(need_h)) break;
-        rc = xs_fastx_parse_block_1pass(fx, a, b, hw, sl.h, segs);
+        rc = xs_fastx_parse_block_1pass(fx, a, b, hw, sl.h, segs, k);
         if (rc != XS_OK) break;
         uint64_t nr = 0, nb = 0, nid = 0;
         for (const FastxSegOut& so : segs) { nr += so.n_rec; nb += so.n_bases; nid += so.n_id; }
+        if (bi == 0 && b < fsize) {      // size the result arrays once from the first block's record density
+            const double scale = (double)fsize / (double)(b - a) * 1.03;
+            const size_t er = (size_t)(nr * scale) + 4096, ei = (size_t)(nid * scale) + 65536;
+            res->best.reserve(er); res->best_count.reserve(er); res->n_best.reserve(er);
+            res->seq_len.reserve(er); res->id_end.reserve(er); res->ids.reserve(ei);
+        }
         need_h = o_b + 2 * align256(nr * 8);
         if (need_h > sl.h_cap) {       // more records than the typical bound: keep the parsed bases, move to a larger buffer
             uint8_t* old = sl.h; sl.h = nullptr; const size_t old_cap = sl.h_cap; sl.h_cap = 0;
@@ -1979,27 +2013,27 @@ int xs_cobs_classify_file(xs_cobs* ix, const char* path, int format, uint32_t st
         uint64_t* h_e = reinterpret_cast<uint64_t*>(sl.h + o_b + align256(nr * 8));
         // compaction of the per-thread record arrays (16 bytes per record) + ids
         const size_t id0 = res->ids.size();
-        res->ids.resize(id0 + nid);
-        res->id_end.resize(rec_total + nr);
-        res->seq_len.resize(rec_total + nr);
+        if (!res->ids.grow(id0 + nid) || !res->id_end.grow(rec_total + nr) || !res->seq_len.grow(rec_total + nr) ||
+            !res->best.grow(rec_total + nr) || !res->best_count.grow(rec_total + nr) || !res->n_best.grow(rec_total + nr)) {
+            rc = fail(XS_ERR_NOMEM, "result arrays");
+            break;
+        }
         uint64_t max_len = 0, n_short = 0, r0 = 0, i0 = 0;
         for (const FastxSegOut& so : segs) {
             if (!so.n_rec) continue;
             memcpy(h_b + r0, so.begin, so.n_rec * 8);
             memcpy(h_e + r0, so.end, so.n_rec * 8);
             memcpy(res->ids.data() + id0 + i0, so.ids, so.n_id);
-            for (uint64_t i = 0; i < so.n_rec; ++i) {
-                const uint64_t len = so.end[i] - so.begin[i];
-                res->seq_len[rec_total + r0 + i] = len;
-                res->id_end[rec_total + r0 + i] = id0 + i0 + so.id_end[i];
-                max_len = std::max(max_len, len);
-                n_short += len <= k;
-            }
+            uint64_t* sl_out = res->seq_len.data() + rec_total + r0;
+            uint64_t* ie_out = res->id_end.data() + rec_total + r0;
+            const uint64_t id_shift = id0 + i0;
+            for (uint64_t i = 0; i < so.n_rec; ++i) { sl_out[i] = so.end[i] - so.begin[i]; ie_out[i] = id_shift + so.id_end[i]; }
+            max_len = std::max(max_len, so.max_len);
+            n_short += so.n_short;
             r0 += so.n_rec; i0 += so.n_id;
         }
         res->n_short += n_short;
         res->n_bases += nb;
-        res->best.resize(rec_total + nr); res->best_count.resize(rec_total + nr); res->n_best.resize(rec_total + nr);
         res->parse_s += now_s() - tp;
         // device side of the block
         const uint64_t max_win = max_len >= k ? (max_len - k) / step + 1 : 0;
