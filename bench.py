@@ -575,7 +575,7 @@ def run_file_e2e(ix, workdir: Path, h_bases: np.ndarray, d_out) -> dict:
     ok = bool((ref.max(dim=1).values.cpu().numpy() == r["best_hits"][:m]).all() and (ref.argmax(dim=1).cpu().numpy() == r["best"][:m]).all())
     path.unlink()
     return {"value": n * (READ_LEN - K + 1) / dt, "unit": "lookups/s", "reads_per_sec": n / dt, "s_per_file": dt, "runs_s": runs,
-            "file": f"{n} reads, 4-line FASTQ, {size} bytes, in the page cache", "parse_s_inside": r["parse_s"],
+            "file": f"{n} reads, 4-line FASTQ, {size} bytes, in the page cache", "parse_s_inside": r["parse_s"], "library_call_s": r["total_s"],
             "api": "CobsIndex.classify_file -> xs_cobs_classify_file (first best document, its count, tie multiplicity, ids, totals)",
             "matches_device_run": ok, "checked_reads": int(m)}
 

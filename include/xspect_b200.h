@@ -299,6 +299,9 @@ int xs_file_calls_info(const xs_file_calls* r, uint64_t* n_records, uint64_t* n_
                        uint64_t* n_docs, double* parse_s, double* total_s);
 int xs_file_calls_read(const xs_file_calls* r, uint32_t* best, uint32_t* best_count, uint32_t* n_best, uint64_t* seq_len,
                        char* ids, uint64_t* id_end, uint64_t* totals);
+/* the same arrays without a copy: pointers into the result, valid until xs_file_calls_free */
+int xs_file_calls_view(const xs_file_calls* r, const uint32_t** best, const uint32_t** best_count, const uint32_t** n_best,
+                       const uint64_t** seq_len, const char** ids, const uint64_t** id_end, const uint64_t** totals);
 int xs_file_calls_free(xs_file_calls* r);
 
 /* ---- result writer (host only) -------------------------------------------------------------------

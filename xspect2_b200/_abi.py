@@ -104,6 +104,7 @@ SYMBOLS = {
     "xs_file_calls_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "xs_file_calls_read": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "xs_file_calls_view": (C.c_int, [_P] + [C.POINTER(_P)] * 7),
     "xs_file_calls_free": (C.c_int, [_P]),
     "xs_result_write_json": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, _P, C.c_uint32, _P, C.c_uint64, _P, _P, _P, _P, _P, _P]),
     "xs_pack_2bit": (C.c_int, [_P, C.c_uint64, C.c_int, _P, _P]),

@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 
+#include <sys/mman.h>
+
 #include <cub/device/device_scan.cuh>
 #include <cuda.h>      // CUtensorMap + cuTensorMapEncodeTiled's signature; the entry point is fetched at run time
 
@@ -227,6 +229,11 @@ struct RawBuf {
         T* q = (T*)realloc(p, c * sizeof(T));
         if (!q) return false;
         p = q; cap = c;
+        // large result arrays are first touched by the copies that fill them: ask for huge pages so that costs a few
+        // hundred faults instead of tens of thousands (a hint; ignored where transparent huge pages are off)
+        const uintptr_t lo = ((uintptr_t)p + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
+        const uintptr_t hi = ((uintptr_t)p + c * sizeof(T)) & ~(uintptr_t)((2u << 20) - 1);
+        if (hi > lo) (void)madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
         return true;
     }
     T* data() { return p; }
@@ -2108,6 +2115,19 @@ int xs_file_calls_read(const xs_file_calls* r, uint32_t* best, uint32_t* best_co
     if (ids) memcpy(ids, r->ids.data(), r->ids.size());
     if (id_end) memcpy(id_end, r->id_end.data(), n * 8);
     if (totals) memcpy(totals, r->totals.data(), r->totals.size() * 8);
+    return XS_OK;
+}
+
+int xs_file_calls_view(const xs_file_calls* r, const uint32_t** best, const uint32_t** best_count, const uint32_t** n_best,
+                       const uint64_t** seq_len, const char** ids, const uint64_t** id_end, const uint64_t** totals) {
+    if (!r) return fail(XS_ERR_ARG, "NULL result");
+    if (best) *best = r->best.data();
+    if (best_count) *best_count = r->best_count.data();
+    if (n_best) *n_best = r->n_best.data();
+    if (seq_len) *seq_len = r->seq_len.data();
+    if (ids) *ids = r->ids.data();
+    if (id_end) *id_end = r->id_end.data();
+    if (totals) *totals = r->totals.data();
     return XS_OK;
 }
 

@@ -265,19 +265,24 @@ class CobsIndex:
         Returns ``best, best_hits, n_best, seq_len, totals`` plus the raw record-id buffer (``id_buf``, ``id_end``)."""
         h = C.c_void_p()
         check(lib().xs_cobs_classify_file(self._h, str(path).encode(), int(fmt), int(step), int(block_bytes), C.byref(h)))
-        try:
-            n, nb, nid, nshort, nd = (C.c_uint64() for _ in range(5))
-            ps, ts = C.c_double(), C.c_double()
-            check(lib().xs_file_calls_info(h, C.byref(n), C.byref(nb), C.byref(nid), C.byref(nshort), C.byref(nd), C.byref(ps), C.byref(ts)))
-            best, cnt, nbst = (np.empty(n.value, np.uint32) for _ in range(3))
-            seq_len, id_end = np.empty(n.value, np.uint64), np.empty(n.value, np.uint64)
-            ids = np.empty(nid.value, np.uint8)
-            totals = np.zeros(nd.value, np.uint64)
-            check(lib().xs_file_calls_read(h, _ptr(best), _ptr(cnt), _ptr(nbst), _ptr(seq_len), _ptr(ids), _ptr(id_end), _ptr(totals)))
-        finally:
-            lib().xs_file_calls_free(h)
+        owner = _FileCalls(h)
+        n, nb, nid, nshort, nd = (C.c_uint64() for _ in range(5))
+        ps, ts = C.c_double(), C.c_double()
+        check(lib().xs_file_calls_info(h, C.byref(n), C.byref(nb), C.byref(nid), C.byref(nshort), C.byref(nd), C.byref(ps), C.byref(ts)))
+        ptr = [C.c_void_p() for _ in range(7)]
+        check(lib().xs_file_calls_view(h, *[C.byref(p) for p in ptr]))
+
+        def view(p, count, dtype):     # zero-copy view of the library's result arrays; `owner` frees them with the last view
+            if not count or not p.value:
+                return np.empty(0, dtype)
+            a = np.frombuffer((C.c_char * (count * np.dtype(dtype).itemsize)).from_address(p.value), dtype=dtype, count=count)
+            owner.keep(a)
+            return a
+        best, cnt, nbst = (view(ptr[i], n.value, np.uint32) for i in range(3))
+        seq_len, ids, id_end = view(ptr[3], n.value, np.uint64), view(ptr[4], nid.value, np.uint8), view(ptr[5], n.value, np.uint64)
+        totals = view(ptr[6], nd.value, np.uint64).copy()
         return {"best": best, "best_hits": cnt, "n_best": nbst, "seq_len": seq_len, "totals": totals, "id_buf": ids, "id_end": id_end,
-                "n_bases": int(nb.value), "n_short": int(nshort.value), "parse_s": ps.value, "total_s": ts.value}
+                "n_bases": int(nb.value), "n_short": int(nshort.value), "parse_s": ps.value, "total_s": ts.value, "_owner": owner}
 
     def query_device(self, d_bases: int, n_bases: int, d_begin: int, d_end: int, n_seq: int, step: int, dtype: int,
                      d_out: int, stream: int = 0, ld: int = 0) -> None:
@@ -319,6 +324,34 @@ def result_order_batch(scores: np.ndarray) -> np.ndarray:
     if s.size:
         check(lib().xs_cobs_result_order_batch(_ptr(s), s.shape[0], s.shape[1], _ptr(order)))
     return order
+
+
+class _FileCalls:
+    """Owner of one ``xs_file_calls`` result: freed when the last numpy view of its arrays is gone."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self._views = []
+
+    def keep(self, arr) -> None:
+        import weakref
+        self._views.append(weakref.ref(arr))
+        # the array's base chain ends in a ctypes object created from an address; tie the owner to it
+        base = arr
+        while getattr(base, "base", None) is not None:
+            base = base.base
+        try:
+            base._xs_owner = self
+        except AttributeError:
+            pass
+
+    def __del__(self):
+        h, self._h = self._h, None
+        if h:
+            try:
+                lib().xs_file_calls_free(h)
+            except Exception:
+                pass
 
 
 class SearchResult:
