@@ -161,6 +161,33 @@ def test_streamed_file_calls_equal_two_pass_reader(world, oracle, tmp_path):
             assert r["n_short"] == 0 and r["n_bases"] == batch.bases.size
     summ = model.predict_summary(fq)
     assert "streamed" in summ and summ["batch"].ids == [r[0] for r in recs]
+    # shapes of real files: CRLF line ends, no newline at the end, blank lines, one record, nothing at all
+    def same(path, fmt):
+        batch = SequenceBatch.from_file(path)
+        exp = ix.classify(batch.bases, batch.begin, batch.end, 1) if len(batch) else None
+        for block in (0, 777):
+            r = ix.classify_file(path, fmt, 1, block_bytes=block)
+            assert r["best"].size == len(batch) and np.array_equal(r["seq_len"], batch.end - batch.begin)
+            assert r["id_buf"].tobytes() == batch._id_buf.tobytes()
+            if exp is not None:
+                assert np.array_equal(r["best"], exp[0]) and np.array_equal(r["best_hits"], exp[1]) and np.array_equal(r["n_best"], exp[2])
+                assert np.array_equal(r["totals"], exp[3])
+    text = lambda x: x if isinstance(x, str) else x.tobytes().decode()
+    crlf = tmp_path / "crlf.fastq"
+    crlf.write_bytes("".join(f"@{rid} extra words\r\n{text(sq)}\r\n+\r\n{'I' * len(text(sq))}\r\n" for rid, sq in recs[:40]).encode())
+    same(crlf, 2)
+    noeol = tmp_path / "noeol.fastq"
+    noeol.write_bytes(("\n\n" + "".join(f"@{rid}\n{text(sq)}\n+{rid}\n{'#' * len(text(sq))}\n\n" for rid, sq in recs[:33])).rstrip("\n").encode())
+    same(noeol, 2)
+    fa2 = tmp_path / "odd.fasta"
+    fa2.write_bytes(("; comment line\n" + "".join(f">{rid} desc\r\n{text(sq)[:70]}\r\n\r\n{text(sq)[70:].lower()}\n" for rid, sq in recs[:25]) + ">last\nACGTNNNNACGTACGTACGTACGTACGTAAAC").encode())
+    same(fa2, 1)
+    one = tmp_path / "one.fna"
+    mf.write_fasta(one, recs[:1])
+    same(one, 1)
+    empty = tmp_path / "empty.fastq"
+    empty.write_bytes(b"")
+    same(empty, 2)
     # wrapped FASTQ: the streaming reader declines, predict_summary falls back to the two-pass reader
     wrapped = tmp_path / "wrapped.fastq"
     with open(wrapped, "w") as f:
