@@ -204,7 +204,9 @@ bool fastq_record_at(const uint8_t* p, const uint8_t* end) {
     const uint8_t* l4 = next_line(l3, end);
     const uint64_t seq_len = (uint64_t)(rstrip(l1, l2) - l1), qual_len = (uint64_t)(rstrip(l3, l4) - l3);
     if (seq_len != qual_len) return false;
-    return l4 >= end || *l4 == '@';
+    const uint8_t* q = l4;                                  // blank lines between records are allowed (parse_fastq)
+    while (q < end && rstrip(q, find_nl(q, end)) == q) q = next_line(q, end);
+    return q >= end || *q == '@';
 }
 
 }  // namespace
