@@ -39,6 +39,22 @@ def _worker(rank: int, world: int, port: int, tmp: str, mode: str):
             cover[lo:hi] = 1
             dist.all_reduce(cover)
             assert bool((cover == 1).all())
+        elif mode == "grid":
+            # 2 column groups x world / 2 read groups: columns all-gathered inside the group, records dealt to the groups
+            c = 2
+            rg, cr, members = xd.grid_layout(rank, world, c)
+            groups = [dist.new_group(list(range(g * c, (g + 1) * c))) for g in range(world // c)]   # every rank creates all
+            shards = xd.column_shards(orc.n_docs, c, align=8)
+            lo, hi = xd.read_shard(b.size, rg, world // c)
+            dlo, dhi = shards[cr]
+            local = torch.from_numpy(np.ascontiguousarray(orc.counts_batch(bases, b[lo:hi], e[lo:hi])[:, dlo:dhi]))
+            got = xd.allgather_columns(local, shards, group=groups[rg])
+            assert np.array_equal(got.numpy(), full[lo:hi])
+            cover = torch.zeros(b.size, dtype=torch.int64)
+            if cr == 0:
+                cover[lo:hi] = 1
+            dist.all_reduce(cover)
+            assert bool((cover == 1).all())
         else:
             shards = xd.column_shards(orc.n_docs, world, align=8 if mode == "cols8" else 128)
             assert shards[0][0] == 0 and shards[-1][1] == orc.n_docs
@@ -85,6 +101,23 @@ def test_column_sharding_allgather_world2(tmp_path):
 
 def test_column_sharding_uneven_world3(tmp_path):
     _run(3, "cols8", tmp_path, 50)
+
+
+def test_grid_world4(tmp_path):
+    _run(4, "grid", tmp_path, 50)
+
+
+def test_grid_layout_and_column_group_policy():
+    from xspect2_b200 import distributed as xd
+    assert [xd.grid_layout(r, 8, 2)[:2] for r in range(8)] == [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1), (3, 0), (3, 1)]
+    assert xd.grid_layout(5, 8, 2)[2] == [4, 5] and xd.grid_layout(3, 4, 4) == (0, 3, [0, 1, 2, 3])
+    with pytest.raises(ValueError):
+        xd.grid_layout(0, 8, 3)
+    hbm = 180 * 10**9
+    # BASELINE config 5: 96 M rows at a 1280-byte stride = 123 GB -> two column groups on 2, 4 and 8 B200s
+    assert [xd.choose_column_groups(96_000_000 * 1280, hbm, w) for w in (1, 2, 4, 8)] == [1, 2, 2, 2]
+    assert xd.choose_column_groups(2_400_000_000, hbm, 8) == 1            # the config-2 index is replicated
+    assert xd.choose_column_groups(600 * 10**9, hbm, 8) == 8 and xd.choose_column_groups(300 * 10**9, hbm, 8) == 4
 
 
 def test_shard_boundaries():

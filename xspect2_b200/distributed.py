@@ -38,6 +38,26 @@ def column_shards(n_docs: int, world: int, align: int = 128) -> list[tuple[int, 
     return out
 
 
+def choose_column_groups(index_bytes: int, hbm_bytes: int, world: int, budget: float = 0.5) -> int:
+    """Fewest document-column groups ``C`` (a divisor of ``world``) whose column shard takes at most ``budget`` of one
+    GPU's HBM; the other ``world / C`` factor shards the records.  Column sharding costs every rank the hashing of
+    every record and — for rows of a few 128-byte DRAM lines — whole lines per probe whatever the shard width, so
+    columns are split only as far as memory demands (180 GB per B200) and the rest of the machine shards records."""
+    for c in range(1, world + 1):
+        if world % c == 0 and index_bytes / c <= budget * hbm_bytes:
+            return c
+    return world
+
+
+def grid_layout(rank: int, world: int, col_groups: int) -> tuple[int, int, list[int]]:
+    """``(read_group, column_rank, ranks of this rank's column group)`` of a ``col_groups x world / col_groups`` grid:
+    the ``col_groups`` ranks that together hold all document columns are neighbours, ``rank = read_group * C + column_rank``."""
+    if col_groups < 1 or world % col_groups:
+        raise ValueError("col_groups must divide the world size")
+    rg, cr = divmod(rank, col_groups)
+    return rg, cr, list(range(rg * col_groups, (rg + 1) * col_groups))
+
+
 def allreduce_totals(local_totals: np.ndarray | torch.Tensor, group=None) -> torch.Tensor:
     """Sum of per-document totals over read-sharded ranks (int64)."""
     t = torch.as_tensor(local_totals).to(torch.int64).clone()
@@ -177,6 +197,17 @@ def make_comm(rank: int, world: int, device: int, group=None):
     return engine.Comm(box[0], rank, world, device)
 
 
+def make_grid_comm(rank: int, world: int, device: int, col_groups: int):
+    """The library communicator of this rank's column group (``grid_layout``): the leader of every group creates an id,
+    one ``all_gather_object`` over the launch group hands every rank its leader's."""
+    from . import engine
+
+    rg, cr, members = grid_layout(rank, world, col_groups)
+    ids = [None] * world
+    dist.all_gather_object(ids, engine.Comm.unique_id() if cr == 0 else None)
+    return engine.Comm(ids[members[0]], cr, col_groups, device)
+
+
 class ShardedScorer:
     """Document-column sharded scoring with the exchange behind the C ABI (BASELINE config 5):
     every rank scores every record tile against its columns into ``[n, w]`` rows of one common padded width
@@ -205,6 +236,8 @@ class ShardedScorer:
         self.all = [torch.empty((self.world, max_tile, self.w), dtype=self.tdt, device=self.dev) for _ in range(self.n_slots)]
         self.comm_stream = torch.cuda.Stream(device=self.dev, priority=-1)
         self.exchange_ms = 0.0
+        self.stall_ms = 0.0        # time the scoring stream waited for a tile slot (time_exchange=True)
+        self.query_ms = 0.0        # span of the scoring calls on the scoring stream (all their kernels)
 
     def run(self, tiles: Iterator[tuple[int, int, int, int, int]], step: int,
             consume: Callable[[int, torch.Tensor, torch.Tensor, torch.Tensor], None], time_exchange: bool = False) -> None:
@@ -216,17 +249,25 @@ class ShardedScorer:
         free = [None] * self.n_slots  # event: the exchange that read local[slot] has finished
         pending = []
         timers = []
+        stalls = []
         for t, (d_bases, n_bases, d_begin, d_end, n_seq) in enumerate(tiles):
             if n_seq > self.max_tile:
                 raise ValueError("tile larger than max_tile")
             slot = t % self.n_slots
+            if time_exchange:
+                w0, w1, q1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                w0.record(compute)
             if free[slot] is not None:
                 compute.wait_event(free[slot])
+            if time_exchange:
+                w1.record(compute)
             loc, al = self.local[slot], self.all[slot]
             self.index.query_device(d_bases, n_bases, d_begin, d_end, n_seq, step, self.dtype, loc.data_ptr(),
                                     compute.cuda_stream, ld=self.w)
-            scored = torch.cuda.Event()
+            scored = torch.cuda.Event(enable_timing=time_exchange)
             scored.record(compute)
+            if time_exchange:
+                stalls.append((w0, w1, scored))
             best = torch.empty(n_seq, dtype=torch.int32, device=self.dev)
             cnt = torch.empty(n_seq, dtype=torch.int32, device=self.dev)
             nb = torch.empty(n_seq, dtype=torch.int32, device=self.dev)
@@ -255,6 +296,8 @@ class ShardedScorer:
             consume(pt, b_, c_, n_)
         if time_exchange:
             self.exchange_ms += sum(a.elapsed_time(b) for a, b in timers)
+            self.stall_ms += sum(a.elapsed_time(b) for a, b, _ in stalls)
+            self.query_ms += sum(b.elapsed_time(c) for _, b, c in stalls)
 
 
 def _doc_count(path) -> int:
