@@ -130,6 +130,11 @@ int xs_cobs_doc_names(const xs_cobs* ix, char* buf, uint64_t cap, uint64_t* need
  * (file_size - data_offset == sum signature_size x row bytes) hold.  Compact files: the zero padding before the
  * end magic may be 0 or one whole page when the data is already aligned.  Never NULL. */
 const char* xs_cobs_header_layout(const xs_cobs* ix);
+/* The scoring kernel this handle's row layout selects for direct (non-bucketed) batches: "k_cobs_narrow" (rows of
+ * <= 16 bytes), "k_cobs_pages" (compact index, several narrow pages), "k_cobs_mid" (one page of 32 / 64 / 128-byte
+ * rows, 129 .. 1024 documents), "k_cobs_wide" (everything else; XS_FORCE_WIDE=1 / XS_NO_MID_KERNEL=1 at open time
+ * force it for measurements).  Results do not depend on the choice.  Never NULL. */
+const char* xs_cobs_kernel(const xs_cobs* ix);
 /* The same header parse without a device (no CUDA call): what a file would load as. */
 typedef struct {
     uint32_t kind, term_size, canonicalize, num_hashes, n_docs, n_pages;

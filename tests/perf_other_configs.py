@@ -152,7 +152,6 @@ def wide(td: Path):
             a = torch.randint(0, 256, (n, row), generator=gen, device=dev, dtype=torch.uint8)
             b = torch.randint(0, 256, (n, row), generator=gen, device=dev, dtype=torch.uint8)
             f.write((a & b).cpu().numpy().tobytes())          # fill 0.25
-    ix = engine.CobsIndex(p)
     n_reads, L = int(os.environ.get('XS_PERF_READS', 1_000_000)), 150
     genome = synth.synth_genome(1_000_000, seed=7)
     reads = synth.synth_reads(genome, n_reads, L, seed=8, device=dev)
@@ -161,21 +160,28 @@ def wide(td: Path):
     d_e = torch.from_numpy(he.view(np.int64)).to(dev)
     out = torch.empty((n_reads, D), dtype=torch.uint8, device=dev)
     s = torch.cuda.current_stream().cuda_stream
-    engine.profile_enable(True)
-    engine.profile_read()
-    ms = timed(lambda: ix.query_device(reads.data_ptr(), n_reads * L, d_b.data_ptr(), d_e.data_ptr(), n_reads, 1, XS_U8, out.data_ptr(), s), steps=3, warm=1)
-    kms, kn = engine.profile_read()
-    engine.profile_enable(False)
     sample = 300
     exp = oracle.CobsOracle(p, load_complete=False).counts_batch(reads[: sample * L].cpu().numpy(), hb[:sample], he[:sample], 1, threads=8)
-    assert np.array_equal(out[:sample].cpu().numpy().astype(np.uint32), np.minimum(exp, 255))
     lookups = n_reads * (L - k + 1)
-    kernel_ms = kms / max(kn, 1)
     algo = lookups * h * row + n_reads * L * 3 // 8 + n_reads * D
-    print(json.dumps({"config": f"wide rows on one GPU: D={D} h={h} S={S} (row {row} B, stride {ix.info.row_stride} B), {n_reads} x 150bp reads",
-                      "ms_per_step": ms, "kernel_ms": kernel_ms, "lookups_per_sec": lookups / ms * 1e3,
-                      "achieved_GBps": algo / kernel_ms / 1e6, "frac_of_hbm_peak": algo / kernel_ms / 1e6 / PEAK,
-                      "parity_sample_reads": sample}), flush=True)
+    # rows of 17 .. 128 bytes: k_cobs_mid (default) and k_cobs_wide (XS_NO_MID_KERNEL=1, read at open time) on the same file
+    for no_mid in (("0", "1") if row <= 128 else ("0",)):
+        os.environ["XS_NO_MID_KERNEL"] = no_mid
+        ix = engine.CobsIndex(p)
+        engine.profile_enable(True)
+        engine.profile_read()
+        ms = timed(lambda: ix.query_device(reads.data_ptr(), n_reads * L, d_b.data_ptr(), d_e.data_ptr(), n_reads, 1, XS_U8, out.data_ptr(), s), steps=3, warm=1)
+        kms, kn = engine.profile_read()
+        engine.profile_enable(False)
+        assert np.array_equal(out[:sample].cpu().numpy().astype(np.uint32), np.minimum(exp, 255))
+        kernel_ms = kms / max(kn, 1)
+        print(json.dumps({"config": f"rows on one GPU: D={D} h={h} S={S} (row {row} B, stride {ix.info.row_stride} B), {n_reads} x 150bp reads",
+                          "kernel": ix.kernel, "ms_per_step": ms, "kernel_ms": kernel_ms, "lookups_per_sec": lookups / ms * 1e3,
+                          "achieved_GBps": algo / kernel_ms / 1e6, "frac_of_hbm_peak": algo / kernel_ms / 1e6 / PEAK,
+                          "dram_fetch_bound_frac": row / max(128, ix.info.row_stride),
+                          "checksum": int(out.to(torch.int64).sum().item()), "parity_sample_reads": sample}), flush=True)
+        ix.close()
+    os.environ.pop("XS_NO_MID_KERNEL", None)
 
 
 def twostage(td: Path):

@@ -15,8 +15,10 @@ def _mk_classic(oracle, tmp_path, rng, n_docs, k, h, length=3000, name="index.co
     return p, docs
 
 
-def _check_cobs(gpu, oracle, path, bases, b, e, step=1, dtype=None, policy=0, **open_kw):
+def _check_cobs(gpu, oracle, path, bases, b, e, step=1, dtype=None, policy=0, kernel=None, **open_kw):
     ix = gpu.CobsIndex(path, **open_kw)
+    if kernel is not None:
+        assert ix.kernel == kernel, (ix.kernel, ix.info.row_stride)
     ix.set_policy(policy)
     orc = oracle.CobsOracle(path, policy=policy)
     got = ix.query(bases, b, e, step=step, dtype=dtype)
@@ -319,6 +321,45 @@ def test_cobs_wide_multi_column_block(gpu, oracle, tmp_path):
     assert got.sum() > 0
     _check_cobs(gpu, oracle, p, bases, b, e, step=2, dtype=1)
     _check_cobs(gpu, oracle, p, bases, b, e, doc_begin=4096, doc_end=12288)
+
+
+@pytest.mark.parametrize("n_docs,k,h", [(129, 21, 7), (200, 21, 7), (256, 31, 1), (300, 21, 7), (300, 15, 3), (512, 21, 7),
+                                        (1000, 21, 7), (1000, 32, 8), (1024, 13, 2)])
+def test_cobs_mid_rows(gpu, oracle, tmp_path, monkeypatch, n_docs, k, h):
+    """Rows at a 32 / 64 / 128-byte stride take k_cobs_mid (lane groups per row): ragged reads with N / lower case / IUPAC,
+    empty and shorter-than-k records, a contig that spans many warp tiles (added into by several warps) and saturates
+    uint8, sampling steps; against the oracle and against k_cobs_wide on the same handle geometry."""
+    rng = np.random.default_rng(1000 + n_docs + h)
+    p, docs = _mk_classic(oracle, tmp_path, rng, n_docs, k, h, length=400)
+    genomes = [s for v in docs.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes, 400, (1, 260), n_rate=0.004, lower=0.002, iupac=0.002)
+    contig = np.concatenate(genomes[:40])                      # 16 000 bp of documents 0..39: counts beyond 255
+    empties = 70                                               # a run of empty records inside the batch
+    b = np.concatenate([b, np.full(empties, e[-1]), [e[-1]]]).astype(np.uint64)
+    e = np.concatenate([e, np.full(empties, e[-1]), [e[-1] + contig.size]]).astype(np.uint64)
+    bases = np.concatenate([bases, contig])
+    got = _check_cobs(gpu, oracle, p, bases, b, e, kernel="k_cobs_mid")
+    assert got.sum() > 0 and got[-1].max() > 255
+    _check_cobs(gpu, oracle, p, bases, b, e, dtype=1, kernel="k_cobs_mid")
+    _check_cobs(gpu, oracle, p, bases, b, e, step=3, dtype=2, kernel="k_cobs_mid")
+    _check_cobs(gpu, oracle, p, bases, b, e, policy=1, kernel="k_cobs_mid")
+    monkeypatch.setenv("XS_NO_MID_KERNEL", "1")
+    wide = _check_cobs(gpu, oracle, p, bases, b, e, kernel="k_cobs_wide")
+    assert np.array_equal(wide, got)
+
+
+def test_cobs_mid_rows_kernel_choice(gpu, oracle, tmp_path):
+    """Column shards choose by their own width; more than 8 hash functions stay on k_cobs_wide."""
+    rng = np.random.default_rng(77)
+    p, docs = _mk_classic(oracle, tmp_path, rng, 2000, 21, 7, length=150)
+    genomes = [s for v in docs.values() for s in v]
+    bases, b, e = synth.sample_reads(rng, genomes, 200, (21, 150), n_rate=0.002)
+    _check_cobs(gpu, oracle, p, bases, b, e, kernel="k_cobs_wide")                                   # 250-byte rows
+    _check_cobs(gpu, oracle, p, bases, b, e, doc_begin=256, doc_end=768, kernel="k_cobs_mid")        # 64 bytes
+    _check_cobs(gpu, oracle, p, bases, b, e, doc_begin=1024, doc_end=2000, kernel="k_cobs_mid")      # 122 -> 128 bytes
+    _check_cobs(gpu, oracle, p, bases, b, e, doc_begin=128, doc_end=256, kernel="k_cobs_narrow")     # 16 bytes
+    p9, docs9 = _mk_classic(oracle, tmp_path, rng, 300, 21, 9, length=150, name="h9.cobs_classic")
+    _check_cobs(gpu, oracle, p9, bases, b, e, kernel="k_cobs_wide")
 
 
 def test_cobs_wide_kernel_on_narrow_index(gpu, oracle, tmp_path, monkeypatch):

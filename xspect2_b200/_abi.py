@@ -62,6 +62,7 @@ SYMBOLS = {
     "xs_cobs_info": (C.c_int, [_P, C.POINTER(CobsInfo)]),
     "xs_cobs_doc_names": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "xs_cobs_header_layout": (C.c_char_p, [_P]),
+    "xs_cobs_kernel": (C.c_char_p, [_P]),
     "xs_cobs_probe_header": (C.c_int, [C.c_char_p, C.POINTER(CobsHeader)]),
     "xs_cobs_doc_fill": (C.c_int, [_P, C.c_uint64, _P]),
     "xs_cobs_set_policy": (C.c_int, [_P, C.c_int]),

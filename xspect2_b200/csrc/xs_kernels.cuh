@@ -311,6 +311,7 @@ struct CobsParams {
     uint64_t ld;        // output row length (all local documents)
     uint64_t seq0;      // output row of sequence 0 of this batch
     uint64_t win_begin; // k_cobs_narrow: first flat window to score (the bucketed path's tail launch), normally 0
+    uint32_t all_rows;  // k_cobs_mid: gather all h rows even when the AND is already empty (measurement switch)
 };
 
 constexpr int NARROW_NT = 256;
@@ -1356,6 +1357,151 @@ __global__ void __launch_bounds__(WIDE_NT) k_cobs_wide(const WideParams wp) {
             if (complete) out_store<OutT>(row + d, v); else out_add<OutT>(row + d, v, nosat);
         }
         __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// COBS, mid-width rows: one page, row_stride = 32 / 64 / 128 bytes (129 .. 1024 documents — species models of large
+// genera, narrow column shards).  k_cobs_wide gives such rows a CTA per (sequence, window chunk): three CTA barriers
+// around ~4 windows per warp for a 150-bp read, and lanes idle whenever the row has fewer than 32 column chunks.
+// Here the warp keeps k_cobs_narrow's barrier-free walk over the flat window space and changes roles between the two
+// halves of a round:
+//   hash     one lane per window: canonical k-mer -> XXH64 x h -> row ids (registers)
+//   gather   LPW = row_stride / 16 lanes per window, 32 / LPW windows at a time: the row ids travel by shuffle, every
+//            lane loads its 16-byte column chunk of the h rows (a row is one 128-byte DRAM line or an aligned part of
+//            one), ANDs them and adds the mask to 4 vertical bit-plane counters; for h > 5 a lane whose AND is already
+//            empty after five rows skips the rest
+// Bit planes spill into a warp-private shared-memory slice of LPW x 128 counters every 15 masks and when the sequence
+// ends; the non-zero counters are written (or added, for a sequence that straddles warp tiles) to the zeroed output.
+// ----------------------------------------------------------------------------------------
+constexpr int MID_NT = 256;
+constexpr int MID_MAXH = 8;             // row ids a lane keeps in registers (generic instantiation: h <= 8)
+
+template <int K, int H, typename OutT, int LPW>
+__global__ void __launch_bounds__(MID_NT, 3) k_cobs_mid(const CobsParams p) {
+    __shared__ uint32_t s_mid_cnt[MID_NT / 32][LPW * 128];
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    constexpr uint32_t SLOTS = 32 / LPW;          // windows the warp gathers at once
+    constexpr int HH = H ? H : MID_MAXH;
+    constexpr int H1 = HH > 5 ? XS_EARLY_EXIT_AFTER : HH;
+    const SeqBatch& sb = p.sb;
+    const PageDesc pg = p.pages[0];
+    const uint32_t k = K ? K : sb.k;
+    const uint32_t h = H ? H : p.num_hashes;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t slot = lane / LPW, cl = lane % LPW;
+    uint32_t* my = s_mid_cnt[warp];
+    for (uint32_t i = lane; i < LPW * 128; i += 32) my[i] = 0;
+    __syncwarp();
+    const uint8_t* colbase = pg.data + cl * 16;
+    OutT* out = reinterpret_cast<OutT*>(p.out);
+
+    const uint64_t n_warps = ((uint64_t)gridDim.x * MID_NT) >> 5;
+    const uint64_t total = __ldg(sb.win_prefix + sb.n_seq);
+    const uint64_t W = walk_tile_windows(total, n_warps);
+    const uint64_t n_tiles = (total + W - 1) / W;
+
+    uint32_t pl[4][4];                            // [plane][word]: vertical counters of this lane's 128 documents
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) pl[a][b] = 0;
+    uint32_t pending = 0;
+    auto spill = [&]() {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            uint32_t any = pl[0][b] | pl[1][b] | pl[2][b] | pl[3][b];
+            while (any) {
+                const uint32_t bit = __ffs(any) - 1; any &= any - 1;
+                const uint32_t c = ((pl[0][b] >> bit) & 1u) | (((pl[1][b] >> bit) & 1u) << 1) |
+                                   (((pl[2][b] >> bit) & 1u) << 2) | (((pl[3][b] >> bit) & 1u) << 3);
+                atomicAdd(&my[cl * 128 + b * 32 + bit], c);      // the SLOTS lanes of one column chunk share counters
+            }
+            pl[0][b] = pl[1][b] = pl[2][b] = pl[3][b] = 0;
+        }
+        pending = 0;
+    };
+    auto add_mask = [&](const uint4& m) {
+        if ((m.x | m.y | m.z | m.w) == 0) return;
+        uint32_t carry[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t tc = pl[a][b] & carry[b];
+                pl[a][b] ^= carry[b];
+                carry[b] = tc;
+            }
+        if (++pending == 15) spill();
+    };
+
+    for (;;) {
+        const uint64_t tile = next_tile(sb.tile_counter, lane);
+        if (tile >= n_tiles) break;
+        const uint64_t t0 = tile * W, t1 = t0 + W < total ? t0 + W : total;
+        uint32_t r[HH];                           // row ids of this lane's window
+        int valid = 0;
+        warp_walk(
+            sb, t0, t1, lane,
+            [&](bool has, uint64_t pos, uint64_t) {
+                valid = 0;
+                if (has) {
+                    Term t;
+                    if (cobs_term<K>(sb, pos, p.canonicalize != 0, p.policy, t)) {
+                        valid = 1;
+                        Xxh64Pre pre;
+                        xxh64_prepare(t, k, pre);
+#pragma unroll
+                        for (int j = 0; j < HH; ++j)
+                            r[j] = (uint32_t)j < h ? (uint32_t)mod_barrett(xxh64_finish(pre, k, (uint64_t)j), pg.sig_size, pg.magic) : 0u;
+                    }
+                }
+            },
+            [&](uint32_t segmask) {
+                const uint32_t first = __ffs(segmask) - 1, count = __popc(segmask);
+                for (uint32_t sub = 0; sub < count; sub += SLOTS) {
+                    const bool in = sub + slot < count;
+                    const uint32_t src = in ? first + sub + slot : first;
+                    const bool ok = __shfl_sync(FULL, valid, src) != 0 && in;
+                    uint32_t rj[HH];
+#pragma unroll
+                    for (int j = 0; j < HH; ++j) rj[j] = __shfl_sync(FULL, r[j], src);
+                    if (!ok) continue;
+                    uint4 m = make_uint4(~0u, ~0u, ~0u, ~0u);
+                    uint4 v[H1];
+#pragma unroll
+                    for (int j = 0; j < H1; ++j)
+                        if (H || (uint32_t)j < h) v[j] = ldg128(colbase + (size_t)rj[j] * (LPW * 16));
+#pragma unroll
+                    for (int j = 0; j < H1; ++j)
+                        if (H || (uint32_t)j < h) { m.x &= v[j].x; m.y &= v[j].y; m.z &= v[j].z; m.w &= v[j].w; }
+                    if (H1 < HH && ((m.x | m.y | m.z | m.w) != 0 || p.all_rows)) {
+#pragma unroll
+                        for (int j = H1; j < HH; ++j)
+                            if (H || (uint32_t)j < h) {
+                                const uint4 w = ldg128(colbase + (size_t)rj[j] * (LPW * 16));
+                                m.x &= w.x; m.y &= w.y; m.z &= w.z; m.w &= w.w;
+                            }
+                    }
+                    add_mask(m);
+                }
+            },
+            [&](uint64_t seq, bool complete, uint64_t nwin) {
+                spill();
+                __syncwarp();
+                const bool nosat = nwin <= (uint64_t)out_max<OutT>();
+                OutT* row = out + (p.seq0 + seq) * p.ld + pg.doc_off;
+                for (uint32_t i = lane; i < LPW * 128; i += 32) {
+                    const uint32_t c = my[i];
+                    if (c) {
+                        if (i < pg.n_docs) {
+                            if (complete) out_store<OutT>(row + i, c); else out_add<OutT>(row + i, c, nosat);
+                        }
+                        my[i] = 0;
+                    }
+                }
+                __syncwarp();
+            });
     }
 }
 

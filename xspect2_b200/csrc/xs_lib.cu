@@ -162,6 +162,7 @@ struct xs_cobs {
     bool pages_kernel = false;   // several narrow pages: k_cobs_pages (one pass, windows hashed once) instead of k_cobs_narrow per page
     int n_sm = 148;
     int force_wide = 0;
+    bool mid = false;            // one page of 32 / 64 / 128-byte rows: k_cobs_mid (warp walk, lane groups per row) instead of k_cobs_wide
     BucketState bk;
 };
 
@@ -567,6 +568,45 @@ static cudaError_t launch_pages(const CobsParams& p, int n_sm, int dt, cudaStrea
     return launch_pages_t<0, 0>(p, n_sm, dt, s);
 }
 
+// one page of mid-width rows (k_cobs_mid): lanes per row from the stride
+template <int K, int H, typename T>
+static void launch_mid_tt(const CobsParams& p, uint32_t stride, int n_sm, cudaStream_t s) {
+    static int occ[3] = {0, 0, 0};
+    auto go = [&](auto kern, int slot) {
+        if (!occ[slot]) {
+            int o = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, MID_NT, 0) != cudaSuccess || o < 1) o = 1;
+            occ[slot] = o;
+        }
+        kern<<<n_sm * occ[slot], MID_NT, 0, s>>>(p);
+    };
+    if (stride == 32) go(k_cobs_mid<K, H, T, 2>, 0);
+    else if (stride == 64) go(k_cobs_mid<K, H, T, 4>, 1);
+    else go(k_cobs_mid<K, H, T, 8>, 2);
+}
+template <int K, int H>
+static void launch_mid_t(const CobsParams& p, uint32_t stride, int n_sm, int dt, cudaStream_t s) {
+    if (dt == XS_U8) launch_mid_tt<K, H, uint8_t>(p, stride, n_sm, s);
+    else if (dt == XS_U16) launch_mid_tt<K, H, uint16_t>(p, stride, n_sm, s);
+    else launch_mid_tt<K, H, uint32_t>(p, stride, n_sm, s);
+}
+static void launch_mid(const CobsParams& p, uint32_t stride, int n_sm, int dt, cudaStream_t s) {
+    if (p.sb.k == 21 && p.num_hashes == 7) launch_mid_t<21, 7>(p, stride, n_sm, dt, s);
+    else if (p.sb.k == 31 && p.num_hashes == 1) launch_mid_t<31, 1>(p, stride, n_sm, dt, s);
+    else launch_mid_t<0, 0>(p, stride, n_sm, dt, s);
+}
+// which kernel family a handle's rows take: the wide kernel's work items need the per-sequence chunk prefix
+static bool uses_wide(const xs_cobs* ix) { return (!ix->narrow && !ix->mid) || ix->force_wide; }
+// k_cobs_mid: a classic index (or a column shard of one) whose rows sit at a 32 / 64 / 128-byte stride
+static bool mid_eligible(const xs_cobs* ix) {
+    const char* off = getenv("XS_NO_MID_KERNEL");
+    if (off && off[0] == '1') return false;
+    if (ix->pages.size() != 1) return false;
+    const PageDesc& pg = ix->pages[0];
+    return (pg.row_stride == 32 || pg.row_stride == 64 || pg.row_stride == 128) && pg.sig_size <= 0xFFFFFFFFull &&
+           ix->info.num_hashes <= (uint32_t)MID_MAXH;
+}
+
 template <int K, int H, typename T>
 static cudaError_t launch_wide_tt(const WideParams& p, dim3 grid, size_t smem, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(k_cobs_wide<K, H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -900,7 +940,7 @@ static int dtype_size(int dt) { return (dt == XS_U8 || dt == XS_U16 || dt == XS_
 static int cobs_launch(xs_cobs* ix, const SeqBatch& sb, const uint64_t* chunk_prefix, int dt, void* d_out, cudaStream_t s,
                        uint64_t ld_override = 0) {
     const uint64_t ld = ld_override ? ld_override : ix->info.doc_end - ix->info.doc_begin;
-    const bool wide = !ix->narrow || ix->force_wide;
+    const bool wide = uses_wide(ix);
     CobsParams p{};
     p.sb = sb; p.pages = ix->d_pages; p.n_pages = (uint32_t)ix->pages.size();
     p.num_hashes = ix->info.num_hashes; p.canonicalize = ix->info.canonicalize; p.policy = ix->info.policy;
@@ -911,6 +951,13 @@ static int cobs_launch(xs_cobs* ix, const SeqBatch& sb, const uint64_t* chunk_pr
             cudaError_t e = launch_pages(p, ix->n_sm, dt, s);
             if (e != cudaSuccess) return fail(XS_ERR_CUDA, std::string("k_cobs_pages: ") + cudaGetErrorString(e));
             return launch_ok("k_cobs_pages");
+        }
+        if (ix->mid) {
+            static const bool all_rows = [] { const char* v = getenv("XS_MID_ALL_ROWS"); return v && v[0] == '1'; }();
+            p.all_rows = all_rows ? 1u : 0u;
+            KernelTimer kt(s);
+            launch_mid(p, ix->pages[0].row_stride, ix->n_sm, dt, s);
+            return launch_ok("k_cobs_mid");
         }
         bool handled = false;
         XS_TRY(cobs_launch_bucketed(ix, p, dt, s, &handled));
@@ -942,7 +989,7 @@ static int cobs_query_dev(xs_cobs* ix, const uint8_t* d_bases, uint64_t n_bases,
     if (n_seq == 0) return XS_OK;
     Workspace ws;
     SeqBatch sb{};
-    const bool wide = !ix->narrow || ix->force_wide;
+    const bool wide = uses_wide(ix);
     XS_TRY(prepare_batch(ws, sb, d_bases, n_bases, d_begin, d_end, n_seq, base_shift, ix->info.term_size, step,
                          wide ? WIDE_CHUNK : 0, ix->n_sm, s));
     return cobs_launch(ix, sb, ws.prefix2, dt, d_out, s, ld_override);   // ws goes back to the stream-ordered pool on scope exit
@@ -1502,6 +1549,7 @@ int xs_cobs_open(const char* path, int device, uint32_t doc_begin, uint32_t doc_
     in.page_bytes = cf.page_bytes; in.row_stride = stride;
     in.sig_size_max = *std::max_element(cf.sig.begin(), cf.sig.end());
     in.hbm_bytes = total; in.device = device; in.policy = XS_NONACGT_SKIP;
+    ix->mid = cf.kind == XS_COBS_CLASSIC && mid_eligible(ix);
     if (ix->narrow && ix->pages.size() == 1 && ix->pages[0].row_stride == 16)
         ix->has_tmap = make_row_tensor_map(ix->pages[0].data, ix->pages[0].sig_size, &ix->tmap);
     *out = ix;
@@ -1563,6 +1611,7 @@ int xs_cobs_create_synthetic(int device, uint32_t n_docs, uint32_t doc_begin, ui
     in.kind = XS_COBS_CLASSIC; in.term_size = term_size; in.canonicalize = 1; in.num_hashes = num_hashes; in.n_docs_total = n_docs;
     in.doc_begin = doc_begin; in.doc_end = doc_end; in.n_pages = 1; in.page_bytes = ((uint64_t)n_docs + 7) / 8; in.row_stride = stride;
     in.sig_size_max = sig_size; in.hbm_bytes = total; in.device = device; in.policy = XS_NONACGT_SKIP;
+    ix->mid = mid_eligible(ix);
     *out = ix;
     return XS_OK;
 }
@@ -1721,6 +1770,13 @@ int xs_cobs_info(const xs_cobs* ix, xs_cobs_info_t* info) {
 
 const char* xs_cobs_header_layout(const xs_cobs* ix) { return ix ? ix->layout.c_str() : ""; }
 
+const char* xs_cobs_kernel(const xs_cobs* ix) {
+    if (!ix) return "";
+    if (uses_wide(ix)) return "k_cobs_wide";
+    if (ix->pages_kernel) return "k_cobs_pages";
+    return ix->mid ? "k_cobs_mid" : "k_cobs_narrow";
+}
+
 int xs_cobs_probe_header(const char* path, xs_cobs_header_t* out) {
     if (!path || !out) return fail(XS_ERR_ARG, "path/out is NULL");
     FILE* f = fopen(path, "rb");
@@ -1838,7 +1894,7 @@ int xs_cobs_query(xs_cobs* ix, const uint8_t* bases, uint64_t n_bases, const uin
     const uint64_t row = ld * (uint64_t)out_dtype;
     {
         bool handled = false;
-        const bool wide = !ix->narrow || ix->force_wide;
+        const bool wide = uses_wide(ix);
         const uint32_t n_counters = (uint32_t)std::max(ix->pages.size(), ix->blocks.size());
         XS_TRY(small_query(ix->info.device, ix->n_sm, ix->info.term_size, step, wide ? WIDE_CHUNK : 0, n_counters, bases, n_bases,
                            seq_begin, seq_end, n_seq, row, out, &handled,

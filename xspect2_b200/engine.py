@@ -174,6 +174,11 @@ class CobsIndex:
         """Which candidate reading of the file header matched (``xs_cobs_header_layout``)."""
         return lib().xs_cobs_header_layout(self._h).decode()
 
+    @property
+    def kernel(self) -> str:
+        """The scoring kernel the handle's row layout selects for direct batches (``xs_cobs_kernel``)."""
+        return lib().xs_cobs_kernel(self._h).decode()
+
     def doc_fill(self, sample_rows: int = 0) -> np.ndarray:
         """Fraction of set bits per local document over evenly spaced sample rows (``xs_cobs_doc_fill``)."""
         fill = np.zeros(self.n_docs, np.float64)
