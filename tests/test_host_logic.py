@@ -430,3 +430,30 @@ def test_columnar_result_json_multi_threaded_writer(tmp_path, monkeypatch):
     hits = {rid: {names[j]: int(counts[i, j]) for j in CobsIndex.result_order(counts[i]).tolist() if include[j]} for i, rid in enumerate(ids)}
     ref = ModelResult("slug", hits, {rid: int(v) for rid, v in zip(ids, nk)}, 1, "101", "x.fq")
     assert outs[0].decode() == json.dumps(ref.to_dict(), indent=4)
+
+
+def test_pipeline_block_plan():
+    """pipeline._plan_blocks: record ranges that cover the batch in order, bounded in records and bytes, with the
+    byte span and the length extremes of each range; records laid out of order fall back to one block."""
+    from xspect2_b200.pipeline import _plan_blocks, min_hits_table
+    rng = np.random.default_rng(3)
+    lens = rng.integers(22, 400, size=10_000).astype(np.uint64)
+    end = np.cumsum(lens, dtype=np.uint64)
+    begin = end - lens
+    blocks = _plan_blocks(begin, end, block_records=1500, block_bytes=100_000)
+    assert blocks[0][0] == 0 and blocks[-1][1] == lens.size
+    assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+    for i0, i1, lo, hi, mn, mx in blocks:
+        assert 0 < i1 - i0 <= 1500 and lo == begin[i0] and hi == end[i1 - 1]
+        assert hi - lo <= 4 * 100_000 + (1 << 20)
+        assert mn == lens[i0:i1].min() and mx == lens[i0:i1].max()
+    assert len(blocks) > 10
+    perm = rng.permutation(lens.size)                     # same records, arbitrary order: spans cover the whole buffer
+    one = _plan_blocks(begin[perm], end[perm], block_records=1500, block_bytes=1000)
+    assert one == [(0, lens.size, 0, int(end[-1]), int(lens.min()), int(lens.max()))]
+    assert _plan_blocks(begin[:0], end[:0], 10, 10) == []
+    # the exact threshold table: smallest h with round(h / n, 2) >= t
+    t = min_hits_table(300, 0.7)
+    for n in (1, 2, 3, 7, 130, 299, 300):
+        h = int(t[n])
+        assert round(h / n, 2) >= 0.7 and (h == 0 or round((h - 1) / n, 2) < 0.7)

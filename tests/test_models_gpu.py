@@ -292,6 +292,11 @@ def test_genus_then_species_matches_the_file_based_stages(world, oracle, tmp_pat
     mf.write_fastq(fq, recs)
     for thr, step in ((0.7, 1), (0.3, 2), (1.0, 1)):
         out = genus_then_species(genus, species, fq, threshold=thr, step=step)
+        # the same input through many small blocks (three in flight, slots reused): identical results
+        small = genus_then_species(genus, species, fq, threshold=thr, step=step, block_records=37)
+        for key in ("genus_hits", "kept", "kept_index", "best", "best_hits", "ambiguous", "num_kmers"):
+            assert np.array_equal(out[key], small[key]), key
+        assert (out["total_hits"], out["total_kmers"], out["prediction"]) == (small["total_hits"], small["total_kmers"], small["prediction"])
         gres = genus.predict(fq, step=step)
         kept_ids = gres.get_filtered_subsequence_labels("Testgenus", thr)
         assert [rid for rid, keep in zip(out["batch"].ids, out["kept"]) if keep] == kept_ids
