@@ -1377,8 +1377,8 @@ __global__ void __launch_bounds__(WIDE_NT) k_cobs_wide(const WideParams wp) {
 constexpr int MID_NT = 256;
 constexpr int MID_MAXH = 8;             // row ids a lane keeps in registers (generic instantiation: h <= 8)
 
-template <int K, int H, typename OutT, int LPW>
-__global__ void __launch_bounds__(MID_NT, 3) k_cobs_mid(const CobsParams p) {
+template <int K, int H, typename OutT, int LPW, int OCC>
+__global__ void __launch_bounds__(MID_NT, OCC) k_cobs_mid(const CobsParams p) {
     __shared__ uint32_t s_mid_cnt[MID_NT / 32][LPW * 128];
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     constexpr uint32_t SLOTS = 32 / LPW;          // windows the warp gathers at once
