@@ -583,10 +583,10 @@ static void launch_mid_tt(const CobsParams& p, uint32_t stride, int n_sm, cudaSt
     // 128-byte rows gather only 4 windows per warp instruction and are bound by dependent DRAM round trips: 64
     // registers (a few spilled words in the hash phase) for 4 CTAs per SM is worth +10 % there (18.7 against 20.7 ms,
     // profiles/r2_mid_rows.md); 32 / 64-byte rows sit on the DRAM fetch rate at 80 registers / 3 CTAs per SM
-    static const int occ = env_int("XS_MID_OCC", 0);          // measurement switch: 3 or 4 for every stride
-    if (stride == 32) { if (occ == 4) go(k_cobs_mid<K, H, T, 2, 4>, 0); else go(k_cobs_mid<K, H, T, 2, 3>, 0); }
-    else if (stride == 64) { if (occ == 4) go(k_cobs_mid<K, H, T, 4, 4>, 1); else go(k_cobs_mid<K, H, T, 4, 3>, 1); }
-    else { if (occ == 3) go(k_cobs_mid<K, H, T, 8, 3>, 2); else go(k_cobs_mid<K, H, T, 8, 4>, 2); }
+    static const int occ_sel = env_int("XS_MID_OCC", 0);      // measurement switch: 3 or 4 for every stride
+    if (stride == 32) { if (occ_sel == 4) go(k_cobs_mid<K, H, T, 2, 4>, 0); else go(k_cobs_mid<K, H, T, 2, 3>, 0); }
+    else if (stride == 64) { if (occ_sel == 4) go(k_cobs_mid<K, H, T, 4, 4>, 1); else go(k_cobs_mid<K, H, T, 4, 3>, 1); }
+    else { if (occ_sel == 3) go(k_cobs_mid<K, H, T, 8, 3>, 2); else go(k_cobs_mid<K, H, T, 8, 4>, 2); }
 }
 template <int K, int H>
 static void launch_mid_t(const CobsParams& p, uint32_t stride, int n_sm, int dt, cudaStream_t s) {
