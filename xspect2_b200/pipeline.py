@@ -75,7 +75,7 @@ def _plan_blocks(begin: np.ndarray, end: np.ndarray, block_records: int, block_b
 
 
 def genus_then_species(genus_model, species_model, sequence_input, threshold: float = 0.7, step: int = 1,
-                       predict: bool = True, block_records: int = 2_000_000, block_bytes: int = 320 << 20) -> dict:
+                       predict: bool = True, block_records: int | None = None, block_bytes: int = 320 << 20) -> dict:
     """Score every record against the genus filter, keep those reaching ``threshold`` and classify them with the
     species model; returns per-record genus hits, the kept mask, read-level species calls for the kept records,
     file-level species totals / scores and (for an SVM species model) the prediction.
@@ -102,6 +102,10 @@ def genus_then_species(genus_model, species_model, sequence_input, threshold: fl
     n = len(batch)
     k = genus_model.k
     n_docs = ix.n_docs
+    if block_records is None:
+        # about eight blocks so that the first copy-in and the last copy-out are a small part of the pass, but blocks of at
+        # least 500 k records (a 150-bp block then still has the 32 Mi windows the bucketed kernels want) and at most 2 M
+        block_records = min(2_000_000, max(500_000, -(-n // 8)))
     blocks = _plan_blocks(batch.begin, batch.end, block_records, block_bytes)
     if blocks and min(bl[4] for bl in blocks) <= k:       # ProbabilisticFilterModel._check_lengths, from the block statistics
         raise ValueError("Invalid sequence, must be longer than k")
