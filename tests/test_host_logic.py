@@ -457,3 +457,40 @@ def test_pipeline_block_plan():
     for n in (1, 2, 3, 7, 130, 299, 300):
         h = int(t[n])
         assert round(h / n, 2) >= 0.7 and (h == 0 or round((h - 1) / n, 2) < 0.7)
+
+
+def test_svm_is_refit_only_when_its_inputs_change(tmp_path):
+    """ProbabilisticFilterSVMModel._get_svm keeps the fitted classifier while scores.csv, kernel, C and the excluded
+    ids stay the same (the reference refits per predict call: same deterministic fit, same predictions)."""
+    import csv
+    import time
+
+    from xspect2_b200.models.probabilistic_filter_svm_model import ProbabilisticFilterSVMModel as M
+    m = M.__new__(M)
+    m.base_path, m.kernel, m.c = tmp_path, "rbf", 1.5
+    m.display_names = {str(1000 + d): f"s{d}" for d in range(5)}
+    m.slug = lambda: "g-species"
+    (tmp_path / "g-species").mkdir()
+
+    def write(seed):
+        rng = np.random.default_rng(seed)
+        with open(tmp_path / "g-species" / "scores.csv", "w", encoding="utf-8") as f:
+            w = csv.writer(f)
+            w.writerow(["file"] + sorted(m.display_names) + ["label"])
+            for d in range(5):
+                for r in range(4):
+                    x = rng.random(5) * 0.3
+                    x[d] = 0.95
+                    w.writerow([f"a{d}{r}"] + [f"{v:.2f}" for v in x] + [str(1000 + d)])
+
+    write(1)
+    a = m._get_svm(None)
+    assert m._get_svm(None) is a
+    c = m._get_svm(["1001"])                       # other excluded ids: a different classifier (4 classes, 4 features)
+    assert c is not a and len(c.classes_) == 4 and c.n_features_in_ == 4
+    d = m._get_svm(None)
+    assert d is not a and list(d.classes_) == list(a.classes_)
+    assert str(d.predict([[0.95, 0.1, 0.1, 0.1, 0.1]])[0]) == "1000"
+    time.sleep(0.01)
+    write(2)                                       # retrained model directory: refit
+    assert m._get_svm(None) is not d

@@ -1,9 +1,10 @@
 """Species model + SVM on the score vector.
 
 API of the reference's ``ProbabilisticFilterSVMModel`` (models/probabilistic_filter_svm_model.py:17-315).
-Scoring runs on the GPU through the parent class; the SVM stays on the host with scikit-learn, refit from the
-model's ``scores.csv`` on every call exactly as the reference does (:225-274), including its handling of
-``exclude_ids``.
+Scoring runs on the GPU through the parent class; the SVM stays on the host with scikit-learn, fit from the
+model's ``scores.csv`` exactly as the reference does (:225-274), including its handling of ``exclude_ids``; the
+fitted classifier is kept while ``scores.csv`` and the excluded ids do not change (the reference refits per call —
+the fit is deterministic, so the predictions are the same).
 """
 
 from __future__ import annotations
@@ -98,11 +99,20 @@ class ProbabilisticFilterSVMModel(ProbabilisticFilterModel):
         sorted; rows labelled with an excluded id are dropped."""
         from sklearn.svm import SVC
 
+        # the fit is deterministic in scores.csv, kernel, C and the excluded ids: keep the fitted classifier while
+        # those do not change (the reference refits on every predict call, ~70 ms for 360 training rows)
+        csv_path = self.base_path / self.slug() / "scores.csv"
+        st = csv_path.stat()
+        key = (st.st_mtime_ns, st.st_size, self.kernel, self.c, tuple(self.display_names.keys()),
+               None if exclude_ids is None else frozenset(exclude_ids))
+        cache = self.__dict__.setdefault("_svm_cache", {})
+        if key in cache:
+            return cache[key]
         svm = SVC(kernel=self.kernel, C=self.c)
         keys = list(self.display_names.keys())
         drop = {i for i, key in enumerate(keys) if exclude_ids is not None and key in exclude_ids}
         x_train, y_train = [], []
-        with open(self.base_path / self.slug() / "scores.csv", "r", encoding="utf-8") as file:
+        with open(csv_path, "r", encoding="utf-8") as file:
             file.readline()
             for row in csv.reader(file):
                 label = row[-1]
@@ -111,6 +121,8 @@ class ProbabilisticFilterSVMModel(ProbabilisticFilterModel):
                 x_train.append([float(v) for i, v in enumerate(row[1:-1]) if i not in drop])
                 y_train.append(label)
         svm.fit(x_train, y_train)
+        cache.clear()                      # one classifier per model object is enough
+        cache[key] = svm
         return svm
 
     @staticmethod
