@@ -1,0 +1,208 @@
+"""Golden vectors of the model-layer flows, produced by the REFERENCE'S OWN Python code.
+
+Run in the build container (needs /root/reference; the result travels, this script's inputs do not):
+
+    python tests/golden/make_reference_flows.py            # writes tests/golden/reference_flows.json
+
+What runs: XspecT's real modules from /root/reference/src (models/probabilistic_filter_model.py,
+probabilistic_single_filter_model.py, probabilistic_filter_svm_model.py, probabilistic_filter_mlst_model.py,
+models/result.py, models/mlst_result.py, file_io.py) — their predict dispatch, per-record loops, exclude / display-name
+handling, _count_kmers, ModelResult arithmetic, the SVM fit on scores.csv, the MLST chunking / `> 50` / per-allele sums /
+has_sufficient_score, MlstResult — on the synthetic model directories of tests/model_fixtures.py.
+
+What does NOT run: the reference's un-vendored native dependencies, which are not installable offline.  They are
+replaced by stand-ins with the same call shapes: `cobs_index.Search` -> oracle.CobsOracle, `rbloom.Bloom` ->
+oracle.BloomOracle, `Bio` -> xspect2_b200.seqio's Seq / SeqRecord / iterators, `slugify` -> model_management.slugify,
+mappy / pysam / loguru / requests -> empty modules (their code is off this path).  The golden file therefore pins the
+model layer (SURVEY.md 8(a) rows a2, a4, a5, a7's Python loop, a8, a9, a10) against the real reference code; the
+third-party layer stays pinned only as DESIGN.md §2 says.
+
+tests/test_reference_golden.py rebuilds the same model directories and inputs from the same seeds and compares (CPU:
+the oracle's restated loops that every GPU test is compared with; GPU: the CUDA-backed models themselves)."""
+from __future__ import annotations
+
+import json
+import sys
+import tempfile
+import types
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+REF_SRC = Path("/root/reference/src")
+OUT = Path(__file__).resolve().parent / "reference_flows.json"
+
+
+def install_stand_ins():
+    from oracle import oracle
+    from xspect2_b200 import seqio
+    from xspect2_b200.model_management import slugify
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    fasta_io = mod("Bio.SeqIO.FastaIO", FastaIterator=seqio.FastaIterator)
+    quality_io = mod("Bio.SeqIO.QualityIO", FastqPhredIterator=seqio.FastqPhredIterator)
+    seq_io = mod("Bio.SeqIO", parse=lambda handle, fmt: seqio.parse(Path(handle), fmt), FastaIO=fasta_io, QualityIO=quality_io,
+                 write=lambda records, handle, fmt: seqio.write_fasta(records, handle))
+    bio_seq = mod("Bio.Seq", Seq=seqio.Seq)
+    bio_rec = mod("Bio.SeqRecord", SeqRecord=seqio.SeqRecord)
+    mod("Bio", SeqIO=seq_io, Seq=bio_seq, SeqRecord=bio_rec)
+    mod("slugify", slugify=slugify)
+
+    class Search:                      # cobs_index.Search(path, load_complete).search(str, step=...) -> [.doc_name, .score]
+        def __init__(self, path, load_complete=False):
+            self._o = oracle.CobsOracle(str(path))
+
+        def search(self, query, step=1):
+            return self._o.search(query, step)
+
+    mod("cobs_index", Search=Search, SearchResult=object, DocumentList=object, ClassicIndexParameters=object,
+        CompactIndexParameters=object)
+
+    class Bloom:                       # rbloom.Bloom.load(path, hash_func) ; `kmer in bloom`
+        def __init__(self, o):
+            self._o = o
+
+        @staticmethod
+        def load(path, hash_func=None):
+            return Bloom(oracle.BloomOracle(str(path), 0))
+
+        def __contains__(self, kmer):
+            return kmer in self._o
+
+    mod("rbloom", Bloom=Bloom)
+    for name in ("mappy", "pysam", "loguru", "requests"):
+        mod(name, logger=types.SimpleNamespace(info=lambda *a, **k: None, warning=lambda *a, **k: None, error=lambda *a, **k: None))
+    sys.path.insert(0, str(REF_SRC))
+
+
+def build_world(base: Path):
+    """The model directories and inputs of tests/test_reference_golden.py (same seeds, same order of RNG draws)."""
+    from oracle import oracle
+    from tests import model_fixtures as mf, synth
+    models = base / "models"
+    models.mkdir(parents=True)
+    rng = np.random.default_rng(2026)
+    sp_json, genomes, svm_genomes = mf.species_model(oracle, models, rng)
+    ge_json = mf.genus_model(oracle, models, list(genomes.values()))
+    ml_json, alleles = mf.mlst_model(oracle, models, rng)
+    r2 = np.random.default_rng(77)
+    gl = list(genomes.values())
+    bases, b, e = synth.sample_reads(r2, gl, 60, (40, 400), sub=0.01, n_rate=0.002)
+    recs = [(f"read{i}", bases[int(x):int(y)].tobytes().decode()) for i, (x, y) in enumerate(zip(b, e))]
+    recs.append(("contig_long", np.concatenate([gl[0], gl[2][:3000]]).tobytes().decode()))
+    recs.append(("read3", gl[1][:500].tobytes().decode()))        # duplicate id: overwrites the earlier read3
+    # an "assembly" for the MLST model: random flanks around one allele of every locus (some mutated), long enough for
+    # the chunked branch (>= 10 000 bp), plus a short record for the unchunked branch
+    r3 = np.random.default_rng(78)
+    parts = [synth.random_dna(r3, 4000)]
+    chosen = {}
+    for li, (locus, al) in enumerate(alleles.items()):
+        name = list(al)[int(r3.integers(0, len(al)))]
+        chosen[locus] = name
+        s = al[name].copy()
+        if li == 1:
+            s = synth.mutate(r3, s, sub=0.01)
+        parts += [s, synth.random_dna(r3, 3000)]
+    assembly = np.concatenate(parts).tobytes().decode()
+    short = alleles[next(iter(alleles))][next(iter(alleles[next(iter(alleles))]))].tobytes().decode()
+    return dict(models=models, sp_json=sp_json, ge_json=ge_json, ml_json=ml_json, genomes=genomes, svm_genomes=svm_genomes,
+                alleles=alleles, recs=recs, assembly=assembly, short=short, chosen=chosen)
+
+
+def result_dict(res) -> dict:
+    d = res.to_dict()
+    # JSON object order is the dict order the reference produced: keep it as lists of pairs where order is part of the contract
+    return {"to_dict": d, "hits_order": {rid: list(h.items()) for rid, h in res.hits.items()}}
+
+
+def main() -> None:
+    install_stand_ins()
+    from Bio.Seq import Seq
+    from Bio.SeqRecord import SeqRecord
+    from tests import model_fixtures as mf
+    from xspect.models.probabilistic_filter_model import ProbabilisticFilterModel
+    from xspect.models.probabilistic_filter_mlst_model import ProbabilisticFilterMlstSchemeModel
+    from xspect.models.probabilistic_filter_svm_model import ProbabilisticFilterSVMModel
+    from xspect.models.probabilistic_single_filter_model import ProbabilisticSingleFilterModel
+    import xspect.models.probabilistic_filter_mlst_model as ref_mlst
+
+    out = {"_generator": "tests/golden/make_reference_flows.py", "_reference": "XspecT, /root/reference/src/xspect (models/*.py, file_io.py)",
+           "_stand_ins": "cobs_index -> oracle.CobsOracle, rbloom -> oracle.BloomOracle, Bio -> xspect2_b200.seqio"}
+    with tempfile.TemporaryDirectory() as td:
+        w = build_world(Path(td))
+        fasta, fastq = Path(td) / "in.fna", Path(td) / "in.fastq"
+        mf.write_fasta(fasta, w["recs"])
+        mf.write_fastq(fastq, w["recs"])
+        rl = [SeqRecord(Seq(s), rid) for rid, s in w["recs"]]
+        ids = list(w["genomes"])
+
+        # ---- species model: predict over the input kinds, steps, exclude ids, display names; ModelResult arithmetic
+        sp = ProbabilisticFilterModel.load(w["sp_json"])
+        cases = {}
+        for name, kw in {"step1": {}, "step3": {"step": 3}, "exclude": {"exclude_ids": [ids[1], ids[4]]},
+                         "display": {"display_name": True}, "exclude_display_step2": {"exclude_ids": [ids[0]], "display_name": True, "step": 2}}.items():
+            res = sp.predict(fasta, **kw)
+            cases[name] = result_dict(res)
+            cases[name]["scores"] = res.get_scores()
+            cases[name]["total_hits"] = res.get_total_hits()
+        cases["single_record"] = result_dict(sp.predict(rl[5]))
+        cases["record_list_head"] = result_dict(sp.predict(rl[:7], step=2))
+        cases["fastq_equals_fasta"] = sp.predict(fastq).to_dict() == sp.predict(fasta).to_dict()
+        cases["count_kmers"] = {f"{len(r.seq)}/{st}": sp._count_kmers(r, st) for r in rl[:12] for st in (1, 2, 3, 7)}
+        res = sp.predict(fasta)
+        cases["filtered_labels"] = {f"{tid}@{thr}": res.get_filtered_subsequence_labels(tid, thr) for tid in ids[:3] for thr in (0.3, 0.7, 0.99)}
+        out["species"] = cases
+
+        # ---- species + SVM: prediction from scores.csv (bug-compatible exclude ids)
+        svm = ProbabilisticFilterSVMModel.load(w["sp_json"])
+        sv = {}
+        for acc, (tid, g) in list(w["svm_genomes"].items())[::4]:
+            rec = SeqRecord(Seq(g.tobytes().decode()), acc)
+            r0 = svm.predict(rec)
+            r1 = svm.predict(rec, exclude_ids=[ids[2]])
+            sv[acc] = {"label": tid, "prediction": r0.prediction, "prediction_excluding": r1.prediction,
+                       "scores_total": r0.get_scores()["total"], "scores_total_excluding": r1.get_scores()["total"]}
+        sv["file"] = {"prediction": svm.predict(fasta).prediction, "prediction_step3": svm.predict(fasta, step=3).prediction}
+        out["svm"] = sv
+
+        # ---- genus model (Bloom filter): the per-k-mer Python loop
+        ge = ProbabilisticSingleFilterModel.load(w["ge_json"])
+        g = {}
+        for name, kw in {"step1": {}, "step4": {"step": 4}}.items():
+            res = ge.predict(fasta, **kw)
+            g[name] = result_dict(res)
+            g[name]["scores"] = res.get_scores()
+        res = ge.predict(fasta)
+        g["filtered_labels"] = {str(thr): res.get_filtered_subsequence_labels("Testgenus", thr) for thr in (0.3, 0.7, 1.0)}
+        out["genus"] = g
+
+        # ---- MLST scheme model: chunked and unchunked branches, per-locus results, sufficient-score flag
+        class Handler:                                  # the PubMLST POST is a network side effect inside the path
+            def get_strain_type_name(self, highest_results, post_url):
+                return {"ST": "golden", "received": highest_results}
+
+        ref_mlst.PubMLSTHandler = Handler
+        ml = ProbabilisticFilterMlstSchemeModel.load(w["ml_json"])
+        m = {"chosen_alleles": w["chosen"]}
+        for name, seq in (("assembly", w["assembly"]), ("short", w["short"])):
+            for step in (1, 2):
+                hits = ml.calculate_hits(Seq(seq), step=step) if "step" in ml.calculate_hits.__code__.co_varnames else ml.calculate_hits(Seq(seq))
+                m[f"{name}_step{step}"] = json.loads(json.dumps(hits, default=lambda o: o.__dict__))
+        asm_fa = Path(td) / "assembly.fna"
+        mf.write_fasta(asm_fa, [("asm1", w["assembly"])])
+        pres = ml.predict(asm_fa)
+        m["predict_file"] = pres.to_dict() if hasattr(pres, "to_dict") else json.loads(json.dumps(pres, default=lambda o: o.__dict__))
+        out["mlst"] = m
+    OUT.write_text(json.dumps(out, indent=1, sort_keys=False))
+    print("wrote", OUT, OUT.stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    main()
