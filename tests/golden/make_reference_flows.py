@@ -86,7 +86,7 @@ def build_world(base: Path):
     """The model directories and inputs of tests/test_reference_golden.py (same seeds, same order of RNG draws)."""
     from oracle import oracle
     from tests import model_fixtures as mf, synth
-    models = base / "models"
+    models = base / "xspect-data" / "models"          # HOME = base makes this the data root of both implementations
     models.mkdir(parents=True)
     rng = np.random.default_rng(2026)
     sp_json, genomes, svm_genomes = mf.species_model(oracle, models, rng)
@@ -114,6 +114,74 @@ def build_world(base: Path):
     short = alleles[next(iter(alleles))][next(iter(alleles[next(iter(alleles))]))].tobytes().decode()
     return dict(models=models, sp_json=sp_json, ge_json=ge_json, ml_json=ml_json, genomes=genomes, svm_genomes=svm_genomes,
                 alleles=alleles, recs=recs, assembly=assembly, short=short, chosen=chosen)
+
+
+def workflow_inputs(td: Path, w: dict) -> dict:
+    """Input files of the workflow cases (shared with tests/test_reference_golden.py)."""
+    from tests import model_fixtures as mf
+    d = td / "wf"
+    (d / "dir").mkdir(parents=True, exist_ok=True)
+    mf.write_fasta(d / "sample.fna", w["recs"])
+    mf.write_fasta(d / "dir" / "a.fna", w["recs"][:20])
+    mf.write_fastq(d / "dir" / "b.fastq", w["recs"][20:45])
+    mf.write_fasta(d / "assembly.fna", [("asm1", w["assembly"]), ("short1", w["short"])])
+    return {"sample": d / "sample.fna", "dir": d / "dir", "assembly": d / "assembly.fna", "out": d}
+
+
+def fasta_records(path: Path) -> list:
+    from xspect2_b200.file_io import get_record_iterator
+    return [[r.id, str(r.seq)] for r in get_record_iterator(path)] if path.exists() else None
+
+
+def workflows(td: Path, w: dict) -> dict:
+    """classify.py / filter_sequences.py / model_management.py / file_io.prepare_input_output_paths of the reference,
+    run as a user would (HOME points at the synthetic data root)."""
+    import os
+    os.environ["HOME"] = str(td)
+    import xspect.classify as cl
+    import xspect.filter_sequences as fs
+    import xspect.model_management as mm
+    import xspect.models.probabilistic_filter_mlst_model as ref_mlst
+    from xspect.definitions import get_xspect_model_path
+    from xspect.file_io import prepare_input_output_paths
+
+    assert get_xspect_model_path() == w["models"]
+    inp = workflow_inputs(td, w)
+    o = inp["out"]
+    ids = list(w["genomes"])
+    rel = lambda p: str(Path(p).relative_to(w["models"]))
+    g = {"model_management": {
+        "genus_model_path": rel(mm.get_genus_model_path("Testgenus")), "species_model_path": rel(mm.get_species_model_path("Testgenus")),
+        "mlst_model_path": rel(mm.get_mlst_model_path("abaumannii", "Oxford")), "is_svm_model": mm.is_svm_model("testgenus-species"),
+        "is_svm_model_genus": mm.is_svm_model("testgenus-genus"), "models": mm.get_models(),
+        "display_names": mm.get_model_display_names("testgenus-species"), "mlst_schemes": mm.get_available_mlst_schemes(),
+        "metadata_keys": list(mm.get_model_metadata("testgenus-species").keys())}}
+    paths, get_out = prepare_input_output_paths(inp["dir"])
+    g["prepare_paths"] = {"dir_inputs": [p.name for p in paths], "dir_outputs": [get_out(i, o / "res.json").name for i in range(len(paths))],
+                          "file_output": prepare_input_output_paths(inp["sample"])[1](0, o / "res.json").name}
+    cl.classify_species("Testgenus", inp["sample"], o / "sp.json", step=2, display_name=True, exclude_ids=[ids[3]])
+    g["classify_species_text"] = (o / "sp.json").read_text()
+    cl.classify_species("Testgenus", inp["dir"], o / "spd.json")
+    g["classify_species_dir"] = {n: json.loads((o / n).read_text()) for n in ("spd_1.json", "spd_2.json")}
+    cl.classify_genus("Testgenus", inp["sample"], o / "ge.json", step=3)
+    g["classify_genus"] = json.loads((o / "ge.json").read_text())
+
+    class Handler:
+        def get_strain_type_name(self, highest_results, post_url):
+            return {"ST": "golden", "received": highest_results}
+
+    ref_mlst.PubMLSTHandler = Handler
+    for limit in (False, True):
+        cl.classify_mlst(inp["assembly"], "abaumannii", "Oxford", o / f"ml{int(limit)}.json", limit)
+        g[f"classify_mlst_limit{int(limit)}"] = json.loads((o / f"ml{int(limit)}.json").read_text())
+    fs.filter_genus("Testgenus", inp["sample"], o / "kept.fasta", 0.7, o / "kept.json", 2)
+    g["filter_genus"] = {"records": fasta_records(o / "kept.fasta"), "classification": json.loads((o / "kept.json").read_text())}
+    for name, thr in (("thr05", 0.5), ("best", -1)):
+        fs.filter_species("Testgenus", ids[0], inp["sample"], o / f"sp_{name}.fasta", thr)
+        g[f"filter_species_{name}"] = {"records": fasta_records(o / f"sp_{name}.fasta")}
+    fs.filter_genus("Testgenus", inp["dir"], o / "keptd.fasta", 0.99)
+    g["filter_genus_dir"] = {n: fasta_records(o / n) for n in ("keptd_1.fasta", "keptd_2.fasta")}
+    return g
 
 
 def result_dict(res) -> dict:
@@ -200,6 +268,7 @@ def main() -> None:
         pres = ml.predict(asm_fa)
         m["predict_file"] = pres.to_dict() if hasattr(pres, "to_dict") else json.loads(json.dumps(pres, default=lambda o: o.__dict__))
         out["mlst"] = m
+        out["workflows"] = workflows(Path(td), w)
     OUT.write_text(json.dumps(out, indent=1, sort_keys=False))
     print("wrote", OUT, OUT.stat().st_size, "bytes")
 

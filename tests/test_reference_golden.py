@@ -209,3 +209,122 @@ def test_gpu_mlst_model_equals_reference_code(world, gpu, tmp_path):
     for d in (got, gold):
         d.pop("Input_source", None)                       # set by the classify workflow, not by predict
     assert json.loads(json.dumps(got)) == gold
+
+
+# ------------------------------------------------------------------------------------------ workflows (classify.py, filter_sequences.py, ...)
+WF = GOLD["workflows"]
+
+
+@pytest.fixture()
+def home(world, monkeypatch):
+    """HOME = the directory that holds the synthetic xspect-data root (definitions.get_xspect_root_path)."""
+    base = Path(world["models"]).parent.parent
+    monkeypatch.setenv("HOME", str(base))
+    return base
+
+
+def test_model_management_and_path_fanout_equal_reference_code(world, home, tmp_path):
+    from tests.golden.make_reference_flows import workflow_inputs
+    from xspect2_b200 import definitions, model_management as mm
+    from xspect2_b200.file_io import prepare_input_output_paths
+    assert definitions.get_xspect_model_path() == Path(world["models"])
+    rel = lambda p: str(Path(p).relative_to(world["models"]))
+    g = WF["model_management"]
+    assert rel(mm.get_genus_model_path("Testgenus")) == g["genus_model_path"]
+    assert rel(mm.get_species_model_path("Testgenus")) == g["species_model_path"]
+    assert rel(mm.get_mlst_model_path("abaumannii", "Oxford")) == g["mlst_model_path"]
+    assert mm.is_svm_model("testgenus-species") is g["is_svm_model"] and mm.is_svm_model("testgenus-genus") is g["is_svm_model_genus"]
+    assert mm.get_models() == g["models"] and mm.get_model_display_names("testgenus-species") == g["display_names"]
+    assert mm.get_available_mlst_schemes() == g["mlst_schemes"]
+    assert list(mm.get_model_metadata("testgenus-species").keys()) == g["metadata_keys"]
+    inp = workflow_inputs(tmp_path, world)
+    paths, get_out = prepare_input_output_paths(inp["dir"])
+    assert [p.name for p in paths] == WF["prepare_paths"]["dir_inputs"]
+    assert [get_out(i, tmp_path / "res.json").name for i in range(len(paths))] == WF["prepare_paths"]["dir_outputs"]
+    assert prepare_input_output_paths(inp["sample"])[1](0, tmp_path / "res.json").name == WF["prepare_paths"]["file_output"]
+
+
+def test_saved_result_bytes_equal_reference_code(world, oracle, tmp_path):
+    """classify_species' output file: the reference's ModelResult.save text, byte for byte, from this package's ModelResult
+    (hits of the restated loop, display-name keys, the SVM prediction of this package's host code)."""
+    from xspect2_b200.models.probabilistic_filter_svm_model import ProbabilisticFilterSVMModel as M
+    from xspect2_b200.models.result import ModelResult
+    meta = json.loads(Path(world["sp_json"]).read_text())
+    ids = list(world["genomes"])
+    ex = [ids[3]]
+    orc = oracle.CobsOracle(Path(world["sp_json"]).parent / meta["model_slug"] / "index.cobs_classic")
+    hits, nk = oracle.reference_predict(orc, world["recs"], meta["k"], ex, 2)
+    m = M.__new__(M)
+    m.base_path, m.kernel, m.c, m.display_names = Path(world["sp_json"]).parent, meta["kernel"], meta["C"], meta["display_names"]
+    m.slug = lambda: meta["model_slug"]
+    plain = ModelResult(meta["model_slug"], hits, nk, sparse_sampling_step=2)
+    pred = str(m._get_svm(ex).predict(m.svm_input(plain))[0])
+    res = ModelResult(meta["model_slug"], _display(meta, hits), nk, sparse_sampling_step=2, prediction=pred, input_source="sample.fna")
+    res.save(tmp_path / "sp.json")
+    assert (tmp_path / "sp.json").read_text() == WF["classify_species_text"]
+
+
+def test_filter_outputs_equal_reference_code(world, oracle, tmp_path):
+    """filter_genus / filter_species: the labels this package's ModelResult keeps (threshold and best-score modes) from the
+    restated loops' hits, written by its native FASTA filter (host code), equal the reference's filtered files record
+    for record — a duplicated id included twice, as the reference's `record.id in included_ids` does."""
+    from tests.golden.make_reference_flows import fasta_records, workflow_inputs
+    from xspect2_b200.file_io import filter_sequences
+    from xspect2_b200.models.result import ModelResult
+    inp = workflow_inputs(tmp_path, world)
+    ids = list(world["genomes"])
+    gm = json.loads(Path(world["ge_json"]).read_text())
+    bf = oracle.BloomOracle(Path(world["ge_json"]).parent / gm["model_slug"] / "filter.bloom", gm["k"])
+    hits, nk = oracle.reference_predict_bloom(bf, "Testgenus", world["recs"], gm["k"], 2)
+    res = ModelResult(gm["model_slug"], hits, nk, sparse_sampling_step=2, input_source="sample.fna")
+    assert json.loads(json.dumps(res.to_dict())) == WF["filter_genus"]["classification"]
+    filter_sequences(inp["sample"], tmp_path / "kept.fasta", res.get_filtered_subsequence_labels("Testgenus", 0.7))
+    assert fasta_records(tmp_path / "kept.fasta") == WF["filter_genus"]["records"]
+    sm = json.loads(Path(world["sp_json"]).read_text())
+    orc = oracle.CobsOracle(Path(world["sp_json"]).parent / sm["model_slug"] / "index.cobs_classic")
+    hits, nk = oracle.reference_predict(orc, world["recs"], sm["k"])
+    res = ModelResult(sm["model_slug"], hits, nk)
+    for name, thr in (("thr05", 0.5), ("best", -1)):
+        filter_sequences(inp["sample"], tmp_path / f"sp_{name}.fasta", res.get_filtered_subsequence_labels(ids[0], thr))
+        assert fasta_records(tmp_path / f"sp_{name}.fasta") == WF[f"filter_species_{name}"]["records"], name
+
+
+@pytest.mark.gpu
+def test_gpu_workflows_equal_reference_code(world, gpu, home, tmp_path, monkeypatch):
+    """classify_species / classify_genus / classify_mlst / filter_genus / filter_species of this package, run as a user
+    would, against the files the reference's workflow functions wrote for the same inputs."""
+    import xspect2_b200.models.probabilistic_filter_mlst_model as mlst_mod
+    from tests.golden.make_reference_flows import fasta_records, workflow_inputs
+    from xspect2_b200 import classify, filter_sequences
+
+    class Handler:
+        def get_strain_type_name(self, highest_results, post_url):
+            return {"ST": "golden", "received": highest_results}
+
+    monkeypatch.setattr(mlst_mod, "PubMLSTHandler", Handler)
+    inp = workflow_inputs(tmp_path, world)
+    o = inp["out"]
+    ids = list(world["genomes"])
+    classify.classify_species("Testgenus", inp["sample"], o / "sp.json", step=2, display_name=True, exclude_ids=[ids[3]])
+    assert (o / "sp.json").read_text() == WF["classify_species_text"]                   # byte for byte
+    classify.classify_species("Testgenus", inp["dir"], o / "spd.json")
+    for n, gold in WF["classify_species_dir"].items():
+        assert json.loads((o / n).read_text()) == gold, n
+    classify.classify_genus("Testgenus", inp["sample"], o / "ge.json", step=3)
+    assert json.loads((o / "ge.json").read_text()) == WF["classify_genus"]
+    for limit in (False, True):
+        classify.classify_mlst(inp["assembly"], "abaumannii", "Oxford", o / f"ml{int(limit)}.json", limit)
+        got, gold = json.loads((o / f"ml{int(limit)}.json").read_text()), WF[f"classify_mlst_limit{int(limit)}"]
+        assert got == gold, limit
+        for rid, res in got["Results"].items():                                         # allele order inside every locus
+            for locus, sc in res[1]["All results"].items():
+                assert list(sc.items()) == list(gold["Results"][rid][1]["All results"][locus].items())
+    filter_sequences.filter_genus("Testgenus", inp["sample"], o / "kept.fasta", 0.7, o / "kept.json", 2)
+    assert fasta_records(o / "kept.fasta") == WF["filter_genus"]["records"]
+    assert json.loads((o / "kept.json").read_text()) == WF["filter_genus"]["classification"]
+    for name, thr in (("thr05", 0.5), ("best", -1)):
+        filter_sequences.filter_species("Testgenus", ids[0], inp["sample"], o / f"sp_{name}.fasta", thr)
+        assert fasta_records(o / f"sp_{name}.fasta") == WF[f"filter_species_{name}"]["records"], name
+    filter_sequences.filter_genus("Testgenus", inp["dir"], o / "keptd.fasta", 0.99)
+    for n, gold in WF["filter_genus_dir"].items():
+        assert fasta_records(o / n) == gold, n
