@@ -184,6 +184,39 @@ def workflows(td: Path, w: dict) -> dict:
     return g
 
 
+def cli_runs(td: Path, w: dict) -> dict:
+    """The reference's click commands (main.py): `models list` and the full `all` pipeline of BASELINE config 3
+    (main.py:84-188: filter_genus -> classify_species on the filtered directory -> MLST when the prediction is 470)."""
+    import re
+    from click.testing import CliRunner
+    import xspect.main as ref_main
+    import xspect.models.probabilistic_filter_mlst_model as ref_mlst
+
+    class Handler:
+        def get_strain_type_name(self, highest_results, post_url):
+            return {"ST": "golden", "received": highest_results}
+
+    ref_mlst.PubMLSTHandler = Handler
+    inp = workflow_inputs(td, w)
+    runner = CliRunner()
+    g = {}
+    r = runner.invoke(ref_main.cli, ["models", "list"])
+    assert r.exit_code == 0, r.output
+    g["models_list_output"] = r.output
+    outdir = inp["out"] / "all"
+    r = runner.invoke(ref_main.cli, ["all", "-g", "Testgenus", "-i", str(inp["sample"]), "-o", str(outdir), "-t", "0.7"])
+    assert r.exit_code == 0, r.output
+    norm = lambda t: re.sub(r"[0-9a-f]{8}-[0-9a-f]{4}-[0-9a-f]{4}-[0-9a-f]{4}-[0-9a-f]{12}", "<run>", t)
+    g["all_output"] = norm(r.output).replace(str(outdir), "<outdir>")
+    files = {}
+    for p in sorted(outdir.rglob("*")):
+        if p.is_file():
+            key = norm(str(p.relative_to(outdir)))
+            files[key] = fasta_records(p) if p.suffix == ".fasta" else json.loads(norm(p.read_text()))
+    g["all_files"] = files
+    return g
+
+
 def result_dict(res) -> dict:
     d = res.to_dict()
     # JSON object order is the dict order the reference produced: keep it as lists of pairs where order is part of the contract
@@ -269,7 +302,8 @@ def main() -> None:
         m["predict_file"] = pres.to_dict() if hasattr(pres, "to_dict") else json.loads(json.dumps(pres, default=lambda o: o.__dict__))
         out["mlst"] = m
         out["workflows"] = workflows(Path(td), w)
-    OUT.write_text(json.dumps(out, indent=1, sort_keys=False))
+        out["cli"] = cli_runs(Path(td), w)
+    OUT.write_text(json.dumps(out, separators=(",", ":"), sort_keys=False))      # compact: a fixture, not a document
     print("wrote", OUT, OUT.stat().st_size, "bytes")
 
 

@@ -328,3 +328,74 @@ def test_gpu_workflows_equal_reference_code(world, gpu, home, tmp_path, monkeypa
     filter_sequences.filter_genus("Testgenus", inp["dir"], o / "keptd.fasta", 0.99)
     for n, gold in WF["filter_genus_dir"].items():
         assert fasta_records(o / n) == gold, n
+
+
+# ------------------------------------------------------------------------------------------ CLI: `models list`, `xspect all`
+CLI = GOLD["cli"]
+
+
+def test_cli_models_list_equals_reference_code(world, home):
+    """`xspect models list` of the reference's click tree == this package's (click choices are evaluated at import)."""
+    import importlib
+
+    from click.testing import CliRunner
+    import xspect2_b200.main as main
+    main = importlib.reload(main)
+    r = CliRunner().invoke(main.cli, ["models", "list"])
+    assert r.exit_code == 0 and r.output == CLI["models_list_output"]
+
+
+def test_all_pipeline_of_the_reference_equals_the_restated_stages(world, oracle, tmp_path):
+    """`xspect all` (main.py:84-188, BASELINE config 3's flow) as the reference ran it: genus classification -> records with
+    round(hits / num_kmers, 2) >= 0.7 written to the filtered FASTA -> species classification (+ SVM) of that file -> MLST
+    of that file because the prediction is 470.  Every file it wrote is reproduced here from the oracle's restated loops,
+    this package's ModelResult / SVM host code / FASTA filter — and the kept set equals the exact integer threshold table
+    of the fused device pipeline (pipeline.min_hits_table)."""
+    from tests.golden.make_reference_flows import fasta_records, workflow_inputs
+    from xspect2_b200.file_io import filter_sequences
+    from xspect2_b200.models.probabilistic_filter_svm_model import ProbabilisticFilterSVMModel as M
+    from xspect2_b200.models.result import ModelResult
+    from xspect2_b200.pipeline import min_hits_table
+    files = CLI["all_files"]
+    inp = workflow_inputs(tmp_path, world)
+    # ---- step 1: genus classification and filter
+    gm = json.loads(Path(world["ge_json"]).read_text())
+    bf = oracle.BloomOracle(Path(world["ge_json"]).parent / gm["model_slug"] / "filter.bloom", gm["k"])
+    hits, nk = oracle.reference_predict_bloom(bf, "Testgenus", world["recs"], gm["k"], 1)
+    genus = ModelResult(gm["model_slug"], hits, nk, input_source="sample.fna")
+    assert json.loads(json.dumps(genus.to_dict())) == files["genus_classification_<run>.json"]
+    labels = genus.get_filtered_subsequence_labels("Testgenus", 0.7)
+    filter_sequences(inp["sample"], tmp_path / "kept.fasta", labels)
+    kept = fasta_records(tmp_path / "kept.fasta")
+    assert kept == files["filtered_sequences/genus_filtered_<run>.fasta"]
+    table = min_hits_table(max(nk.values()), 0.7)             # the fused pipeline's keep rule, per record id
+    assert {rid for rid in hits if hits[rid]["Testgenus"] >= table[nk[rid]]} == set(labels)
+    # ---- step 2: species classification of the filtered file (directory input -> numbered output)
+    sm = json.loads(Path(world["sp_json"]).read_text())
+    orc = oracle.CobsOracle(Path(world["sp_json"]).parent / sm["model_slug"] / "index.cobs_classic")
+    recs = [(rid, seq) for rid, seq in kept]
+    shits, snk = oracle.reference_predict(orc, recs, sm["k"])
+    m = M.__new__(M)
+    m.base_path, m.kernel, m.c, m.display_names = Path(world["sp_json"]).parent, sm["kernel"], sm["C"], sm["display_names"]
+    m.slug = lambda: sm["model_slug"]
+    plain = ModelResult(sm["model_slug"], shits, snk)
+    pred = str(m._get_svm(None).predict(m.svm_input(plain))[0])
+    species = ModelResult(sm["model_slug"], shits, snk, prediction=pred, input_source="genus_filtered_<run>.fasta")
+    gold = files["species_classification_<run>_1.json"]
+    assert json.loads(json.dumps(species.to_dict())) == gold and pred == "470"
+    assert [list(v.items()) for v in species.hits.values()] == [list(v.items()) for v in gold["hits"].values()]
+    # ---- step 3: MLST of the filtered file (reads: the unchunked branch for every record)
+    mm = json.loads(Path(world["ml_json"]).read_text())
+    base = Path(world["ml_json"]).parent / mm["model_slug"]
+    gold = files["mlst_classification_<run>_1.json"]
+    assert gold["Scheme"] == "Oxford" and gold["Input_source"] == "genus_filtered_<run>.fasta" and list(gold["Results"]) == list(dict(recs))
+    indices = [oracle.CobsOracle(base / f"{locus}.cobs_compact", load_complete=False) for locus in mm["loci"]]
+    for rid, seq in dict(recs).items():
+        allres = gold["Results"][rid][1]["All results"]
+        strain = gold["Results"][rid][0]["Strain type"]
+        for li, locus in enumerate(mm["loci"]):
+            sc = oracle.mlst_locus_scores(indices[li], seq, mm["average_locus_base_pair_size"][li], 1)
+            assert list(sc.items()) == list(allres[locus].items()), (rid, locus)
+            first = next(iter(sc))
+            assert strain[locus] == {first: sc[first]}
+    assert "Step 3/3: Running MLST classification for abaumannii..." in CLI["all_output"]
