@@ -7,7 +7,11 @@ TEST INFRASTRUCTURE ONLY — see the header of ``xs_oracle.cpp``.  Nothing under
 PARITY STATUS: "parity unpinned" for the cobs-reloaded / rbloom pieces (file layouts, hash
 seeds, non-ACGT handling, result order, LCG constants — SURVEY.md Appendix A, [UNVERIFIED-3P]);
 pinned for XXH64 / XXH3-64 (python-xxhash known answers) and for every in-tree semantic
-(reference file:line cited at each function).
+(reference file:line cited at each function): the restated loops at the end of this module
+(``reference_predict*``, ``mlst_locus_scores``, ``sequence_splitter``) are checked against the
+outputs of the reference's own Python code run over this module's ``CobsOracle`` / ``BloomOracle``
+(tests/golden/make_reference_flows.py -> tests/golden/reference_flows.json,
+tests/test_reference_golden.py).
 
 Contents
   * readers for ``index.cobs_classic`` / ``<locus>.cobs_compact`` / ``filter.bloom`` (A.1, A.3, A.4)
