@@ -35,12 +35,18 @@ REF_SRC = Path("/root/reference/src")
 OUT = Path(__file__).resolve().parent / "reference_flows.json"
 
 
-def install_stand_ins():
+def install_stand_ins(real: bool = False):
+    """real=True (a box that has cobs-reloaded, rbloom and Biopython installed): the reference runs on its REAL
+    dependencies and only modules that are absent get an empty stand-in; the output must then equal the committed file,
+    which pins the third-party layer too (tests/test_live_reference.py::test_reference_flows_with_the_real_wheels)."""
+    import importlib.util
     from oracle import oracle
     from xspect2_b200 import seqio
     from xspect2_b200.model_management import slugify
 
     def mod(name, **attrs):
+        if real and importlib.util.find_spec(name.split(".")[0]) is not None:
+            return None
         m = types.ModuleType(name)
         m.__dict__.update(attrs)
         sys.modules[name] = m
@@ -224,7 +230,15 @@ def result_dict(res) -> dict:
 
 
 def main() -> None:
-    install_stand_ins()
+    import argparse
+    global OUT, REF_SRC
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--real", action="store_true", help="use the installed cobs_index / rbloom / Bio instead of the stand-ins")
+    ap.add_argument("--out", default=str(OUT))
+    ap.add_argument("--reference-src", default=str(REF_SRC))
+    args = ap.parse_args()
+    OUT, REF_SRC = Path(args.out), Path(args.reference_src)
+    install_stand_ins(real=args.real)
     from Bio.Seq import Seq
     from Bio.SeqRecord import SeqRecord
     from tests import model_fixtures as mf
@@ -236,6 +250,7 @@ def main() -> None:
 
     out = {"_generator": "tests/golden/make_reference_flows.py", "_reference": "XspecT, /root/reference/src/xspect (models/*.py, file_io.py)",
            "_stand_ins": "cobs_index -> oracle.CobsOracle, rbloom -> oracle.BloomOracle, Bio -> xspect2_b200.seqio"}
+    # (the header is the same with --real: the file must not depend on which implementation of the natives ran)
     with tempfile.TemporaryDirectory() as td:
         w = build_world(Path(td))
         fasta, fastq = Path(td) / "in.fna", Path(td) / "in.fastq"

@@ -50,3 +50,28 @@ def test_bloom_against_real_rbloom(tmp_path, oracle):
     for _ in range(2000):
         km = synth.random_dna(rng, 21).tobytes().decode()
         assert (km in orc) == (km in bf)
+
+
+def test_reference_flows_with_the_real_wheels(tmp_path):
+    """The committed model / workflow / CLI golden vectors were produced by the reference's own Python code over
+    oracle-backed stand-ins for its two native wheels (tests/golden/make_reference_flows.py).  Where the real wheels and
+    the reference's source are available, the same generator runs on them — and must write the same file: one command
+    that pins header layout, bit order, hash seeds, non-ACGT handling, result order and the rbloom constants at once."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    pytest.importorskip("cobs_index")
+    pytest.importorskip("rbloom")
+    pytest.importorskip("Bio")
+    src = Path(os.environ.get("XS_REFERENCE_SRC", "/root/reference/src"))
+    if not (src / "xspect" / "models").is_dir():
+        pytest.skip("the reference's source tree is not available (XS_REFERENCE_SRC)")
+    root = Path(__file__).resolve().parent.parent
+    out = tmp_path / "flows_real.json"
+    subprocess.run([sys.executable, str(root / "tests" / "golden" / "make_reference_flows.py"), "--real", "--out", str(out),
+                    "--reference-src", str(src)], check=True, cwd=root)
+    got, gold = json.loads(out.read_text()), json.loads((root / "tests" / "golden" / "reference_flows.json").read_text())
+    for section in gold:
+        assert got[section] == gold[section], section
